@@ -1,0 +1,156 @@
+"""ctypes loader for the C ABI in include/nolzss_b200.h (libnolzss_b200.so, built by build.py).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc; if that fails, or
+if no CUDA device is present when a compute entry point is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+NLZ_OK, NLZ_ERR_RUNTIME, NLZ_ERR_INVALID, NLZ_ERR_CUDA = 0, 1, 2, 3
+MODE_GENERAL, MODE_RC_PREPARED, MODE_DNA_RC = 0, 1, 2
+RC_MASK = 1 << 63
+
+_u64 = ctypes.c_uint64
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u64pp = ctypes.POINTER(_u64p)
+_vp = ctypes.c_void_p
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("n_text", _u64), ("n_suffixes", _u64), ("n_factorized", _u64), ("n_factors", _u64),
+        ("active_sum", _u64), ("workspace_bytes", _u64),
+        ("key_bits", ctypes.c_uint32), ("sym_bits", ctypes.c_uint32), ("key_syms", ctypes.c_uint32),
+        ("doubling_rounds", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32),
+        ("host_syncs", ctypes.c_uint32),
+        ("ms_total", ctypes.c_float), ("ms_prepare", ctypes.c_float), ("ms_keys", ctypes.c_float),
+        ("ms_sort0", ctypes.c_float), ("ms_doubling", ctypes.c_float), ("ms_lcp", ctypes.c_float),
+        ("ms_lpnf", ctypes.c_float), ("ms_chain", ctypes.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# name -> (restype, argtypes); every symbol declared in include/nolzss_b200.h
+SIGNATURES = {
+    "nlz_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "nlz_ctx_destroy": (None, [_vp]),
+    "nlz_last_error": (ctypes.c_char_p, []),
+    "nlz_free": (None, [_vp]),
+    "nlz_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
+    "nlz_version": (ctypes.c_char_p, []),
+    "nlz_factorize_mode": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _u64pp, _u64p]),
+    "nlz_factorize_mode_into": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _vp, _u64, _u64p]),
+    "nlz_count_mode": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _u64p]),
+    "nlz_factorize_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _vp, _vp, _u64, _u64p]),
+    "nlz_factorize": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64pp, _u64p]),
+    "nlz_count_factors": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64p]),
+    "nlz_factorize_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64pp, _u64p]),
+    "nlz_count_factors_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64p]),
+    "nlz_factorize_multiple_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64pp, _u64p]),
+    "nlz_count_factors_multiple_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64p]),
+    "nlz_debug_index": (ctypes.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "nlz_debug_sort_pairs_u64": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int, ctypes.c_int]),
+    "nlz_debug_sort_pairs_u32": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int, ctypes.c_int]),
+    "nlz_debug_per_position": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _vp, _vp, _u64, _u64p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+_ctx = {}
+
+
+def load():
+    """Loads (building if needed) the shared library and binds every declared symbol."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            path = _build.LIB
+            if not os.path.exists(path):
+                _build.build()
+            L = ctypes.CDLL(path)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)   # AttributeError here means header and library disagree
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def _raise(rc: int):
+    msg = load().nlz_last_error().decode("utf-8", "replace")
+    if rc == NLZ_ERR_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def check(rc: int):
+    if rc != NLZ_OK:
+        _raise(rc)
+
+
+def context(device: int | None = None) -> int:
+    """Process-wide context handle for `device` (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("NOLZSS_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _lib_lock:
+        h = _ctx.get(device)
+    if h is None:
+        L = load()
+        out = _vp()
+        check(L.nlz_ctx_create(device, ctypes.byref(out)))
+        with _lib_lock:
+            h = _ctx.setdefault(device, out.value)
+    return h
+
+
+def _as_buffer(data):
+    """bytes-like -> (address, length, keepalive); itemsize-1, 1-D, like bindings.cpp:58-67."""
+    mv = memoryview(data)
+    if mv.itemsize != 1:
+        raise ValueError("buffer must be a bytes-like object with itemsize==1")
+    if mv.ndim != 1:
+        raise ValueError("buffer must be a 1-dimensional bytes-like object")
+    if not mv.c_contiguous:
+        mv = memoryview(bytes(mv))
+    arr = np.frombuffer(mv, dtype=np.uint8)
+    return arr.ctypes.data if arr.size else None, arr.size, arr
+
+
+def factorize_array(mode: int, data, start_pos: int = 0, device: int | None = None) -> np.ndarray:
+    """(z, 3) uint64 array of (start, length, ref-with-RC_MASK)."""
+    L = load()
+    addr, n, keep = _as_buffer(data)
+    out = _u64p()
+    cnt = _u64(0)
+    check(L.nlz_factorize_mode(context(device), mode, addr, n, start_pos, ctypes.byref(out), ctypes.byref(cnt)))
+    z = cnt.value
+    if z == 0:
+        return np.zeros((0, 3), dtype=np.uint64)
+    try:
+        arr = np.ctypeslib.as_array(out, shape=(z * 3,)).copy().reshape(z, 3)
+    finally:
+        L.nlz_free(out)
+    return arr
+
+
+def count(mode: int, data, start_pos: int = 0, device: int | None = None) -> int:
+    L = load()
+    addr, n, keep = _as_buffer(data)
+    cnt = _u64(0)
+    check(L.nlz_count_mode(context(device), mode, addr, n, start_pos, ctypes.byref(cnt)))
+    return cnt.value
+
+
+def stats(device: int | None = None) -> dict:
+    s = Stats()
+    check(load().nlz_get_stats(context(device), ctypes.byref(s)))
+    return s.as_dict()

@@ -1,0 +1,742 @@
+// C ABI + pipeline orchestration of the B200 noLZSS factorizer (see include/nolzss_b200.h).
+//
+// Pipeline (all on one CUDA stream; host reads back only the byte histogram, the per-round active
+// count and the final factor count):
+//   S0 prepare   text -> X (raw bytes in HBM, padded); DNA_RC mode builds S = T s0 rc(T) s1 on device
+//   S1 SA        keys -> stable LSD radix sort -> prefix doubling with discarding       (sa.cuh)
+//   S2 LCP       chunked Kasai on raw bytes, scattered to rank order                   (lcp.cuh)
+//   S3 LPnF      32-ary summary trees + per-rank LCP-interval climb -> LR[i]           (lpnf.cuh)
+//   S4 chain     chunk exits -> exit-node doubling -> marks -> scan -> triples         (chain.cuh)
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nolzss_b200.h"
+#include "chain.cuh"
+#include "common.cuh"
+#include "lcp.cuh"
+#include "lpnf.cuh"
+#include "radix_sort.cuh"
+#include "sa.cuh"
+
+namespace nlz {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+enum Ev { EV_BEGIN = 0, EV_PREP, EV_KEYS, EV_SORT0, EV_DOUBLING, EV_LCP, EV_LPNF, EV_CHAIN, EV_COUNT };
+
+struct Arena {
+    u8* base = nullptr;
+    size_t cap = 0, off = 0;
+    template <typename T> T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+struct Workspace {
+    u32 n1 = 0;
+    u8* X = nullptr;
+    u32 *SA = nullptr, *RANK = nullptr, *LCP = nullptr;
+    u64* KEY[2] = {nullptr, nullptr};
+    u32* VAL[2] = {nullptr, nullptr};
+    u32* SLOT[2] = {nullptr, nullptr};
+    u32 *HIST = nullptr, *PMAX = nullptr, *PSUM = nullptr, *CTR = nullptr, *BYTEHIST = nullptr;
+    u32* tl[TREE_MAX_LEVELS] = {};
+    u32* tf[TREE_MAX_LEVELS] = {};
+    u32* tr[TREE_MAX_LEVELS] = {};
+};
+
+}  // namespace nlz
+
+using namespace nlz;
+
+struct nlz_ctx {
+    int device = 0;
+    std::mutex mu;
+    Arena arena;
+    Workspace ws;
+    u64* d_out = nullptr;       // device triples for the host-buffer entry points
+    size_t d_out_cap = 0;       // in factors
+    u32* h_pinned = nullptr;    // 4 KB pinned readback area
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[EV_COUNT];
+    nlz_stats stats;
+};
+
+namespace nlz {
+
+static size_t workspace_bytes_for(u64 n1) {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t t = 0;
+    t += al(n1 + 192);               // X
+    t += al((n1 + 2) * 4) * 3;       // SA, RANK, LCP
+    t += al(n1 * 8) * 2;             // KEY
+    t += al(n1 * 4) * 4;             // VAL, SLOT
+    t += al((size_t)RS_BINS * RS_MAX_CTAS * 4);
+    size_t tiles = (n1 + RG_TILE - 1) / RG_TILE + 1;
+    t += al(tiles * 4) * 2;
+    t += al(64 * 4) + al(256 * 4);
+    u64 c = n1 + 1;
+    for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
+        c = (c + 31) / 32;
+        t += al((c + 1) * 4) * 3;
+    }
+    return t + 4096;
+}
+
+static int ensure_workspace(nlz_ctx* c, u64 n1) {
+    size_t need = workspace_bytes_for(n1);
+    if (need > c->arena.cap) {
+        if (c->arena.base) {
+            NLZ_CK(cudaDeviceSynchronize());
+            NLZ_CK(cudaFree(c->arena.base));
+            c->arena.base = nullptr;
+            c->arena.cap = 0;
+        }
+        size_t want = need + need / 8;
+        cudaError_t e = cudaMalloc(&c->arena.base, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = need;
+            e = cudaMalloc(&c->arena.base, want);
+        }
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc of %zu workspace bytes failed: %s", want, cudaGetErrorString(e));
+            return ERR_CUDA;
+        }
+        c->arena.cap = want;
+    }
+    Arena& a = c->arena;
+    Workspace& w = c->ws;
+    a.off = 0;
+    w.n1 = (u32)n1;
+    w.X = a.take<u8>(n1 + 192);
+    w.SA = a.take<u32>(n1 + 2);
+    w.RANK = a.take<u32>(n1 + 2);
+    w.LCP = a.take<u32>(n1 + 2);
+    for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(n1);
+    for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(n1);
+    for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(n1);
+    w.HIST = a.take<u32>((size_t)RS_BINS * RS_MAX_CTAS);
+    size_t tiles = (n1 + RG_TILE - 1) / RG_TILE + 1;
+    w.PMAX = a.take<u32>(tiles);
+    w.PSUM = a.take<u32>(tiles);
+    w.CTR = a.take<u32>(64);
+    w.BYTEHIST = a.take<u32>(256);
+    u64 cnt = n1 + 1;
+    for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
+        cnt = (cnt + 31) / 32;
+        w.tl[lev] = a.take<u32>(cnt + 1);
+        w.tf[lev] = a.take<u32>(cnt + 1);
+        w.tr[lev] = a.take<u32>(cnt + 1);
+    }
+    c->stats.workspace_bytes = c->arena.cap;
+    return OK;
+}
+
+// ---------------------------------------------------------------- S0 kernels
+__global__ void __launch_bounds__(256)
+k_prepare_dna_rc(const u8* __restrict__ T, u32 n, u8* __restrict__ S, u32* __restrict__ first_bad) {
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        u8 c = T[i];
+        u8 u = c, k = 0;
+        switch (c) {
+            case 'A': case 'a': u = 'A'; k = 'T'; break;
+            case 'C': case 'c': u = 'C'; k = 'G'; break;
+            case 'G': case 'g': u = 'G'; k = 'C'; break;
+            case 'T': case 't': u = 'T'; k = 'A'; break;
+            default: atomicMin(first_bad, i); k = c; break;
+        }
+        S[i] = u;
+        S[2 * (u64)n - i] = k;   // rc block starts at n+1; base i maps to n+1+(n-1-i)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S[n] = 1;                 // sentinel 0: factorizer.cpp:110-125 (first byte of 1..255 not in ACGT)
+        S[2 * (u64)n + 1] = 2;    // sentinel 1
+    }
+}
+
+__global__ void k_zero_pad(u8* __restrict__ X, u64 L) {
+    if (threadIdx.x < 128) X[L + threadIdx.x] = 0;
+}
+
+__global__ void k_set_u32(u32* p, u32 v) { *p = v; }
+
+// ---------------------------------------------------------------- pipeline
+struct Problem {
+    int mode;
+    u64 n_in;       // bytes handed in
+    u64 L;          // indexed text length
+    u32 n1;         // suffixes
+    u32 nfac;       // factorized positions [0, nfac)
+    u32 N;          // RC: |S|/2-1
+    u64 start_pos;
+    bool rc;
+};
+
+static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout& lay) {
+    int sigma = 0;
+    for (int c = 0; c < 256; ++c) {
+        if (hist[c] >= 2) tab.cls[c] = (u8)sigma++;
+        else tab.cls[c] = (u8)SENT_CLASS;   // unique or absent byte: sentinel class
+    }
+    int b = 1;
+    while ((1 << b) < sigma) ++b;
+    // 32-bit keys while the expected number of random collisions stays small, else 64-bit keys
+    int w32 = 28 / b;
+    if (w32 > 14) w32 = 14;
+    bool use32 = false;
+    if (w32 >= 1) {
+        double space = 1.0;
+        for (int i = 0; i < w32; ++i) space *= (double)(sigma > 1 ? sigma : 2);
+        use32 = space >= 16.0 * (double)n1;
+    }
+    if (use32) {
+        lay.key_bits = 32; lay.b = b; lay.W = w32; lay.D = 4;
+    } else {
+        int w64 = 59 / b;
+        if (w64 > 29) w64 = 29;
+        lay.key_bits = 64; lay.b = b; lay.W = w64; lay.D = 5;
+    }
+    return OK;
+}
+
+static int bits_for(u32 maxval) {
+    int nb = 1;
+    while (nb < 32 && (maxval >> nb) != 0) ++nb;
+    return nb;
+}
+
+template <typename KeyT>
+static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay,
+                                    cudaStream_t st, int* cur_out, u32* m_out) {
+    Workspace& w = c->ws;
+    const u32 n1 = pb.n1;
+    KeyT* k[2] = {reinterpret_cast<KeyT*>(w.KEY[0]), reinterpret_cast<KeyT*>(w.KEY[1])};
+    u32* v[2] = {w.VAL[0], w.VAL[1]};
+    k_build_keys<KeyT><<<ceil_div_u32(n1, 2048), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, k[0], v[0]);
+    c->stats.kernel_launches += 1;
+    NLZ_CK(cudaEventRecord(c->ev[EV_KEYS], st));
+    DigitPlan plan;
+    const int used_lo = lay.key_bits - lay.W * lay.b;   // lowest symbol bit
+    if (used_lo - lay.D >= 6) {                         // wide unused gap: skip it
+        plan_add_range(plan, 0, lay.D);                 // sentinel-offset field
+        plan_add_range(plan, used_lo, lay.key_bits);    // symbols
+    } else {
+        plan_add_range(plan, 0, lay.key_bits);
+    }
+    int res = 0;
+    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, n1, plan, w.HIST, st, &res, &c->stats.kernel_launches));
+    NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
+    const KeyT dist_mask = ((KeyT)1 << lay.D) - 1;
+    const u32 tiles = ceil_div_u32(n1, RG_TILE);
+    // compaction target must not alias the sorted buffers: use the other KEY/VAL pair
+    k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], n1, dist_mask, w.PMAX, w.PSUM);
+    k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
+    k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, n1, dist_mask, w.PMAX,
+                                                              w.PSUM, w.SA, w.RANK, w.KEY[res ^ 1],
+                                                              w.VAL[res ^ 1], w.SLOT[0]);
+    c->stats.kernel_launches += 3;
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaStreamSynchronize(st));
+    c->stats.host_syncs += 1;
+    *m_out = c->h_pinned[0];
+    *cur_out = res ^ 1;
+    return OK;
+}
+
+static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host, cudaStream_t st,
+                        u64* d_out, u64 capacity, bool count_only, bool stop_after_index,
+                        bool stop_after_lpnf, u64* out_count) {
+    Workspace& w = c->ws;
+    nlz_stats& S = c->stats;
+    const u32 n1 = pb.n1;
+    NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
+
+    // ---- S0: text into X
+    if (pb.mode == NLZ_MODE_DNA_RC) {
+        const u8* dT = static_cast<const u8*>(src);
+        if (src_on_host) {
+            u8* tmp = reinterpret_cast<u8*>(w.KEY[1]);
+            NLZ_CK(cudaMemcpyAsync(tmp, src, pb.n_in, cudaMemcpyHostToDevice, st));
+            dT = tmp;
+        }
+        k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, 0xFFFFFFFFu);
+        u32 grid = ceil_div_u32(pb.n_in, 256);
+        if (grid > (u32)kNumSM * 16) grid = kNumSM * 16;
+        k_prepare_dna_rc<<<grid, 256, 0, st>>>(dT, (u32)pb.n_in, w.X, w.CTR + 8);
+        S.kernel_launches += 2;
+    } else {
+        NLZ_CK(cudaMemcpyAsync(w.X, src, pb.n_in, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    }
+    k_zero_pad<<<1, 128, 0, st>>>(w.X, pb.L);
+    NLZ_CK(cudaMemsetAsync(w.BYTEHIST, 0, 256 * 4, st));
+    {
+        u32 grid = ceil_div_u32(pb.L / 4 + 1, 256 * 8);
+        if (grid > (u32)kNumSM * 8) grid = kNumSM * 8;
+        k_byte_hist<<<grid, 256, 0, st>>>(w.X, pb.L, w.BYTEHIST);
+    }
+    S.kernel_launches += 2;
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 16, w.BYTEHIST, 256 * 4, cudaMemcpyDeviceToHost, st));
+    if (pb.mode == NLZ_MODE_DNA_RC) NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaEventRecord(c->ev[EV_PREP], st));
+    NLZ_CK(cudaStreamSynchronize(st));
+    S.host_syncs += 1;
+    if (pb.mode == NLZ_MODE_DNA_RC && c->h_pinned[8] != 0xFFFFFFFFu) {
+        u32 bad = c->h_pinned[8];
+        u8 ch = 0;
+        if (src_on_host) ch = static_cast<const u8*>(src)[bad];
+        else NLZ_CK(cudaMemcpy(&ch, static_cast<const u8*>(src) + bad, 1, cudaMemcpyDeviceToHost));
+        // message of prepare_multiple_dna_sequences_w_rc, factorizer.cpp:91-92
+        set_error("Invalid nucleotide '%c' found in sequence 0", (char)ch);
+        return ERR_RUNTIME;
+    }
+
+    // ---- S1: suffix array
+    ClassTable tab;
+    KeyLayout lay;
+    choose_layout(c->h_pinned + 16, n1, tab, lay);
+    S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
+    int cur = 0;
+    u32 m = 0;
+    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, &cur, &m));
+    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, &cur, &m));
+
+    {
+        const int nb = bits_for(n1 - 1);
+        DigitPlan plan;
+        plan_add_range(plan, 0, nb);
+        plan_add_range(plan, 32, 32 + nb);
+        u64 h = (u64)lay.W;
+        int sc = 0;
+        while (m > 0) {
+            S.doubling_rounds += 1;
+            S.active_sum += m;
+            u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
+            u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
+            k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(k[0], v[0], m, w.RANK, h, n1);
+            int res = 0;
+            NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, &S.kernel_launches));
+            const int rb = res == 0 ? cur : (cur ^ 1);   // physical index of the sorted buffers
+            const u32 tiles = ceil_div_u32(m, RG_TILE);
+            k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
+            k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
+            k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
+                                                                    w.PMAX, w.PSUM, w.SA, w.RANK, w.KEY[rb ^ 1],
+                                                                    w.VAL[rb ^ 1], w.SLOT[sc ^ 1]);
+            S.kernel_launches += 4;
+            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 4, cudaMemcpyDeviceToHost, st));
+            NLZ_CK(cudaStreamSynchronize(st));
+            S.host_syncs += 1;
+            m = c->h_pinned[0];
+            cur = rb ^ 1;
+            sc ^= 1;
+            h *= 2;
+            if (S.doubling_rounds > 40) { set_error("prefix doubling did not converge"); return ERR_RUNTIME; }
+        }
+    }
+    NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
+
+    // ---- S2: LCP
+    k_lcp_kasai<<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP);
+    S.kernel_launches += 1;
+    NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
+    if (stop_after_index) {
+        NLZ_CK(cudaGetLastError());
+        return OK;
+    }
+
+    // ---- S3: summary trees + per-rank walk
+    Trees T;
+    memset(&T, 0, sizeof(T));
+    WalkParams wp;
+    wp.n1 = n1; wp.nfac = pb.nfac; wp.N = pb.N; wp.twoN = 2 * pb.N;
+    T.lcp[0] = w.LCP; T.cntL[0] = n1 + 1;
+    T.f[0] = w.SA; T.r[0] = w.SA; T.cntS[0] = n1;
+    int lev = 0;
+    while (T.cntL[lev] > 32 && lev + 1 < TREE_MAX_LEVELS) {
+        u32 cl = (T.cntL[lev] + 31) / 32, cs = (T.cntS[lev] + 31) / 32;
+        u32 nodes = cl > cs ? cl : cs;
+        u32 grid = ceil_div_u32((u64)nodes * 32, 256);
+        if (lev == 0) {
+            if (pb.rc) k_tree_level1<true><<<grid, 256, 0, st>>>(w.LCP, T.cntL[0], w.SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
+            else k_tree_level1<false><<<grid, 256, 0, st>>>(w.LCP, T.cntL[0], w.SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
+        } else {
+            if (pb.rc) k_tree_level_up<true><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
+            else k_tree_level_up<false><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
+        }
+        S.kernel_launches += 1;
+        ++lev;
+        T.lcp[lev] = w.tl[lev]; T.f[lev] = w.tf[lev]; T.r[lev] = w.tr[lev];
+        T.cntL[lev] = cl; T.cntS[lev] = cs;
+    }
+    T.nlev = lev + 1;
+    u64* LR = w.KEY[0];
+    if (pb.rc) k_lpnf_walk<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR);
+    else k_lpnf_walk<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR);
+    S.kernel_launches += 1;
+    NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
+    if (stop_after_lpnf) {
+        NLZ_CK(cudaGetLastError());
+        return OK;
+    }
+
+    // ---- S4: chain
+    const u32 nfac = pb.nfac;
+    const u32 nchunks = ceil_div_u32(nfac, CH_CHUNK);
+    u32* EXIT = w.VAL[0];
+    u32* J2 = w.VAL[1];
+    u32* alist = w.SLOT[0];
+    u8* REACH = reinterpret_cast<u8*>(w.SLOT[1]);
+    u32* MASK = reinterpret_cast<u32*>(w.KEY[1]);
+    u32* CNT = MASK + (size_t)nchunks * 32;
+    u32* acount = w.CTR + 1;
+    NLZ_CK(cudaMemsetAsync(REACH, 0, nfac, st));
+    k_chain_init<<<1, 1, 0, st>>>(alist, acount, REACH, (u32)pb.start_pos);
+    k_chain_exit<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, EXIT, alist, acount);
+    S.kernel_launches += 2;
+    {
+        int rounds = bits_for(nchunks) + 1;
+        u32* Ja = EXIT;
+        u32* Jb = J2;
+        u32 grid = nchunks < (u32)kNumSM * 2 ? (nchunks ? nchunks : 1) : kNumSM * 2;
+        for (int r = 0; r < rounds; ++r) {
+            k_chain_double<<<grid, 256, 0, st>>>(alist, acount, Ja, Jb, REACH, nfac);
+            u32* t = Ja; Ja = Jb; Jb = t;
+        }
+        S.kernel_launches += rounds;
+    }
+    k_chain_mark<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, REACH, MASK, CNT);
+    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(CNT, nchunks, w.CTR + 2);
+    S.kernel_launches += 2;
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 2, w.CTR + 2, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaStreamSynchronize(st));
+    S.host_syncs += 1;
+    const u64 z = c->h_pinned[2];
+    *out_count = z;
+    S.n_factors = z;
+    if (!count_only) {
+        u64* dst = d_out;
+        if (!dst) {   // host-buffer entry points: library-owned device output
+            if (z > c->d_out_cap) {
+                if (c->d_out) NLZ_CK(cudaFree(c->d_out));
+                c->d_out = nullptr; c->d_out_cap = 0;
+                size_t want = z + z / 4 + 1024;
+                NLZ_CK(cudaMalloc(&c->d_out, want * 24));
+                c->d_out_cap = want;
+            }
+            dst = c->d_out;
+            capacity = c->d_out_cap;
+        }
+        if (z > capacity) {
+            set_error("output capacity %llu factors is too small for %llu factors",
+                      (unsigned long long)capacity, (unsigned long long)z);
+            return ERR_RUNTIME;
+        }
+        if (pb.rc) k_chain_emit<true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity);
+        else k_chain_emit<false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity);
+        S.kernel_launches += 1;
+    }
+    NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
+    NLZ_CK(cudaGetLastError());
+    return OK;
+}
+
+// Validates sizes the way the reference entry points do; returns OK with *empty = true when the
+// reference would return zero factors without building an index.
+static int make_problem(int mode, u64 n, u64 start_pos, Problem& pb, bool* empty) {
+    *empty = false;
+    pb.mode = mode; pb.n_in = n; pb.start_pos = start_pos; pb.N = 0;
+    if (mode == NLZ_MODE_GENERAL) {
+        pb.rc = false; pb.L = n; pb.nfac = (u32)n;
+        if (n == 0 || start_pos >= n) { *empty = true; return OK; }   // factorizer_core.hpp:66
+    } else if (mode == NLZ_MODE_RC_PREPARED) {
+        pb.rc = true; pb.L = n;
+        if (n < 4) { *empty = true; return OK; }                      // factorizer_core.hpp:180-193
+        u64 N = n / 2 - 1;                                            // :195
+        if (N == 0) { *empty = true; return OK; }                     // :196-200
+        if (start_pos >= N) {                                         // :203-205
+            set_error("start_pos must be less than the original sequence length");
+            return ERR_INVALID;
+        }
+        pb.N = (u32)N; pb.nfac = (u32)N;
+    } else if (mode == NLZ_MODE_DNA_RC) {
+        pb.rc = true;
+        if (n == 0) { *empty = true; return OK; }                     // factorizer_core.hpp:143
+        pb.L = 2 * n + 2; pb.N = (u32)n; pb.nfac = (u32)n;
+        if (start_pos != 0) { set_error("start_pos is not supported in DNA_RC mode"); return ERR_INVALID; }
+    } else {
+        set_error("unknown mode %d", mode);
+        return ERR_INVALID;
+    }
+    if (pb.L + 1 >= 0xFFFFFFF0ull) {
+        set_error("text of %llu symbols exceeds the 32-bit index path of this build",
+                  (unsigned long long)pb.L);
+        return ERR_RUNTIME;
+    }
+    pb.n1 = (u32)(pb.L + 1);
+    return OK;
+}
+
+static void finish_stats(nlz_ctx* c, const Problem& pb) {
+    nlz_stats& S = c->stats;
+    S.n_text = pb.n_in; S.n_suffixes = pb.n1; S.n_factorized = pb.nfac;
+    auto el = [&](int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0; } return ms; };
+    S.ms_prepare = el(EV_BEGIN, EV_PREP);
+    S.ms_keys = el(EV_PREP, EV_KEYS);
+    S.ms_sort0 = el(EV_KEYS, EV_SORT0);
+    S.ms_doubling = el(EV_SORT0, EV_DOUBLING);
+    S.ms_lcp = el(EV_DOUBLING, EV_LCP);
+    S.ms_lpnf = el(EV_LCP, EV_LPNF);
+    S.ms_chain = el(EV_LPNF, EV_CHAIN);
+    S.ms_total = el(EV_BEGIN, EV_CHAIN);
+}
+
+static void reset_stats(nlz_ctx* c) {
+    size_t wsb = c->stats.workspace_bytes;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.workspace_bytes = wsb;
+}
+
+static int host_call(nlz_ctx* c, int mode, const u8* text, u64 n, u64 start_pos, u64** out_alloc,
+                     u64* out_into, u64 capacity, bool count_only, u64* out_count) {
+    if (!c) { set_error("null context"); return ERR_INVALID; }
+    if (!out_count) { set_error("null out_count"); return ERR_INVALID; }
+    if (n && !text) { set_error("null text"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    *out_count = 0;
+    if (out_alloc) *out_alloc = nullptr;
+    Problem pb;
+    bool empty = false;
+    NLZ_TRY(make_problem(mode, n, start_pos, pb, &empty));
+    reset_stats(c);
+    if (empty) return OK;
+    NLZ_TRY(ensure_workspace(c, pb.n1));
+    cudaStream_t st = c->own_stream;
+    u64 z = 0;
+    NLZ_TRY(run_pipeline(c, pb, text, true, st, nullptr, 0, count_only, false, false, &z));
+    if (!count_only && z) {
+        u64* dst = out_into;
+        if (out_alloc) {
+            dst = static_cast<u64*>(malloc((size_t)z * 24));
+            if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)z); return ERR_RUNTIME; }
+            *out_alloc = dst;
+        } else if (z > capacity) {
+            *out_count = z;
+            NLZ_CK(cudaStreamSynchronize(st));
+            set_error("output capacity %llu factors is too small for %llu factors",
+                      (unsigned long long)capacity, (unsigned long long)z);
+            return ERR_RUNTIME;
+        }
+        NLZ_CK(cudaMemcpyAsync(dst, c->d_out, (size_t)z * 24, cudaMemcpyDeviceToHost, st));
+    }
+    NLZ_CK(cudaStreamSynchronize(st));
+    finish_stats(c, pb);
+    *out_count = z;
+    return OK;
+}
+
+}  // namespace nlz
+
+template <typename KeyT>
+static int debug_sort(nlz_ctx* c, KeyT* keys, uint32_t* vals, uint64_t m, int lo, int hi) {
+    if (!c) { set_error("null context"); return ERR_INVALID; }
+    if (m == 0) return OK;
+    if (m >= 0xFFFFFFF0ull) { set_error("too many pairs"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    NLZ_TRY(ensure_workspace(c, m + 1));
+    cudaStream_t st = c->own_stream;
+    Workspace& w = c->ws;
+    KeyT* k[2] = {reinterpret_cast<KeyT*>(w.KEY[0]), reinterpret_cast<KeyT*>(w.KEY[1])};
+    u32* v[2] = {w.VAL[0], w.VAL[1]};
+    NLZ_CK(cudaMemcpyAsync(k[0], keys, m * sizeof(KeyT), cudaMemcpyHostToDevice, st));
+    NLZ_CK(cudaMemcpyAsync(v[0], vals, m * 4, cudaMemcpyHostToDevice, st));
+    DigitPlan plan;
+    plan_add_range(plan, lo, hi);
+    int res = 0;
+    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, (u32)m, plan, w.HIST, st, &res));
+    NLZ_CK(cudaMemcpyAsync(keys, k[res], m * sizeof(KeyT), cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaMemcpyAsync(vals, v[res], m * 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* nlz_last_error(void) { return nlz::g_err.c_str(); }
+const char* nlz_version(void) { return "1.2.0+b200.r1"; }
+void nlz_free(void* p) { free(p); }
+
+int nlz_ctx_create(int device, nlz_ctx** out) {
+    if (!out) { set_error("null out"); return ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); nolzss_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range [0,%d)", device, count); return ERR_INVALID; }
+    NLZ_CK(cudaSetDevice(device));
+    nlz_ctx* c = new nlz_ctx();
+    c->device = device;
+    memset(&c->stats, 0, sizeof(c->stats));
+    NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));
+    for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
+    *out = c;
+    return OK;
+}
+
+void nlz_ctx_destroy(nlz_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->arena.base) cudaFree(c->arena.base);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int nlz_get_stats(nlz_ctx* c, nlz_stats* out) {
+    if (!c || !out) { set_error("null argument"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    *out = c->stats;
+    return OK;
+}
+
+int nlz_factorize_mode(nlz_ctx* c, int mode, const uint8_t* text, uint64_t n, uint64_t start_pos,
+                       uint64_t** out_triples, uint64_t* out_count) {
+    if (!out_triples) { set_error("null out_triples"); return ERR_INVALID; }
+    return host_call(c, mode, text, n, start_pos, out_triples, nullptr, 0, false, out_count);
+}
+int nlz_factorize_mode_into(nlz_ctx* c, int mode, const uint8_t* text, uint64_t n, uint64_t start_pos,
+                            uint64_t* out_triples, uint64_t capacity, uint64_t* out_count) {
+    if (!out_triples && capacity) { set_error("null out_triples"); return ERR_INVALID; }
+    return host_call(c, mode, text, n, start_pos, nullptr, out_triples, capacity, false, out_count);
+}
+int nlz_count_mode(nlz_ctx* c, int mode, const uint8_t* text, uint64_t n, uint64_t start_pos, uint64_t* out_count) {
+    return host_call(c, mode, text, n, start_pos, nullptr, nullptr, 0, true, out_count);
+}
+
+int nlz_factorize_device(nlz_ctx* c, int mode, const void* d_text, uint64_t n, uint64_t start_pos,
+                         void* cuda_stream, void* d_out_triples, uint64_t capacity, uint64_t* out_count) {
+    if (!c || !out_count) { set_error("null argument"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    *out_count = 0;
+    Problem pb;
+    bool empty = false;
+    NLZ_TRY(make_problem(mode, n, start_pos, pb, &empty));
+    reset_stats(c);
+    if (empty) return OK;
+    NLZ_TRY(ensure_workspace(c, pb.n1));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    u64 z = 0;
+    const bool count_only = (d_out_triples == nullptr);
+    NLZ_TRY(run_pipeline(c, pb, d_text, false, st, static_cast<u64*>(d_out_triples), capacity, count_only,
+                         false, false, &z));
+    NLZ_CK(cudaStreamSynchronize(st));
+    finish_stats(c, pb);
+    *out_count = z;
+    return OK;
+}
+
+int nlz_factorize(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t sp, uint64_t** o, uint64_t* cnt) {
+    return nlz_factorize_mode(c, NLZ_MODE_GENERAL, t, n, sp, o, cnt);
+}
+int nlz_count_factors(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t sp, uint64_t* cnt) {
+    return nlz_count_mode(c, NLZ_MODE_GENERAL, t, n, sp, cnt);
+}
+int nlz_factorize_dna_w_rc(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t** o, uint64_t* cnt) {
+    return nlz_factorize_mode(c, NLZ_MODE_DNA_RC, t, n, 0, o, cnt);
+}
+int nlz_count_factors_dna_w_rc(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t* cnt) {
+    return nlz_count_mode(c, NLZ_MODE_DNA_RC, t, n, 0, cnt);
+}
+int nlz_factorize_multiple_dna_w_rc(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t sp, uint64_t** o, uint64_t* cnt) {
+    return nlz_factorize_mode(c, NLZ_MODE_RC_PREPARED, t, n, sp, o, cnt);
+}
+int nlz_count_factors_multiple_dna_w_rc(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t sp, uint64_t* cnt) {
+    return nlz_count_mode(c, NLZ_MODE_RC_PREPARED, t, n, sp, cnt);
+}
+
+// ---- stage probes ---------------------------------------------------------------------------
+int nlz_debug_index(nlz_ctx* c, const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp) {
+    if (!c) { set_error("null context"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    Problem pb;
+    bool empty = false;
+    NLZ_TRY(make_problem(NLZ_MODE_GENERAL, n, 0, pb, &empty));
+    if (empty) { set_error("empty text"); return ERR_INVALID; }
+    reset_stats(c);
+    NLZ_TRY(ensure_workspace(c, pb.n1));
+    cudaStream_t st = c->own_stream;
+    u64 z = 0;
+    NLZ_TRY(run_pipeline(c, pb, text, true, st, nullptr, 0, true, true, false, &z));
+    NLZ_CK(cudaStreamSynchronize(st));
+    if (sa) NLZ_CK(cudaMemcpy(sa, c->ws.SA, (size_t)pb.n1 * 4, cudaMemcpyDeviceToHost));
+    if (isa) NLZ_CK(cudaMemcpy(isa, c->ws.RANK, (size_t)pb.n1 * 4, cudaMemcpyDeviceToHost));
+    if (lcp) NLZ_CK(cudaMemcpy(lcp, c->ws.LCP, ((size_t)pb.n1 + 1) * 4, cudaMemcpyDeviceToHost));
+    return OK;
+}
+
+int nlz_debug_sort_pairs_u64(nlz_ctx* c, uint64_t* keys, uint32_t* vals, uint64_t m, int lo, int hi) {
+    return debug_sort<u64>(c, keys, vals, m, lo, hi);
+}
+int nlz_debug_sort_pairs_u32(nlz_ctx* c, uint32_t* keys, uint32_t* vals, uint64_t m, int lo, int hi) {
+    return debug_sort<u32>(c, keys, vals, m, lo, hi);
+}
+
+int nlz_debug_per_position(nlz_ctx* c, int mode, const uint8_t* text, uint64_t n, uint64_t* len_out,
+                           uint64_t* ref_out, uint64_t capacity, uint64_t* nfac_out) {
+    if (!c || !nfac_out) { set_error("null argument"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    Problem pb;
+    bool empty = false;
+    NLZ_TRY(make_problem(mode, n, 0, pb, &empty));
+    *nfac_out = 0;
+    if (empty) return OK;
+    reset_stats(c);
+    NLZ_TRY(ensure_workspace(c, pb.n1));
+    cudaStream_t st = c->own_stream;
+    u64 z = 0;
+    NLZ_TRY(run_pipeline(c, pb, text, true, st, nullptr, 0, true, false, true, &z));
+    NLZ_CK(cudaStreamSynchronize(st));
+    *nfac_out = pb.nfac;
+    if (capacity < pb.nfac) { set_error("capacity too small"); return ERR_RUNTIME; }
+    std::vector<u64> lr(pb.nfac);
+    NLZ_CK(cudaMemcpy(lr.data(), c->ws.KEY[0], (size_t)pb.nfac * 8, cudaMemcpyDeviceToHost));
+    for (u32 i = 0; i < pb.nfac; ++i) {
+        u32 ref32 = (u32)(lr[i] >> 32);
+        if (len_out) len_out[i] = (u32)lr[i];
+        if (ref_out)
+            ref_out[i] = pb.rc ? ((u64)(ref32 & ~LR_RC_FLAG) | ((ref32 & LR_RC_FLAG) ? NLZ_RC_MASK : 0ull)) : (u64)ref32;
+    }
+    return OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// Stage 0/1: symbol classes, packed-prefix keys and suffix-array construction by prefix doubling.
+//
+// Replaces the reference's construct_im(cst, text, 1) (SDSL; call sites
+// /root/reference/src/cpp/factorizer.cpp:381 and factorizer_core.hpp:208): the suffix array of
+// text·$ and its inverse.  Design (B200-first, not the CSA of the reference):
+//   * bytes that occur exactly once in the text (record sentinels, and the virtual terminator at
+//     position L) are "sentinel class": unique symbols, ordered by text position, smaller than
+//     every repeated byte.  The factorization only depends on the suffix TREE, which is invariant
+//     under any order of the alphabet, so this order is free to choose.
+//   * repeated bytes get dense b-bit codes (b=2 for DNA); the first W symbols of every suffix are
+//     packed MSB-first into one 32- or 64-bit key whose low D bits hold the offset of the first
+//     sentinel inside the window (all ones = none).  One stable LSD radix sort of those keys orders
+//     all suffixes by their first W symbols; suffixes whose window holds a sentinel are already
+//     unique and correctly ordered (stable sort == position order).
+//   * the remaining tie groups are refined by prefix doubling (Manber-Myers / Larsson-Sadakane)
+//     with discarding: only suffixes still in a group of size >= 2 are re-sorted, by the 64-bit
+//     key (group head slot, rank[s+h]).  RANK doubles as the inverse suffix array at the end.
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace nlz {
+
+constexpr u32 SENT_CLASS = 0xFFu;
+
+struct ClassTable {
+    u8 cls[256];  // dense code, or SENT_CLASS
+};
+
+struct KeyLayout {
+    int key_bits;   // 32 or 64
+    int b;          // bits per symbol
+    int W;          // symbols per key
+    int D;          // bits of the sentinel-offset field
+};
+
+// ---------------------------------------------------------------- byte histogram
+__global__ void __launch_bounds__(256) k_byte_hist(const u8* __restrict__ x, u64 L, u32* __restrict__ hist) {
+    __shared__ u32 h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const u32 w = threadIdx.x >> 5;
+    const u64 nwords = L >> 2;
+    const u32* xw = reinterpret_cast<const u32*>(x);
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < nwords; i += (u64)gridDim.x * 256) {
+        u32 v = xw[i];
+        atomicAdd(&h[w][v & 255], 1u);
+        atomicAdd(&h[w][(v >> 8) & 255], 1u);
+        atomicAdd(&h[w][(v >> 16) & 255], 1u);
+        atomicAdd(&h[w][v >> 24], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (L & 3)) atomicAdd(&h[0][x[(nwords << 2) + threadIdx.x]], 1u);
+    __syncthreads();
+    u32 s = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += h[ww][threadIdx.x];
+    if (s) atomicAdd(&hist[threadIdx.x], s);
+}
+
+// ---------------------------------------------------------------- key construction
+// One thread per suffix; the CTA stages its text window in shared memory (coalesced 4-byte loads).
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay,
+             KeyT* __restrict__ keys, u32* __restrict__ vals) {
+    constexpr int TP = 2048;            // suffixes per CTA
+    constexpr int HALO = 32;            // >= max W
+    __shared__ u8 cls[256];
+    __shared__ __align__(16) u8 tile[TP + HALO];
+    cls[threadIdx.x] = tab.cls[threadIdx.x];
+    const u64 base = (u64)blockIdx.x * TP;
+    // x is padded with >= 64 readable bytes past L (workspace contract)
+    const u32* xw = reinterpret_cast<const u32*>(x + base);
+    u32* tw = reinterpret_cast<u32*>(tile);
+    for (int i = threadIdx.x; i < (TP + HALO) / 4; i += 256) {
+        u64 byte0 = base + (u64)i * 4;
+        tw[i] = (byte0 < L + 64) ? xw[i] : 0u;
+    }
+    __syncthreads();
+    const int kb = lay.key_bits, b = lay.b, W = lay.W;
+    const KeyT dist_none = ((KeyT)1 << lay.D) - 1;
+#pragma unroll 1
+    for (int r = 0; r < TP / 256; ++r) {
+        const int o = r * 256 + threadIdx.x;
+        const u64 p = base + o;
+        if (p >= n1) break;
+        KeyT key = 0;
+        KeyT dist = dist_none;
+        int sh = kb - b;
+        for (int t = 0; t < W; ++t, sh -= b) {
+            u32 c = (p + t < L) ? (u32)cls[tile[o + t]] : SENT_CLASS;
+            if (c == SENT_CLASS) { dist = (KeyT)t; break; }
+            key |= (KeyT)c << sh;
+        }
+        keys[p] = key | dist;
+        vals[p] = (u32)p;
+    }
+}
+
+// ---------------------------------------------------------------- regroup (head flags, ranks, compaction)
+constexpr int RG_THREADS = 256;
+constexpr int RG_ITEMS = 8;
+constexpr int RG_TILE = RG_THREADS * RG_ITEMS;
+
+template <typename KeyT, bool INITIAL>
+__device__ __forceinline__ bool rg_is_head(const KeyT* __restrict__ keys, u32 e, KeyT dist_mask) {
+    if (e == 0) return true;
+    KeyT k = keys[e];
+    if (INITIAL && (k & dist_mask) != dist_mask) return true;  // window holds a sentinel: unique
+    return k != keys[e - 1];
+}
+
+// phase A: per-tile (max head index + 1, number of still-active elements)
+template <typename KeyT, bool INITIAL>
+__global__ void __launch_bounds__(RG_THREADS)
+k_regroup_reduce(const KeyT* __restrict__ keys, u32 m, KeyT dist_mask, u32* __restrict__ pmax,
+                 u32* __restrict__ psum) {
+    __shared__ u32 smax[RG_THREADS / 32], ssum[RG_THREADS / 32];
+    const u64 tile_start = (u64)blockIdx.x * RG_TILE;
+    u32 lmax = 0, lsum = 0;
+#pragma unroll
+    for (int t = 0; t < RG_ITEMS; ++t) {
+        u64 e = tile_start + (u64)t * RG_THREADS + threadIdx.x;
+        if (e < m) {
+            bool h = rg_is_head<KeyT, INITIAL>(keys, (u32)e, dist_mask);
+            bool hn = (e + 1 < m) ? rg_is_head<KeyT, INITIAL>(keys, (u32)e + 1, dist_mask) : true;
+            if (h) lmax = max(lmax, (u32)e + 1);
+            lsum += (h && hn) ? 0u : 1u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = lmax; ssum[threadIdx.x >> 5] = lsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 a = 0, b = 0;
+        for (int i = 0; i < RG_THREADS / 32; ++i) { a = max(a, smax[i]); b += ssum[i]; }
+        pmax[blockIdx.x] = a;
+        psum[blockIdx.x] = b;
+    }
+}
+
+// phase B: exclusive (max, sum) scan of the tile partials by one CTA; writes the new active count.
+__global__ void __launch_bounds__(1024)
+k_regroup_scan_partials(u32* __restrict__ pmax, u32* __restrict__ psum, u32 ntiles, u32* __restrict__ m_out) {
+    __shared__ u32 wmax[32], wsum[32];
+    const u32 per = (ntiles + 1023) / 1024;
+    u32 b = threadIdx.x * per, e = b + per;
+    if (b > ntiles) b = ntiles;
+    if (e > ntiles) e = ntiles;
+    u32 lm = 0, ls = 0;
+    for (u32 i = b; i < e; ++i) { lm = max(lm, pmax[i]); ls += psum[i]; }
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 im = lm, is = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 tm = __shfl_up_sync(0xffffffffu, im, o), ts = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) { im = max(im, tm); is += ts; }
+    }
+    if (lane == 31) { wmax[w] = im; wsum[w] = is; }
+    __syncthreads();
+    u32 cm = 0, cs = 0, tot = 0;
+    for (u32 i = 0; i < 32; ++i) {
+        if (i < w) { cm = max(cm, wmax[i]); cs += wsum[i]; }
+        tot += wsum[i];
+    }
+    // exclusive prefix for this thread = carries of previous warps + previous lanes
+    u32 pm = __shfl_up_sync(0xffffffffu, im, 1), ps = __shfl_up_sync(0xffffffffu, is, 1);
+    if (lane == 0) { pm = 0; ps = 0; }
+    u32 rm = max(cm, pm), rs = cs + ps;
+    for (u32 i = b; i < e; ++i) {
+        u32 tm = pmax[i], ts = psum[i];
+        pmax[i] = rm;
+        psum[i] = rs;
+        rm = max(rm, tm);
+        rs += ts;
+    }
+    if (threadIdx.x == 0) *m_out = tot;
+}
+
+// phase C: ranks, SA write-back and compaction of the still-active elements.
+template <typename KeyT, bool INITIAL>
+__global__ void __launch_bounds__(RG_THREADS)
+k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ slots,
+                u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
+                u32* __restrict__ SA, u32* __restrict__ RANK, u64* __restrict__ key_next,
+                u32* __restrict__ val_next, u32* __restrict__ slot_next) {
+    __shared__ u8 sh_head[RG_TILE + 8];
+    __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
+    const u64 tile_start = (u64)blockIdx.x * RG_TILE;
+    const u32 valid = (u32)((m - tile_start) < (u64)RG_TILE ? (m - tile_start) : (u64)RG_TILE);
+#pragma unroll
+    for (int t = 0; t < RG_ITEMS; ++t) {
+        u32 idx = t * RG_THREADS + threadIdx.x;
+        if (idx < valid) sh_head[idx] = rg_is_head<KeyT, INITIAL>(keys, (u32)(tile_start + idx), dist_mask) ? 1 : 0;
+    }
+    if (threadIdx.x == 0) {
+        u64 e = tile_start + valid;
+        sh_head[valid] = (e < m) ? (rg_is_head<KeyT, INITIAL>(keys, (u32)e, dist_mask) ? 1 : 0) : 1;
+    }
+    __syncthreads();
+    const u32 i0 = threadIdx.x * RG_ITEMS;
+    u32 hm[RG_ITEMS], ps[RG_ITEMS];
+    bool act[RG_ITEMS];
+    u32 run_max = 0, run_sum = 0;
+#pragma unroll
+    for (int q = 0; q < RG_ITEMS; ++q) {
+        u32 idx = i0 + q;
+        hm[q] = 0; ps[q] = 0; act[q] = false;
+        if (idx < valid) {
+            bool h = sh_head[idx] != 0;
+            bool a = !(h && sh_head[idx + 1] != 0);
+            if (h) run_max = (u32)(tile_start + idx) + 1;
+            hm[q] = run_max;
+            ps[q] = run_sum;
+            run_sum += a ? 1u : 0u;
+            act[q] = a;
+        }
+    }
+    // CTA-wide exclusive (max, sum) scan of the per-thread aggregates
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 im = run_max, is = run_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 tm = __shfl_up_sync(0xffffffffu, im, o), ts = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) { im = max(im, tm); is += ts; }
+    }
+    if (lane == 31) { wmax[w] = im; wsum[w] = is; }
+    __syncthreads();
+    u32 cm = pmax[blockIdx.x], cs = psum[blockIdx.x];
+    for (u32 i = 0; i < w; ++i) { cm = max(cm, wmax[i]); cs += wsum[i]; }
+    u32 pm = __shfl_up_sync(0xffffffffu, im, 1), pps = __shfl_up_sync(0xffffffffu, is, 1);
+    if (lane == 0) { pm = 0; pps = 0; }
+    cm = max(cm, pm);
+    cs += pps;
+#pragma unroll
+    for (int q = 0; q < RG_ITEMS; ++q) {
+        u32 idx = i0 + q;
+        if (idx < valid) {
+            u32 e = (u32)(tile_start + idx);
+            u32 hj = max(hm[q], cm) - 1;          // index (in this sorted list) of the group head
+            u32 newrank = INITIAL ? hj : slots[hj];
+            u32 s = vals[e];
+            u32 slot = INITIAL ? e : slots[e];
+            RANK[s] = newrank;
+            SA[slot] = s;
+            if (act[q]) {
+                u32 pos = cs + ps[q];
+                key_next[pos] = (u64)newrank << 32;
+                val_next[pos] = s;
+                slot_next[pos] = slot;
+            }
+        }
+    }
+}
+
+// KEY[j] |= RANK[VAL[j] + h]   (second half of the doubling key)
+__global__ void __launch_bounds__(256)
+k_gather_rank(u64* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ RANK, u64 h, u32 n1) {
+    u32 j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    u64 p = (u64)val[j] + h;
+    u32 r = p < n1 ? RANK[p] : 0u;   // p < n1 always holds for active suffixes; guard keeps reads in range
+    key[j] |= (u64)r;
+}
+
+}  // namespace nlz

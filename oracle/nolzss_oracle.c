@@ -321,3 +321,23 @@ int nlzo_factorize_multiple_dna_w_rc(const uint8_t *S, uint64_t len_S, uint64_t 
 }
 
 void nlzo_free(void *p) { free(p); }
+
+/* LCP array (Kasai) of an int32 string s[0..n) for a GIVEN suffix array: lcp[k] = LCP(sa[k-1], sa[k]),
+ * lcp[0] = 0.  Used by the stage-parity tests to check the GPU LCP array under the GPU's own
+ * symbol order. */
+int nlzo_lcp_from_sa_i32(const int32_t *s, int32_t n, const int32_t *sa, int32_t *lcp) {
+    idx_t *isa = (idx_t *)malloc(sizeof(idx_t) * (size_t)n);
+    if (!isa) return -1;
+    for (idx_t k = 0; k < n; ++k) isa[sa[k]] = k;
+    idx_t l = 0;
+    for (idx_t i = 0; i < n; ++i) {
+        idx_t r = isa[i];
+        if (r == 0) { lcp[0] = 0; l = 0; continue; }
+        idx_t j = sa[r - 1];
+        while (i + l < n && j + l < n && s[i + l] == s[j + l]) ++l;
+        lcp[r] = l;
+        if (l > 0) --l;
+    }
+    free(isa);
+    return 0;
+}

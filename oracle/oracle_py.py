@@ -43,6 +43,8 @@ def lib():
         L.nlzo_suffix_array_i32.restype = ctypes.c_int
         L.nlzo_sa_lcp_bytes.argtypes = [u8p, u64, ctypes.c_void_p, ctypes.c_void_p]
         L.nlzo_sa_lcp_bytes.restype = ctypes.c_int
+        L.nlzo_lcp_from_sa_i32.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        L.nlzo_lcp_from_sa_i32.restype = ctypes.c_int
         L.nlzo_last_timing.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.nlzo_last_timing.restype = None
         _lib = L
@@ -98,4 +100,47 @@ def sa_lcp_bytes(data: bytes):
     lcp = np.empty(n1 + 1, dtype=np.int32)
     rc = lib().nlzo_sa_lcp_bytes(data, len(data), sa.ctypes.data, lcp.ctypes.data)
     assert rc == 0
+    return sa, lcp
+
+
+def lcp_from_sa_i32(s: np.ndarray, sa: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(s, dtype=np.int32)
+    sa = np.ascontiguousarray(sa, dtype=np.int32)
+    lcp = np.zeros(len(s), dtype=np.int32)
+    rc = lib().nlzo_lcp_from_sa_i32(s.ctypes.data, len(s), sa.ctypes.data, lcp.ctypes.data)
+    assert rc == 0
+    return lcp
+
+
+def gpu_order_recode(data: bytes):
+    """int32 recoding of data·$ under the symbol order the CUDA path sorts by (csrc/sa.cuh):
+    bytes that occur once, and the terminator, are sentinel symbols ordered by text position and
+    smaller than every repeated byte.  A real smallest terminator 0 is appended for SA-IS.
+    Returns (s, K)."""
+    x = np.frombuffer(bytes(data), dtype=np.uint8)
+    hist = np.bincount(x, minlength=256)
+    dense = np.full(256, -1, dtype=np.int64)
+    rep = np.nonzero(hist >= 2)[0]
+    dense[rep] = np.arange(len(rep))
+    codes = dense[x]
+    sent_pos = np.nonzero(codes < 0)[0]
+    S = len(sent_pos) + 1                      # + virtual terminator at position len(x)
+    out = np.empty(len(x) + 2, dtype=np.int32)
+    out[: len(x)] = codes + (S + 1)
+    out[sent_pos] = np.arange(1, len(sent_pos) + 1)
+    out[len(x)] = S
+    out[len(x) + 1] = 0
+    return out, int(S + 1 + len(rep))
+
+
+def gpu_order_sa_lcp(data: bytes):
+    """(SA, LCP) of data·$ in the CUDA path's symbol order: SA has len+1 entries, LCP len+2
+    (LCP[0] = LCP[len+1] = 0)."""
+    s, K = gpu_order_recode(data)
+    sa_full = suffix_array_i32(s, K)
+    assert sa_full[0] == len(s) - 1
+    sa = sa_full[1:]
+    lcp_full = lcp_from_sa_i32(s, sa_full)
+    lcp = np.zeros(len(sa) + 1, dtype=np.int32)
+    lcp[1 : len(sa)] = lcp_full[2:]
     return sa, lcp

@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (bit-exact)."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+import treewalk_model as tm
+from kats import ATAT_THIRD, GENERAL_KATS, RC_KATS, plain_tuples, rc_tuples
+from nolzss_b200 import _lib as L
+from nolzss_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _sort_case(dtype, m, lo, hi, seed, dup=False):
+    rng = np.random.default_rng(seed)
+    bits = 32 if dtype == np.uint32 else 64
+    keys = rng.integers(0, 2**bits, m, dtype=np.uint64).astype(dtype)
+    if dup:
+        keys = (keys % dtype(7)).astype(dtype) << dtype(lo)
+    vals = np.arange(m, dtype=np.uint32)
+    mask = ((1 << (hi - lo)) - 1)
+    field = (keys.astype(np.uint64) >> np.uint64(lo)) & np.uint64(mask)
+    order = np.argsort(field, kind="stable")
+    k2, v2 = keys.copy(), vals.copy()
+    fn = L.load().nlz_debug_sort_pairs_u32 if dtype == np.uint32 else L.load().nlz_debug_sort_pairs_u64
+    L.check(fn(L.context(), k2.ctypes.data, v2.ctypes.data, m, lo, hi))
+    assert np.array_equal(v2, vals[order]), (dtype, m, lo, hi)
+    assert np.array_equal(k2, keys[order])
+
+
+@pytest.mark.parametrize("m", [1, 2, 31, 257, 4096, 4097, 70_001, 1_300_003])
+def test_radix_sort_pairs(m):
+    _sort_case(np.uint32, m, 0, 32, m)
+    _sort_case(np.uint64, m, 0, 64, m + 1)
+    _sort_case(np.uint64, m, 32, 53, m + 2)
+    _sort_case(np.uint32, m, 4, 13, m + 3)
+    _sort_case(np.uint64, m, 3, 11, m + 4, dup=True)
+
+
+def _index_case(data: bytes):
+    n = len(data)
+    sa = np.empty(n + 1, dtype=np.uint32)
+    isa = np.empty(n + 1, dtype=np.uint32)
+    lcp = np.empty(n + 2, dtype=np.uint32)
+    arr = np.frombuffer(data, dtype=np.uint8)
+    L.check(L.load().nlz_debug_index(L.context(), arr.ctypes.data, n, sa.ctypes.data, isa.ctypes.data, lcp.ctypes.data))
+    esa, elcp = orc.gpu_order_sa_lcp(data)
+    assert np.array_equal(sa.astype(np.int64), esa.astype(np.int64)), "suffix array differs"
+    assert np.array_equal(isa[sa], np.arange(n + 1, dtype=np.uint32)), "ISA is not the inverse of SA"
+    assert np.array_equal(lcp.astype(np.int64), elcp.astype(np.int64)), "LCP array differs"
+
+
+def test_index_small_and_edge():
+    rnd = random.Random(1)
+    for data in [b"A", b"AC", b"AAAA", b"abracadabra", b"ACGT" * 50, b"A" * 3000, b"AC" * 2500]:
+        _index_case(data)
+    for it in range(60):
+        sig = rnd.randint(1, 6)
+        s = bytes(rnd.choice(b"ACGTXY"[:sig]) for _ in range(rnd.randint(1, 400)))
+        if it % 3 == 0:
+            s = s + b"\x01" + s[::-1] + b"\x02"
+        _index_case(s)
+
+
+def test_index_medium():
+    _index_case(wl.uniform_dna(200_000, 4).tobytes())
+    _index_case(wl.planted_dna(300_000, 7, scale=0.2).tobytes())
+    _index_case(wl.prepare_w_rc_single(wl.planted_dna(150_000, 8, scale=0.2).tobytes()))
+    rng = np.random.default_rng(3)
+    _index_case(rng.integers(1, 256, 100_000, dtype=np.uint8).tobytes())          # sigma = 255, 64-bit keys
+    _index_case(rng.integers(97, 123, 100_000, dtype=np.uint8).tobytes())         # sigma = 26
+
+
+def test_kats_through_abi():
+    for text, exp in GENERAL_KATS.items():
+        assert plain_tuples(L.factorize_array(L.MODE_GENERAL, text)) == exp
+        assert L.count(L.MODE_GENERAL, text) == len(exp)
+    for text, exp in RC_KATS.items():
+        assert rc_tuples(L.factorize_array(L.MODE_DNA_RC, text)) == exp
+        assert rc_tuples(L.factorize_array(L.MODE_RC_PREPARED, wl.prepare_w_rc_single(text))) == exp
+        assert L.count(L.MODE_DNA_RC, text) == len(exp)
+    assert rc_tuples(L.factorize_array(L.MODE_DNA_RC, b"ATAT"))[2] == ATAT_THIRD
+    assert rc_tuples(L.factorize_array(L.MODE_DNA_RC, b"ATCGATCG"))[3:] == [(3, 3, 0, True), (6, 2, 2, False)]
+    assert (7, 2, 0, False) in rc_tuples(L.factorize_array(L.MODE_DNA_RC, b"CAAGCACCACCGCGGCGACCGAGGCA"))
+
+
+def test_random_small_vs_oracle():
+    rnd = random.Random(2)
+    for it in range(300):
+        sig = rnd.randint(1, 4)
+        s = bytes(rnd.choice(b"ACGT"[:sig]) for _ in range(rnd.randint(1, 120)))
+        sp = rnd.randint(0, len(s) - 1) if it % 2 else 0
+        assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s, sp), orc.factorize(s, sp)), (s, sp)
+        seqs = [bytes(rnd.choice(b"ACGT"[:sig]) for _ in range(rnd.randint(1, 60))) for _ in range(rnd.randint(1, 3))]
+        S, _, _ = tm.prepare_multiple_dna_sequences_w_rc(seqs)
+        N = len(S) // 2 - 1
+        sp = rnd.randint(0, N - 1) if it % 2 else 0
+        assert np.array_equal(L.factorize_array(L.MODE_RC_PREPARED, S, sp), orc.factorize_multiple_dna_w_rc(S, sp)), (S, sp)
+        assert np.array_equal(L.factorize_array(L.MODE_DNA_RC, seqs[0]),
+                              orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(seqs[0]))), seqs[0]
+
+
+def test_general_bytes_vs_oracle():
+    rng = np.random.default_rng(12)
+    for n, lo, hi in [(5000, 1, 4), (20000, 97, 123), (50000, 1, 256), (3000, 65, 66)]:
+        s = rng.integers(lo, hi, n, dtype=np.uint8).tobytes()
+        assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s), orc.factorize(s))
+    s = (b"the quick brown fox jumps over the lazy dog " * 500) + b"!"
+    assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s), orc.factorize(s))
+
+
+def test_degenerate_runs_and_tandems():
+    for s in [b"A" * 1, b"A" * 2, b"A" * 1000, b"A" * 40_000, b"AC" * 20_000, b"ACG" * 7000 + b"T",
+              b"A" * 5000 + b"C" + b"A" * 5000]:
+        assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s), orc.factorize(s)), s[:20]
+        assert np.array_equal(L.factorize_array(L.MODE_DNA_RC, s),
+                              orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s))), s[:20]
+
+
+def test_c1_config_general_1mbp():
+    t = wl.c1_text()
+    got = L.factorize_array(L.MODE_GENERAL, t)
+    exp = orc.factorize(t)
+    assert np.array_equal(got, exp)
+    assert L.count(L.MODE_GENERAL, t) == len(exp)
+    st = L.stats()
+    assert st["n_factors"] == len(exp) and st["kernel_launches"] > 0
+
+
+def test_planted_repeats_rc_mode():
+    t = wl.planted_dna(600_000, 21, scale=0.3).tobytes()
+    exp = orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(t))
+    assert np.array_equal(L.factorize_array(L.MODE_DNA_RC, t), exp)
+    assert np.array_equal(L.factorize_array(L.MODE_RC_PREPARED, wl.prepare_w_rc_single(t)), exp)
+    assert np.array_equal(L.factorize_array(L.MODE_GENERAL, t), orc.factorize(t))
+
+
+def test_c2_config_rc_5mbp():
+    t = wl.c2_text()
+    got = L.factorize_array(L.MODE_DNA_RC, t)
+    exp = orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(t))
+    assert np.array_equal(got, exp)
+
+
+def test_multi_record_prepared_and_start_pos():
+    recs = [r for _, r in wl.c3_records(6, 3000, 9)]
+    S, ol, sent = tm.prepare_multiple_dna_sequences_w_rc(recs)
+    for sp in (0, len(recs[0]) + 1, ol - 5):
+        assert np.array_equal(L.factorize_array(L.MODE_RC_PREPARED, S, sp), orc.factorize_multiple_dna_w_rc(S, sp))
+
+
+def test_errors_through_abi():
+    with pytest.raises(RuntimeError, match="Invalid nucleotide"):
+        L.factorize_array(L.MODE_DNA_RC, b"ACGTNACGT")
+    S = wl.prepare_w_rc_single(b"ACGT")
+    with pytest.raises(ValueError, match="start_pos"):
+        L.factorize_array(L.MODE_RC_PREPARED, S, 4)
+    assert len(L.factorize_array(L.MODE_GENERAL, b"")) == 0
+    assert len(L.factorize_array(L.MODE_DNA_RC, b"")) == 0
+    assert len(L.factorize_array(L.MODE_RC_PREPARED, b"A\x01")) == 0
+
+
+def test_device_entry_point_matches_host_entry_point():
+    import torch
+
+    t = wl.planted_dna(400_000, 33, scale=0.2).tobytes()
+    exp = orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(t))
+    d_text = torch.frombuffer(bytearray(t), dtype=torch.uint8).cuda()
+    d_out = torch.empty((len(t), 3), dtype=torch.int64, device="cuda")
+    cnt = ctypes.c_uint64(0)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.load().nlz_factorize_device(L.context(0), L.MODE_DNA_RC, d_text.data_ptr(), len(t), 0, st,
+                                          d_out.data_ptr(), d_out.shape[0], ctypes.byref(cnt)))
+    got = d_out[: cnt.value].cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, exp)

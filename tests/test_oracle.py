@@ -1,0 +1,78 @@
+"""CPU: the oracle (C restatement + literal tree-walk model) against the reference's own vectors."""
+import random
+
+import numpy as np
+
+import oracle_py as orc
+import treewalk_model as tm
+from kats import ATAT_THIRD, GENERAL_KATS, RC_KATS, plain_tuples, rc_tuples
+from nolzss_b200 import workloads as wl
+
+
+def test_general_kats_model_and_oracle():
+    for text, exp in GENERAL_KATS.items():
+        assert tm.factorize(text) == exp
+        assert plain_tuples(orc.factorize(text)) == exp
+
+
+def test_rc_kats_model_and_oracle():
+    for text, exp in RC_KATS.items():
+        assert tm.factorize_dna_w_rc(text) == exp
+        S = wl.prepare_w_rc_single(text)
+        assert rc_tuples(orc.factorize_multiple_dna_w_rc(S)) == exp
+    assert tm.factorize_dna_w_rc(b"ATAT")[2] == ATAT_THIRD
+    assert rc_tuples(orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(b"ATAT")))[2] == ATAT_THIRD
+
+
+def test_survey_traps():
+    # the code (not docs/RC_ALGORITHM.md) is the authority
+    assert tm.factorize_dna_w_rc(b"ATCGATCG")[3:] == [(3, 3, 0, True), (6, 2, 2, False)]
+    f = tm.factorize_dna_w_rc(b"CAAGCACCACCGCGGCGACCGAGGCA")
+    assert (7, 2, 0, False) in f      # forward-candidate quirk (factorizer_core.hpp:279-287, 322-326)
+
+
+def test_oracle_matches_literal_model_random():
+    rnd = random.Random(11)
+    for it in range(600):
+        sig = rnd.randint(1, 4)
+        s = bytes(rnd.choice(b"ACGT"[:sig]) for _ in range(rnd.randint(1, 60)))
+        sp = rnd.randint(0, len(s) - 1)
+        assert plain_tuples(orc.factorize(s)) == tm.factorize(s)
+        assert plain_tuples(orc.factorize(s, sp)) == tm.factorize(s, sp)
+        seqs = [bytes(rnd.choice(b"ACGT"[:sig]) for _ in range(rnd.randint(1, 30))) for _ in range(rnd.randint(1, 3))]
+        S, _, _ = tm.prepare_multiple_dna_sequences_w_rc(seqs)
+        N = len(S) // 2 - 1
+        sp = rnd.randint(0, N - 1) if it % 2 else 0
+        assert plain_tuples(orc.factorize_multiple_dna_w_rc(S, sp)) == tm.nolzss_multiple_dna_w_rc(S, sp)
+
+
+def test_oracle_invariants_on_planted_dna():
+    t = wl.planted_dna(60_000, 5, scale=0.05).tobytes()
+    f = orc.factorize(t)
+    assert int(f[0, 0]) == 0 and int((f[:, 1]).sum()) == len(t)
+    assert np.all(f[1:, 0] == f[:-1, 0] + f[:-1, 1])
+    x = np.frombuffer(t, dtype=np.uint8)
+    for s, l, r in f[:: max(1, len(f) // 300)]:
+        s, l, r = int(s), int(l), int(r)
+        if r == s:
+            assert l == 1
+        else:
+            assert r + l <= s and np.array_equal(x[r:r + l], x[s:s + l])
+    S = wl.prepare_w_rc_single(t)
+    g = orc.factorize_multiple_dna_w_rc(S)
+    assert int(g[:, 1].sum()) == len(t)
+    for s, l, r in g[:: max(1, len(g) // 300)]:
+        s, l, r = int(s), int(l), int(r)
+        if r & orc.RC_MASK:
+            r &= ~orc.RC_MASK
+            assert r + l <= s and np.array_equal(wl.revcomp(x[r:r + l]), x[s:s + l])
+        elif r != s:
+            assert r + l <= s and np.array_equal(x[r:r + l], x[s:s + l])
+
+
+def test_prepare_functions():
+    S, ol, sent = tm.prepare_multiple_dna_sequences_w_rc([b"ATCG", b"ggcc"])
+    assert S == b"ATCG\x01GGCC\x02GGCC\x03CGAT\x04" and ol == 10 and sent == [4, 9, 14, 19]
+    S, ol, sent = tm.prepare_multiple_dna_sequences_no_rc([b"ATCG", b"GGCC", b"TT"])
+    assert S == b"ATCG\x01GGCC\x02TT" and ol == len(S) and sent == [4, 9]
+    assert [tm.sentinel_byte(i) for i in (0, 63, 64, 65, 66)] == [1, 64, 66, 68, 69]
