@@ -48,6 +48,7 @@ typedef struct nlz_stats {
     uint64_t n_factorized;  /* positions whose factor rule was evaluated */
     uint64_t n_factors;     /* z */
     uint64_t active_sum;    /* sum over doubling rounds of suffixes still being sorted */
+    uint64_t walk_nodes;    /* suffix-tree path nodes visited by the per-position rule */
     uint64_t workspace_bytes;
     uint32_t key_bits, sym_bits, key_syms;
     uint32_t doubling_rounds;
@@ -64,6 +65,12 @@ const char* nlz_last_error(void);
 void nlz_free(void* p);
 int nlz_get_stats(nlz_ctx* ctx, nlz_stats* out);
 const char* nlz_version(void); /* bindings.cpp:1513-1517 (__version__) */
+/* per-kernel-class accounting of the last call: launches and algorithmic bytes always, device time
+ * (CUDA events around every launch, on the launching stream) when profiling is switched on */
+int nlz_set_profiling(nlz_ctx* ctx, int on);
+int nlz_kernel_class_count(void);
+int nlz_get_kernel_stats(nlz_ctx* ctx, int cls, const char** name, double* ms, uint64_t* bytes,
+                         uint32_t* launches);
 
 /* ---- generic entry points (HOST buffers; H2D/D2H copies happen inside the call) ---------- */
 int nlz_factorize_mode(nlz_ctx* ctx, int mode, const uint8_t* text, uint64_t n, uint64_t start_pos,

@@ -26,7 +26,7 @@ _vp = ctypes.c_void_p
 class Stats(ctypes.Structure):
     _fields_ = [
         ("n_text", _u64), ("n_suffixes", _u64), ("n_factorized", _u64), ("n_factors", _u64),
-        ("active_sum", _u64), ("workspace_bytes", _u64),
+        ("active_sum", _u64), ("walk_nodes", _u64), ("workspace_bytes", _u64),
         ("key_bits", ctypes.c_uint32), ("sym_bits", ctypes.c_uint32), ("key_syms", ctypes.c_uint32),
         ("doubling_rounds", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32),
         ("host_syncs", ctypes.c_uint32),
@@ -47,6 +47,11 @@ SIGNATURES = {
     "nlz_free": (None, [_vp]),
     "nlz_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
     "nlz_version": (ctypes.c_char_p, []),
+    "nlz_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "nlz_kernel_class_count": (ctypes.c_int, []),
+    "nlz_get_kernel_stats": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                             ctypes.POINTER(ctypes.c_double), _u64p,
+                                             ctypes.POINTER(ctypes.c_uint32)]),
     "nlz_factorize_mode": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _u64pp, _u64p]),
     "nlz_factorize_mode_into": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _vp, _u64, _u64p]),
     "nlz_count_mode": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _u64p]),
@@ -154,3 +159,22 @@ def stats(device: int | None = None) -> dict:
     s = Stats()
     check(load().nlz_get_stats(context(device), ctypes.byref(s)))
     return s.as_dict()
+
+
+def set_profiling(on: bool, device: int | None = None):
+    check(load().nlz_set_profiling(context(device), 1 if on else 0))
+
+
+def kernel_stats(device: int | None = None) -> dict:
+    """{class name: {"ms", "bytes", "launches"}} for the last call on this device's context."""
+    Lb = load()
+    out = {}
+    for cls in range(Lb.nlz_kernel_class_count()):
+        name = ctypes.c_char_p()
+        ms = ctypes.c_double(0)
+        by = _u64(0)
+        ln = ctypes.c_uint32(0)
+        check(Lb.nlz_get_kernel_stats(context(device), cls, ctypes.byref(name), ctypes.byref(ms),
+                                      ctypes.byref(by), ctypes.byref(ln)))
+        out[name.value.decode()] = {"ms": ms.value, "bytes": by.value, "launches": ln.value}
+    return out

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "lcp.cuh"
 #include "lpnf.cuh"
+#include "prof.cuh"
 #include "radix_sort.cuh"
 #include "sa.cuh"
 
@@ -75,6 +76,7 @@ struct nlz_ctx {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[EV_COUNT];
     nlz_stats stats;
+    Profiler prof;
 };
 
 namespace nlz {
@@ -225,11 +227,13 @@ template <typename KeyT>
 static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay,
                                     cudaStream_t st, int* cur_out, u32* m_out) {
     Workspace& w = c->ws;
+    Profiler& P = c->prof;
     const u32 n1 = pb.n1;
+    const u64 kb = sizeof(KeyT);
     KeyT* k[2] = {reinterpret_cast<KeyT*>(w.KEY[0]), reinterpret_cast<KeyT*>(w.KEY[1])};
     u32* v[2] = {w.VAL[0], w.VAL[1]};
-    k_build_keys<KeyT><<<ceil_div_u32(n1, 2048), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, k[0], v[0]);
-    c->stats.kernel_launches += 1;
+    KL(P, KC_KEYS, (u64)n1 * (1 + kb + 4), st,
+       (k_build_keys<KeyT><<<ceil_div_u32(n1, 2048), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, k[0], v[0])));
     NLZ_CK(cudaEventRecord(c->ev[EV_KEYS], st));
     DigitPlan plan;
     const int used_lo = lay.key_bits - lay.W * lay.b;   // lowest symbol bit
@@ -240,17 +244,18 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
         plan_add_range(plan, 0, lay.key_bits);
     }
     int res = 0;
-    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, n1, plan, w.HIST, st, &res, &c->stats.kernel_launches));
+    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, n1, plan, w.HIST, st, &res, P));
     NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
     const KeyT dist_mask = ((KeyT)1 << lay.D) - 1;
     const u32 tiles = ceil_div_u32(n1, RG_TILE);
     // compaction target must not alias the sorted buffers: use the other KEY/VAL pair
+    P.begin(st);
     k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], n1, dist_mask, w.PMAX, w.PSUM);
     k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
     k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, n1, dist_mask, w.PMAX,
                                                               w.PSUM, w.SA, w.RANK, w.KEY[res ^ 1],
                                                               w.VAL[res ^ 1], w.SLOT[0]);
-    c->stats.kernel_launches += 3;
+    P.end(KC_REGROUP, (u64)n1 * (2 * kb + 4 + 8), st, 3);
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     c->stats.host_syncs += 1;
@@ -264,10 +269,13 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
                         bool stop_after_lpnf, u64* out_count) {
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
+    Profiler& P = c->prof;
     const u32 n1 = pb.n1;
     NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
 
     // ---- S0: text into X
+    P.begin(st);
+    u32 prep_launches = 2;
     if (pb.mode == NLZ_MODE_DNA_RC) {
         const u8* dT = static_cast<const u8*>(src);
         if (src_on_host) {
@@ -279,7 +287,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
         u32 grid = ceil_div_u32(pb.n_in, 256);
         if (grid > (u32)kNumSM * 16) grid = kNumSM * 16;
         k_prepare_dna_rc<<<grid, 256, 0, st>>>(dT, (u32)pb.n_in, w.X, w.CTR + 8);
-        S.kernel_launches += 2;
+        prep_launches += 2;
     } else {
         NLZ_CK(cudaMemcpyAsync(w.X, src, pb.n_in, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
     }
@@ -290,7 +298,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
         if (grid > (u32)kNumSM * 8) grid = kNumSM * 8;
         k_byte_hist<<<grid, 256, 0, st>>>(w.X, pb.L, w.BYTEHIST);
     }
-    S.kernel_launches += 2;
+    P.end(KC_PREPARE, pb.n_in + 2 * pb.L, st, prep_launches);
     NLZ_CK(cudaMemcpyAsync(c->h_pinned + 16, w.BYTEHIST, 256 * 4, cudaMemcpyDeviceToHost, st));
     if (pb.mode == NLZ_MODE_DNA_RC) NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaEventRecord(c->ev[EV_PREP], st));
@@ -328,17 +336,19 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
             S.active_sum += m;
             u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
             u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
-            k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(k[0], v[0], m, w.RANK, h, n1);
+            KL(P, KC_GATHER, (u64)m * 24, st,
+               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(k[0], v[0], m, w.RANK, h, n1)));
             int res = 0;
-            NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, &S.kernel_launches));
+            NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
             const int rb = res == 0 ? cur : (cur ^ 1);   // physical index of the sorted buffers
             const u32 tiles = ceil_div_u32(m, RG_TILE);
+            P.begin(st);
             k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
             k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
             k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
                                                                     w.PMAX, w.PSUM, w.SA, w.RANK, w.KEY[rb ^ 1],
                                                                     w.VAL[rb ^ 1], w.SLOT[sc ^ 1]);
-            S.kernel_launches += 4;
+            P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 4, cudaMemcpyDeviceToHost, st));
             NLZ_CK(cudaStreamSynchronize(st));
             S.host_syncs += 1;
@@ -352,8 +362,8 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
     // ---- S2: LCP
-    k_lcp_kasai<<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP);
-    S.kernel_launches += 1;
+    KL(P, KC_LCP, (u64)n1 * 28, st,
+       (k_lcp_kasai<<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP)));
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
     if (stop_after_index) {
         NLZ_CK(cudaGetLastError());
@@ -368,6 +378,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     T.lcp[0] = w.LCP; T.cntL[0] = n1 + 1;
     T.f[0] = w.SA; T.r[0] = w.SA; T.cntS[0] = n1;
     int lev = 0;
+    P.begin(st);
     while (T.cntL[lev] > 32 && lev + 1 < TREE_MAX_LEVELS) {
         u32 cl = (T.cntL[lev] + 31) / 32, cs = (T.cntS[lev] + 31) / 32;
         u32 nodes = cl > cs ? cl : cs;
@@ -379,16 +390,22 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
             if (pb.rc) k_tree_level_up<true><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
             else k_tree_level_up<false><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
         }
-        S.kernel_launches += 1;
         ++lev;
         T.lcp[lev] = w.tl[lev]; T.f[lev] = w.tf[lev]; T.r[lev] = w.tr[lev];
         T.cntL[lev] = cl; T.cntS[lev] = cs;
     }
     T.nlev = lev + 1;
+    P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
     u64* LR = w.KEY[0];
-    if (pb.rc) k_lpnf_walk<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR);
-    else k_lpnf_walk<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR);
-    S.kernel_launches += 1;
+    unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);
+    NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 8, st));
+    // algorithmic bytes: SA[r] for every rank, then per factorized position the two LCP neighbours,
+    // the LR store and (added after the run, from the visit counter) 16 bytes per path node visited
+    P.begin(st);
+    if (pb.rc) k_lpnf_walk<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR, visit_ctr);
+    else k_lpnf_walk<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR, visit_ctr);
+    P.end(KC_WALK, (u64)n1 * 4 + (u64)pb.nfac * 16, st);
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 4, visit_ctr, 8, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
     if (stop_after_lpnf) {
         NLZ_CK(cudaGetLastError());
@@ -405,12 +422,12 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     u32* MASK = reinterpret_cast<u32*>(w.KEY[1]);
     u32* CNT = MASK + (size_t)nchunks * 32;
     u32* acount = w.CTR + 1;
+    P.begin(st);
     NLZ_CK(cudaMemsetAsync(REACH, 0, nfac, st));
     k_chain_init<<<1, 1, 0, st>>>(alist, acount, REACH, (u32)pb.start_pos);
     k_chain_exit<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, EXIT, alist, acount);
-    S.kernel_launches += 2;
+    int rounds = bits_for(nchunks) + 1;
     {
-        int rounds = bits_for(nchunks) + 1;
         u32* Ja = EXIT;
         u32* Jb = J2;
         u32 grid = nchunks < (u32)kNumSM * 2 ? (nchunks ? nchunks : 1) : kNumSM * 2;
@@ -418,15 +435,20 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
             k_chain_double<<<grid, 256, 0, st>>>(alist, acount, Ja, Jb, REACH, nfac);
             u32* t = Ja; Ja = Jb; Jb = t;
         }
-        S.kernel_launches += rounds;
     }
     k_chain_mark<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, REACH, MASK, CNT);
     k_scan_u32_single_cta<<<1, 1024, 0, st>>>(CNT, nchunks, w.CTR + 2);
-    S.kernel_launches += 2;
+    P.end(KC_CHAIN, (u64)nfac * (8 + 4 + 1 + 8 + 1), st, (u32)(4 + rounds));
     NLZ_CK(cudaMemcpyAsync(c->h_pinned + 2, w.CTR + 2, 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     S.host_syncs += 1;
     const u64 z = c->h_pinned[2];
+    {
+        unsigned long long visits = 0;
+        memcpy(&visits, c->h_pinned + 4, 8);
+        S.walk_nodes = visits;
+        P.bytes[KC_WALK] += (u64)visits * 16;
+    }
     *out_count = z;
     S.n_factors = z;
     if (!count_only) {
@@ -447,9 +469,10 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
                       (unsigned long long)capacity, (unsigned long long)z);
             return ERR_RUNTIME;
         }
+        P.begin(st);
         if (pb.rc) k_chain_emit<true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity);
         else k_chain_emit<false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity);
-        S.kernel_launches += 1;
+        P.end(KC_CHAIN, (u64)nfac / 8 + z * 32, st);
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
     NLZ_CK(cudaGetLastError());
@@ -504,12 +527,15 @@ static void finish_stats(nlz_ctx* c, const Problem& pb) {
     S.ms_lpnf = el(EV_LCP, EV_LPNF);
     S.ms_chain = el(EV_LPNF, EV_CHAIN);
     S.ms_total = el(EV_BEGIN, EV_CHAIN);
+    c->prof.collect();
+    S.kernel_launches = c->prof.total_launches();
 }
 
 static void reset_stats(nlz_ctx* c) {
     size_t wsb = c->stats.workspace_bytes;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.workspace_bytes = wsb;
+    c->prof.reset();
 }
 
 static int host_call(nlz_ctx* c, int mode, const u8* text, u64 n, u64 start_pos, u64** out_alloc,
@@ -570,7 +596,8 @@ static int debug_sort(nlz_ctx* c, KeyT* keys, uint32_t* vals, uint64_t m, int lo
     DigitPlan plan;
     plan_add_range(plan, lo, hi);
     int res = 0;
-    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, (u32)m, plan, w.HIST, st, &res));
+    c->prof.reset();
+    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, (u32)m, plan, w.HIST, st, &res, c->prof));
     NLZ_CK(cudaMemcpyAsync(keys, k[res], m * sizeof(KeyT), cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaMemcpyAsync(vals, v[res], m * 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
@@ -600,6 +627,7 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     nlz_ctx* c = new nlz_ctx();
     c->device = device;
     memset(&c->stats, 0, sizeof(c->stats));
+    c->prof.reset();
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
@@ -615,6 +643,7 @@ void nlz_ctx_destroy(nlz_ctx* c) {
     if (c->d_out) cudaFree(c->d_out);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    c->prof.destroy();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -623,6 +652,25 @@ int nlz_get_stats(nlz_ctx* c, nlz_stats* out) {
     if (!c || !out) { set_error("null argument"); return ERR_INVALID; }
     std::lock_guard<std::mutex> lock(c->mu);
     *out = c->stats;
+    return OK;
+}
+
+int nlz_set_profiling(nlz_ctx* c, int on) {
+    if (!c) { set_error("null context"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->prof.timing = on != 0;
+    return OK;
+}
+
+int nlz_kernel_class_count(void) { return KC_COUNT; }
+
+int nlz_get_kernel_stats(nlz_ctx* c, int cls, const char** name, double* ms, uint64_t* bytes, uint32_t* launches) {
+    if (!c || cls < 0 || cls >= KC_COUNT) { set_error("bad kernel class"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (name) *name = kClassNames[cls];
+    if (ms) *ms = c->prof.ms[cls];
+    if (bytes) *bytes = c->prof.bytes[cls];
+    if (launches) *launches = c->prof.launches[cls];
     return OK;
 }
 

@@ -235,15 +235,11 @@ __device__ __forceinline__ void agg_range(const Trees& T, const WalkParams& p, i
 // LR[i] = (ref | rc_flag<<31) << 32 | len        for every factorized position i = SA[r]
 constexpr u32 LR_RC_FLAG = 0x80000000u;
 
+// Evaluates the factor rule for suffix i at rank r; returns the number of path nodes visited.
 template <bool RC>
-__global__ void __launch_bounds__(256)
-k_lpnf_walk(Trees T, WalkParams p, u64* __restrict__ LR) {
-    const u32 r = blockIdx.x * 256 + threadIdx.x;
-    if (r >= p.n1) return;
-    const u32* SA = T.f[0];
+__device__ __forceinline__ u32 lpnf_one(const Trees& T, const WalkParams& p, u32 r, u32 i, u64* __restrict__ LR) {
     const u32* LCP = T.lcp[0];
-    const u32 i = SA[r];
-    if (i >= p.nfac) return;
+    u32 visited = 0;
 
     u32 lo = r, hi = r;
     u32 curF = i;        // F-min over the current node (the leaf holds suffix i, which is in T)
@@ -257,6 +253,7 @@ k_lpnf_walk(Trees T, WalkParams p, u64* __restrict__ LR) {
         u32 dl = LCP[lo], dh = LCP[hi + 1];
         u32 d = max(dl, dh);
         if (d == 0) break;                      // parent is the root
+        ++visited;
         u32 nlo = (dl >= d) ? find_prev_less(T, lo - 1, d) : lo;
         u32 nhi = (dh >= d) ? find_next_less(T, hi + 2, d) - 1 : hi;
         u32 childF = curF;
@@ -302,6 +299,21 @@ k_lpnf_walk(Trees T, WalkParams p, u64* __restrict__ LR) {
         }
     }
     LR[i] = ((u64)ref << 32) | (u64)len;
+    return visited;
+}
+
+template <bool RC>
+__global__ void __launch_bounds__(256)
+k_lpnf_walk(Trees T, WalkParams p, u64* __restrict__ LR, unsigned long long* __restrict__ visit_counter) {
+    const u32 r = blockIdx.x * 256 + threadIdx.x;
+    u32 visited = 0;
+    if (r < p.n1) {
+        const u32 i = T.f[0][r];
+        if (i < p.nfac) visited = lpnf_one<RC>(T, p, r, i, LR);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) visited += __shfl_xor_sync(0xffffffffu, visited, o);
+    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(visit_counter, (unsigned long long)visited);
 }
 
 }  // namespace nlz

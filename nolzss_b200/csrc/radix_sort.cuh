@@ -9,6 +9,7 @@
 //   * passes are described by a DigitPlan so callers sort only the bit ranges that can differ.
 #pragma once
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace nlz {
 
@@ -223,7 +224,7 @@ k_rs_scatter(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
 // index of the buffer pair that holds the sorted output.  `d_hist` needs 256*RS_MAX_CTAS words.
 template <typename KeyT>
 int radix_sort_pairs(KeyT* const k[2], u32* const v[2], u32 m, const DigitPlan& plan, u32* d_hist,
-                     cudaStream_t st, int* res, u32* launches = nullptr) {
+                     cudaStream_t st, int* res, Profiler& P) {
     int cur = 0;
     if (m > 1) {
         constexpr u32 TS = RS_THREADS * RsCfg<KeyT>::ITEMS;
@@ -231,14 +232,17 @@ int radix_sort_pairs(KeyT* const k[2], u32* const v[2], u32 m, const DigitPlan& 
         u32 ctas = nt < (u32)RS_MAX_CTAS ? nt : (u32)RS_MAX_CTAS;
         u32 tpc = ceil_div_u32(nt, ctas);
         ctas = ceil_div_u32(nt, tpc);
+        const u64 kb = sizeof(KeyT);
         for (int p = 0; p < plan.npass; ++p) {
             u32 mask = (1u << plan.bits[p]) - 1u;
-            k_rs_hist<KeyT><<<ctas, RS_THREADS, 0, st>>>(k[cur], m, plan.shift[p], mask, tpc, d_hist);
-            k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d_hist, RS_BINS * ctas, nullptr);
-            k_rs_scatter<KeyT><<<ctas, RS_THREADS, 0, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], m,
-                                                            plan.shift[p], mask, tpc, d_hist);
+            KL(P, KC_RS_HIST, (u64)m * kb, st,
+               (k_rs_hist<KeyT><<<ctas, RS_THREADS, 0, st>>>(k[cur], m, plan.shift[p], mask, tpc, d_hist)));
+            KL(P, KC_RS_SCAN, (u64)RS_BINS * ctas * 8, st,
+               (k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d_hist, RS_BINS * ctas, nullptr)));
+            KL(P, KC_RS_SCATTER, (u64)m * 2 * (kb + 4), st,
+               (k_rs_scatter<KeyT><<<ctas, RS_THREADS, 0, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], m,
+                                                               plan.shift[p], mask, tpc, d_hist)));
             cur ^= 1;
-            if (launches) *launches += 3;
         }
         NLZ_CK(cudaGetLastError());
     }

@@ -1,0 +1,18 @@
+"""Prints the per-stage device times of one pipeline run (development aid)."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nolzss_b200 import _lib as L, workloads as wl
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+if which == "c1":
+    t, mode = wl.c1_text(), L.MODE_GENERAL
+elif which == "c2":
+    t, mode = wl.c2_text(), L.MODE_DNA_RC
+else:
+    n = int(which); t, mode = wl.planted_dna(n, 4, scale=max(1.0, n / 5e6)).tobytes(), L.MODE_DNA_RC
+for it in range(4):
+    t0 = time.perf_counter()
+    z = L.count(mode, t)
+    dt = time.perf_counter() - t0
+    s = L.stats()
+    print(f"iter {it}: wall {dt*1e3:.2f} ms  z={z}  " + "  ".join(f"{k}={v:.3f}" if isinstance(v, float) else f"{k}={v}" for k, v in s.items()))
