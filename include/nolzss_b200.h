@@ -48,10 +48,12 @@ typedef struct nlz_stats {
     uint64_t n_factorized;  /* positions whose factor rule was evaluated */
     uint64_t n_factors;     /* z */
     uint64_t active_sum;    /* sum over doubling rounds of suffixes still being sorted */
-    uint64_t walk_nodes;    /* suffix-tree path nodes visited by the per-position rule */
+    uint64_t walk_nodes;    /* suffix-tree path nodes / depth probes evaluated by the per-position rule */
+    uint64_t hard_positions;/* positions resolved by the text-order depth search (deep nestings) */
     uint64_t workspace_bytes;
     uint32_t key_bits, sym_bits, key_syms;
     uint32_t doubling_rounds;
+    uint32_t tile_sort_rounds; /* doubling rounds sorted entirely in shared memory */
     uint32_t kernel_launches;
     uint32_t host_syncs;
     /* device time per stage (CUDA events on the call's stream), milliseconds */

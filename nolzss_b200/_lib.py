@@ -26,9 +26,9 @@ _vp = ctypes.c_void_p
 class Stats(ctypes.Structure):
     _fields_ = [
         ("n_text", _u64), ("n_suffixes", _u64), ("n_factorized", _u64), ("n_factors", _u64),
-        ("active_sum", _u64), ("walk_nodes", _u64), ("workspace_bytes", _u64),
+        ("active_sum", _u64), ("walk_nodes", _u64), ("hard_positions", _u64), ("workspace_bytes", _u64),
         ("key_bits", ctypes.c_uint32), ("sym_bits", ctypes.c_uint32), ("key_syms", ctypes.c_uint32),
-        ("doubling_rounds", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32),
+        ("doubling_rounds", ctypes.c_uint32), ("tile_sort_rounds", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32),
         ("host_syncs", ctypes.c_uint32),
         ("ms_total", ctypes.c_float), ("ms_prepare", ctypes.c_float), ("ms_keys", ctypes.c_float),
         ("ms_sort0", ctypes.c_float), ("ms_doubling", ctypes.c_float), ("ms_lcp", ctypes.c_float),

@@ -22,6 +22,7 @@
 #include "prof.cuh"
 #include "radix_sort.cuh"
 #include "sa.cuh"
+#include "tile_sort.cuh"
 
 namespace nlz {
 
@@ -85,17 +86,17 @@ static size_t workspace_bytes_for(u64 n1) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
     t += al(n1 + 192);               // X
-    t += al((n1 + 2) * 4) * 3;       // SA, RANK, LCP
+    t += al((n1 + 72) * 4) * 3;      // SA, RANK, LCP (+ one padded line for whole-line reads)
     t += al(n1 * 8) * 2;             // KEY
     t += al(n1 * 4) * 4;             // VAL, SLOT
-    t += al((size_t)RS_BINS * RS_MAX_CTAS * 4);
+    t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
     size_t tiles = (n1 + RG_TILE - 1) / RG_TILE + 1;
     t += al(tiles * 4) * 2;
     t += al(64 * 4) + al(256 * 4);
     u64 c = n1 + 1;
     for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
         c = (c + 31) / 32;
-        t += al((c + 1) * 4) * 3;
+        t += al((c + 72) * 4) * 3;
     }
     return t + 4096;
 }
@@ -127,13 +128,13 @@ static int ensure_workspace(nlz_ctx* c, u64 n1) {
     a.off = 0;
     w.n1 = (u32)n1;
     w.X = a.take<u8>(n1 + 192);
-    w.SA = a.take<u32>(n1 + 2);
-    w.RANK = a.take<u32>(n1 + 2);
-    w.LCP = a.take<u32>(n1 + 2);
+    w.SA = a.take<u32>(n1 + 72);
+    w.RANK = a.take<u32>(n1 + 72);
+    w.LCP = a.take<u32>(n1 + 72);
     for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(n1);
     for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(n1);
     for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(n1);
-    w.HIST = a.take<u32>((size_t)RS_BINS * RS_MAX_CTAS);
+    w.HIST = a.take<u32>((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS);
     size_t tiles = (n1 + RG_TILE - 1) / RG_TILE + 1;
     w.PMAX = a.take<u32>(tiles);
     w.PSUM = a.take<u32>(tiles);
@@ -142,9 +143,9 @@ static int ensure_workspace(nlz_ctx* c, u64 n1) {
     u64 cnt = n1 + 1;
     for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
         cnt = (cnt + 31) / 32;
-        w.tl[lev] = a.take<u32>(cnt + 1);
-        w.tf[lev] = a.take<u32>(cnt + 1);
-        w.tr[lev] = a.take<u32>(cnt + 1);
+        w.tl[lev] = a.take<u32>(cnt + 72);
+        w.tf[lev] = a.take<u32>(cnt + 72);
+        w.tr[lev] = a.take<u32>(cnt + 72);
     }
     c->stats.workspace_bytes = c->arena.cap;
     return OK;
@@ -225,7 +226,7 @@ static int bits_for(u32 maxval) {
 
 template <typename KeyT>
 static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay,
-                                    cudaStream_t st, int* cur_out, u32* m_out) {
+                                    cudaStream_t st, int* cur_out, u32* m_out, u32* maxg_out) {
     Workspace& w = c->ws;
     Profiler& P = c->prof;
     const u32 n1 = pb.n1;
@@ -254,12 +255,13 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
     k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, n1, dist_mask, w.PMAX,
                                                               w.PSUM, w.SA, w.RANK, w.KEY[res ^ 1],
-                                                              w.VAL[res ^ 1], w.SLOT[0]);
+                                                              w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
     P.end(KC_REGROUP, (u64)n1 * (2 * kb + 4 + 8), st, 3);
-    NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     c->stats.host_syncs += 1;
     *m_out = c->h_pinned[0];
+    *maxg_out = c->h_pinned[3];
     *cur_out = res ^ 1;
     return OK;
 }
@@ -320,9 +322,9 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     choose_layout(c->h_pinned + 16, n1, tab, lay);
     S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
     int cur = 0;
-    u32 m = 0;
-    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, &cur, &m));
-    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, &cur, &m));
+    u32 m = 0, maxg = 0;
+    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, &cur, &m, &maxg));
+    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, &cur, &m, &maxg));
 
     {
         const int nb = bits_for(n1 - 1);
@@ -334,25 +336,50 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
         while (m > 0) {
             S.doubling_rounds += 1;
             S.active_sum += m;
-            u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
-            u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
-            KL(P, KC_GATHER, (u64)m * 24, st,
-               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(k[0], v[0], m, w.RANK, h, n1)));
-            int res = 0;
-            NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
-            const int rb = res == 0 ? cur : (cur ^ 1);   // physical index of the sorted buffers
+            int rb;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
+            static const bool trace = getenv("NLZ_TRACE") != nullptr;
+            cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+            if (trace) { cudaEventCreate(&tev0); cudaEventCreate(&tev1); cudaEventRecord(tev0, st); }
+            if (maxg <= (u32)TSORT_SLOTS / 2) {
+                // every tie group fits in shared memory: fused gather + segmented sort, one pass
+                u32 cap = 32;
+                while (cap < maxg) cap <<= 1;
+                const u32 tile = TSORT_SLOTS - cap;
+                KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 12), st,
+                   (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                       w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1, tile, cap, w.KEY[cur ^ 1], w.VAL[cur ^ 1])));
+                rb = cur ^ 1;
+                S.tile_sort_rounds += 1;
+            } else {
+                u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
+                u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
+                KL(P, KC_GATHER, (u64)m * 24, st,
+                   (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(k[0], v[0], m, w.RANK, h, n1)));
+                int res = 0;
+                NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
+                rb = res == 0 ? cur : (cur ^ 1);
+            }
+            if (trace) cudaEventRecord(tev1, st);
             const u32 tiles = ceil_div_u32(m, RG_TILE);
             P.begin(st);
             k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
             k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
             k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
                                                                     w.PMAX, w.PSUM, w.SA, w.RANK, w.KEY[rb ^ 1],
-                                                                    w.VAL[rb ^ 1], w.SLOT[sc ^ 1]);
+                                                                    w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
             P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
-            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 4, cudaMemcpyDeviceToHost, st));
+            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
             NLZ_CK(cudaStreamSynchronize(st));
             S.host_syncs += 1;
+            if (trace) {
+                float tms = 0.f;
+                cudaEventElapsedTime(&tms, tev0, tev1);
+                fprintf(stderr, "[nlz] round %u h=%llu m=%u maxg=%u sort_ms=%.3f -> m'=%u maxg'=%u\n", S.doubling_rounds,
+                        (unsigned long long)h, m, maxg, tms, c->h_pinned[0], c->h_pinned[3]);
+                cudaEventDestroy(tev0); cudaEventDestroy(tev1);
+            }
             m = c->h_pinned[0];
+            maxg = c->h_pinned[3];
             cur = rb ^ 1;
             sc ^= 1;
             h *= 2;
@@ -397,15 +424,42 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     T.nlev = lev + 1;
     P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
     u64* LR = w.KEY[0];
-    unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);
-    NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 8, st));
-    // algorithmic bytes: SA[r] for every rank, then per factorized position the two LCP neighbours,
-    // the LR store and (added after the run, from the visit counter) 16 bytes per path node visited
+    u8* HARDF = reinterpret_cast<u8*>(w.SLOT[0]);
+    RNear rn;
+    memset(&rn, 0, sizeof(rn));
+    if (pb.rc) {
+        // nearest rc(T) rank on either side of every rank + LCP minimum on the way (two segmented scans)
+        u32* PR = reinterpret_cast<u32*>(w.KEY[1]);
+        u32* ML = PR + n1;
+        u32* NR = w.VAL[0];
+        u32* MR = w.VAL[1];
+        const u32 tiles = ceil_div_u32(n1, RN_TILE);
+        P.begin(st);
+        k_rnear_reduce<0><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM);
+        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
+        k_rnear_apply<0><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM, PR, ML);
+        k_rnear_reduce<1><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM);
+        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
+        k_rnear_apply<1><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM, NR, MR);
+        P.end(KC_RNEAR, (u64)n1 * (4 * 8 + 4 * 4), st, 6);
+        rn.PR = PR; rn.ML = ML; rn.NR = NR; rn.MR = MR;
+    }
+    unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);   // [0] probes, [1] hard
+    NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 16, st));
+    // algorithmic bytes: SA[r] for every rank; per factorized position the two LCP neighbours, the
+    // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
-    if (pb.rc) k_lpnf_walk<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR, visit_ctr);
-    else k_lpnf_walk<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, LR, visit_ctr);
-    P.end(KC_WALK, (u64)n1 * 4 + (u64)pb.nfac * 16, st);
-    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 4, visit_ctr, 8, cudaMemcpyDeviceToHost, st));
+    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, LR, HARDF, visit_ctr);
+    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, LR, HARDF, visit_ctr);
+    P.end(KC_WALK, (u64)n1 * 4 + (u64)pb.nfac * 17, st);
+    {
+        const u32 grid = ceil_div_u32(ceil_div_u32(pb.nfac, WALK_Q), 256);
+        P.begin(st);
+        if (pb.rc) k_lpnf_hard<true><<<grid, 256, 0, st>>>(T, wp, w.RANK, LR, HARDF, visit_ctr);
+        else k_lpnf_hard<false><<<grid, 256, 0, st>>>(T, wp, w.RANK, LR, HARDF, visit_ctr);
+        P.end(KC_WALK_HARD, (u64)pb.nfac, st);
+    }
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 4, visit_ctr, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
     if (stop_after_lpnf) {
         NLZ_CK(cudaGetLastError());
@@ -444,10 +498,12 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     S.host_syncs += 1;
     const u64 z = c->h_pinned[2];
     {
-        unsigned long long visits = 0;
-        memcpy(&visits, c->h_pinned + 4, 8);
-        S.walk_nodes = visits;
-        P.bytes[KC_WALK] += (u64)visits * 16;
+        unsigned long long visits[2] = {0, 0};
+        memcpy(visits, c->h_pinned + 4, 16);
+        S.walk_nodes = visits[0];
+        S.hard_positions = visits[1];
+        P.bytes[KC_WALK] += (u64)visits[0] * 16;
+        P.bytes[KC_WALK_HARD] += (u64)visits[1] * (4 + 8 + 8 + 8);
     }
     *out_count = z;
     S.n_factors = z;
@@ -630,6 +686,7 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     c->prof.reset();
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));
+    NLZ_CK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
     *out = c;
     return OK;

@@ -22,40 +22,89 @@ __device__ __forceinline__ u64 load8_unaligned(const u64* __restrict__ xw, u64 p
     return (lo >> sh) | (hi << (64 - sh));
 }
 
-// number of equal leading bytes of x[a..L) and x[b..L), given that the first l0 are known equal
-__device__ __forceinline__ u32 extend_match(const u64* __restrict__ xw, u64 L, u64 a, u64 b, u32 l0) {
-    const u64 hi = a > b ? a : b;
-    const u32 maxl = (u32)(L - hi);
-    u32 l = l0;
-    while (l < maxl) {
-        u64 x = load8_unaligned(xw, a + l) ^ load8_unaligned(xw, b + l);
-        if (x) { l += (u32)(__ffsll((long long)x) - 1) >> 3; break; }
-        l += 8;
-    }
-    return l < maxl ? l : maxl;
-}
+constexpr int LCP_Q = 32;        // consecutive text positions per thread (Kasai run)
+constexpr int LCP_LOCAL_WORDS = 2;  // 8-byte words a lane compares alone before asking the warp for help
 
-constexpr int LCP_Q = 16;  // consecutive text positions per thread
-
+// Each lane runs Kasai over LCP_Q consecutive text positions.  A lane whose match outlasts
+// LCP_LOCAL_WORDS words (a repeat) hands the comparison to its whole warp: 32 lanes compare 32
+// consecutive words of the two suffixes per step (two coalesced 256-byte reads), a ballot finds the
+// first mismatch.  This removes the single-thread tail that a 100-kbp tandem repeat otherwise causes
+// while keeping the Kasai carry (l-1) inside the lane.
 __global__ void __launch_bounds__(256)
 k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
             const u32* __restrict__ RANK, u32* __restrict__ LCP) {
     const u64* xw = reinterpret_cast<const u64*>(x);
+    const u32 lane = threadIdx.x & 31;
     const u64 c = (u64)blockIdx.x * 256 + threadIdx.x;
-    u64 i = c * LCP_Q;
-    if (i >= n1) return;
-    u64 iend = i + LCP_Q;
-    if (iend > n1) iend = n1;
+    const u64 i0 = c * LCP_Q;
+    if ((c - lane) * LCP_Q >= n1) return;          // whole warp out of range (warp-uniform)
+    if (c == 0) LCP[n1] = 0;                       // right guard used by the interval walks
     u32 l = 0;
-    for (; i < iend; ++i) {
-        u32 r = RANK[i];
-        if (r == 0) { LCP[0] = 0; l = 0; continue; }
-        u32 j = SA[r - 1];
-        l = extend_match(xw, L, i, (u64)j, l);
-        LCP[r] = l;
-        if (l) --l;
+#pragma unroll 1
+    for (int k = 0; k < LCP_Q; ++k) {
+        const u64 i = i0 + k;
+        u32 r = 0, j = 0, maxl = 0;
+        bool need = false;
+        if (i < n1) {
+            r = RANK[i];
+            if (r == 0) { LCP[0] = 0; l = 0; }
+            else {
+                j = SA[r - 1];
+                maxl = (u32)(L - (i > j ? i : (u64)j));
+                if (l > maxl) l = maxl;
+                need = true;
+            }
+        }
+        bool pending_me = false;
+        if (need) {
+            pending_me = true;
+#pragma unroll
+            for (int t = 0; t < LCP_LOCAL_WORDS; ++t) {
+                if (pending_me) {
+                    if (l >= maxl) { l = maxl; pending_me = false; }
+                    else {
+                        u64 d = load8_unaligned(xw, i + l) ^ load8_unaligned(xw, (u64)j + l);
+                        if (d) {
+                            l += (u32)(__ffsll((long long)d) - 1) >> 3;
+                            if (l > maxl) l = maxl;
+                            pending_me = false;
+                        } else {
+                            l += 8;
+                        }
+                    }
+                }
+            }
+            if (pending_me && l >= maxl) { l = maxl; pending_me = false; }
+        }
+        u32 pending = __ballot_sync(0xffffffffu, pending_me);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            const u64 a = __shfl_sync(0xffffffffu, i, src);
+            const u64 b = (u64)__shfl_sync(0xffffffffu, j, src);
+            const u32 l0 = __shfl_sync(0xffffffffu, l, src);
+            const u32 ml = __shfl_sync(0xffffffffu, maxl, src);
+            u32 res = ml;
+            for (u32 off = l0; off < ml; off += 256) {
+                const u32 my = off + 8 * lane;
+                u64 d = 0;
+                if (my < ml) d = load8_unaligned(xw, a + my) ^ load8_unaligned(xw, b + my);
+                const u32 hb = __ballot_sync(0xffffffffu, d != 0);
+                if (hb) {
+                    const int f = __ffs(hb) - 1;
+                    const u64 df = __shfl_sync(0xffffffffu, d, f);
+                    res = off + 8 * f + ((u32)(__ffsll((long long)df) - 1) >> 3);
+                    if (res > ml) res = ml;
+                    break;
+                }
+            }
+            if ((int)lane == src) l = res;
+            pending &= pending - 1;
+        }
+        if (need) {
+            LCP[r] = l;
+            if (l) --l;
+        }
     }
-    if (c == 0) LCP[n1] = 0;  // right guard used by the interval walks
 }
 
 }  // namespace nlz

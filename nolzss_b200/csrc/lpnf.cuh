@@ -2,9 +2,8 @@
 //
 // f(i) = (length, ref) is a pure function of the text, so it is evaluated
 // for every text position in parallel and the greedy chain i -> i+len is extracted afterwards
-// (chain.cuh).  One thread owns one suffix-array rank r (rank space keeps the SA/LCP neighbourhood
-// of a warp in the same cache lines) and climbs the LCP-interval ancestors of leaf r, i.e. the
-// suffix-tree path the reference walks with level_anc (factorizer_core.hpp:70-78, :256-300):
+// (chain.cuh).  For each position the kernels search the LCP-interval ancestors of leaf r = ISA[i],
+// i.e. the suffix-tree path the reference walks with level_anc (factorizer_core.hpp:70-78, :256-300):
 //
 //   general mode (detail::nolzss, factorizer_core.hpp:51-119)
 //     u = deepest path node with  min SA(u) + depth(u) <= i ;  v = path node just below u
@@ -16,8 +15,23 @@
 //     rc_len  = depth(vR)  (:328-330);  forward wins ties, RC needs > 1 without a forward (:338-352)
 //
 // Interval boundaries (previous/next smaller LCP value) and the range aggregates (min / max of SA
-// over an interval) are answered from 32-ary summary trees: one 128-byte line per tree node, so a
-// probe costs O(log32 n) line reads; short ranges are scanned directly.
+// over an interval) are answered from 32-ary summary trees (one 128-byte line per tree node).
+//   k_rnear_*    two segmented scans over the suffix array give, for every rank, the nearest rank
+//                to the left / right that holds an rc(T) suffix and the minimum LCP on the way
+//                (PR/ML, NR/MR).  With them the RC candidate -- the LCA of leaf r with the nearest
+//                QUALIFYING rc(T) suffix on either side, PSV/NSV-style -- is found by hopping over
+//                rc(T) ranks only, skipping the long forward-only runs that tandem repeats create.
+//   k_lpnf_rank  one thread per suffix-array RANK (a warp shares the SA/LCP cache lines around its
+//                ranks): climbs the LCP-interval ancestors for the forward candidate, growing the
+//                interval incrementally (1-2 nodes on random DNA, up to the copy count inside
+//                tandem arrays), then applies the selection rule.  The RC source position (a range
+//                max over the chosen node) is only evaluated when the RC candidate wins.
+//                Positions that exhaust the climb budget (low-complexity text) are flagged.
+//   k_lpnf_hard  text order over the flagged positions: the forward predicate is monotone in the
+//                string depth D, so the answer is a binary search over D that grows interval(D)
+//                incrementally from the deepest failing node; a Kasai-style carry (the match at i
+//                is at least the match at i-1 minus one) makes consecutive positions O(1) probes.
+//                Tree lines are read with eight independent 16-byte loads (one latency per level).
 #pragma once
 #include "common.cuh"
 
@@ -109,17 +123,66 @@ k_tree_level_up(const u32* __restrict__ lcpA, u32 cntLA, const u32* __restrict__
 }
 
 // ---- queries --------------------------------------------------------------------------------
-// largest k <= p with LCP[k] < d   (exists: LCP[0] = 0 < d since d >= 1)
-__device__ __forceinline__ u32 find_prev_less(const Trees& T, u32 p, u32 d) {
-    i64 k = p;
+// Two flavours of every query: scalar (early-exit word probes; cheap when the answer is a few
+// entries away, the common case in rank order where neighbouring lanes share the lines) and
+// line-vectorised (a thread inspects a whole 128-byte node with eight independent 16-byte loads:
+// one memory latency per tree level, used where searches are long).  All arrays are padded so a
+// whole line can be read at the end of an array.
+struct Line32 { uint4 q[8]; };
+
+__device__ __forceinline__ Line32 load_line(const u32* __restrict__ g) {
+    const uint4* v = reinterpret_cast<const uint4*>(g);
+    Line32 l;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l.q[k] = __ldg(v + k);
+    return l;
+}
+__device__ __forceinline__ u32 line_get(const Line32& l, int k) {
+    const uint4& q = l.q[k >> 2];
+    return (k & 3) == 0 ? q.x : (k & 3) == 1 ? q.y : (k & 3) == 2 ? q.z : q.w;
+}
+__device__ __forceinline__ u32 valid_mask(i64 count) {   // count >= 1
+    return count >= 32 ? 0xFFFFFFFFu : ((1u << (u32)count) - 1u);
+}
+__device__ __forceinline__ u32 bits_upto(u32 hi_bit) {   // bits [0, hi_bit]
+    return hi_bit >= 31 ? 0xFFFFFFFFu : ((2u << hi_bit) - 1u);
+}
+
+// bit k set iff LCP-tree node (lev, gstart + k) < d   (whole line)
+__device__ __forceinline__ u32 mask_lcp_less_v(const Trees& T, int lev, i64 gstart, u32 d) {
+    const Line32 l = load_line(T.lcp[lev] + gstart);
+    u32 m = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) m |= (line_get(l, k) < d ? 1u : 0u) << k;
+    return m & valid_mask((i64)T.cntL[lev] - gstart);
+}
+
+// largest k <= pos with LCP[k] < d   (exists: LCP[0] = 0 < d since d >= 1)
+template <bool VEC>
+__device__ __forceinline__ u32 find_prev_less(const Trees& T, u32 pos, u32 d) {
+    i64 idx = pos;
+    int lev = 0;
+    if (VEC) {
+        for (;;) {
+            const i64 gstart = idx & ~31LL;
+            const u32 m = mask_lcp_less_v(T, lev, gstart, d) & bits_upto((u32)(idx - gstart));
+            if (m) { idx = gstart + (31 - __clz(m)); break; }
+            idx = (gstart >> 5) - 1;      // >= 0: the group holding LCP[0] always matches
+            ++lev;
+        }
+        while (lev > 0) {
+            --lev;
+            const i64 gstart = idx << 5;
+            idx = gstart + (31 - __clz(mask_lcp_less_v(T, lev, gstart, d)));
+        }
+        return (u32)idx;
+    }
     const u32* l0 = T.lcp[0];
 #pragma unroll 1
     for (int s = 0; s < 12; ++s) {
-        if (l0[k] < d) return (u32)k;
-        --k;
+        if (l0[idx] < d) return (u32)idx;
+        --idx;
     }
-    int lev = 0;
-    i64 idx = k;
     for (;;) {
         const u32* a = T.lcp[lev];
         const i64 gstart = idx & ~31LL;
@@ -143,17 +206,32 @@ __device__ __forceinline__ u32 find_prev_less(const Trees& T, u32 p, u32 d) {
     return (u32)idx;
 }
 
-// smallest k >= p with LCP[k] < d   (exists: LCP[n1] = 0)
-__device__ __forceinline__ u32 find_next_less(const Trees& T, u32 p, u32 d) {
-    i64 k = p;
+// smallest k >= pos with LCP[k] < d   (exists: LCP[n1] = 0)
+template <bool VEC>
+__device__ __forceinline__ u32 find_next_less(const Trees& T, u32 pos, u32 d) {
+    i64 idx = pos;
+    int lev = 0;
+    if (VEC) {
+        for (;;) {
+            const i64 gstart = idx & ~31LL;
+            const u32 m = mask_lcp_less_v(T, lev, gstart, d) & ~(bits_upto((u32)(idx - gstart)) >> 1);
+            if (m) { idx = gstart + (__ffs(m) - 1); break; }
+            idx = (gstart >> 5) + 1;      // exists: the last group of every level holds LCP[n1] = 0
+            ++lev;
+        }
+        while (lev > 0) {
+            --lev;
+            const i64 gstart = idx << 5;
+            idx = gstart + (__ffs(mask_lcp_less_v(T, lev, gstart, d)) - 1);
+        }
+        return (u32)idx;
+    }
     const u32* l0 = T.lcp[0];
 #pragma unroll 1
     for (int s = 0; s < 12; ++s) {
-        if (l0[k] < d) return (u32)k;
-        ++k;
+        if (l0[idx] < d) return (u32)idx;
+        ++idx;
     }
-    int lev = 0;
-    i64 idx = k;
     for (;;) {
         const u32* a = T.lcp[lev];
         i64 gend = idx | 31;
@@ -179,141 +257,565 @@ __device__ __forceinline__ u32 find_next_less(const Trees& T, u32 p, u32 d) {
     return (u32)idx;
 }
 
-// aggregate F-min / R-max of SA over ranks [a, b] (inclusive; empty when a > b)
-template <bool RC>
-__device__ __forceinline__ void agg_range(const Trees& T, const WalkParams& p, i64 a, i64 b, u32& fmin, u32& rmax) {
-    if (a > b) return;
-    const u32* sa = T.f[0];
-    if (b - a < 96) {
-        for (i64 k = a; k <= b; ++k) {
-            u32 s = sa[k];
-            fmin = min(fmin, f_value<RC>(s, p));
-            if (RC) rmax = max(rmax, r_value(s, p));
+__device__ __forceinline__ u32 r_node(const Trees& T, const WalkParams& p, int lev, i64 j) {
+    return lev == 0 ? r_value(T.f[0][j], p) : T.r[lev][j];
+}
+// largest k <= q with r_value(SA[k]) > thr, or -1 (scalar; fallback of the RC neighbour hop)
+__device__ __forceinline__ i64 find_prev_r_greater(const Trees& T, const WalkParams& p, i64 q, u32 thr) {
+    if (q < 0) return -1;
+    int lev = 0;
+    i64 idx = q;
+    for (;;) {
+        const i64 gstart = idx & ~31LL;
+        i64 j = idx;
+        for (; j >= gstart; --j)
+            if (r_node(T, p, lev, j) > thr) break;
+        if (j >= gstart) { idx = j; break; }
+        if (gstart == 0) return -1;
+        idx = (gstart >> 5) - 1;
+        ++lev;
+    }
+    while (lev > 0) {
+        --lev;
+        const i64 base = idx << 5;
+        i64 j = base + 31;
+        if (j > (i64)T.cntS[lev] - 1) j = (i64)T.cntS[lev] - 1;
+        for (; j > base; --j)
+            if (r_node(T, p, lev, j) > thr) break;
+        idx = j;
+    }
+    return idx;
+}
+// smallest k >= q with r_value(SA[k]) > thr, or -1
+__device__ __forceinline__ i64 find_next_r_greater(const Trees& T, const WalkParams& p, i64 q, u32 thr) {
+    if (q >= (i64)T.cntS[0]) return -1;
+    int lev = 0;
+    i64 idx = q;
+    for (;;) {
+        i64 gend = idx | 31;
+        if (gend > (i64)T.cntS[lev] - 1) gend = (i64)T.cntS[lev] - 1;
+        i64 j = idx;
+        for (; j <= gend; ++j)
+            if (r_node(T, p, lev, j) > thr) break;
+        if (j <= gend) { idx = j; break; }
+        idx = (idx >> 5) + 1;
+        ++lev;
+        if (lev >= T.nlev || idx >= (i64)T.cntS[lev]) return -1;
+    }
+    while (lev > 0) {
+        --lev;
+        const i64 base = idx << 5;
+        i64 top = base + 31;
+        if (top > (i64)T.cntS[lev] - 1) top = (i64)T.cntS[lev] - 1;
+        i64 j = base;
+        for (; j < top; ++j)
+            if (r_node(T, p, lev, j) > thr) break;
+        idx = j;
+    }
+    return idx;
+}
+
+// fold entries [lob, hib] of node line (lev, gstart) into the F-min / R-max aggregates
+template <bool RC, bool WANT_R, bool VEC>
+__device__ __forceinline__ void agg_line(const Trees& T, const WalkParams& p, int lev, i64 gstart, u32 lob, u32 hib,
+                                         u32& fmin, u32& rmax) {
+    if (VEC) {
+        const Line32 lf = load_line(T.f[lev] + gstart);
+        if (lev == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if ((u32)k >= lob && (u32)k <= hib) {
+                    const u32 s = line_get(lf, k);
+                    fmin = min(fmin, f_value<RC>(s, p));
+                    if (WANT_R) rmax = max(rmax, r_value(s, p));
+                }
+            }
+        } else {
+            Line32 lr;
+            if (WANT_R) lr = load_line(T.r[lev] + gstart);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if ((u32)k >= lob && (u32)k <= hib) {
+                    fmin = min(fmin, line_get(lf, k));
+                    if (WANT_R) rmax = max(rmax, line_get(lr, k));
+                }
+            }
         }
         return;
     }
-    while (a & 31) {
-        u32 s = sa[a++];
-        fmin = min(fmin, f_value<RC>(s, p));
-        if (RC) rmax = max(rmax, r_value(s, p));
+    if (lev == 0) {
+        const u32* sa = T.f[0] + gstart;
+        for (u32 k = lob; k <= hib; ++k) {
+            const u32 s = sa[k];
+            fmin = min(fmin, f_value<RC>(s, p));
+            if (WANT_R) rmax = max(rmax, r_value(s, p));
+        }
+    } else {
+        const u32* fa = T.f[lev] + gstart;
+        const u32* ra = T.r[lev] + gstart;
+        for (u32 k = lob; k <= hib; ++k) {
+            fmin = min(fmin, fa[k]);
+            if (WANT_R) rmax = max(rmax, ra[k]);
+        }
     }
-    while ((b + 1) & 31) {
-        u32 s = sa[b--];
-        fmin = min(fmin, f_value<RC>(s, p));
-        if (RC) rmax = max(rmax, r_value(s, p));
-    }
-    a >>= 5;
-    b = ((b + 1) >> 5) - 1;
-    int lev = 1;
+}
+
+// aggregate F-min / R-max of SA over ranks [a, b] (inclusive; empty when a > b): at most two
+// partial lines per level
+template <bool RC, bool WANT_R, bool VEC>
+__device__ __forceinline__ void agg_range(const Trees& T, const WalkParams& p, i64 a, i64 b, u32& fmin, u32& rmax) {
+    int lev = 0;
     while (a <= b) {
-        const u32* fa = T.f[lev];
-        const u32* ra = T.r[lev];
-        if (b - a < 64 || lev == T.nlev - 1) {
-            for (i64 k = a; k <= b; ++k) {
-                fmin = min(fmin, fa[k]);
-                if (RC) rmax = max(rmax, ra[k]);
-            }
-            return;
-        }
-        while (a & 31) {
-            fmin = min(fmin, fa[a]);
-            if (RC) rmax = max(rmax, ra[a]);
-            ++a;
-        }
-        while ((b + 1) & 31) {
-            fmin = min(fmin, fa[b]);
-            if (RC) rmax = max(rmax, ra[b]);
-            --b;
-        }
+        const i64 ga = a & ~31LL, gb = b & ~31LL;
+        if (ga == gb) { agg_line<RC, WANT_R, VEC>(T, p, lev, ga, (u32)(a - ga), (u32)(b - ga), fmin, rmax); return; }
+        if (a != ga) { agg_line<RC, WANT_R, VEC>(T, p, lev, ga, (u32)(a - ga), 31u, fmin, rmax); a = ga + 32; }
+        if (((b + 1) & 31) != 0) { agg_line<RC, WANT_R, VEC>(T, p, lev, gb, 0u, (u32)(b - gb), fmin, rmax); b = gb - 1; }
+        if (a > b) return;
         a >>= 5;
         b = ((b + 1) >> 5) - 1;
         ++lev;
     }
 }
 
-// ---- the walk -------------------------------------------------------------------------------
-// LR[i] = (ref | rc_flag<<31) << 32 | len        for every factorized position i = SA[r]
-constexpr u32 LR_RC_FLAG = 0x80000000u;
-
-// Evaluates the factor rule for suffix i at rank r; returns the number of path nodes visited.
-template <bool RC>
-__device__ __forceinline__ u32 lpnf_one(const Trees& T, const WalkParams& p, u32 r, u32 i, u64* __restrict__ LR) {
-    const u32* LCP = T.lcp[0];
-    u32 visited = 0;
-
-    u32 lo = r, hi = r;
-    u32 curF = i;        // F-min over the current node (the leaf holds suffix i, which is in T)
-    u32 curR = 0;        // R-max over the current node (none)
-    bool have_f = false, have_r = false;
-    u32 dF = 0, jF = 0, belowF = i;   // deepest ok-forward node: depth, min start, F-min of its path child
-    u32 dR = 0, mR = 0;               // deepest ok-RC node: depth, R-max
-    u32 lastF = i;                    // F-min of the last node visited (child of root when the loop ends)
-
-    for (;;) {
-        u32 dl = LCP[lo], dh = LCP[hi + 1];
-        u32 d = max(dl, dh);
-        if (d == 0) break;                      // parent is the root
-        ++visited;
-        u32 nlo = (dl >= d) ? find_prev_less(T, lo - 1, d) : lo;
-        u32 nhi = (dh >= d) ? find_next_less(T, hi + 2, d) - 1 : hi;
-        u32 childF = curF;
-        agg_range<RC>(T, p, (i64)nlo, (i64)lo - 1, curF, curR);
-        agg_range<RC>(T, p, (i64)hi + 1, (i64)nhi, curF, curR);
-        lo = nlo; hi = nhi;
-        lastF = curF;
-        if (!have_f && curF != NONE_MIN && (u64)curF + d <= (u64)i) {
-            have_f = true; dF = d; jF = curF; belowF = childF;
-            if (!RC) break;
-        }
-        if (RC && !have_r && curR != 0 && (p.twoN - curR) < i) {
-            have_r = true; dR = d; mR = curR;
-        }
-        if (RC && have_f && have_r) break;
+// min LCP[a..b] (inclusive, a <= b), scalar
+__device__ __forceinline__ u32 lcp_range_min(const Trees& T, i64 a, i64 b) {
+    u32 m = NONE_MIN;
+    int lev = 0;
+    while (a <= b) {
+        const u32* la = T.lcp[lev];
+        const i64 ga = a & ~31LL, gb = b & ~31LL;
+        if (ga == gb) { for (i64 k = a; k <= b; ++k) m = min(m, la[k]); return m; }
+        if (a != ga) { for (i64 k = a; k < ga + 32; ++k) m = min(m, la[k]); a = ga + 32; }
+        if (((b + 1) & 31) != 0) { for (i64 k = gb; k <= b; ++k) m = min(m, la[k]); b = gb - 1; }
+        if (a > b) return m;
+        a >>= 5;
+        b = ((b + 1) >> 5) - 1;
+        ++lev;
     }
+    return m;
+}
 
+// ---- nearest rc(T) rank on either side, with the LCP minimum on the way -----------------------
+// PR[k] = largest k' <= k with SA[k'] in rc(T) (NONE_MIN if none), ML[k] = min LCP[PR[k]+1 .. k]
+// NR[k] = smallest k' >= k with SA[k'] in rc(T) (NONE_MIN if none), MR[k] = min LCP[k+1 .. NR[k]]
+// (ML/MR = NONE_MIN when the range is empty, i.e. k itself is an rc(T) rank.)  Three-phase
+// segmented scans; tiles of RN_TILE ranks.
+constexpr int RN_THREADS = 256;
+constexpr int RN_ITEMS = 8;
+constexpr int RN_TILE = RN_THREADS * RN_ITEMS;
+
+struct RnState { u32 idx; u32 mn; };   // last rc rank seen (NONE_MIN: none yet) and min LCP since
+__device__ __forceinline__ RnState rn_combine(RnState a, RnState b) {   // a then b
+    RnState o;
+    if (b.idx != NONE_MIN) { o.idx = b.idx; o.mn = b.mn; }
+    else { o.idx = a.idx; o.mn = min(a.mn, b.mn); }
+    return o;
+}
+__device__ __forceinline__ bool is_r_class(u32 s, const WalkParams& p) { return s > p.N && s <= p.twoN; }
+
+// element e of the scan in direction DIR (0: left-to-right over k, 1: right-to-left)
+template <int DIR>
+__device__ __forceinline__ RnState rn_element(const u32* __restrict__ SA, const u32* __restrict__ LCP, u32 k,
+                                              const WalkParams& p) {
+    RnState e;
+    if (is_r_class(SA[k], p)) { e.idx = k; e.mn = NONE_MIN; }
+    else { e.idx = NONE_MIN; e.mn = DIR == 0 ? LCP[k] : LCP[k + 1]; }
+    return e;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(RN_THREADS)
+k_rnear_reduce(const u32* __restrict__ SA, const u32* __restrict__ LCP, WalkParams p, u32* __restrict__ tile_idx,
+               u32* __restrict__ tile_mn) {
+    __shared__ RnState wagg[RN_THREADS / 32];
+    const u32 n1 = p.n1;
+    const u64 tile_start = (u64)blockIdx.x * RN_TILE;
+    RnState acc; acc.idx = NONE_MIN; acc.mn = NONE_MIN;
+#pragma unroll
+    for (int q = 0; q < RN_ITEMS; ++q) {
+        const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;     // scan position
+        if (o < n1) {
+            const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
+            acc = rn_combine(acc, rn_element<DIR>(SA, LCP, k, p));
+        }
+    }
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        RnState t;
+        t.idx = __shfl_up_sync(0xffffffffu, acc.idx, o);
+        t.mn = __shfl_up_sync(0xffffffffu, acc.mn, o);
+        if (lane >= (u32)o) acc = rn_combine(t, acc);
+    }
+    if (lane == 31) wagg[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        RnState a = wagg[0];
+        for (int i = 1; i < RN_THREADS / 32; ++i) a = rn_combine(a, wagg[i]);
+        tile_idx[blockIdx.x] = a.idx;
+        tile_mn[blockIdx.x] = a.mn;
+    }
+}
+
+// exclusive scan of the tile aggregates by one CTA (sequential per thread chunk + warp scans)
+__global__ void __launch_bounds__(1024)
+k_rnear_scan_tiles(u32* __restrict__ tile_idx, u32* __restrict__ tile_mn, u32 ntiles) {
+    __shared__ RnState wagg[32];
+    const u32 per = (ntiles + 1023) / 1024;
+    u32 b = threadIdx.x * per, e = b + per;
+    if (b > ntiles) b = ntiles;
+    if (e > ntiles) e = ntiles;
+    RnState acc; acc.idx = NONE_MIN; acc.mn = NONE_MIN;
+    for (u32 i = b; i < e; ++i) { RnState t; t.idx = tile_idx[i]; t.mn = tile_mn[i]; acc = rn_combine(acc, t); }
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    RnState inc = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        RnState t;
+        t.idx = __shfl_up_sync(0xffffffffu, inc.idx, o);
+        t.mn = __shfl_up_sync(0xffffffffu, inc.mn, o);
+        if (lane >= (u32)o) inc = rn_combine(t, inc);
+    }
+    if (lane == 31) wagg[w] = inc;
+    __syncthreads();
+    RnState carry; carry.idx = NONE_MIN; carry.mn = NONE_MIN;
+    for (u32 i = 0; i < w; ++i) carry = rn_combine(carry, wagg[i]);
+    RnState prevl;
+    prevl.idx = __shfl_up_sync(0xffffffffu, inc.idx, 1);
+    prevl.mn = __shfl_up_sync(0xffffffffu, inc.mn, 1);
+    if (lane > 0) carry = rn_combine(carry, prevl);
+    for (u32 i = b; i < e; ++i) {
+        RnState t; t.idx = tile_idx[i]; t.mn = tile_mn[i];
+        tile_idx[i] = carry.idx; tile_mn[i] = carry.mn;
+        carry = rn_combine(carry, t);
+    }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(RN_THREADS)
+k_rnear_apply(const u32* __restrict__ SA, const u32* __restrict__ LCP, WalkParams p, const u32* __restrict__ tile_idx,
+              const u32* __restrict__ tile_mn, u32* __restrict__ out_idx, u32* __restrict__ out_mn) {
+    __shared__ RnState wagg[RN_THREADS / 32];
+    const u32 n1 = p.n1;
+    const u64 tile_start = (u64)blockIdx.x * RN_TILE;
+    RnState el[RN_ITEMS];
+    RnState acc; acc.idx = NONE_MIN; acc.mn = NONE_MIN;
+#pragma unroll
+    for (int q = 0; q < RN_ITEMS; ++q) {
+        const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;
+        el[q].idx = NONE_MIN; el[q].mn = NONE_MIN;
+        if (o < n1) {
+            const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
+            el[q] = rn_element<DIR>(SA, LCP, k, p);
+            acc = rn_combine(acc, el[q]);
+        }
+    }
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    RnState inc = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        RnState t;
+        t.idx = __shfl_up_sync(0xffffffffu, inc.idx, o);
+        t.mn = __shfl_up_sync(0xffffffffu, inc.mn, o);
+        if (lane >= (u32)o) inc = rn_combine(t, inc);
+    }
+    if (lane == 31) wagg[w] = inc;
+    __syncthreads();
+    RnState carry; carry.idx = tile_idx[blockIdx.x]; carry.mn = tile_mn[blockIdx.x];
+    for (u32 i = 0; i < w; ++i) carry = rn_combine(carry, wagg[i]);
+    RnState prevl;
+    prevl.idx = __shfl_up_sync(0xffffffffu, inc.idx, 1);
+    prevl.mn = __shfl_up_sync(0xffffffffu, inc.mn, 1);
+    if (lane > 0) carry = rn_combine(carry, prevl);
+#pragma unroll
+    for (int q = 0; q < RN_ITEMS; ++q) {
+        const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;
+        if (o < n1) {
+            const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
+            carry = rn_combine(carry, el[q]);       // inclusive state at k
+            out_idx[k] = carry.idx;
+            out_mn[k] = carry.mn;
+        }
+    }
+}
+
+struct RNear {
+    const u32* PR; const u32* ML;   // left
+    const u32* NR; const u32* MR;   // right
+};
+
+// depth of the LCA of leaf r with the nearest rc(T) suffix whose T-end is < i (value > thr), on one side
+// (DIR 0: left).  Hops over rc ranks only; falls back to the summary trees after RHOP_MAX hops.
+constexpr int RHOP_MAX = 24;
+template <int DIR>
+__device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p, const RNear& rn, u32 r, u32 thr) {
+    const u32* SA = T.f[0];
+    const u32* LCP = T.lcp[0];
+    u32 k = r;            // current rank (start: the F-class leaf itself)
+    u32 run = NONE_MIN;   // min LCP between k and r
+#pragma unroll 1
+    for (int hop = 0; hop < RHOP_MAX; ++hop) {
+        // step to the neighbouring rank, then (if it is not an rc rank) jump to the nearest rc rank beyond it
+        if (DIR == 0) {
+            if (k == 0) return 0;
+            run = min(run, LCP[k]);
+            u32 nb = k - 1;
+            const u32 tgt = rn.PR[nb];
+            if (tgt == NONE_MIN) return 0;
+            if (tgt != nb) run = min(run, rn.ML[nb]);
+            k = tgt;
+        } else {
+            if (k + 1 >= p.n1) return 0;
+            run = min(run, LCP[k + 1]);
+            u32 nb = k + 1;
+            const u32 tgt = rn.NR[nb];
+            if (tgt == NONE_MIN) return 0;
+            if (tgt != nb) run = min(run, rn.MR[nb]);
+            k = tgt;
+        }
+        if (run == 0) return 0;                       // left the last non-root ancestor
+        if (SA[k] > thr) return run;                  // rc rank (<= 2N by construction) that qualifies
+    }
+    // rare: many non-qualifying rc suffixes in a row -> summary-tree search from k
+    if (DIR == 0) {
+        const i64 kl = find_prev_r_greater(T, p, (i64)k - 1, thr);
+        if (kl < 0) return 0;
+        return min(run, lcp_range_min(T, kl + 1, (i64)k));
+    }
+    const i64 kr = find_next_r_greater(T, p, (i64)k + 1, thr);
+    if (kr < 0) return 0;
+    return min(run, lcp_range_min(T, (i64)k + 1, kr));
+}
+
+// ---- the factor rule ------------------------------------------------------------------------
+// LR[i] = (ref | rc_flag<<31) << 32 | len        for every factorized position i
+constexpr u32 LR_RC_FLAG = 0x80000000u;
+constexpr int WALK_MAX_NODES = 640;    // ancestors climbed in rank order before a position is "hard"
+constexpr int WALK_Q = 8;              // consecutive text positions per thread in k_lpnf_hard
+
+struct NodeState {
+    u32 lo, hi;   // rank interval
+    u32 F;        // min of F-class suffix starts in the interval
+    u32 R;        // max of R-class suffix starts in the interval (only when asked for)
+};
+
+// State of interval(D) = maximal rank interval around `s` whose LCP values are all >= D, for any
+// D <= depth(s): grows the interval and folds only the newly covered ranks into the aggregates.
+template <bool RC, bool WANT_R, bool VEC>
+__device__ __forceinline__ NodeState extend_to(const Trees& T, const WalkParams& p, NodeState s, u32 D) {
+    const u32* LCP = T.lcp[0];
+    const u32 nlo = (LCP[s.lo] >= D) ? find_prev_less<VEC>(T, s.lo - 1, D) : s.lo;
+    const u32 nhi = (LCP[s.hi + 1] >= D) ? find_next_less<VEC>(T, s.hi + 2, D) - 1 : s.hi;
+    agg_range<RC, WANT_R, VEC>(T, p, (i64)nlo, (i64)s.lo - 1, s.F, s.R);
+    agg_range<RC, WANT_R, VEC>(T, p, (i64)s.hi + 1, (i64)nhi, s.F, s.R);
+    s.lo = nlo;
+    s.hi = nhi;
+    return s;
+}
+
+// forward predicate of the reference (factorizer_core.hpp:75 and :266): min start + depth <= i
+__device__ __forceinline__ bool pred_f(const NodeState& s, u32 D, u32 i) {
+    return s.F != NONE_MIN && (u64)s.F + D <= (u64)i;
+}
+
+// Selection between forward candidate, RC candidate and literal (factorizer_core.hpp:335-365), or the
+// general-mode answer (:82-108).  The RC source (largest rc start = smallest T-end inside the chosen
+// node, :290-299) is a range max over interval(dR) and is only evaluated when the RC candidate wins.
+template <bool RC, bool VEC>
+__device__ __forceinline__ u64 select_factor(const Trees& T, const WalkParams& p, u32 r, u32 i, bool have_f,
+                                             u32 fwd_len, u32 jF, u32 gen_len, u32 gen_ref, u32 dR) {
     u32 len, ref;
     if (!RC) {
-        // v = node just below u (or the child of the root when no u exists)
-        u32 v_min = have_f ? belowF : lastF;
-        if (v_min == i) {                                   // factorizer_core.hpp:82
-            if (!have_f) { len = 1; ref = i; }              // :83-87
-            else { len = dF; ref = jF; }                    // :89-94
-        } else {
-            u32 Lc = i - v_min;                             // :96-97 (lcp(i, v_min) >= depth(v) > i - v_min)
-            if (!have_f || Lc > dF) { len = Lc; ref = v_min; }   // :104-107
-            else { len = dF; ref = jF; }                    // :98-102
-        }
+        if (gen_len >= 1) { len = gen_len; ref = gen_ref; }
+        else { len = 1; ref = i; }
     } else {
-        u32 fwd_len = 0;
-        if (have_f) fwd_len = (belowF == jF) ? (i - jF) : dF;    // :322-326
-        u32 rc_len = have_r ? dR : 0;                            // :328-330
+        const bool have_r = dR >= 1;
+        const u32 rc_len = dR;                                                  // :328-330
         bool use_fwd = false, use_lit = false;
-        if (have_f && fwd_len >= 1) use_fwd = !(have_r && rc_len > fwd_len);   // :338-344
-        else if (!(have_r && rc_len > 1)) use_lit = true;                      // :346-351
+        if (have_f && fwd_len >= 1) use_fwd = !(have_r && rc_len > fwd_len);    // :338-344
+        else if (!(have_r && rc_len > 1)) use_lit = true;                       // :346-351
         if (use_lit) { len = 1; ref = i; }
         else if (use_fwd) { len = fwd_len; ref = jF; }
         else {
-            u32 e = p.twoN - mR;                                 // smallest RC end in T coordinates
+            NodeState leaf;
+            leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
+            const u32 mR = extend_to<RC, true, VEC>(T, p, leaf, dR).R;
+            const u32 e = p.twoN - mR;                           // smallest RC end in T coordinates
             len = rc_len;
             ref = (e - rc_len + 1) | LR_RC_FLAG;                 // :362-364 (start-anchored + RC flag)
         }
     }
-    LR[i] = ((u64)ref << 32) | (u64)len;
-    return visited;
+    return ((u64)ref << 32) | (u64)len;
+}
+
+// ---- kernel 1: rank order ---------------------------------------------------------------------
+constexpr int WALK_LINEAR_BUDGET = 48;   // ranks a climb step may add by plain neighbour probes
+
+template <bool RC>
+__global__ void __launch_bounds__(256)
+k_lpnf_rank(Trees T, WalkParams p, RNear rn, u64* __restrict__ LR, u8* __restrict__ HARD,
+            unsigned long long* __restrict__ counters) {
+    const u32 r = blockIdx.x * 256 + threadIdx.x;
+    u32 visited = 0, hard = 0;
+    const u32* LCP = T.lcp[0];
+    const u32* SA = T.f[0];
+    u32 i = 0xFFFFFFFFu;
+    if (r < p.n1) i = SA[r];
+    if (i < p.nfac) {
+        NodeState cur;                   // deepest path node known to fail the forward predicate
+        cur.lo = r; cur.hi = r; cur.F = i; cur.R = 0;
+        bool have_f = false, at_root = false;
+        u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
+#pragma unroll 1
+        for (int step = 0;; ++step) {
+            const u32 dl = LCP[cur.lo], dh = LCP[cur.hi + 1];
+            const u32 d = max(dl, dh);                            // depth of the parent of `cur`
+            if (d == 0) { at_root = true; break; }
+            if (step == WALK_MAX_NODES) break;
+            ++visited;
+            const u32 childF = cur.F;
+            // fast path: the parent usually adds a handful of neighbouring ranks (exactly one inside
+            // a tandem array) -> plain probes; wide parents go through the summary trees
+            u32 lo = cur.lo, hi = cur.hi, F = cur.F;
+            int budget = WALK_LINEAR_BUDGET;
+            if (dl >= d) {
+                do {
+                    --lo;
+                    F = min(F, f_value<RC>(SA[lo], p));
+                } while (--budget > 0 && LCP[lo] >= d);            // LCP[0] = 0 stops at the left end
+            }
+            if (budget > 0 && dh >= d) {
+                do {
+                    ++hi;
+                    F = min(F, f_value<RC>(SA[hi], p));
+                } while (--budget > 0 && LCP[hi + 1] >= d);        // LCP[n1] = 0 stops at the right end
+            }
+            if (budget > 0) { cur.lo = lo; cur.hi = hi; cur.F = F; }
+            else cur = extend_to<RC, false, false>(T, p, cur, d);
+            if (pred_f(cur, d, i)) { have_f = true; dF = d; jF = cur.F; belowF = childF; break; }
+        }
+        u32 dR = 0;
+        if (RC) {
+            const u32 thr = p.twoN - i;
+            dR = max(rc_side_depth<0>(T, p, rn, r, thr), rc_side_depth<1>(T, p, rn, r, thr));
+            visited += 2;
+        }
+        if (have_f || at_root) {
+            u32 gen_len, gen_ref, fwd_len = 0;
+            if (have_f) {
+                const u32 part = (belowF != i) ? i - belowF : 0;
+                if (part > dF) { gen_len = part; gen_ref = belowF; }    // :104-107
+                else { gen_len = dF; gen_ref = jF; }                    // :89-94, :98-102
+                fwd_len = (belowF == jF) ? (i - jF) : dF;               // :322-326
+            } else {
+                const u32 v_min = cur.F;                                // child of the root (or the leaf itself)
+                gen_len = (v_min != i) ? i - v_min : 0;                 // :96-107 with u = root, or literal
+                gen_ref = v_min;
+            }
+            LR[i] = select_factor<RC, false>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
+            HARD[i] = 0;
+        } else {
+            LR[i] = (u64)dR;             // park the RC candidate depth for k_lpnf_hard
+            HARD[i] = 1;
+            hard = 1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        visited += __shfl_xor_sync(0xffffffffu, visited, o);
+        hard += __shfl_xor_sync(0xffffffffu, hard, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (visited) atomicAdd(counters, (unsigned long long)visited);
+        if (hard) atomicAdd(counters + 1, (unsigned long long)hard);
+    }
+}
+
+// ---- kernel 2: text order over the hard positions ----------------------------------------------
+// Largest D in [loD, hiD) that satisfies the forward predicate (loD: known true, or 0; hiD: known
+// false; `cur`: a failing state of depth >= hiD).  U = interval(D*) when D* > initial loD,
+// L = interval(D*+1).  Every probe extends the deepest known-failing node.
+template <bool RC>
+__device__ __forceinline__ u32 depth_search(const Trees& T, const WalkParams& p, u32 i, const NodeState& cur,
+                                            u32 loD, u32 hiD, NodeState& U, NodeState& L, u32& probes) {
+    L = cur;
+    while (hiD - loD > 1) {
+        const u32 mid = loD + ((hiD - loD) >> 1);
+        const NodeState cand = extend_to<RC, false, true>(T, p, L, mid);
+        if (pred_f(cand, mid, i)) { loD = mid; U = cand; }
+        else { hiD = mid; L = cand; }
+        ++probes;
+    }
+    return loD;
 }
 
 template <bool RC>
 __global__ void __launch_bounds__(256)
-k_lpnf_walk(Trees T, WalkParams p, u64* __restrict__ LR, unsigned long long* __restrict__ visit_counter) {
-    const u32 r = blockIdx.x * 256 + threadIdx.x;
+k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict__ LR,
+            const u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
+    const u64 c = (u64)blockIdx.x * 256 + threadIdx.x;
+    const u64 i0 = c * WALK_Q;
     u32 visited = 0;
-    if (r < p.n1) {
-        const u32 i = T.f[0][r];
-        if (i < p.nfac) visited = lpnf_one<RC>(T, p, r, i, LR);
+    if (i0 < p.nfac) {
+        const u32* LCP = T.lcp[0];
+        u64 iend = i0 + WALK_Q;
+        if (iend > p.nfac) iend = p.nfac;
+        u32 prevF = 0;               // true longest non-overlapping forward match of the previous position
+        for (u64 ii = i0; ii < iend; ++ii) {
+            if (!HARD[ii]) { prevF = 0; continue; }
+            const u32 i = (u32)ii;
+            const u32 r = RANK[i];
+            NodeState leaf;
+            leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
+            const u32 Dtop = max(LCP[r], LCP[r + 1]) + 1;        // deeper than the leaf's parent nothing matches
+            const u32 lb = prevF > 0 ? prevF - 1 : 0;            // Kasai-style lower bound (known to hold)
+            NodeState U = leaf, L = leaf;
+            u32 Ds;
+            if (lb >= 1 && lb + 1 < Dtop) {
+                const NodeState st = extend_to<RC, false, true>(T, p, leaf, lb + 1);
+                ++visited;
+                if (pred_f(st, lb + 1, i)) {
+                    U = st;
+                    Ds = depth_search<RC>(T, p, i, leaf, lb + 1, Dtop, U, L, visited);
+                } else {
+                    Ds = lb; L = st;
+                    U = extend_to<RC, false, true>(T, p, st, lb);
+                    ++visited;
+                }
+            } else if (lb >= 1) {                                // lb + 1 == Dtop
+                Ds = lb; L = leaf;
+                U = extend_to<RC, false, true>(T, p, leaf, lb);
+                ++visited;
+            } else {
+                Ds = depth_search<RC>(T, p, i, leaf, 0, Dtop, U, L, visited);
+            }
+            prevF = Ds;
+            bool have_f = false;
+            u32 fwd_len = 0, jF = 0, gen_len = 0, gen_ref = i;
+            if (Ds >= 1) {
+                gen_len = Ds; gen_ref = U.F;
+                if (RC) {
+                    if (U.lo != L.lo || U.hi != L.hi) {          // U is a node of depth Ds, L its path child
+                        have_f = true; jF = U.F;
+                        fwd_len = (L.F == U.F) ? (i - jF) : Ds;
+                    } else {                                     // Ds lies inside U's edge: vF = parent(U)
+                        const u32 du = max(LCP[U.lo], LCP[U.hi + 1]);
+                        if (du > 0) {
+                            const NodeState P = extend_to<RC, false, true>(T, p, U, du);
+                            ++visited;
+                            have_f = true; jF = P.F;
+                            fwd_len = (U.F == P.F) ? (i - jF) : du;
+                        }
+                    }
+                }
+            }
+            const u32 dR = (u32)LR[i];
+            LR[i] = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) visited += __shfl_xor_sync(0xffffffffu, visited, o);
-    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(visit_counter, (unsigned long long)visited);
+    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(counters, (unsigned long long)visited);
 }
 
 }  // namespace nlz

@@ -126,11 +126,44 @@ __global__ void __launch_bounds__(1024) k_scan_u32_single_cta(u32* __restrict__ 
     }
 }
 
+// Histogram table is [256 digits][ctas].  One CTA per digit row: exclusive scan across the CTAs of
+// that row (coalesced), row total to row_tot[digit].  The cross-digit prefix is taken by every
+// scatter CTA itself from the 256 row totals, so no serial whole-table scan remains.
+__global__ void __launch_bounds__(1024) k_rs_scan_rows(u32* __restrict__ hist, u32 ctas, u32* __restrict__ row_tot) {
+    __shared__ u32 wsum[32];
+    u32* row = hist + (size_t)blockIdx.x * ctas;
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 carry = 0;
+    for (u32 base = 0; base < ctas; base += 1024) {
+        u32 i = base + threadIdx.x;
+        u32 v = i < ctas ? row[i] : 0u;
+        u32 inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        u32 wp = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            u32 x = wsum[k];
+            if (k < (int)w) wp += x;
+            tot += x;
+        }
+        if (i < ctas) row[i] = carry + wp + inc - v;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_tot[blockIdx.x] = carry;
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __restrict__ kout,
              u32* __restrict__ vout, u32 m, int shift, u32 mask, u32 tiles_per_cta,
-             const u32* __restrict__ hist) {
+             const u32* __restrict__ hist, const u32* __restrict__ row_tot) {
     constexpr int ITEMS = RsCfg<KeyT>::ITEMS;
     constexpr u32 TS = RS_THREADS * ITEMS;
     __shared__ u32 warp_cnt[RS_WARPS][RS_BINS + 1];  // bin 256 collects out-of-range lanes
@@ -142,7 +175,10 @@ k_rs_scatter(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
     __shared__ u32 sval[TS];
 
     const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    digit_base[tid] = hist[tid * gridDim.x + blockIdx.x];
+    {
+        u32 dig_excl = block_excl_scan_256(row_tot[tid], ws);   // start of digit `tid` in the output
+        digit_base[tid] = dig_excl + hist[tid * gridDim.x + blockIdx.x];
+    }
     const u32 ntiles = (u32)(((u64)m + TS - 1) / TS);
     const u32 tile0 = blockIdx.x * tiles_per_cta;
     u32 tile1 = tile0 + tiles_per_cta;
@@ -221,7 +257,7 @@ k_rs_scatter(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
 }
 
 // Sorts m pairs held in (k[0], v[0]); buffers (k[1], v[1]) are scratch.  Returns through *res the
-// index of the buffer pair that holds the sorted output.  `d_hist` needs 256*RS_MAX_CTAS words.
+// index of the buffer pair that holds the sorted output.  `d_hist` needs 256*RS_MAX_CTAS + 256 words.
 template <typename KeyT>
 int radix_sort_pairs(KeyT* const k[2], u32* const v[2], u32 m, const DigitPlan& plan, u32* d_hist,
                      cudaStream_t st, int* res, Profiler& P) {
@@ -238,10 +274,11 @@ int radix_sort_pairs(KeyT* const k[2], u32* const v[2], u32 m, const DigitPlan& 
             KL(P, KC_RS_HIST, (u64)m * kb, st,
                (k_rs_hist<KeyT><<<ctas, RS_THREADS, 0, st>>>(k[cur], m, plan.shift[p], mask, tpc, d_hist)));
             KL(P, KC_RS_SCAN, (u64)RS_BINS * ctas * 8, st,
-               (k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d_hist, RS_BINS * ctas, nullptr)));
+               (k_rs_scan_rows<<<RS_BINS, 1024, 0, st>>>(d_hist, ctas, d_hist + (size_t)RS_BINS * RS_MAX_CTAS)));
             KL(P, KC_RS_SCATTER, (u64)m * 2 * (kb + 4), st,
                (k_rs_scatter<KeyT><<<ctas, RS_THREADS, 0, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], m,
-                                                               plan.shift[p], mask, tpc, d_hist)));
+                                                               plan.shift[p], mask, tpc, d_hist,
+                                                               d_hist + (size_t)RS_BINS * RS_MAX_CTAS)));
             cur ^= 1;
         }
         NLZ_CK(cudaGetLastError());

@@ -146,6 +146,8 @@ k_regroup_reduce(const KeyT* __restrict__ keys, u32 m, KeyT dist_mask, u32* __re
 // phase B: exclusive (max, sum) scan of the tile partials by one CTA; writes the new active count.
 __global__ void __launch_bounds__(1024)
 k_regroup_scan_partials(u32* __restrict__ pmax, u32* __restrict__ psum, u32 ntiles, u32* __restrict__ m_out) {
+    // m_out[0] = new active count; m_out[3] = largest new group (atomicMax'ed by k_regroup_apply)
+    if (threadIdx.x == 0) m_out[3] = 0;
     __shared__ u32 wmax[32], wsum[32];
     const u32 per = (ntiles + 1023) / 1024;
     u32 b = threadIdx.x * per, e = b + per;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(RG_THREADS)
 k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ slots,
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
                 u32* __restrict__ SA, u32* __restrict__ RANK, u64* __restrict__ key_next,
-                u32* __restrict__ val_next, u32* __restrict__ slot_next) {
+                u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out) {
     __shared__ u8 sh_head[RG_TILE + 8];
     __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
     const u64 tile_start = (u64)blockIdx.x * RG_TILE;
@@ -205,6 +207,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
     const u32 i0 = threadIdx.x * RG_ITEMS;
     u32 hm[RG_ITEMS], ps[RG_ITEMS];
     bool act[RG_ITEMS];
+    u32 gmax = 0;
     u32 run_max = 0, run_sum = 0;
 #pragma unroll
     for (int q = 0; q < RG_ITEMS; ++q) {
@@ -252,9 +255,13 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
                 key_next[pos] = (u64)newrank << 32;
                 val_next[pos] = s;
                 slot_next[pos] = slot;
+                if (sh_head[idx + 1] != 0) gmax = max(gmax, e - hj + 1);   // last element of its group
             }
         }
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (lane == 0 && gmax > 1) atomicMax(maxg_out, gmax);
 }
 
 // KEY[j] |= RANK[VAL[j] + h]   (second half of the doubling key)

@@ -214,6 +214,111 @@ class Trees:
             idx = j
         return idx
 
+    def find_prev_r_greater(self, p, thr):
+        """largest k <= p with rval(SA[k]) > thr, or -1."""
+        k = p
+        for _ in range(8):
+            if k < 0:
+                return -1
+            if self.rval(self.f[0][k]) > thr:
+                return k
+            k -= 1
+        if k < 0:
+            return -1
+        lev, idx = 0, k
+        while True:
+            gstart = idx & ~31
+            j = idx
+            while j >= gstart and not self._rv(lev, j) > thr:
+                j -= 1
+            if j >= gstart:
+                idx = j
+                break
+            if gstart == 0:
+                return -1
+            idx = (gstart >> 5) - 1
+            lev += 1
+        while lev > 0:
+            lev -= 1
+            base = idx << 5
+            j = min(base + 31, self._rcount(lev) - 1)
+            while j > base and not self._rv(lev, j) > thr:
+                j -= 1
+            idx = j
+        return idx
+
+    def find_next_r_greater(self, p, thr):
+        """smallest k >= p with rval(SA[k]) > thr, or -1."""
+        n1 = len(self.f[0])
+        k = p
+        for _ in range(8):
+            if k >= n1:
+                return -1
+            if self.rval(self.f[0][k]) > thr:
+                return k
+            k += 1
+        if k >= n1:
+            return -1
+        lev, idx = 0, k
+        while True:
+            cnt = self._rcount(lev)
+            gend = min(idx | 31, cnt - 1)
+            j = idx
+            while j <= gend and not self._rv(lev, j) > thr:
+                j += 1
+            if j <= gend:
+                idx = j
+                break
+            idx = (idx >> 5) + 1
+            lev += 1
+            if lev >= self.nlev or idx >= self._rcount(lev):
+                return -1
+        while lev > 0:
+            lev -= 1
+            base = idx << 5
+            top = min(base + 31, self._rcount(lev) - 1)
+            j = base
+            while j < top and not self._rv(lev, j) > thr:
+                j += 1
+            idx = j
+        return idx
+
+    def _rv(self, lev, j):
+        return self.rval(self.f[0][j]) if lev == 0 else self.r[lev][j]
+
+    def _rcount(self, lev):
+        return len(self.f[0]) if lev == 0 else len(self.r[lev])
+
+    def lcp_range_min(self, a, b):
+        """min LCP[a..b] (inclusive, a <= b)."""
+        m = NONE_MIN
+        l0 = self.lcp[0]
+        if b - a < 96:
+            for k in range(a, b + 1):
+                m = min(m, l0[k])
+            return m
+        while a & 31:
+            m = min(m, l0[a]); a += 1
+        while (b + 1) & 31:
+            m = min(m, l0[b]); b -= 1
+        a >>= 5
+        b = ((b + 1) >> 5) - 1
+        lev = 1
+        while a <= b:
+            la = self.lcp[lev]
+            if b - a < 64 or lev == self.nlev - 1:
+                for k in range(a, b + 1):
+                    m = min(m, la[k])
+                return m
+            while a & 31:
+                m = min(m, la[a]); a += 1
+            while (b + 1) & 31:
+                m = min(m, la[b]); b -= 1
+            a >>= 5
+            b = ((b + 1) >> 5) - 1
+            lev += 1
+        return m
+
     def agg(self, a, b, fmin, rmax):
         if a > b:
             return fmin, rmax
@@ -255,65 +360,151 @@ class Trees:
         return fmin, rmax
 
 
-def walk(T: Trees, n1, nfac):
-    """k_lpnf_walk: LR[i] = (len, ref32)."""
+K_LIN = 4  # path nodes climbed one by one before switching to a binary search over string depth
+
+
+def _extend(T, st, D):
+    """Node state (lo, hi, F, R) -> state of interval(D) (D <= current depth), incrementally."""
+    lo, hi, F, R = st
+    LCP = T.lcp[0]
+    nlo = T.find_prev_less(lo - 1, D) if LCP[lo] >= D else lo
+    nhi = T.find_next_less(hi + 2, D) - 1 if LCP[hi + 1] >= D else hi
+    F, R = T.agg(nlo, lo - 1, F, R)
+    F, R = T.agg(hi + 1, nhi, F, R)
+    return (nlo, nhi, F, R)
+
+
+def _search(T, cur, loD, hiD, pred, U0=None):
+    """max D in [loD, hiD) with pred (loD known true or 0, hiD known false; `cur` = a failing state of
+    depth >= hiD).  Returns (D*, U = interval(D*) state or None, L = interval(D*+1) state)."""
+    L, U = cur, U0
+    while hiD - loD > 1:
+        mid = (loD + hiD) // 2
+        cand = _extend(T, L, mid)
+        if pred(cand, mid):
+            loD, U = mid, cand
+        else:
+            hiD, L = mid, cand
+    return loD, U, L
+
+
+def _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo):
+    """Selection rule shared by both kernels: general answer, or RC forward/RC/literal choice."""
+    if not rc:
+        return gen if gen else (1, i)
+    have_r, dR, mR = rinfo
+    rc_len = dR if have_r else 0
+    use_fwd = use_lit = False
+    if have_f and fwd_len >= 1:
+        use_fwd = not (have_r and rc_len > fwd_len)
+    elif not (have_r and rc_len > 1):
+        use_lit = True
+    if use_lit:
+        return 1, i
+    if use_fwd:
+        return fwd_len, jF
+    e = twoN - mR
+    return rc_len, (e - rc_len + 1) | LR_RC_FLAG
+
+
+def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16):
+    """Stage 3 = k_lpnf_rank (rank order, bounded climb, direct RC candidate; marks `hard` positions)
+    followed by k_lpnf_hard (text order over hard positions with a Kasai-style carry)."""
     SA, LCP = T.f[0], T.lcp[0]
     rc, twoN = T.rc, T.twoN
     LR = [None] * nfac
+    HARD = [None] * nfac
+    i = 0
+
+    def pred_f(st, D):
+        return st[2] != NONE_MIN and st[2] + D <= i
+
+    # ---- kernel 1: rank order
     for r in range(n1):
         i = SA[r]
         if i >= nfac:
             continue
-        lo = hi = r
-        curF, curR = i, 0
-        have_f = have_r = False
+        leaf = (r, r, i, 0)
+        cur = leaf
+        d_node = None
+        have_f = at_root = False
         dF = jF = 0
         belowF = i
-        dR = mR = 0
-        lastF = i
+        steps = 0
         while True:
-            dl, dh = LCP[lo], LCP[hi + 1]
-            d = max(dl, dh)
+            d = max(LCP[cur[0]], LCP[cur[1] + 1])
             if d == 0:
+                at_root = True
                 break
-            nlo = T.find_prev_less(lo - 1, d) if dl >= d else lo
-            nhi = T.find_next_less(hi + 2, d) - 1 if dh >= d else hi
-            childF = curF
-            curF, curR = T.agg(nlo, lo - 1, curF, curR)
-            curF, curR = T.agg(hi + 1, nhi, curF, curR)
-            lo, hi = nlo, nhi
-            lastF = curF
-            if not have_f and curF != NONE_MIN and curF + d <= i:
-                have_f, dF, jF, belowF = True, d, curF, childF
-                if not rc:
-                    break
-            if rc and not have_r and curR != 0 and (twoN - curR) < i:
-                have_r, dR, mR = True, d, curR
-            if rc and have_f and have_r:
+            if steps == k_lin:
                 break
-        if not rc:
-            v_min = belowF if have_f else lastF
-            if v_min == i:
-                ln, ref = (1, i) if not have_f else (dF, jF)
-            else:
-                Lc = i - v_min
-                ln, ref = (Lc, v_min) if (not have_f or Lc > dF) else (dF, jF)
+            steps += 1
+            childF = cur[2]
+            cur = _extend(T, cur, d)
+            d_node = d
+            if pred_f(cur, d):
+                have_f, dF, jF, belowF = True, d, cur[2], childF
+                break
+        rinfo = (False, 0, 0)
+        if rc:
+            thr = twoN - i
+            kl = T.find_prev_r_greater(r - 1, thr)
+            kr = T.find_next_r_greater(r + 1, thr)
+            dl = T.lcp_range_min(kl + 1, r) if kl >= 0 else 0
+            dr = T.lcp_range_min(r + 1, kr) if kr >= 0 else 0
+            dR = max(dl, dr)
+            if dR >= 1:
+                rinfo = (True, dR, _extend(T, leaf, dR)[3])
+        gen, fwd_len = None, 0
+        if have_f:
+            part = (i - belowF) if belowF != i else 0
+            gen = (part, belowF) if part > dF else (dF, jF)
+            fwd_len = (i - jF) if belowF == jF else dF
+        elif at_root:
+            v_min = cur[2]
+            gen = (i - v_min, v_min) if v_min != i else None
         else:
-            fwd_len = ((i - jF) if belowF == jF else dF) if have_f else 0
-            rc_len = dR if have_r else 0
-            use_fwd = use_lit = False
-            if have_f and fwd_len >= 1:
-                use_fwd = not (have_r and rc_len > fwd_len)
-            elif not (have_r and rc_len > 1):
-                use_lit = True
-            if use_lit:
-                ln, ref = 1, i
-            elif use_fwd:
-                ln, ref = fwd_len, jF
+            HARD[i] = (cur, d_node if d_node is not None else d + 1, rinfo)
+            continue
+        LR[i] = _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo)
+
+    # ---- kernel 2: text order over the hard positions, carrying the true forward match length
+    for c0 in range(0, nfac, Q):
+        prevF = 0
+        for i in range(c0, min(c0 + Q, nfac)):
+            if HARD[i] is None:
+                prevF = 0
+                continue
+            cur, Dtop, rinfo = HARD[i]
+            # (the CUDA kernel re-derives `cur` as interval(Dtop-ish) from the leaf; same state)
+            lb = prevF - 1 if prevF > 0 else 0
+            U = L = None
+            if lb >= 1 and lb + 1 < Dtop:
+                st = _extend(T, cur, lb + 1)
+                if pred_f(st, lb + 1):
+                    Ds, U, L = _search(T, cur, lb + 1, Dtop, pred_f, st)
+                else:
+                    Ds, L = lb, st
+                    U = _extend(T, st, lb)
+            elif lb >= 1:
+                Ds, L = lb, cur
+                U = _extend(T, cur, lb)
             else:
-                e = twoN - mR
-                ln, ref = rc_len, (e - rc_len + 1) | LR_RC_FLAG
-        LR[i] = (ln, ref)
+                Ds, U, L = _search(T, cur, 0, Dtop, pred_f)
+            prevF = Ds
+            gen = (Ds, U[2]) if Ds >= 1 else None
+            have_f, fwd_len, jF = False, 0, 0
+            if rc and Ds >= 1:
+                if (U[0], U[1]) != (L[0], L[1]):
+                    have_f, jF = True, U[2]
+                    fwd_len = (i - jF) if L[2] == U[2] else Ds
+                else:
+                    du = max(LCP[U[0]], LCP[U[1] + 1])
+                    if du > 0:
+                        P = _extend(T, U, du)
+                        have_f, jF = True, P[2]
+                        fwd_len = (i - jF) if U[2] == P[2] else du
+            LR[i] = _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo)
     return LR
 
 
@@ -362,7 +553,8 @@ def chain(LR, nfac, start_pos, rc, chunk=1024):
 
 
 # ------------------------------------------------------------------ whole pipeline
-def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, force_bits=None, chunk=1024):
+def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, force_bits=None, chunk=1024,
+                    k_lin=K_LIN, walk_q=16):
     """mode: 'general' | 'rc_prepared'."""
     data = bytes(data)
     if mode == "general":
@@ -382,5 +574,5 @@ def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, forc
     SA, RANK, _ = suffix_array(data, force_bits)
     LCP = lcp_array(data, SA, RANK)
     T = Trees(LCP, SA, rc, N)
-    LR = walk(T, n1, nfac)
+    LR = walk(T, n1, nfac, RANK, k_lin, walk_q)
     return chain(LR, nfac, start_pos, rc, chunk)
