@@ -106,6 +106,63 @@ int nlz_factorize_multiple_dna_w_rc(nlz_ctx* ctx, const uint8_t* prepared, uint6
 int nlz_count_factors_multiple_dna_w_rc(nlz_ctx* ctx, const uint8_t* prepared, uint64_t n, uint64_t start_pos,
                                         uint64_t* out_count);
 
+/* ---- host side of the path: text preparation, FASTA, noLZSSv2 factor files ----------------- */
+/* prepare_multiple_dna_sequences_w_rc / _no_rc            src/cpp/factorizer.cpp:54-172, :194-294
+ * (S = T1 s0 .. Tk s(k-1) rc(Tk) sk .. rc(T1) s(2k-1); no_rc: sentinels only between records).
+ * Outputs are malloc'ed (release with nlz_free). */
+int nlz_prepare_multiple_dna_sequences_w_rc(const uint8_t* const* seqs, const uint64_t* lens, uint64_t k,
+                                            uint8_t** prepared, uint64_t* prepared_len, uint64_t* original_length,
+                                            uint64_t** sentinel_positions, uint64_t* n_sentinels);
+int nlz_prepare_multiple_dna_sequences_no_rc(const uint8_t* const* seqs, const uint64_t* lens, uint64_t k,
+                                             uint8_t** prepared, uint64_t* prepared_len, uint64_t* original_length,
+                                             uint64_t** sentinel_positions, uint64_t* n_sentinels);
+
+/* parse_fasta_sequences_and_ids                            src/cpp/fasta_processor.cpp:28-128
+ * sanitize_mode: 0 = "remove_ambiguous", 1 = "strict" (fasta_processor.hpp:10-13, bindings.cpp:29-37) */
+typedef struct nlz_fasta nlz_fasta;
+int nlz_fasta_parse(const char* path, int sanitize_mode, nlz_fasta** out);
+uint64_t nlz_fasta_num_sequences(const nlz_fasta* fa);
+const char* nlz_fasta_id(const nlz_fasta* fa, uint64_t idx);
+const uint8_t* nlz_fasta_sequence(const nlz_fasta* fa, uint64_t idx, uint64_t* len);
+void nlz_fasta_free(nlz_fasta* fa);
+
+/* identify_sentinel_factors                                src/cpp/fasta_processor.cpp:131-163 */
+int nlz_identify_sentinel_factors(const uint64_t* triples, uint64_t count, const uint64_t* sentinel_positions,
+                                  uint64_t n_positions, uint64_t** out_idx, uint64_t* out_n);
+/* [factors][meta][FactorFileFooter] with footer_size = 48 + meta_len   src/cpp/factorizer.hpp:64-77 */
+int nlz_write_factor_file(const char* out_path, const uint64_t* triples, uint64_t count, const uint8_t* meta,
+                          uint64_t meta_len, uint64_t num_sequences, uint64_t num_sentinels, uint64_t total_length);
+
+/* factorize_file / count_factors_file (+ _dna_w_rc, _multiple_dna_w_rc)  src/cpp/factorizer.cpp:359-363, :401-406,
+ * :525-535, :659-690: the raw file bytes are the text */
+int nlz_factorize_file_mode(nlz_ctx* ctx, int mode, const char* path, uint64_t start_pos, uint64_t** out_triples,
+                            uint64_t* out_count);
+int nlz_count_file_mode(nlz_ctx* ctx, int mode, const char* path, uint64_t start_pos, uint64_t* out_count);
+/* write_factors_binary_file (mode GENERAL), _dna_w_rc (DNA_RC), _multiple_dna_w_rc (RC_PREPARED)
+ *                                                          src/cpp/factorizer.cpp:424-459, :597-635, :751-790 */
+int nlz_write_factors_binary_file_mode(nlz_ctx* ctx, int mode, const char* in_path, const char* out_path,
+                                       uint64_t start_pos, uint64_t* out_count);
+/* parallel_factorize_to_file / parallel_factorize_dna_w_rc_to_file  src/cpp/parallel_factorizer.cpp:55-144, :1001-1017
+ * (footer: 0 sequences, 0 sentinels, total_length = sum of factor lengths, :754-767) */
+int nlz_parallel_factorize_to_file(nlz_ctx* ctx, int mode, const uint8_t* text, uint64_t n, const char* out_path,
+                                   uint64_t start_pos, uint64_t* out_count);
+/* factorize_dna_w_reference_seq(_file) (dna = 1) / factorize_w_reference(_file) (dna = 0)
+ *                                                          src/cpp/factorizer.cpp:825-1021; out_path/out may be NULL */
+int nlz_factorize_w_reference(nlz_ctx* ctx, int dna, const uint8_t* ref, uint64_t ref_len, const uint8_t* tgt,
+                              uint64_t tgt_len, const char* out_path, uint64_t** out_triples, uint64_t* out_count);
+/* factorize_fasta_multiple_dna_{w,no}_rc, factorize_dna_rc_w_ref_fasta_files (ref_fasta != NULL) and the
+ * (parallel_)write_factors_binary_file_fasta_multiple_dna_{w,no}_rc /
+ * write_factors_dna_w_reference_fasta_files_to_binary writers (out_path != NULL)
+ *                                 src/cpp/fasta_processor.cpp:298-423, src/cpp/parallel_fasta_processor.cpp:29-257 */
+int nlz_factorize_fasta(nlz_ctx* ctx, const char* ref_fasta, const char* fasta_path, int with_rc, int sanitize_mode,
+                        const char* out_path, uint64_t** out_triples, uint64_t* out_count, uint64_t** sentinel_idx,
+                        uint64_t* n_sentinel_idx, nlz_fasta** ids_out);
+/* factorize_/count_factors_/write_factors_binary_file_fasta_dna_{w,no}_rc_per_sequence (+ parallel_ writers)
+ *                                 src/cpp/fasta_processor.cpp:428-561, src/cpp/parallel_fasta_processor.cpp:268-465 */
+int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int with_rc, int sanitize_mode,
+                                     const char* out_dir, int want_factors, uint64_t** out_triples,
+                                     uint64_t** per_seq_counts, uint64_t* total_count, nlz_fasta** ids_out);
+
 /* ---- stage probes used by the parity tests (device results copied to host arrays) -------- */
 /* suffix array (n+1 entries, terminator included), inverse, and LCP (n+2 entries, LCP[0]=LCP[n+1]=0)
  * of text·$ under this library's symbol order (see csrc/sa.cuh).  Any output may be NULL. */

@@ -62,6 +62,24 @@ SIGNATURES = {
     "nlz_count_factors_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64p]),
     "nlz_factorize_multiple_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64pp, _u64p]),
     "nlz_count_factors_multiple_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64p]),
+    "nlz_prepare_multiple_dna_sequences_w_rc": (ctypes.c_int, [_vp, _vp, _u64, ctypes.POINTER(_vp), _u64p, _u64p, _u64pp, _u64p]),
+    "nlz_prepare_multiple_dna_sequences_no_rc": (ctypes.c_int, [_vp, _vp, _u64, ctypes.POINTER(_vp), _u64p, _u64p, _u64pp, _u64p]),
+    "nlz_fasta_parse": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "nlz_fasta_num_sequences": (_u64, [_vp]),
+    "nlz_fasta_id": (ctypes.c_char_p, [_vp, _u64]),
+    "nlz_fasta_sequence": (_vp, [_vp, _u64, _u64p]),
+    "nlz_fasta_free": (None, [_vp]),
+    "nlz_identify_sentinel_factors": (ctypes.c_int, [_vp, _u64, _vp, _u64, _u64pp, _u64p]),
+    "nlz_write_factor_file": (ctypes.c_int, [ctypes.c_char_p, _vp, _u64, _vp, _u64, _u64, _u64, _u64]),
+    "nlz_factorize_file_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _u64, _u64pp, _u64p]),
+    "nlz_count_file_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _u64, _u64p]),
+    "nlz_write_factors_binary_file_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, _u64, _u64p]),
+    "nlz_parallel_factorize_to_file": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, ctypes.c_char_p, _u64, _u64p]),
+    "nlz_factorize_w_reference": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _vp, _u64, ctypes.c_char_p, _u64pp, _u64p]),
+    "nlz_factorize_fasta": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                            _u64pp, _u64p, _u64pp, _u64p, ctypes.POINTER(_vp)]),
+    "nlz_factorize_fasta_per_sequence": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                                         ctypes.c_int, _u64pp, _u64pp, _u64p, ctypes.POINTER(_vp)]),
     "nlz_debug_index": (ctypes.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "nlz_debug_sort_pairs_u64": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int, ctypes.c_int]),
     "nlz_debug_sort_pairs_u32": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int, ctypes.c_int]),

@@ -1,0 +1,511 @@
+// Host side of the noLZSS path: text preparation, FASTA parsing, noLZSSv2 factor files and the
+// file-level entry points that combine them with the GPU factorizer (include/nolzss_b200.h).
+//
+// Behaviour (sentinel bytes, limits, warnings, error strings, the eight footer variants) follows
+// /root/reference/src/cpp/factorizer.cpp, fasta_processor.cpp, parallel_fasta_processor.cpp and
+// parallel_factorizer.cpp; each function cites the lines it mirrors.  No factor is ever computed
+// on the host: every composite ends in nlz_factorize_mode / nlz_count_mode (CUDA).
+#include <cctype>
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include <sys/stat.h>
+
+#include "../../include/nolzss_b200.h"
+
+namespace nlz {
+void set_error(const char* fmt, ...);   // api.cu
+}
+using nlz::set_error;
+
+namespace {
+
+struct Footer {            // factorizer.hpp:64-77 (48 bytes, written raw, little endian hosts)
+    char magic[8];
+    uint64_t num_factors, num_sequences, num_sentinels, footer_size, total_length;
+};
+static_assert(sizeof(Footer) == 48, "footer layout");
+
+// factorizer.cpp:110-125 -- index-th byte of 1..255 (wrapping past 255 back to 1) that is not A/C/G/T
+uint8_t sentinel_byte(size_t index) {
+    uint8_t s = 1;
+    size_t count = 0;
+    for (;;) {
+        if (s != 0 && s != 'A' && s != 'C' && s != 'G' && s != 'T') {
+            if (count == index) return s;
+            ++count;
+        }
+        ++s;
+        if (s == 0) s = 1;
+    }
+}
+
+inline bool is_acgt_any_case(uint8_t c) {
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't';
+}
+inline uint8_t upper_ascii(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 'a' + 'A') : c; }
+inline uint8_t complement(uint8_t c) {
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; default: return 'A'; }
+}
+
+struct Prepared {
+    std::string s;
+    uint64_t original_length = 0;
+    std::vector<uint64_t> sentinels;
+};
+
+// factorizer.cpp:54-172 (with_rc) and :194-294 (no_rc)
+int prepare(const std::vector<std::string>& seqs, bool with_rc, Prepared& out) {
+    out = Prepared();
+    if (seqs.empty()) return NLZ_OK;                                   // :55-57
+    size_t non_empty = 0, empty = 0;
+    for (const auto& q : seqs) (q.empty() ? empty : non_empty)++;
+    if (empty > 0)                                                     // :71-73
+        std::cerr << "Warning: Skipping " << empty << " empty sequence(s) in prepare_multiple_dna_sequences_"
+                  << (with_rc ? "w_rc" : "no_rc") << std::endl;
+    if (non_empty == 0) {                                              // :76-78
+        set_error("All sequences are empty - cannot prepare for factorization");
+        return NLZ_ERR_RUNTIME;
+    }
+    const size_t limit = with_rc ? 125 : 250;                          // :81-83 / :221-223
+    if (non_empty > limit) {
+        set_error("Too many sequences: maximum %zu sequences supported (due to sentinel character limitations)", limit);
+        return NLZ_ERR_INVALID;
+    }
+    for (size_t i = 0; i < seqs.size(); ++i)                           // :86-95
+        for (unsigned char c : seqs[i])
+            if (!is_acgt_any_case(c)) {
+                set_error("Invalid nucleotide '%c' found in sequence %zu", (char)c, i);
+                return NLZ_ERR_RUNTIME;
+            }
+    size_t total = 0;
+    for (const auto& q : seqs) total += q.size();
+    out.s.reserve(with_rc ? 2 * (total + non_empty) : total + non_empty);
+    size_t sidx = 0, processed = 0;
+    for (const auto& q : seqs) {                                       // :128-145 / :270-289
+        if (q.empty()) continue;
+        for (unsigned char c : q) out.s.push_back((char)upper_ascii(c));
+        ++processed;
+        if (with_rc || processed < non_empty) {                        // no_rc: sentinels only BETWEEN records
+            out.sentinels.push_back(out.s.size());
+            out.s.push_back((char)sentinel_byte(sidx++));
+        }
+    }
+    out.original_length = out.s.size();                                // :147 / :291
+    if (with_rc) {
+        for (size_t k = seqs.size(); k-- > 0;) {                       // :150-169 reverse record order
+            const auto& q = seqs[k];
+            if (q.empty()) continue;
+            for (size_t j = q.size(); j-- > 0;) out.s.push_back((char)complement(upper_ascii((unsigned char)q[j])));
+            out.sentinels.push_back(out.s.size());
+            out.s.push_back((char)sentinel_byte(sidx++));
+        }
+    }
+    return NLZ_OK;
+}
+
+int read_whole_file(const char* path, const char* what, std::string& data) {
+    std::ifstream is(path, std::ios::binary);
+    if (!is) { set_error("%s: %s", what, path); return NLZ_ERR_RUNTIME; }
+    data.assign((std::istreambuf_iterator<char>(is)), std::istreambuf_iterator<char>());
+    return NLZ_OK;
+}
+
+// [factors][meta][footer]; footer_size = 48 + |meta|
+int write_factor_file(const char* out_path, const uint64_t* triples, uint64_t count, const std::string& meta,
+                      uint64_t num_sequences, uint64_t num_sentinels, uint64_t total_length) {
+    FILE* f = fopen(out_path, "wb");
+    if (!f) { set_error("Cannot create output file: %s", out_path); return NLZ_ERR_RUNTIME; }
+    static const size_t kBuf = 1 << 20;                                // 1 MiB stream buffer, factorizer.cpp:439
+    std::vector<char> buf(kBuf);
+    setvbuf(f, buf.data(), _IOFBF, kBuf);
+    bool ok = true;
+    if (count) ok = fwrite(triples, 24, (size_t)count, f) == (size_t)count;
+    if (ok && !meta.empty()) ok = fwrite(meta.data(), 1, meta.size(), f) == meta.size();
+    Footer ft;
+    memcpy(ft.magic, "noLZSSv2", 8);
+    ft.num_factors = count;
+    ft.num_sequences = num_sequences;
+    ft.num_sentinels = num_sentinels;
+    ft.footer_size = sizeof(Footer) + meta.size();
+    ft.total_length = total_length;
+    if (ok) ok = fwrite(&ft, sizeof(ft), 1, f) == 1;
+    if (fclose(f) != 0) ok = false;
+    if (!ok) { set_error("Error writing output file: %s", out_path); return NLZ_ERR_RUNTIME; }
+    return NLZ_OK;
+}
+
+// fasta_processor.cpp:131-163
+int identify_sentinels(const uint64_t* t, uint64_t count, const std::vector<uint64_t>& pos, bool checks,
+                       std::vector<uint64_t>& idx) {
+    idx.clear();
+    size_t s = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint64_t start = t[3 * i], len = t[3 * i + 1], ref = t[3 * i + 2];
+        while (s < pos.size() && pos[s] < start) ++s;
+        if (s < pos.size() && start == pos[s]) {
+            if (checks && len != 1) {
+                set_error("Sentinel factor has unexpected length: %llu", (unsigned long long)len);
+                return NLZ_ERR_RUNTIME;
+            }
+            if (checks && ref != start) {
+                set_error("Sentinel factor reference mismatch: ref=%llu, pos=%llu", (unsigned long long)ref,
+                          (unsigned long long)start);
+                return NLZ_ERR_RUNTIME;
+            }
+            idx.push_back(i);
+            ++s;
+        }
+    }
+    return NLZ_OK;
+}
+
+std::string names_and_indices(const std::vector<std::string>& ids, const std::vector<uint64_t>& sent_idx) {
+    std::string meta;                                                  // parallel_fasta_processor.cpp:29-62
+    for (const auto& n : ids) { meta.append(n); meta.push_back('\0'); }
+    for (uint64_t v : sent_idx) meta.append(reinterpret_cast<const char*>(&v), 8);
+    return meta;
+}
+
+uint64_t sum_lengths(const uint64_t* t, uint64_t count) {
+    uint64_t s = 0;
+    for (uint64_t i = 0; i < count; ++i) s += t[3 * i + 1];
+    return s;
+}
+
+struct Triples {           // RAII for buffers returned by nlz_factorize_mode
+    uint64_t* p = nullptr;
+    uint64_t n = 0;
+    ~Triples() { nlz_free(p); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ FASTA handle
+struct nlz_fasta {
+    std::vector<std::string> ids, seqs;
+};
+
+extern "C" {
+
+// fasta_processor.cpp:28-128.  sanitize_mode: 0 = remove_ambiguous, 1 = strict (hpp:10-13)
+int nlz_fasta_parse(const char* path, int sanitize_mode, nlz_fasta** out) {
+    if (!out || !path) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    *out = nullptr;
+    if (sanitize_mode != 0 && sanitize_mode != 1) {
+        set_error("Invalid sanitize_mode. Expected 'remove_ambiguous' or 'strict'.");   // bindings.cpp:29-37
+        return NLZ_ERR_INVALID;
+    }
+    std::ifstream file(path);
+    if (!file.is_open()) { set_error("Cannot open FASTA file: %s", path); return NLZ_ERR_RUNTIME; }
+    nlz_fasta* fa = new nlz_fasta();
+    std::string line, cur_seq, cur_id;
+    size_t empty_count = 0, removed = 0;
+    auto flush = [&]() {
+        if (cur_id.empty()) return;
+        if (!cur_seq.empty()) { fa->seqs.push_back(cur_seq); fa->ids.push_back(cur_id); }
+        else { std::cerr << "Warning: Skipping empty sequence with ID: " << cur_id << std::endl; ++empty_count; }
+        cur_seq.clear();
+    };
+    while (std::getline(file, line)) {
+        while (!line.empty() && std::isspace((unsigned char)line.back())) line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            flush();
+            size_t a = 1;
+            while (a < line.size() && std::isspace((unsigned char)line[a])) ++a;
+            size_t b = a;
+            while (b < line.size() && !std::isspace((unsigned char)line[b])) ++b;
+            if (a < line.size()) cur_id = line.substr(a, b - a);
+            else { delete fa; set_error("Empty sequence header in FASTA file"); return NLZ_ERR_RUNTIME; }
+        } else {
+            for (unsigned char c : line) {
+                if (std::isspace(c)) continue;
+                if (is_acgt_any_case(c)) cur_seq.push_back((char)upper_ascii(c));
+                else if (sanitize_mode == 1) {
+                    set_error("Invalid nucleotide '%c' found in sequence with ID: %s", (char)c, cur_id.c_str());
+                    delete fa;
+                    return NLZ_ERR_RUNTIME;
+                } else ++removed;
+            }
+        }
+    }
+    flush();
+    if (empty_count > 0) std::cerr << "Warning: Skipped " << empty_count << " empty sequence(s) in FASTA file" << std::endl;
+    if (sanitize_mode == 0 && removed > 0)
+        std::cerr << "Warning: Removed " << removed << " ambiguous nucleotide(s) from FASTA input" << std::endl;
+    if (fa->seqs.empty()) { delete fa; set_error("No valid sequences found in FASTA file"); return NLZ_ERR_RUNTIME; }
+    *out = fa;
+    return NLZ_OK;
+}
+uint64_t nlz_fasta_num_sequences(const nlz_fasta* fa) { return fa ? fa->seqs.size() : 0; }
+const char* nlz_fasta_id(const nlz_fasta* fa, uint64_t i) { return (fa && i < fa->ids.size()) ? fa->ids[i].c_str() : ""; }
+const uint8_t* nlz_fasta_sequence(const nlz_fasta* fa, uint64_t i, uint64_t* len) {
+    if (!fa || i >= fa->seqs.size()) { if (len) *len = 0; return nullptr; }
+    if (len) *len = fa->seqs[i].size();
+    return reinterpret_cast<const uint8_t*>(fa->seqs[i].data());
+}
+void nlz_fasta_free(nlz_fasta* fa) { delete fa; }
+
+// ------------------------------------------------------------------ prepare
+static int prepare_abi(const uint8_t* const* seqs, const uint64_t* lens, uint64_t k, bool with_rc, uint8_t** prepared,
+                       uint64_t* prepared_len, uint64_t* original_length, uint64_t** sentinels, uint64_t* n_sent) {
+    if (!prepared || !prepared_len || !original_length || !sentinels || !n_sent) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    std::vector<std::string> v(k);
+    for (uint64_t i = 0; i < k; ++i) v[i].assign(reinterpret_cast<const char*>(seqs[i]), (size_t)lens[i]);
+    Prepared p;
+    int rc = prepare(v, with_rc, p);
+    if (rc != NLZ_OK) return rc;
+    *prepared = static_cast<uint8_t*>(malloc(p.s.size() + 1));
+    *sentinels = static_cast<uint64_t*>(malloc((p.sentinels.size() + 1) * 8));
+    if (!*prepared || !*sentinels) { set_error("out of host memory"); return NLZ_ERR_RUNTIME; }
+    memcpy(*prepared, p.s.data(), p.s.size());
+    if (!p.sentinels.empty()) memcpy(*sentinels, p.sentinels.data(), p.sentinels.size() * 8);
+    *prepared_len = p.s.size();
+    *original_length = p.original_length;
+    *n_sent = p.sentinels.size();
+    return NLZ_OK;
+}
+int nlz_prepare_multiple_dna_sequences_w_rc(const uint8_t* const* seqs, const uint64_t* lens, uint64_t k, uint8_t** prepared,
+                                            uint64_t* prepared_len, uint64_t* original_length, uint64_t** sentinels,
+                                            uint64_t* n_sent) {
+    return prepare_abi(seqs, lens, k, true, prepared, prepared_len, original_length, sentinels, n_sent);
+}
+int nlz_prepare_multiple_dna_sequences_no_rc(const uint8_t* const* seqs, const uint64_t* lens, uint64_t k, uint8_t** prepared,
+                                             uint64_t* prepared_len, uint64_t* original_length, uint64_t** sentinels,
+                                             uint64_t* n_sent) {
+    return prepare_abi(seqs, lens, k, false, prepared, prepared_len, original_length, sentinels, n_sent);
+}
+
+// ------------------------------------------------------------------ helpers exposed to the shim
+int nlz_identify_sentinel_factors(const uint64_t* triples, uint64_t count, const uint64_t* sentinel_positions, uint64_t n_pos,
+                                  uint64_t** out_idx, uint64_t* out_n) {
+    if (!out_idx || !out_n) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    std::vector<uint64_t> pos(sentinel_positions, sentinel_positions + n_pos), idx;
+    int rc = identify_sentinels(triples, count, pos, true, idx);
+    if (rc != NLZ_OK) return rc;
+    *out_idx = static_cast<uint64_t*>(malloc((idx.size() + 1) * 8));
+    if (!*out_idx) { set_error("out of host memory"); return NLZ_ERR_RUNTIME; }
+    if (!idx.empty()) memcpy(*out_idx, idx.data(), idx.size() * 8);
+    *out_n = idx.size();
+    return NLZ_OK;
+}
+
+// generic writer: [factors][meta bytes][footer], footer_size = 48 + meta_len
+int nlz_write_factor_file(const char* out_path, const uint64_t* triples, uint64_t count, const uint8_t* meta, uint64_t meta_len,
+                          uint64_t num_sequences, uint64_t num_sentinels, uint64_t total_length) {
+    std::string m(reinterpret_cast<const char*>(meta), (size_t)meta_len);
+    return write_factor_file(out_path, triples, count, m, num_sequences, num_sentinels, total_length);
+}
+
+// ------------------------------------------------------------------ file -> factors
+// factorize_file / factorize_file_dna_w_rc / factorize_file_multiple_dna_w_rc
+// (factorizer.cpp:401-406, :525-529 via :487-492, :659-674): raw file bytes, no newline stripping
+int nlz_factorize_file_mode(nlz_ctx* ctx, int mode, const char* path, uint64_t start_pos, uint64_t** out, uint64_t* count) {
+    std::string data;
+    int rc = read_whole_file(path, mode == NLZ_MODE_RC_PREPARED ? "Cannot open file" : "Cannot open input file", data);
+    if (rc != NLZ_OK) return rc;
+    return nlz_factorize_mode(ctx, mode, reinterpret_cast<const uint8_t*>(data.data()), data.size(), start_pos, out, count);
+}
+int nlz_count_file_mode(nlz_ctx* ctx, int mode, const char* path, uint64_t start_pos, uint64_t* count) {
+    std::string data;
+    int rc = read_whole_file(path, mode == NLZ_MODE_RC_PREPARED ? "Cannot open file" : "Cannot open input file", data);
+    if (rc != NLZ_OK) return rc;
+    return nlz_count_mode(ctx, mode, reinterpret_cast<const uint8_t*>(data.data()), data.size(), start_pos, count);
+}
+
+// write_factors_binary_file (V1, factorizer.cpp:424-459), write_factors_binary_file_dna_w_rc (V2, :597-635),
+// write_factors_binary_file_multiple_dna_w_rc (V3, :751-790)
+int nlz_write_factors_binary_file_mode(nlz_ctx* ctx, int mode, const char* in_path, const char* out_path, uint64_t start_pos,
+                                       uint64_t* count) {
+    if (!count) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    std::string data;
+    int rc = read_whole_file(in_path, "Cannot open input file", data);
+    if (rc != NLZ_OK) return rc;
+    // the reference opens (truncates) the output before factorizing
+    { FILE* f = fopen(out_path, "wb"); if (!f) { set_error("Cannot create output file: %s", out_path); return NLZ_ERR_RUNTIME; } fclose(f); }
+    Triples t;
+    rc = nlz_factorize_mode(ctx, mode, reinterpret_cast<const uint8_t*>(data.data()), data.size(), start_pos, &t.p, &t.n);
+    if (rc != NLZ_OK) return rc;
+    *count = t.n;
+    if (mode == NLZ_MODE_GENERAL) return write_factor_file(out_path, t.p, t.n, std::string(), 0, 0, data.size());
+    if (mode == NLZ_MODE_DNA_RC) return write_factor_file(out_path, t.p, t.n, std::string(1, '\0'), 1, 0, data.size());
+    return write_factor_file(out_path, t.p, t.n, std::string(), 0, 0, data.size() - start_pos);
+}
+
+// text -> file with the parallel-mode footer (V6: 0/0/48, total = sum of lengths; parallel_factorizer.cpp:754-767)
+// mode GENERAL: parallel_factorize (:55-61); mode DNA_RC: parallel_factorize_dna_w_rc (:1001-1017)
+int nlz_parallel_factorize_to_file(nlz_ctx* ctx, int mode, const uint8_t* text, uint64_t n, const char* out_path,
+                                   uint64_t start_pos, uint64_t* count) {
+    if (!count) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    *count = 0;
+    if (n == 0) return NLZ_OK;                                         // returns 0 without touching the file
+    if (mode == NLZ_MODE_GENERAL && start_pos >= n) {
+        set_error("start_pos must be less than text length");
+        return NLZ_ERR_INVALID;
+    }
+    Triples t;
+    int rc;
+    if (mode == NLZ_MODE_DNA_RC && start_pos != 0) {
+        std::vector<std::string> one(1, std::string(reinterpret_cast<const char*>(text), (size_t)n));
+        Prepared p;
+        rc = prepare(one, true, p);
+        if (rc != NLZ_OK) return rc;
+        rc = nlz_factorize_mode(ctx, NLZ_MODE_RC_PREPARED, reinterpret_cast<const uint8_t*>(p.s.data()), p.s.size(), start_pos, &t.p, &t.n);
+    } else {
+        rc = nlz_factorize_mode(ctx, mode, text, n, start_pos, &t.p, &t.n);
+    }
+    if (rc != NLZ_OK) return rc;
+    *count = t.n;
+    return write_factor_file(out_path, t.p, t.n, std::string(), 0, 0, sum_lengths(t.p, t.n));
+}
+
+// reference + target, text variants (V4/V5): factorize_dna_w_reference_seq(_file) factorizer.cpp:825-908,
+// factorize_w_reference(_file) :934-1021.  out_path may be NULL (no file); out/count may be NULL when only the file is wanted.
+int nlz_factorize_w_reference(nlz_ctx* ctx, int dna, const uint8_t* ref, uint64_t ref_len, const uint8_t* tgt, uint64_t tgt_len,
+                              const char* out_path, uint64_t** out, uint64_t* count) {
+    if (!count) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    FILE* probe = nullptr;
+    if (out_path) {
+        probe = fopen(out_path, "wb");
+        if (!probe) { set_error("Cannot create output file: %s", out_path); return NLZ_ERR_RUNTIME; }
+        fclose(probe);
+    }
+    Triples t;
+    int rc;
+    const uint64_t start = ref_len + 1;                                // :833 / :945
+    if (dna) {
+        std::vector<std::string> two = {std::string(reinterpret_cast<const char*>(ref), (size_t)ref_len),
+                                        std::string(reinterpret_cast<const char*>(tgt), (size_t)tgt_len)};
+        Prepared p;
+        rc = prepare(two, true, p);
+        if (rc != NLZ_OK) return rc;
+        rc = nlz_factorize_mode(ctx, NLZ_MODE_RC_PREPARED, reinterpret_cast<const uint8_t*>(p.s.data()), p.s.size(), start, &t.p, &t.n);
+    } else {
+        std::string comb(reinterpret_cast<const char*>(ref), (size_t)ref_len);
+        comb.push_back('\x01');                                        // :942
+        comb.append(reinterpret_cast<const char*>(tgt), (size_t)tgt_len);
+        rc = nlz_factorize_mode(ctx, NLZ_MODE_GENERAL, reinterpret_cast<const uint8_t*>(comb.data()), comb.size(), start, &t.p, &t.n);
+    }
+    if (rc != NLZ_OK) return rc;
+    *count = t.n;
+    if (out_path) {
+        rc = write_factor_file(out_path, t.p, t.n, std::string(), 2, 1, tgt_len);   // :897-906: no names written
+        if (rc != NLZ_OK) return rc;
+    }
+    if (out) { *out = t.p; t.p = nullptr; }
+    return NLZ_OK;
+}
+
+// ------------------------------------------------------------------ FASTA composites
+// concatenated FASTA (fasta_processor.cpp:298-341, parallel_fasta_processor.cpp:64-179): factors, sentinel factor
+// indices and, when out_path != NULL, the V7 file [factors][ids\0...][u64 sentinel idx...][footer], total = sum of lengths.
+// ref_fasta != NULL selects the reference+target form (fasta_processor.cpp:393-423), RC only.
+int nlz_factorize_fasta(nlz_ctx* ctx, const char* ref_fasta, const char* fasta_path, int with_rc, int sanitize_mode,
+                        const char* out_path, uint64_t** out, uint64_t* count, uint64_t** sent_idx, uint64_t* n_sent_idx,
+                        nlz_fasta** ids_out) {
+    if (!count) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    nlz_fasta* all = new nlz_fasta();
+    uint64_t start = 0;
+    const char* paths[2] = {ref_fasta, fasta_path};
+    for (int k = 0; k < 2; ++k) {
+        if (!paths[k]) continue;
+        nlz_fasta* fa = nullptr;
+        int rc = nlz_fasta_parse(paths[k], sanitize_mode, &fa);
+        if (rc != NLZ_OK) { delete all; return rc; }
+        if (k == 0) for (const auto& q : fa->seqs) start += q.size() + 1;    // target_start_index, :236-239
+        for (size_t i = 0; i < fa->seqs.size(); ++i) { all->seqs.push_back(std::move(fa->seqs[i])); all->ids.push_back(std::move(fa->ids[i])); }
+        delete fa;
+    }
+    Prepared p;
+    int rc = prepare(all->seqs, with_rc != 0, p);
+    if (rc != NLZ_OK) { delete all; return rc; }
+    Triples t;
+    rc = nlz_factorize_mode(ctx, with_rc ? NLZ_MODE_RC_PREPARED : NLZ_MODE_GENERAL,
+                            reinterpret_cast<const uint8_t*>(p.s.data()), p.s.size(), start, &t.p, &t.n);
+    if (rc != NLZ_OK) { delete all; return rc; }
+    std::vector<uint64_t> idx;
+    rc = identify_sentinels(t.p, t.n, p.sentinels, out_path == nullptr, idx);   // the file writer does not sanity-check
+    if (rc != NLZ_OK) { delete all; return rc; }
+    if (out_path) {
+        rc = write_factor_file(out_path, t.p, t.n, names_and_indices(all->ids, idx), all->ids.size(), idx.size(),
+                               sum_lengths(t.p, t.n));
+        if (rc != NLZ_OK) { delete all; return rc; }
+    }
+    *count = t.n;
+    if (sent_idx && n_sent_idx) {
+        *sent_idx = static_cast<uint64_t*>(malloc((idx.size() + 1) * 8));
+        if (!idx.empty()) memcpy(*sent_idx, idx.data(), idx.size() * 8);
+        *n_sent_idx = idx.size();
+    }
+    if (out) { *out = t.p; t.p = nullptr; }
+    if (ids_out) *ids_out = all; else delete all;
+    return NLZ_OK;
+}
+
+// per-sequence FASTA (fasta_processor.cpp:428-561, parallel_fasta_processor.cpp:268-465).  Results are returned as one
+// concatenated triple array plus per-record counts; out_dir != NULL also writes <out_dir>/<sanitized id>.bin (V8).
+// The no-RC variants drop the last nucleotide of every record, like the reference (fasta_processor.cpp:469-471).
+int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int with_rc, int sanitize_mode, const char* out_dir,
+                                     int want_factors, uint64_t** out, uint64_t** per_seq_counts, uint64_t* total,
+                                     nlz_fasta** ids_out) {
+    if (!total) { set_error("null argument"); return NLZ_ERR_INVALID; }
+    nlz_fasta* fa = nullptr;
+    int rc = nlz_fasta_parse(fasta_path, sanitize_mode, &fa);
+    if (rc != NLZ_OK) return rc;
+    if (out_dir) {
+        std::string d(out_dir);
+        for (size_t i = 1; i <= d.size(); ++i)
+            if (i == d.size() || d[i] == '/') { std::string sub = d.substr(0, i); if (!sub.empty()) mkdir(sub.c_str(), 0777); }
+    }
+    const size_t k = fa->seqs.size();
+    std::vector<uint64_t> counts(k, 0), all;
+    uint64_t sum = 0;
+    for (size_t i = 0; i < k; ++i) {
+        Triples t;
+        const std::string& q = fa->seqs[i];
+        const bool need_triples = want_factors || out_dir;
+        if (with_rc) {
+            if (need_triples) rc = nlz_factorize_mode(ctx, NLZ_MODE_DNA_RC, reinterpret_cast<const uint8_t*>(q.data()), q.size(), 0, &t.p, &t.n);
+            else rc = nlz_count_mode(ctx, NLZ_MODE_DNA_RC, reinterpret_cast<const uint8_t*>(q.data()), q.size(), 0, &t.n);
+        } else {
+            const uint64_t n = q.size() - 1;
+            if (need_triples) rc = nlz_factorize_mode(ctx, NLZ_MODE_GENERAL, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.p, &t.n);
+            else rc = nlz_count_mode(ctx, NLZ_MODE_GENERAL, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.n);
+        }
+        if (rc != NLZ_OK) { delete fa; return rc; }
+        counts[i] = t.n;
+        sum += t.n;
+        if (out_dir) {
+            std::string safe = fa->ids[i];                             // parallel_fasta_processor.cpp:307-317
+            for (char& c : safe)
+                if (c == '/' || c == '\\' || c == ':' || c == '*' || c == '?' || c == '"' || c == '<' || c == '>' || c == '|' || c == ' ') c = '_';
+            std::string path = std::string(out_dir) + "/" + safe + ".bin";
+            std::string meta = fa->ids[i];
+            meta.push_back('\0');
+            rc = write_factor_file(path.c_str(), t.p, t.n, meta, 1, 0, sum_lengths(t.p, t.n));   // :268-297
+            if (rc != NLZ_OK) { delete fa; return rc; }
+        }
+        if (want_factors && t.n) all.insert(all.end(), t.p, t.p + 3 * t.n);
+    }
+    *total = sum;
+    if (per_seq_counts) {
+        *per_seq_counts = static_cast<uint64_t*>(malloc((k + 1) * 8));
+        memcpy(*per_seq_counts, counts.data(), k * 8);
+    }
+    if (out) {
+        *out = static_cast<uint64_t*>(malloc((all.size() + 1) * 8));
+        if (!all.empty()) memcpy(*out, all.data(), all.size() * 8);
+    }
+    if (ids_out) *ids_out = fa; else delete fa;
+    return NLZ_OK;
+}
+
+}  // extern "C"
