@@ -60,6 +60,7 @@ struct Workspace {
     u32* tl[TREE_MAX_LEVELS] = {};
     u32* tf[TREE_MAX_LEVELS] = {};
     u32* tr[TREE_MAX_LEVELS] = {};
+    u32 *PSV = nullptr, *NSV = nullptr, *MINF = nullptr;   // per-node tables of stage 3
 };
 
 }  // namespace nlz
@@ -86,7 +87,7 @@ static size_t workspace_bytes_for(u64 n1) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
     t += al(n1 + 192);               // X
-    t += al((n1 + 72) * 4) * 3;      // SA, RANK, LCP (+ one padded line for whole-line reads)
+    t += al((n1 + 72) * 4) * 6;      // SA, RANK, LCP, PSV, NSV, MINF (+ one padded line for whole-line reads)
     t += al(n1 * 8) * 2;             // KEY
     t += al(n1 * 4) * 4;             // VAL, SLOT
     t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
@@ -131,6 +132,9 @@ static int ensure_workspace(nlz_ctx* c, u64 n1) {
     w.SA = a.take<u32>(n1 + 72);
     w.RANK = a.take<u32>(n1 + 72);
     w.LCP = a.take<u32>(n1 + 72);
+    w.PSV = a.take<u32>(n1 + 72);
+    w.NSV = a.take<u32>(n1 + 72);
+    w.MINF = a.take<u32>(n1 + 72);
     for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(n1);
     for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(n1);
     for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(n1);
@@ -423,6 +427,9 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     }
     T.nlev = lev + 1;
     P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
+    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 12), st,
+       (pb.rc ? k_node_tables<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)
+              : k_node_tables<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)));
     u64* LR = w.KEY[0];
     u8* HARDF = reinterpret_cast<u8*>(w.SLOT[0]);
     RNear rn;
@@ -449,11 +456,14 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     // algorithmic bytes: SA[r] for every rank; per factorized position the two LCP neighbours, the
     // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
-    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, LR, HARDF, visit_ctr);
-    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, LR, HARDF, visit_ctr);
+    static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
+    NodeTables nt;
+    nt.PSV = w.PSV; nt.NSV = w.NSV; nt.MINF = w.MINF;
+    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
+    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
     P.end(KC_WALK, (u64)n1 * 4 + (u64)pb.nfac * 17, st);
     {
-        const u32 grid = ceil_div_u32(ceil_div_u32(pb.nfac, WALK_Q), 256);
+        const u32 grid = ceil_div_u32((u64)ceil_div_u32(pb.nfac, WALK_Q) * 8, 256);   // one 8-lane tile per run
         P.begin(st);
         if (pb.rc) k_lpnf_hard<true><<<grid, 256, 0, st>>>(T, wp, w.RANK, LR, HARDF, visit_ctr);
         else k_lpnf_hard<false><<<grid, 256, 0, st>>>(T, wp, w.RANK, LR, HARDF, visit_ctr);

@@ -21,21 +21,29 @@
 //                (PR/ML, NR/MR).  With them the RC candidate -- the LCA of leaf r with the nearest
 //                QUALIFYING rc(T) suffix on either side, PSV/NSV-style -- is found by hopping over
 //                rc(T) ranks only, skipping the long forward-only runs that tandem repeats create.
-//   k_lpnf_rank  one thread per suffix-array RANK (a warp shares the SA/LCP cache lines around its
-//                ranks): climbs the LCP-interval ancestors for the forward candidate, growing the
-//                interval incrementally (1-2 nodes on random DNA, up to the copy count inside
-//                tandem arrays), then applies the selection rule.  The RC source position (a range
-//                max over the chosen node) is only evaluated when the RC candidate wins.
-//                Positions that exhaust the climb budget (low-complexity text) are flagged.
+//   k_node_tables for every rank k, the LCP interval it names (previous / next smaller LCP value)
+//                and the minimum forward start inside it: the suffix tree's internal nodes,
+//                tabulated once so that a climb step is five word loads and no search.
+//   k_lpnf_rank  one thread per suffix-array RANK (a warp shares the cache lines around its ranks):
+//                climbs the ancestors of its leaf for the forward candidate (1-2 nodes on random
+//                DNA, up to the copy count inside tandem arrays), then applies the selection rule.
+//                The RC source position (a range max over the chosen node) is only evaluated when
+//                the RC candidate wins.  Positions that exhaust the climb budget (low-complexity
+//                text) are flagged.
 //   k_lpnf_hard  text order over the flagged positions: the forward predicate is monotone in the
 //                string depth D, so the answer is a binary search over D that grows interval(D)
 //                incrementally from the deepest failing node; a Kasai-style carry (the match at i
 //                is at least the match at i-1 minus one) makes consecutive positions O(1) probes.
 //                Tree lines are read with eight independent 16-byte loads (one latency per level).
 #pragma once
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
 #include "common.cuh"
 
 namespace nlz {
+
+namespace cg = cooperative_groups;
 
 constexpr int TREE_MAX_LEVELS = 8;
 constexpr u32 NONE_MIN = 0xFFFFFFFFu;
@@ -123,24 +131,15 @@ k_tree_level_up(const u32* __restrict__ lcpA, u32 cntLA, const u32* __restrict__
 }
 
 // ---- queries --------------------------------------------------------------------------------
-// Two flavours of every query: scalar (early-exit word probes; cheap when the answer is a few
-// entries away, the common case in rank order where neighbouring lanes share the lines) and
-// line-vectorised (a thread inspects a whole 128-byte node with eight independent 16-byte loads:
-// one memory latency per tree level, used where searches are long).  All arrays are padded so a
-// whole line can be read at the end of an array.
-struct Line32 { uint4 q[8]; };
+// Two flavours of every query: scalar (one thread, early-exit word probes; cheap when the answer is
+// a few entries away, the common case in rank order where neighbouring lanes share the lines) and
+// cooperative (VEC = true: the 8 lanes of a thread_block_tile<8> call with identical arguments, each
+// lane owns 16 bytes of the 128-byte node line, so a node costs one 16-byte load per lane plus a
+// redux -- one memory latency per tree level at full coalescing; used where searches are long).
+// All arrays are padded so a whole line can be read at the end of an array.
+using Tile8 = cg::thread_block_tile<8>;
+__device__ __forceinline__ Tile8 tile8() { return cg::tiled_partition<8>(cg::this_thread_block()); }
 
-__device__ __forceinline__ Line32 load_line(const u32* __restrict__ g) {
-    const uint4* v = reinterpret_cast<const uint4*>(g);
-    Line32 l;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) l.q[k] = __ldg(v + k);
-    return l;
-}
-__device__ __forceinline__ u32 line_get(const Line32& l, int k) {
-    const uint4& q = l.q[k >> 2];
-    return (k & 3) == 0 ? q.x : (k & 3) == 1 ? q.y : (k & 3) == 2 ? q.z : q.w;
-}
 __device__ __forceinline__ u32 valid_mask(i64 count) {   // count >= 1
     return count >= 32 ? 0xFFFFFFFFu : ((1u << (u32)count) - 1u);
 }
@@ -148,12 +147,13 @@ __device__ __forceinline__ u32 bits_upto(u32 hi_bit) {   // bits [0, hi_bit]
     return hi_bit >= 31 ? 0xFFFFFFFFu : ((2u << hi_bit) - 1u);
 }
 
-// bit k set iff LCP-tree node (lev, gstart + k) < d   (whole line)
+// bit k set iff LCP-tree node (lev, gstart + k) < d   (whole line, cooperative)
 __device__ __forceinline__ u32 mask_lcp_less_v(const Trees& T, int lev, i64 gstart, u32 d) {
-    const Line32 l = load_line(T.lcp[lev] + gstart);
-    u32 m = 0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) m |= (line_get(l, k) < d ? 1u : 0u) << k;
+    const Tile8 t = tile8();
+    const u32 q = t.thread_rank();
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(T.lcp[lev] + gstart) + q);
+    const u32 m4 = (x.x < d ? 1u : 0u) | (x.y < d ? 2u : 0u) | (x.z < d ? 4u : 0u) | (x.w < d ? 8u : 0u);
+    const u32 m = cg::reduce(t, m4 << (4 * q), cg::bit_or<u32>());
     return m & valid_mask((i64)T.cntL[lev] - gstart);
 }
 
@@ -320,27 +320,35 @@ template <bool RC, bool WANT_R, bool VEC>
 __device__ __forceinline__ void agg_line(const Trees& T, const WalkParams& p, int lev, i64 gstart, u32 lob, u32 hib,
                                          u32& fmin, u32& rmax) {
     if (VEC) {
-        const Line32 lf = load_line(T.f[lev] + gstart);
+        const Tile8 t = tile8();
+        const u32 q = t.thread_rank();
+        const uint4 xf = __ldg(reinterpret_cast<const uint4*>(T.f[lev] + gstart) + q);
+        const u32 fv4[4] = {xf.x, xf.y, xf.z, xf.w};
+        u32 fv = NONE_MIN, rv = 0;
         if (lev == 0) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if ((u32)k >= lob && (u32)k <= hib) {
-                    const u32 s = line_get(lf, k);
-                    fmin = min(fmin, f_value<RC>(s, p));
-                    if (WANT_R) rmax = max(rmax, r_value(s, p));
+            for (int j = 0; j < 4; ++j) {
+                const u32 k = 4 * q + j;
+                if (k >= lob && k <= hib) {
+                    fv = min(fv, f_value<RC>(fv4[j], p));
+                    if (WANT_R) rv = max(rv, r_value(fv4[j], p));
                 }
             }
         } else {
-            Line32 lr;
-            if (WANT_R) lr = load_line(T.r[lev] + gstart);
+            uint4 xr = make_uint4(0, 0, 0, 0);
+            if (WANT_R) xr = __ldg(reinterpret_cast<const uint4*>(T.r[lev] + gstart) + q);
+            const u32 rv4[4] = {xr.x, xr.y, xr.z, xr.w};
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if ((u32)k >= lob && (u32)k <= hib) {
-                    fmin = min(fmin, line_get(lf, k));
-                    if (WANT_R) rmax = max(rmax, line_get(lr, k));
+            for (int j = 0; j < 4; ++j) {
+                const u32 k = 4 * q + j;
+                if (k >= lob && k <= hib) {
+                    fv = min(fv, fv4[j]);
+                    if (WANT_R) rv = max(rv, rv4[j]);
                 }
             }
         }
+        fmin = min(fmin, cg::reduce(t, fv, cg::less<u32>()));
+        if (WANT_R) rmax = max(rmax, cg::reduce(t, rv, cg::greater<u32>()));
         return;
     }
     if (lev == 0) {
@@ -590,8 +598,8 @@ __device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p
 // ---- the factor rule ------------------------------------------------------------------------
 // LR[i] = (ref | rc_flag<<31) << 32 | len        for every factorized position i
 constexpr u32 LR_RC_FLAG = 0x80000000u;
-constexpr int WALK_MAX_NODES = 640;    // ancestors climbed in rank order before a position is "hard"
-constexpr int WALK_Q = 8;              // consecutive text positions per thread in k_lpnf_hard
+constexpr int WALK_MAX_NODES = 2048;   // default: ancestors climbed in rank order before a position is "hard"
+constexpr int WALK_Q = 8;              // consecutive text positions per 8-lane tile in k_lpnf_hard
 
 struct NodeState {
     u32 lo, hi;   // rank interval
@@ -648,13 +656,37 @@ __device__ __forceinline__ u64 select_factor(const Trees& T, const WalkParams& p
     return ((u64)ref << 32) | (u64)len;
 }
 
-// ---- kernel 1: rank order ---------------------------------------------------------------------
-constexpr int WALK_LINEAR_BUDGET = 48;   // ranks a climb step may add by plain neighbour probes
-
+// ---- per-node tables ---------------------------------------------------------------------------
+// Every rank k with LCP[k] > 0 names the LCP interval ("node") [PSV[k], NSV[k]-1] of string depth
+// LCP[k] (PSV/NSV = nearest strictly smaller LCP value to the left / right).  With the F-min of each
+// node tabulated once (MINF), a leaf climbs to its parent with five word loads and no search:
+// parent of [a, b] is the node named by a if LCP[a] >= LCP[b+1], else by b+1.  Rank order, scalar
+// probes: neighbouring lanes name nested or identical nodes and share the cache lines.
 template <bool RC>
 __global__ void __launch_bounds__(256)
-k_lpnf_rank(Trees T, WalkParams p, RNear rn, u64* __restrict__ LR, u8* __restrict__ HARD,
-            unsigned long long* __restrict__ counters) {
+k_node_tables(Trees T, WalkParams p, u32* __restrict__ PSV, u32* __restrict__ NSV, u32* __restrict__ MINF) {
+    const u32 k = blockIdx.x * 256 + threadIdx.x;
+    if (k == 0 || k >= p.n1) return;
+    const u32 d = T.lcp[0][k];
+    if (d == 0) return;                              // names the root: never looked up
+    const u32 a = find_prev_less<false>(T, k - 1, d);
+    const u32 b1 = find_next_less<false>(T, k + 1, d);
+    u32 fmin = NONE_MIN, rmax = 0;
+    agg_range<RC, false, false>(T, p, (i64)a, (i64)b1 - 1, fmin, rmax);
+    PSV[k] = a;
+    NSV[k] = b1;
+    MINF[k] = fmin;
+}
+
+struct NodeTables {
+    const u32* PSV; const u32* NSV; const u32* MINF;
+};
+
+// ---- kernel 1: rank order ---------------------------------------------------------------------
+template <bool RC>
+__global__ void __launch_bounds__(256)
+k_lpnf_rank(Trees T, WalkParams p, RNear rn, NodeTables nt, int max_nodes, u64* __restrict__ LR,
+            u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
     const u32 r = blockIdx.x * 256 + threadIdx.x;
     u32 visited = 0, hard = 0;
     const u32* LCP = T.lcp[0];
@@ -662,37 +694,29 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, u64* __restrict__ LR, u8* __restric
     u32 i = 0xFFFFFFFFu;
     if (r < p.n1) i = SA[r];
     if (i < p.nfac) {
-        NodeState cur;                   // deepest path node known to fail the forward predicate
-        cur.lo = r; cur.hi = r; cur.F = i; cur.R = 0;
         bool have_f = false, at_root = false;
         u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
+        u32 childF = i;                  // F-min of the last node that failed (starts at the leaf)
+        {
+            const u32 dl = LCP[r], dh = LCP[r + 1];
+            u32 k = dl >= dh ? r : r + 1;            // names the parent of the leaf
+            u32 d = max(dl, dh);
 #pragma unroll 1
-        for (int step = 0;; ++step) {
-            const u32 dl = LCP[cur.lo], dh = LCP[cur.hi + 1];
-            const u32 d = max(dl, dh);                            // depth of the parent of `cur`
-            if (d == 0) { at_root = true; break; }
-            if (step == WALK_MAX_NODES) break;
-            ++visited;
-            const u32 childF = cur.F;
-            // fast path: the parent usually adds a handful of neighbouring ranks (exactly one inside
-            // a tandem array) -> plain probes; wide parents go through the summary trees
-            u32 lo = cur.lo, hi = cur.hi, F = cur.F;
-            int budget = WALK_LINEAR_BUDGET;
-            if (dl >= d) {
-                do {
-                    --lo;
-                    F = min(F, f_value<RC>(SA[lo], p));
-                } while (--budget > 0 && LCP[lo] >= d);            // LCP[0] = 0 stops at the left end
+            for (int step = 0;; ++step) {
+                if (d == 0) { at_root = true; break; }
+                if (step == max_nodes) break;
+                ++visited;
+                const u32 m = nt.MINF[k];
+                if (m != NONE_MIN && (u64)m + d <= (u64)i) {          // factorizer_core.hpp:75 / :266
+                    have_f = true; dF = d; jF = m; belowF = childF;
+                    break;
+                }
+                childF = m;
+                const u32 a = nt.PSV[k], b1 = nt.NSV[k];
+                const u32 la = LCP[a], lb = LCP[b1];
+                k = la >= lb ? a : b1;
+                d = max(la, lb);
             }
-            if (budget > 0 && dh >= d) {
-                do {
-                    ++hi;
-                    F = min(F, f_value<RC>(SA[hi], p));
-                } while (--budget > 0 && LCP[hi + 1] >= d);        // LCP[n1] = 0 stops at the right end
-            }
-            if (budget > 0) { cur.lo = lo; cur.hi = hi; cur.F = F; }
-            else cur = extend_to<RC, false, false>(T, p, cur, d);
-            if (pred_f(cur, d, i)) { have_f = true; dF = d; jF = cur.F; belowF = childF; break; }
         }
         u32 dR = 0;
         if (RC) {
@@ -708,7 +732,7 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, u64* __restrict__ LR, u8* __restric
                 else { gen_len = dF; gen_ref = jF; }                    // :89-94, :98-102
                 fwd_len = (belowF == jF) ? (i - jF) : dF;               // :322-326
             } else {
-                const u32 v_min = cur.F;                                // child of the root (or the leaf itself)
+                const u32 v_min = childF;                               // child of the root (or the leaf itself)
                 gen_len = (v_min != i) ? i - v_min : 0;                 // :96-107 with u = root, or literal
                 gen_ref = v_min;
             }
@@ -731,7 +755,7 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, u64* __restrict__ LR, u8* __restric
     }
 }
 
-// ---- kernel 2: text order over the hard positions ----------------------------------------------
+// ---- kernel 2: text order over the hard positions, one 8-lane tile per run ----------------------
 // Largest D in [loD, hiD) that satisfies the forward predicate (loD: known true, or 0; hiD: known
 // false; `cur`: a failing state of depth >= hiD).  U = interval(D*) when D* > initial loD,
 // L = interval(D*+1).  Every probe extends the deepest known-failing node.
@@ -753,69 +777,74 @@ template <bool RC>
 __global__ void __launch_bounds__(256)
 k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict__ LR,
             const u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
-    const u64 c = (u64)blockIdx.x * 256 + threadIdx.x;
-    const u64 i0 = c * WALK_Q;
+    const Tile8 t8 = tile8();
+    const u64 tile_id = ((u64)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const u64 i0 = tile_id * WALK_Q;
+    if (i0 >= p.nfac) return;                                   // tile-uniform
+    const u32 q = t8.thread_rank();
+    u32 todo = t8.ballot((i0 + q < p.nfac) && HARD[i0 + q] != 0);
+    if (!todo) return;
+    const u32* LCP = T.lcp[0];
     u32 visited = 0;
-    if (i0 < p.nfac) {
-        const u32* LCP = T.lcp[0];
-        u64 iend = i0 + WALK_Q;
-        if (iend > p.nfac) iend = p.nfac;
-        u32 prevF = 0;               // true longest non-overlapping forward match of the previous position
-        for (u64 ii = i0; ii < iend; ++ii) {
-            if (!HARD[ii]) { prevF = 0; continue; }
-            const u32 i = (u32)ii;
-            const u32 r = RANK[i];
-            NodeState leaf;
-            leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
-            const u32 Dtop = max(LCP[r], LCP[r + 1]) + 1;        // deeper than the leaf's parent nothing matches
-            const u32 lb = prevF > 0 ? prevF - 1 : 0;            // Kasai-style lower bound (known to hold)
-            NodeState U = leaf, L = leaf;
-            u32 Ds;
-            if (lb >= 1 && lb + 1 < Dtop) {
-                const NodeState st = extend_to<RC, false, true>(T, p, leaf, lb + 1);
-                ++visited;
-                if (pred_f(st, lb + 1, i)) {
-                    U = st;
-                    Ds = depth_search<RC>(T, p, i, leaf, lb + 1, Dtop, U, L, visited);
-                } else {
-                    Ds = lb; L = st;
-                    U = extend_to<RC, false, true>(T, p, st, lb);
-                    ++visited;
-                }
-            } else if (lb >= 1) {                                // lb + 1 == Dtop
-                Ds = lb; L = leaf;
-                U = extend_to<RC, false, true>(T, p, leaf, lb);
-                ++visited;
+    u32 prevF = 0;               // true longest non-overlapping forward match of the previous position
+    int prev_k = -2;
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (k != prev_k + 1) prevF = 0;                          // the carry only links consecutive positions
+        prev_k = k;
+        const u32 i = (u32)(i0 + k);
+        const u32 r = __ldg(RANK + i);
+        NodeState leaf;
+        leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
+        const u32 Dtop = max(__ldg(LCP + r), __ldg(LCP + r + 1)) + 1;   // deeper than the leaf's parent nothing matches
+        const u32 lb = prevF > 0 ? prevF - 1 : 0;                // Kasai-style lower bound (known to hold)
+        NodeState U = leaf, L = leaf;
+        u32 Ds;
+        if (lb >= 1 && lb + 1 < Dtop) {
+            const NodeState st = extend_to<RC, false, true>(T, p, leaf, lb + 1);
+            ++visited;
+            if (pred_f(st, lb + 1, i)) {
+                U = st;
+                Ds = depth_search<RC>(T, p, i, leaf, lb + 1, Dtop, U, L, visited);
             } else {
-                Ds = depth_search<RC>(T, p, i, leaf, 0, Dtop, U, L, visited);
+                Ds = lb; L = st;
+                U = extend_to<RC, false, true>(T, p, st, lb);
+                ++visited;
             }
-            prevF = Ds;
-            bool have_f = false;
-            u32 fwd_len = 0, jF = 0, gen_len = 0, gen_ref = i;
-            if (Ds >= 1) {
-                gen_len = Ds; gen_ref = U.F;
-                if (RC) {
-                    if (U.lo != L.lo || U.hi != L.hi) {          // U is a node of depth Ds, L its path child
-                        have_f = true; jF = U.F;
-                        fwd_len = (L.F == U.F) ? (i - jF) : Ds;
-                    } else {                                     // Ds lies inside U's edge: vF = parent(U)
-                        const u32 du = max(LCP[U.lo], LCP[U.hi + 1]);
-                        if (du > 0) {
-                            const NodeState P = extend_to<RC, false, true>(T, p, U, du);
-                            ++visited;
-                            have_f = true; jF = P.F;
-                            fwd_len = (U.F == P.F) ? (i - jF) : du;
-                        }
+        } else if (lb >= 1) {                                    // lb + 1 == Dtop
+            Ds = lb; L = leaf;
+            U = extend_to<RC, false, true>(T, p, leaf, lb);
+            ++visited;
+        } else {
+            Ds = depth_search<RC>(T, p, i, leaf, 0, Dtop, U, L, visited);
+        }
+        prevF = Ds;
+        bool have_f = false;
+        u32 fwd_len = 0, jF = 0, gen_len = 0, gen_ref = i;
+        if (Ds >= 1) {
+            gen_len = Ds; gen_ref = U.F;
+            if (RC) {
+                if (U.lo != L.lo || U.hi != L.hi) {              // U is a node of depth Ds, L its path child
+                    have_f = true; jF = U.F;
+                    fwd_len = (L.F == U.F) ? (i - jF) : Ds;
+                } else {                                         // Ds lies inside U's edge: vF = parent(U)
+                    const u32 du = max(__ldg(LCP + U.lo), __ldg(LCP + U.hi + 1));
+                    if (du > 0) {
+                        const NodeState P = extend_to<RC, false, true>(T, p, U, du);
+                        ++visited;
+                        have_f = true; jF = P.F;
+                        fwd_len = (U.F == P.F) ? (i - jF) : du;
                     }
                 }
             }
-            const u32 dR = (u32)LR[i];
-            LR[i] = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
         }
+        const u32 dR = (u32)LR[i];                               // parked by k_lpnf_rank
+        const u64 lr = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
+        t8.sync();                                               // every lane has read the parked value
+        if (q == 0) LR[i] = lr;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) visited += __shfl_xor_sync(0xffffffffu, visited, o);
-    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(counters, (unsigned long long)visited);
+    if (q == 0 && visited) atomicAdd(counters, (unsigned long long)visited);
 }
 
 }  // namespace nlz

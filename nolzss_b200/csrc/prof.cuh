@@ -18,6 +18,7 @@ enum KClass : int {
     KC_REGROUP,       // head flags, ranks, SA write-back, compaction
     KC_LCP,           // chunked Kasai LCP
     KC_TREE,          // 32-ary summary trees
+    KC_NODES,         // per-node tables: LCP interval named by every rank + its minimum forward start
     KC_RNEAR,         // nearest rc(T) rank on either side of every rank (segmented scans)
     KC_WALK,          // factor rule, rank order (bounded climb + direct RC candidate)
     KC_WALK_HARD,     // factor rule, text order over deep-nesting positions (depth search + carry)
@@ -27,7 +28,7 @@ enum KClass : int {
 
 static const char* const kClassNames[KC_COUNT] = {
     "prepare", "build_keys", "radix_hist", "radix_scan", "radix_scatter", "gather_rank",
-    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain"};
+    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain"};
 
 struct Profiler {
     bool timing = false;
