@@ -4,9 +4,18 @@
 // The active list is a concatenation of tie groups (equal high key half g = group head slot), each
 // contiguous.  CTA t owns the groups whose head lies in [t*tile, (t+1)*tile); because no group is
 // larger than `maxg` (checked on the host from the previous regroup), its elements fit in
-// tile + maxg <= 4096 shared-memory slots.  A bitonic network on the 64-bit composite key
-// (g, RANK[s+h]) sorts all owned groups at once; foreign slots are padded with the maximum key.
-// Rounds whose largest group exceeds the capacity fall back to the global radix sort.
+// tile + maxg <= 4096 shared-memory slots.  Rounds whose largest group exceeds that capacity fall
+// back to the global radix sort.
+//
+// Sorting inside a tile exploits what prefix doubling does to repeats: in a round, most members of a
+// large group (a tandem array, a repeat family) receive the SAME second key -- they are still tied
+// -- and only a few "outliers" separate.  Per group a pivot (majority of three samples) splits the
+// members into  [smaller outliers | pivot-equal block | larger outliers]:
+//   * pivot-equal members keep their order: position = #smaller + (segmented prefix count);
+//   * every other member ranks itself by counting smaller keys in its group (all-pairs);
+//   * if the all-pairs work of a tile would be excessive (large groups without a majority), the
+//     tile falls back to a bitonic network on the composite key (group, rank).
+// Work per member is O(1) for the tied majority instead of O(log^2) compare-exchanges.
 #pragma once
 #include "common.cuh"
 
@@ -14,28 +23,87 @@ namespace nlz {
 
 constexpr int TSORT_THREADS = 256;
 constexpr int TSORT_SLOTS = 4096;
-constexpr size_t TSORT_SMEM = (size_t)TSORT_SLOTS * 12 + 16;
-constexpr u32 TSORT_ALLPAIRS_MAX = 256;   // CTA-local group size up to which counting beats the bitonic network
+constexpr int TSORT_PER_THREAD = TSORT_SLOTS / TSORT_THREADS;   // 16
+constexpr u32 TSORT_ALLPAIRS_BUDGET = 384u * 1024u;             // compare steps a tile may spend on counting
+// shared memory layout (dynamic)
+constexpr size_t TSORT_OFF_KEY = 0;                                        // u64[SLOTS]
+constexpr size_t TSORT_OFF_VAL = TSORT_OFF_KEY + (size_t)TSORT_SLOTS * 8;  // u32[SLOTS]
+constexpr size_t TSORT_OFF_PIV = TSORT_OFF_VAL + (size_t)TSORT_SLOTS * 4;  // u32[SLOTS]  pivot rank, by group start
+constexpr size_t TSORT_OFF_LESS = TSORT_OFF_PIV + (size_t)TSORT_SLOTS * 4; // u32[SLOTS]  #members < pivot, by group start
+constexpr size_t TSORT_OFF_GS = TSORT_OFF_LESS + (size_t)TSORT_SLOTS * 4;  // u16[SLOTS]  group start of every member
+constexpr size_t TSORT_OFF_EQ = TSORT_OFF_GS + (size_t)TSORT_SLOTS * 2;    // u16[SLOTS]  exclusive prefix of pivot-equal flags
+constexpr size_t TSORT_OFF_END = TSORT_OFF_EQ + (size_t)TSORT_SLOTS * 2;   // u16[SLOTS]  group end, by group start
+constexpr size_t TSORT_OFF_FLAG = TSORT_OFF_END + (size_t)TSORT_SLOTS * 2; // u8 [SLOTS]  head / equal flags
+constexpr size_t TSORT_OFF_MISC = TSORT_OFF_FLAG + (size_t)TSORT_SLOTS;    // u32[16]
+constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 64;
+
+// Scans over the SLOTS one-byte flags, 16 consecutive flags per thread.
+// MAXPOS: out[o] = index of the last set flag at or before o (flag[0] must be set).
+// otherwise: out[o] = number of set flags before o (exclusive prefix count).
+template <bool MAXPOS>
+__device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, unsigned short* __restrict__ out,
+                                                 u32* __restrict__ wscratch) {
+    const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const u32 base = t * TSORT_PER_THREAD;
+    const uint4 raw = *reinterpret_cast<const uint4*>(flag + base);
+    const u32 words[4] = {raw.x, raw.y, raw.z, raw.w};
+    u32 loc[TSORT_PER_THREAD];
+    u32 run = 0;
+#pragma unroll
+    for (int j = 0; j < TSORT_PER_THREAD; ++j) {
+        const u32 f = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        if (MAXPOS) { if (f) run = base + j + 1; loc[j] = run; }
+        else { loc[j] = run; run += f; }
+    }
+    u32 inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc = MAXPOS ? max(inc, x) : inc + x;
+    }
+    if (lane == 31) wscratch[w] = inc;
+    __syncthreads();
+    u32 carry = 0;
+    for (u32 i = 0; i < w; ++i) carry = MAXPOS ? max(carry, wscratch[i]) : carry + wscratch[i];
+    u32 prevl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prevl = 0;
+    carry = MAXPOS ? max(carry, prevl) : carry + prevl;
+#pragma unroll
+    for (int j = 0; j < TSORT_PER_THREAD; ++j)
+        out[base + j] = (unsigned short)(MAXPOS ? (max(loc[j], carry) - 1) : (loc[j] + carry));
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(TSORT_THREADS)
 k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 m,
             const u32* __restrict__ RANK, u64 h, u32 n1, u32 tile, u32 maxg,
             u64* __restrict__ key_out, u32* __restrict__ val_out) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
-    u64* skey = reinterpret_cast<u64*>(tsort_smem);
-    u32* sval = reinterpret_cast<u32*>(tsort_smem + (size_t)TSORT_SLOTS * 8);
-    u32& s_first = *reinterpret_cast<u32*>(tsort_smem + (size_t)TSORT_SLOTS * 12);
-    u32& s_end = *reinterpret_cast<u32*>(tsort_smem + (size_t)TSORT_SLOTS * 12 + 4);
+    u64* skey = reinterpret_cast<u64*>(tsort_smem + TSORT_OFF_KEY);
+    u32* sval = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_VAL);
+    u32* gpiv = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_PIV);
+    u32* gless = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_LESS);
+    unsigned short* sgs = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_GS);
+    unsigned short* seq = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_EQ);
+    unsigned short* gend = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_END);
+    u8* flag = reinterpret_cast<u8*>(tsort_smem + TSORT_OFF_FLAG);
+    u32* misc = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_MISC);
+    u32& s_first = misc[0];
+    u32& s_end = misc[1];
+    u32& s_cost = misc[2];
+    u32* wscratch = misc + 4;   // 8 words
+
+    const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 a = blockIdx.x * tile;
     u32 b = a + tile;
     if (b > m) b = m;
     u32 load_end = b + maxg;          // a group headed before b ends before b + maxg
     if (load_end > m) load_end = m;
     const u32 nload = load_end - a;   // <= TSORT_SLOTS
-    if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_end = load_end; }
+    if (tid == 0) { s_first = 0xFFFFFFFFu; s_end = load_end; s_cost = 0; }
     __syncthreads();
     // pass 1: find the first owned head (>= a) and the first foreign head (>= b)
-    for (u32 o = threadIdx.x; o < nload; o += TSORT_THREADS) {
+    for (u32 o = tid; o < nload; o += TSORT_THREADS) {
         const u32 j = a + o;
         const u32 g = (u32)(key_in[j] >> 32);
         const bool head = (j == 0) || ((u32)(key_in[j - 1] >> 32) != g);
@@ -48,10 +116,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
     const u32 first = s_first, end = s_end;
     if (first == 0xFFFFFFFFu) return;             // no group starts in this tile
     const u32 cnt = end - first;                  // owned elements [first, end)
-    u32 ns = 32;
-    while (ns < cnt) ns <<= 1;
-    // pass 2: build composite keys for the owned elements, pad the rest
-    for (u32 o = threadIdx.x; o < ns; o += TSORT_THREADS) {
+    // pass 2: composite keys (group head slot, RANK[s+h]) of the owned elements; head flags
+    for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS) {
         u64 k = ~0ull;
         u32 v = 0;
         if (o < cnt) {
@@ -65,46 +131,83 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
         sval[o] = v;
     }
     __syncthreads();
-    // largest owned group (heads measure their group by a forward scan)
-    u32& s_gmax = *reinterpret_cast<u32*>(tsort_smem + (size_t)TSORT_SLOTS * 12 + 8);
-    if (threadIdx.x == 0) s_gmax = 0;
+    for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
+        flag[o] = (o < cnt && (o == 0 || (u32)(skey[o] >> 32) != (u32)(skey[o - 1] >> 32))) ? 1 : 0;
     __syncthreads();
-    for (u32 o = threadIdx.x; o < cnt; o += TSORT_THREADS) {
-        const u32 g = (u32)(skey[o] >> 32);
-        if (o == 0 || (u32)(skey[o - 1] >> 32) != g) {
-            u32 e = o + 1;
-            while (e < cnt && (u32)(skey[e] >> 32) == g) ++e;
-            atomicMax(&s_gmax, e - o);
+    tsort_scan_flags<true>(flag, sgs, wscratch);                  // sgs[o] = start of o's group
+    // group ends, by group start
+    for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
+        if (o > 0 && flag[o]) gend[sgs[o - 1]] = (unsigned short)o;
+        if (o == cnt - 1) gend[sgs[o]] = (unsigned short)cnt;
+    }
+    __syncthreads();
+    // pivot per group: majority of the ranks of its first, middle and last member
+    for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
+        if (flag[o]) {
+            const u32 e = gend[o];
+            const u32 ka = (u32)skey[o], kb = (u32)skey[(o + e) >> 1], kc = (u32)skey[e - 1];
+            gpiv[o] = (ka == kb || ka == kc) ? ka : kb;
+            gless[o] = 0;
         }
     }
     __syncthreads();
-    if (s_gmax <= TSORT_ALLPAIRS_MAX) {
-        // small groups: rank every element inside its group by counting (no barriers, ~s steps)
-        for (u32 o = threadIdx.x; o < cnt; o += TSORT_THREADS) {
+    // members below the pivot (warp-aggregated counting) and pivot-equal flags
+    for (u32 ob = 0; ob < cnt; ob += TSORT_THREADS) {
+        const u32 o = ob + tid;
+        const bool valid = o < cnt;
+        u32 gs = 0xFFFFFFFFu;
+        bool less = false, eq = false;
+        if (valid) {
+            gs = sgs[o];
+            const u32 k2 = (u32)skey[o], pv = gpiv[gs];
+            less = k2 < pv;
+            eq = k2 == pv;
+            flag[o] = eq ? 1 : 0;
+        }
+        const u32 same = __match_any_sync(0xffffffffu, gs);
+        const u32 lessm = __ballot_sync(0xffffffffu, less);
+        const u32 c = __popc(same & lessm);
+        if (valid && c && lane == (u32)(__ffs(same) - 1)) atomicAdd(&gless[gs], c);
+    }
+    __syncthreads();
+    tsort_scan_flags<false>(flag, seq, wscratch);                 // seq[o] = pivot-equal members before o (tile-wide)
+    // all-pairs budget: sum over groups of outliers x size
+    for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
+        if (o == 0 || sgs[o] != sgs[o - 1]) {
+            const u32 e = gend[o], size = e - o;
+            const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
+            const u32 outl = size - eqc;
+            if (outl) atomicAdd(&s_cost, outl * size);
+        }
+    }
+    __syncthreads();
+    if (s_cost <= TSORT_ALLPAIRS_BUDGET) {
+        for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
+            const u32 gs = sgs[o];
             const u64 k = skey[o];
-            const u32 g = (u32)(k >> 32);
-            u32 before = 0, smaller = 0;
-            for (u32 q = o; q-- > 0;) {
-                const u64 kq = skey[q];
-                if ((u32)(kq >> 32) != g) break;
-                ++before;
-                smaller += (kq <= k) ? 1u : 0u;       // ties keep their current order
+            u32 pos;
+            if (flag[o]) {
+                pos = gs + gless[gs] + ((u32)seq[o] - (u32)seq[gs]);
+            } else {
+                const u32 e = gend[gs];
+                u32 smaller = 0;
+                for (u32 q = gs; q < e; ++q) {
+                    const u64 kq = skey[q];
+                    smaller += (kq < k || (kq == k && q < o)) ? 1u : 0u;
+                }
+                pos = gs + smaller;
             }
-            for (u32 q = o + 1; q < cnt; ++q) {
-                const u64 kq = skey[q];
-                if ((u32)(kq >> 32) != g) break;
-                smaller += (kq < k) ? 1u : 0u;
-            }
-            const u32 dst = first + (o - before) + smaller;
-            key_out[dst] = k;
-            val_out[dst] = sval[o];
+            key_out[first + pos] = k;
+            val_out[first + pos] = sval[o];
         }
         return;
     }
-    // bitonic sort of ns slots by key
-    for (u32 k = 2, lk = 1; k <= ns; k <<= 1, ++lk) {
+    // fallback: bitonic network over the padded tile, composite key
+    u32 ns = 32;
+    while (ns < cnt) ns <<= 1;
+    for (u32 k = 2; k <= ns; k <<= 1) {
         for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 t = threadIdx.x; t < (ns >> 1); t += TSORT_THREADS) {
+            for (u32 t = tid; t < (ns >> 1); t += TSORT_THREADS) {
                 const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const u32 l = i + j;
                 const bool asc = (i & k) == 0;
@@ -118,7 +221,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
             __syncthreads();
         }
     }
-    for (u32 o = threadIdx.x; o < cnt; o += TSORT_THREADS) {
+    for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
         key_out[first + o] = skey[o];
         val_out[first + o] = sval[o];
     }
