@@ -71,6 +71,9 @@ const char* nlz_version(void); /* bindings.cpp:1513-1517 (__version__) */
  * (CUDA events around every launch, on the launching stream) when profiling is switched on */
 int nlz_set_profiling(nlz_ctx* ctx, int on);
 int nlz_kernel_class_count(void);
+/* test hook: forces the fallback paths of the shared-memory group sort (1 bitonic network, 2 no pivot fast path,
+ * 4 counting only); 0 = normal operation */
+int nlz_set_debug_flags(nlz_ctx* ctx, int flags);
 int nlz_get_kernel_stats(nlz_ctx* ctx, int cls, const char** name, double* ms, uint64_t* bytes,
                          uint32_t* launches);
 

@@ -49,6 +49,7 @@ SIGNATURES = {
     "nlz_version": (ctypes.c_char_p, []),
     "nlz_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
     "nlz_kernel_class_count": (ctypes.c_int, []),
+    "nlz_set_debug_flags": (ctypes.c_int, [_vp, ctypes.c_int]),
     "nlz_get_kernel_stats": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
                                              ctypes.POINTER(ctypes.c_double), _u64p,
                                              ctypes.POINTER(ctypes.c_uint32)]),

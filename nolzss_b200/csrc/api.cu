@@ -79,6 +79,7 @@ struct nlz_ctx {
     cudaEvent_t ev[EV_COUNT];
     nlz_stats stats;
     Profiler prof;
+    int debug_flags = 0;        // test hook: 1 force the bitonic tile path, 2 disable the pivot fast path, 4 force counting
 };
 
 namespace nlz {
@@ -340,38 +341,42 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
         while (m > 0) {
             S.doubling_rounds += 1;
             S.active_sum += m;
-            int rb;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
             static const bool trace = getenv("NLZ_TRACE") != nullptr;
             cudaEvent_t tev0 = nullptr, tev1 = nullptr;
             if (trace) { cudaEventCreate(&tev0); cudaEventCreate(&tev1); cudaEventRecord(tev0, st); }
-            if (maxg <= (u32)TSORT_SLOTS / 2) {
-                // every tie group fits in shared memory: fused gather + segmented sort, one pass
+            int rb;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
+            const bool fused = maxg <= (u32)TSORT_SLOTS / 2;
+            KL(P, KC_GATHER, (u64)m * 24, st,
+               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1,
+                                                                     fused ? w.CTR : nullptr)));
+            if (fused) {
+                // every tie group fits in shared memory: segmented sort + regroup in one pass
                 u32 cap = 32;
                 while (cap < maxg) cap <<= 1;
                 const u32 tile = TSORT_SLOTS - cap;
-                KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 12), st,
+                KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
                    (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
-                       w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1, tile, cap, w.KEY[cur ^ 1], w.VAL[cur ^ 1])));
-                rb = cur ^ 1;
+                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, tile, cap, w.SA, w.RANK, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
+                       w.SLOT[sc ^ 1], w.CTR, c->debug_flags)));
+                rb = cur;                       // next round's lists were written to the cur^1 buffers
                 S.tile_sort_rounds += 1;
+                if (trace) cudaEventRecord(tev1, st);
             } else {
                 u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
                 u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
-                KL(P, KC_GATHER, (u64)m * 24, st,
-                   (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(k[0], v[0], m, w.RANK, h, n1)));
                 int res = 0;
                 NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
                 rb = res == 0 ? cur : (cur ^ 1);
+                if (trace) cudaEventRecord(tev1, st);
+                const u32 tiles = ceil_div_u32(m, RG_TILE);
+                P.begin(st);
+                k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
+                k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
+                k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
+                                                                        w.PMAX, w.PSUM, w.SA, w.RANK, w.KEY[rb ^ 1],
+                                                                        w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
+                P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
             }
-            if (trace) cudaEventRecord(tev1, st);
-            const u32 tiles = ceil_div_u32(m, RG_TILE);
-            P.begin(st);
-            k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
-            k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
-            k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
-                                                                    w.PMAX, w.PSUM, w.SA, w.RANK, w.KEY[rb ^ 1],
-                                                                    w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
-            P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
             NLZ_CK(cudaStreamSynchronize(st));
             S.host_syncs += 1;
@@ -726,6 +731,13 @@ int nlz_set_profiling(nlz_ctx* c, int on) {
     if (!c) { set_error("null context"); return ERR_INVALID; }
     std::lock_guard<std::mutex> lock(c->mu);
     c->prof.timing = on != 0;
+    return OK;
+}
+
+int nlz_set_debug_flags(nlz_ctx* c, int flags) {
+    if (!c) { set_error("null context"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->debug_flags = flags;
     return OK;
 }
 

@@ -266,8 +266,10 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
 
 // KEY[j] |= RANK[VAL[j] + h]   (second half of the doubling key)
 __global__ void __launch_bounds__(256)
-k_gather_rank(u64* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ RANK, u64 h, u32 n1) {
+k_gather_rank(u64* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ RANK, u64 h, u32 n1,
+              u32* __restrict__ ctr) {
     u32 j = blockIdx.x * 256 + threadIdx.x;
+    if (j == 0 && ctr) { ctr[0] = 0; ctr[3] = 0; }   // next round's active count / largest group (fused regroup)
     if (j >= m) return;
     u64 p = (u64)val[j] + h;
     u32 r = p < n1 ? RANK[p] : 0u;   // p < n1 always holds for active suffixes; guard keeps reads in range

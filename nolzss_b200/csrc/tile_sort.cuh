@@ -16,6 +16,12 @@
 //   * if the all-pairs work of a tile would be excessive (large groups without a majority), the
 //     tile falls back to a bitonic network on the composite key (group, rank).
 // Work per member is O(1) for the tied majority instead of O(log^2) compare-exchanges.
+//
+// The same CTA then regroups its (now sorted) groups -- they never straddle tiles -- so a doubling
+// round is two launches: k_gather_rank (reads a consistent RANK snapshot) and this kernel, which also
+// detects the new sub-groups, writes the refined ranks (RANK = ISA in the end) and the suffix array
+// slots, and appends the members that are still tied to the next round's list (one atomic range
+// reservation per tile; the order of groups in that list is irrelevant).
 #pragma once
 #include "common.cuh"
 
@@ -75,9 +81,10 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
 }
 
 __global__ void __launch_bounds__(TSORT_THREADS)
-k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 m,
-            const u32* __restrict__ RANK, u64 h, u32 n1, u32 tile, u32 maxg,
-            u64* __restrict__ key_out, u32* __restrict__ val_out) {
+k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in, u32 m,
+            u32 tile, u32 maxg, u32* __restrict__ SA, u32* __restrict__ RANK, u64* __restrict__ key_next,
+            u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ ctr /* [0] m', [3] max group */,
+            int dbg) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
     u64* skey = reinterpret_cast<u64*>(tsort_smem + TSORT_OFF_KEY);
     u32* sval = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_VAL);
@@ -91,6 +98,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
     u32& s_first = misc[0];
     u32& s_end = misc[1];
     u32& s_cost = misc[2];
+    u32& s_base = misc[3];
     u32* wscratch = misc + 4;   // 8 words
 
     const u32 tid = threadIdx.x, lane = tid & 31;
@@ -116,17 +124,11 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
     const u32 first = s_first, end = s_end;
     if (first == 0xFFFFFFFFu) return;             // no group starts in this tile
     const u32 cnt = end - first;                  // owned elements [first, end)
-    // pass 2: composite keys (group head slot, RANK[s+h]) of the owned elements; head flags
+    // pass 2: composite keys (group head slot, RANK[s+h]) of the owned elements
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS) {
         u64 k = ~0ull;
         u32 v = 0;
-        if (o < cnt) {
-            const u32 j = first + o;
-            v = val_in[j];
-            const u64 p = (u64)v + h;
-            const u32 r = p < n1 ? RANK[p] : 0u;
-            k = (key_in[j] & 0xFFFFFFFF00000000ull) | (u64)r;
-        }
+        if (o < cnt) { k = key_in[first + o]; v = val_in[first + o]; }
         skey[o] = k;
         sval[o] = v;
     }
@@ -162,6 +164,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
             const u32 k2 = (u32)skey[o], pv = gpiv[gs];
             less = k2 < pv;
             eq = k2 == pv;
+            if (dbg & 2) eq = false;
             flag[o] = eq ? 1 : 0;
         }
         const u32 same = __match_any_sync(0xffffffffu, gs);
@@ -181,49 +184,105 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, u32 
         }
     }
     __syncthreads();
-    if (s_cost <= TSORT_ALLPAIRS_BUDGET) {
-        for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
-            const u32 gs = sgs[o];
-            const u64 k = skey[o];
-            u32 pos;
-            if (flag[o]) {
-                pos = gs + gless[gs] + ((u32)seq[o] - (u32)seq[gs]);
-            } else {
-                const u32 e = gend[gs];
-                u32 smaller = 0;
-                for (u32 q = gs; q < e; ++q) {
-                    const u64 kq = skey[q];
-                    smaller += (kq < k || (kq == k && q < o)) ? 1u : 0u;
+    if ((s_cost <= TSORT_ALLPAIRS_BUDGET || (dbg & 4)) && !(dbg & 1)) {
+        // every thread computes the sorted positions of its members, then the tile is permuted in place
+        u64 rk[TSORT_PER_THREAD];
+        u32 rv[TSORT_PER_THREAD];
+        unsigned short rp[TSORT_PER_THREAD];
+#pragma unroll 1
+        for (int q = 0; q < TSORT_PER_THREAD; ++q) {
+            const u32 o = q * TSORT_THREADS + tid;
+            rk[q] = 0; rv[q] = 0; rp[q] = 0xFFFF;
+            if (o < cnt) {
+                const u32 gs = sgs[o];
+                const u64 k = skey[o];
+                u32 pos;
+                if (flag[o]) {
+                    pos = gs + gless[gs] + ((u32)seq[o] - (u32)seq[gs]);
+                } else {
+                    const u32 e = gend[gs];
+                    u32 smaller = 0;
+                    for (u32 x = gs; x < e; ++x) {
+                        const u64 kx = skey[x];
+                        smaller += (kx < k || (kx == k && x < o)) ? 1u : 0u;
+                    }
+                    pos = gs + smaller;
                 }
-                pos = gs + smaller;
+                rk[q] = k; rv[q] = sval[o]; rp[q] = (unsigned short)pos;
             }
-            key_out[first + pos] = k;
-            val_out[first + pos] = sval[o];
         }
-        return;
-    }
-    // fallback: bitonic network over the padded tile, composite key
-    u32 ns = 32;
-    while (ns < cnt) ns <<= 1;
-    for (u32 k = 2; k <= ns; k <<= 1) {
-        for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 t = tid; t < (ns >> 1); t += TSORT_THREADS) {
-                const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const u32 l = i + j;
-                const bool asc = (i & k) == 0;
-                const u64 ki = skey[i], kl = skey[l];
-                if ((ki > kl) == asc) {
-                    skey[i] = kl; skey[l] = ki;
-                    const u32 vi = sval[i];
-                    sval[i] = sval[l]; sval[l] = vi;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TSORT_PER_THREAD; ++q)
+            if (rp[q] != 0xFFFF) { skey[rp[q]] = rk[q]; sval[rp[q]] = rv[q]; }
+        __syncthreads();
+    } else {
+        // fallback: bitonic network over the padded tile.  The groups of the list are in no particular
+        // order of their head slots, so the network sorts by (position of the group in the tile, rank):
+        // groups stay where they are, members are ordered inside them.
+        for (u32 o = tid; o < cnt; o += TSORT_THREADS) skey[o] = ((u64)sgs[o] << 32) | (u64)(u32)skey[o];
+        __syncthreads();
+        u32 ns = 32;
+        while (ns < cnt) ns <<= 1;
+        for (u32 k = 2; k <= ns; k <<= 1) {
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 t = tid; t < (ns >> 1); t += TSORT_THREADS) {
+                    const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const u32 l = i + j;
+                    const bool asc = (i & k) == 0;
+                    const u64 ki = skey[i], kl = skey[l];
+                    if ((ki > kl) == asc) {
+                        skey[i] = kl; skey[l] = ki;
+                        const u32 vi = sval[i];
+                        sval[i] = sval[l]; sval[l] = vi;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
+    // ---- regroup: the tile's members are sorted by (group, rank); sub-groups = runs of equal keys
+    u32* sslot = gpiv;                                            // suffix-array slots of the owned range
+    for (u32 o = tid; o < cnt; o += TSORT_THREADS) sslot[o] = slot_in[first + o];
+    for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
+        flag[o] = (o < cnt && (o == 0 || skey[o] != skey[o - 1])) ? 1 : 0;
+    __syncthreads();
+    tsort_scan_flags<true>(flag, sgs, wscratch);                  // sgs[o] = start of o's new sub-group
+    // still-tied members: not (head and next is head); flags reused: bit0 head, bit1 active
+    u32 gmax = 0;
+    for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS) {
+        u8 f = 0;
+        if (o < cnt) {
+            const bool hd = flag[o] != 0;
+            const bool nh = (o + 1 >= cnt) || flag[o + 1] != 0;
+            f = (hd && nh) ? 0 : 1;
+            if (nh) gmax = max(gmax, o - (u32)sgs[o] + 1);          // last member of its sub-group
+        }
+        reinterpret_cast<u8*>(gend)[o] = f;                        // active flags (gend is free now)
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (lane == 0 && gmax > 1) atomicMax(&ctr[3], gmax);
+    __syncthreads();
+    tsort_scan_flags<false>(reinterpret_cast<u8*>(gend), seq, wscratch);   // seq[o] = active members before o
+    if (tid == 0) {
+        const u32 total = (u32)seq[cnt - 1] + reinterpret_cast<u8*>(gend)[cnt - 1];
+        s_base = total ? atomicAdd(&ctr[0], total) : 0u;
+    }
+    __syncthreads();
+    const u32 base = s_base;
     for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
-        key_out[first + o] = skey[o];
-        val_out[first + o] = sval[o];
+        const u32 s = sval[o];
+        const u32 slot = sslot[o];
+        const u32 newrank = sslot[sgs[o]];
+        RANK[s] = newrank;
+        SA[slot] = s;
+        if (reinterpret_cast<u8*>(gend)[o]) {
+            const u32 pos = base + seq[o];
+            key_next[pos] = (u64)newrank << 32;
+            val_next[pos] = s;
+            slot_next[pos] = slot;
+        }
     }
 }
 

@@ -176,3 +176,18 @@ def test_device_entry_point_matches_host_entry_point():
                                           d_out.data_ptr(), d_out.shape[0], ctypes.byref(cnt)))
     got = d_out[: cnt.value].cpu().numpy().view(np.uint64)
     assert np.array_equal(got, exp)
+
+
+def test_group_sort_fallback_paths():
+    """The shared-memory group sort has three paths (pivot partition, counting, bitonic network);
+    force each of them and check the factors."""
+    cases = [(b"the quick brown fox jumps over the lazy dog " * 500) + b"!",
+             wl.planted_dna(300_000, 41, scale=0.3).tobytes(), b"AC" * 1500 + b"G" + b"AC" * 700]
+    exp = [orc.factorize(s) for s in cases]
+    try:
+        for flags in (1, 2, 4, 6):
+            L.check(L.load().nlz_set_debug_flags(L.context(), flags))
+            for s, e in zip(cases, exp):
+                assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s), e), flags
+    finally:
+        L.check(L.load().nlz_set_debug_flags(L.context(), 0))
