@@ -25,11 +25,34 @@ __device__ __forceinline__ u64 load8_unaligned(const u64* __restrict__ xw, u64 p
 constexpr int LCP_Q = 32;        // consecutive text positions per thread (Kasai run)
 constexpr int LCP_LOCAL_WORDS = 2;  // 8-byte words a lane compares alone before asking the warp for help
 
-// Each lane runs Kasai over LCP_Q consecutive text positions.  A lane whose match outlasts
-// LCP_LOCAL_WORDS words (a repeat) hands the comparison to its whole warp: 32 lanes compare 32
-// consecutive words of the two suffixes per step (two coalesced 256-byte reads), a ballot finds the
-// first mismatch.  This removes the single-thread tail that a 100-kbp tandem repeat otherwise causes
-// while keeping the Kasai carry (l-1) inside the lane.
+// 32 lanes compare x[a+l0 ..) with x[b+l0 ..), 32 consecutive 8-byte words per step (two coalesced
+// 256-byte reads), a ballot finds the first mismatch.  All lanes pass the same arguments.
+__device__ __forceinline__ u32 warp_extend_match(const u64* __restrict__ xw, u64 a, u64 b, u32 l0, u32 ml, u32 lane) {
+    u32 res = ml;
+    for (u32 off = l0; off < ml; off += 256) {
+        const u32 my = off + 8 * lane;
+        u64 d = 0;
+        if (my < ml) d = load8_unaligned(xw, a + my) ^ load8_unaligned(xw, b + my);
+        const u32 hb = __ballot_sync(0xffffffffu, d != 0);
+        if (hb) {
+            const int f = __ffs(hb) - 1;
+            const u64 df = __shfl_sync(0xffffffffu, d, f);
+            res = off + 8 * f + ((u32)(__ffsll((long long)df) - 1) >> 3);
+            if (res > ml) res = ml;
+            break;
+        }
+    }
+    return res;
+}
+
+// Each lane runs Kasai over LCP_Q consecutive text positions; a warp therefore owns 32*LCP_Q
+// consecutive positions.
+//  * run starts (k = 0): Kasai's inequality PLCP[i+d] >= PLCP[i] - d also links the STARTS of
+//    neighbouring lanes (d = LCP_Q), so the 32 start comparisons are done by the whole warp in lane
+//    order, each beginning LCP_Q symbols short of its predecessor's result: a 100-kbp tandem repeat
+//    costs the warp one long comparison instead of 32.
+//  * inside a run (k > 0): the lane continues from l-1 on its own; a lane whose match still outlasts
+//    LCP_LOCAL_WORDS words hands the comparison to its warp.
 __global__ void __launch_bounds__(256)
 k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
             const u32* __restrict__ RANK, u32* __restrict__ LCP) {
@@ -55,50 +78,57 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
                 need = true;
             }
         }
-        bool pending_me = false;
-        if (need) {
-            pending_me = true;
+        if (k == 0) {
+            u32 carry = 0;                          // result at the previous lane's run start
+#pragma unroll 1
+            for (int src = 0; src < 32; ++src) {
+                const u64 a = __shfl_sync(0xffffffffu, i, src);
+                const u64 b = (u64)__shfl_sync(0xffffffffu, j, src);
+                const u32 ml = __shfl_sync(0xffffffffu, maxl, src);
+                const bool nd = __shfl_sync(0xffffffffu, need ? 1u : 0u, src) != 0;
+                u32 res = 0;
+                if (nd) {
+                    u32 l0 = carry > (u32)LCP_Q ? carry - LCP_Q : 0u;
+                    if (l0 > ml) l0 = ml;
+                    l0 &= ~7u;                      // keep the word grid of the first lane's offset
+                    res = warp_extend_match(xw, a, b, l0, ml, lane);
+                }
+                if ((int)lane == src) l = res;
+                carry = res;
+            }
+        } else {
+            bool pending_me = false;
+            if (need) {
+                pending_me = true;
 #pragma unroll
-            for (int t = 0; t < LCP_LOCAL_WORDS; ++t) {
-                if (pending_me) {
-                    if (l >= maxl) { l = maxl; pending_me = false; }
-                    else {
-                        u64 d = load8_unaligned(xw, i + l) ^ load8_unaligned(xw, (u64)j + l);
-                        if (d) {
-                            l += (u32)(__ffsll((long long)d) - 1) >> 3;
-                            if (l > maxl) l = maxl;
-                            pending_me = false;
-                        } else {
-                            l += 8;
+                for (int t = 0; t < LCP_LOCAL_WORDS; ++t) {
+                    if (pending_me) {
+                        if (l >= maxl) { l = maxl; pending_me = false; }
+                        else {
+                            u64 d = load8_unaligned(xw, i + l) ^ load8_unaligned(xw, (u64)j + l);
+                            if (d) {
+                                l += (u32)(__ffsll((long long)d) - 1) >> 3;
+                                if (l > maxl) l = maxl;
+                                pending_me = false;
+                            } else {
+                                l += 8;
+                            }
                         }
                     }
                 }
+                if (pending_me && l >= maxl) { l = maxl; pending_me = false; }
             }
-            if (pending_me && l >= maxl) { l = maxl; pending_me = false; }
-        }
-        u32 pending = __ballot_sync(0xffffffffu, pending_me);
-        while (pending) {
-            const int src = __ffs(pending) - 1;
-            const u64 a = __shfl_sync(0xffffffffu, i, src);
-            const u64 b = (u64)__shfl_sync(0xffffffffu, j, src);
-            const u32 l0 = __shfl_sync(0xffffffffu, l, src);
-            const u32 ml = __shfl_sync(0xffffffffu, maxl, src);
-            u32 res = ml;
-            for (u32 off = l0; off < ml; off += 256) {
-                const u32 my = off + 8 * lane;
-                u64 d = 0;
-                if (my < ml) d = load8_unaligned(xw, a + my) ^ load8_unaligned(xw, b + my);
-                const u32 hb = __ballot_sync(0xffffffffu, d != 0);
-                if (hb) {
-                    const int f = __ffs(hb) - 1;
-                    const u64 df = __shfl_sync(0xffffffffu, d, f);
-                    res = off + 8 * f + ((u32)(__ffsll((long long)df) - 1) >> 3);
-                    if (res > ml) res = ml;
-                    break;
-                }
+            u32 pending = __ballot_sync(0xffffffffu, pending_me);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                const u64 a = __shfl_sync(0xffffffffu, i, src);
+                const u64 b = (u64)__shfl_sync(0xffffffffu, j, src);
+                const u32 l0 = __shfl_sync(0xffffffffu, l, src);
+                const u32 ml = __shfl_sync(0xffffffffu, maxl, src);
+                const u32 res = warp_extend_match(xw, a, b, l0, ml, lane);
+                if ((int)lane == src) l = res;
+                pending &= pending - 1;
             }
-            if ((int)lane == src) l = res;
-            pending &= pending - 1;
         }
         if (need) {
             LCP[r] = l;
