@@ -27,23 +27,25 @@
 
 namespace nlz {
 
-constexpr int TSORT_THREADS = 256;
+constexpr int TSORT_THREADS = 512;
 constexpr int TSORT_SLOTS = 4096;
-constexpr int TSORT_PER_THREAD = TSORT_SLOTS / TSORT_THREADS;   // 16
+constexpr int TSORT_PER_THREAD = TSORT_SLOTS / TSORT_THREADS;   // 8
 constexpr u32 TSORT_ALLPAIRS_BUDGET = 384u * 1024u;             // compare steps a tile may spend on counting
-// shared memory layout (dynamic)
-constexpr size_t TSORT_OFF_KEY = 0;                                        // u64[SLOTS]
-constexpr size_t TSORT_OFF_VAL = TSORT_OFF_KEY + (size_t)TSORT_SLOTS * 8;  // u32[SLOTS]
-constexpr size_t TSORT_OFF_PIV = TSORT_OFF_VAL + (size_t)TSORT_SLOTS * 4;  // u32[SLOTS]  pivot rank, by group start
-constexpr size_t TSORT_OFF_LESS = TSORT_OFF_PIV + (size_t)TSORT_SLOTS * 4; // u32[SLOTS]  #members < pivot, by group start
-constexpr size_t TSORT_OFF_GS = TSORT_OFF_LESS + (size_t)TSORT_SLOTS * 4;  // u16[SLOTS]  group start of every member
-constexpr size_t TSORT_OFF_EQ = TSORT_OFF_GS + (size_t)TSORT_SLOTS * 2;    // u16[SLOTS]  exclusive prefix of pivot-equal flags
-constexpr size_t TSORT_OFF_END = TSORT_OFF_EQ + (size_t)TSORT_SLOTS * 2;   // u16[SLOTS]  group end, by group start
-constexpr size_t TSORT_OFF_FLAG = TSORT_OFF_END + (size_t)TSORT_SLOTS * 2; // u8 [SLOTS]  head / equal flags
-constexpr size_t TSORT_OFF_MISC = TSORT_OFF_FLAG + (size_t)TSORT_SLOTS;    // u32[16]
-constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 64;
+// shared memory layout (dynamic).  Groups of the active list have >= 2 members, so group start / 2 is
+// a unique per-group index: the per-group tables need SLOTS/2 entries.
+constexpr size_t TSORT_OFF_KEY = 0;                                          // u64[SLOTS]
+constexpr size_t TSORT_OFF_VAL = TSORT_OFF_KEY + (size_t)TSORT_SLOTS * 8;    // u32[SLOTS]
+constexpr size_t TSORT_OFF_SLOT = TSORT_OFF_VAL + (size_t)TSORT_SLOTS * 4;   // u32[SLOTS]   suffix-array slots of the owned range
+constexpr size_t TSORT_OFF_PIV = TSORT_OFF_SLOT + (size_t)TSORT_SLOTS * 4;   // u32[SLOTS/2] pivot rank of the group
+constexpr size_t TSORT_OFF_GLE = TSORT_OFF_PIV + (size_t)TSORT_SLOTS * 2;    // u32[SLOTS/2] group end << 16 | #members < pivot
+constexpr size_t TSORT_OFF_GS = TSORT_OFF_GLE + (size_t)TSORT_SLOTS * 2;     // u16[SLOTS]   group start of every member
+constexpr size_t TSORT_OFF_EQ = TSORT_OFF_GS + (size_t)TSORT_SLOTS * 2;      // u16[SLOTS]   exclusive prefix counts
+constexpr size_t TSORT_OFF_FLAG = TSORT_OFF_EQ + (size_t)TSORT_SLOTS * 2;    // u8 [SLOTS]   head / pivot-equal flags
+constexpr size_t TSORT_OFF_ACT = TSORT_OFF_FLAG + (size_t)TSORT_SLOTS;       // u8 [SLOTS]   still-tied flags
+constexpr size_t TSORT_OFF_MISC = TSORT_OFF_ACT + (size_t)TSORT_SLOTS;       // u32[32]
+constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 128;
 
-// Scans over the SLOTS one-byte flags, 16 consecutive flags per thread.
+// Scans over the SLOTS one-byte flags, 8 consecutive flags per thread.
 // MAXPOS: out[o] = index of the last set flag at or before o (flag[0] must be set).
 // otherwise: out[o] = number of set flags before o (exclusive prefix count).
 template <bool MAXPOS>
@@ -51,8 +53,9 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
                                                  u32* __restrict__ wscratch) {
     const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
     const u32 base = t * TSORT_PER_THREAD;
-    const uint4 raw = *reinterpret_cast<const uint4*>(flag + base);
-    const u32 words[4] = {raw.x, raw.y, raw.z, raw.w};
+    static_assert(TSORT_PER_THREAD == 8, "flag scan reads one 8-byte word per thread");
+    const uint2 raw = *reinterpret_cast<const uint2*>(flag + base);
+    const u32 words[2] = {raw.x, raw.y};
     u32 loc[TSORT_PER_THREAD];
     u32 run = 0;
 #pragma unroll
@@ -89,17 +92,18 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     u64* skey = reinterpret_cast<u64*>(tsort_smem + TSORT_OFF_KEY);
     u32* sval = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_VAL);
     u32* gpiv = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_PIV);
-    u32* gless = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_LESS);
+    u32* gle = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_GLE);
     unsigned short* sgs = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_GS);
     unsigned short* seq = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_EQ);
-    unsigned short* gend = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_END);
     u8* flag = reinterpret_cast<u8*>(tsort_smem + TSORT_OFF_FLAG);
+    u8* act = reinterpret_cast<u8*>(tsort_smem + TSORT_OFF_ACT);
+    u32* sslot = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_SLOT);
     u32* misc = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_MISC);
     u32& s_first = misc[0];
     u32& s_end = misc[1];
     u32& s_cost = misc[2];
     u32& s_base = misc[3];
-    u32* wscratch = misc + 4;   // 8 words
+    u32* wscratch = misc + 8;   // one word per warp
 
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 a = blockIdx.x * tile;
@@ -127,29 +131,29 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     // pass 2: composite keys (group head slot, RANK[s+h]) of the owned elements
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS) {
         u64 k = ~0ull;
-        u32 v = 0;
-        if (o < cnt) { k = key_in[first + o]; v = val_in[first + o]; }
+        u32 v = 0, sl = 0;
+        if (o < cnt) { k = key_in[first + o]; v = val_in[first + o]; sl = slot_in[first + o]; }
         skey[o] = k;
         sval[o] = v;
+        sslot[o] = sl;
     }
     __syncthreads();
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
         flag[o] = (o < cnt && (o == 0 || (u32)(skey[o] >> 32) != (u32)(skey[o - 1] >> 32))) ? 1 : 0;
     __syncthreads();
     tsort_scan_flags<true>(flag, sgs, wscratch);                  // sgs[o] = start of o's group
-    // group ends, by group start
+    // group ends (high half of gle), by group
     for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
-        if (o > 0 && flag[o]) gend[sgs[o - 1]] = (unsigned short)o;
-        if (o == cnt - 1) gend[sgs[o]] = (unsigned short)cnt;
+        if (o > 0 && flag[o]) gle[sgs[o - 1] >> 1] = o << 16;
+        if (o == cnt - 1) gle[sgs[o] >> 1] = cnt << 16;
     }
     __syncthreads();
     // pivot per group: majority of the ranks of its first, middle and last member
     for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
         if (flag[o]) {
-            const u32 e = gend[o];
+            const u32 e = gle[o >> 1] >> 16;
             const u32 ka = (u32)skey[o], kb = (u32)skey[(o + e) >> 1], kc = (u32)skey[e - 1];
-            gpiv[o] = (ka == kb || ka == kc) ? ka : kb;
-            gless[o] = 0;
+            gpiv[o >> 1] = (ka == kb || ka == kc) ? ka : kb;
         }
     }
     __syncthreads();
@@ -161,7 +165,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         bool less = false, eq = false;
         if (valid) {
             gs = sgs[o];
-            const u32 k2 = (u32)skey[o], pv = gpiv[gs];
+            const u32 k2 = (u32)skey[o], pv = gpiv[gs >> 1];
             less = k2 < pv;
             eq = k2 == pv;
             if (dbg & 2) eq = false;
@@ -170,14 +174,14 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         const u32 same = __match_any_sync(0xffffffffu, gs);
         const u32 lessm = __ballot_sync(0xffffffffu, less);
         const u32 c = __popc(same & lessm);
-        if (valid && c && lane == (u32)(__ffs(same) - 1)) atomicAdd(&gless[gs], c);
+        if (valid && c && lane == (u32)(__ffs(same) - 1)) atomicAdd(&gle[gs >> 1], c);   // low half: < 2^16
     }
     __syncthreads();
     tsort_scan_flags<false>(flag, seq, wscratch);                 // seq[o] = pivot-equal members before o (tile-wide)
     // all-pairs budget: sum over groups of outliers x size
     for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
         if (o == 0 || sgs[o] != sgs[o - 1]) {
-            const u32 e = gend[o], size = e - o;
+            const u32 e = gle[o >> 1] >> 16, size = e - o;
             const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
             const u32 outl = size - eqc;
             if (outl) atomicAdd(&s_cost, outl * size);
@@ -197,10 +201,11 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
                 const u32 gs = sgs[o];
                 const u64 k = skey[o];
                 u32 pos;
+                const u32 ge = gle[gs >> 1];
                 if (flag[o]) {
-                    pos = gs + gless[gs] + ((u32)seq[o] - (u32)seq[gs]);
+                    pos = gs + (ge & 0xFFFFu) + ((u32)seq[o] - (u32)seq[gs]);
                 } else {
-                    const u32 e = gend[gs];
+                    const u32 e = ge >> 16;
                     u32 smaller = 0;
                     for (u32 x = gs; x < e; ++x) {
                         const u64 kx = skey[x];
@@ -242,8 +247,6 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         }
     }
     // ---- regroup: the tile's members are sorted by (group, rank); sub-groups = runs of equal keys
-    u32* sslot = gpiv;                                            // suffix-array slots of the owned range
-    for (u32 o = tid; o < cnt; o += TSORT_THREADS) sslot[o] = slot_in[first + o];
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
         flag[o] = (o < cnt && (o == 0 || skey[o] != skey[o - 1])) ? 1 : 0;
     __syncthreads();
@@ -258,15 +261,15 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
             f = (hd && nh) ? 0 : 1;
             if (nh) gmax = max(gmax, o - (u32)sgs[o] + 1);          // last member of its sub-group
         }
-        reinterpret_cast<u8*>(gend)[o] = f;                        // active flags (gend is free now)
+        act[o] = f;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if (lane == 0 && gmax > 1) atomicMax(&ctr[3], gmax);
     __syncthreads();
-    tsort_scan_flags<false>(reinterpret_cast<u8*>(gend), seq, wscratch);   // seq[o] = active members before o
+    tsort_scan_flags<false>(act, seq, wscratch);                  // seq[o] = still-tied members before o
     if (tid == 0) {
-        const u32 total = (u32)seq[cnt - 1] + reinterpret_cast<u8*>(gend)[cnt - 1];
+        const u32 total = (u32)seq[cnt - 1] + act[cnt - 1];
         s_base = total ? atomicAdd(&ctr[0], total) : 0u;
     }
     __syncthreads();
@@ -277,7 +280,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         const u32 newrank = sslot[sgs[o]];
         RANK[s] = newrank;
         SA[slot] = s;
-        if (reinterpret_cast<u8*>(gend)[o]) {
+        if (act[o]) {
             const u32 pos = base + seq[o];
             key_next[pos] = (u64)newrank << 32;
             val_next[pos] = s;
