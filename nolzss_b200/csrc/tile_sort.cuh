@@ -27,9 +27,9 @@
 
 namespace nlz {
 
-constexpr int TSORT_THREADS = 512;
+constexpr int TSORT_THREADS = 1024;
 constexpr int TSORT_SLOTS = 4096;
-constexpr int TSORT_PER_THREAD = TSORT_SLOTS / TSORT_THREADS;   // 8
+constexpr int TSORT_PER_THREAD = TSORT_SLOTS / TSORT_THREADS;   // 4
 constexpr u32 TSORT_ALLPAIRS_BUDGET = 384u * 1024u;             // compare steps a tile may spend on counting
 // shared memory layout (dynamic).  Groups of the active list have >= 2 members, so group start / 2 is
 // a unique per-group index: the per-group tables need SLOTS/2 entries.
@@ -42,10 +42,10 @@ constexpr size_t TSORT_OFF_GS = TSORT_OFF_GLE + (size_t)TSORT_SLOTS * 2;     // 
 constexpr size_t TSORT_OFF_EQ = TSORT_OFF_GS + (size_t)TSORT_SLOTS * 2;      // u16[SLOTS]   exclusive prefix counts
 constexpr size_t TSORT_OFF_FLAG = TSORT_OFF_EQ + (size_t)TSORT_SLOTS * 2;    // u8 [SLOTS]   head / pivot-equal flags
 constexpr size_t TSORT_OFF_ACT = TSORT_OFF_FLAG + (size_t)TSORT_SLOTS;       // u8 [SLOTS]   still-tied flags
-constexpr size_t TSORT_OFF_MISC = TSORT_OFF_ACT + (size_t)TSORT_SLOTS;       // u32[32]
-constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 128;
+constexpr size_t TSORT_OFF_MISC = TSORT_OFF_ACT + (size_t)TSORT_SLOTS;       // u32[64]
+constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 256;
 
-// Scans over the SLOTS one-byte flags, 8 consecutive flags per thread.
+// Scans over the SLOTS one-byte flags, 4 consecutive flags per thread.
 // MAXPOS: out[o] = index of the last set flag at or before o (flag[0] must be set).
 // otherwise: out[o] = number of set flags before o (exclusive prefix count).
 template <bool MAXPOS>
@@ -53,9 +53,8 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
                                                  u32* __restrict__ wscratch) {
     const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
     const u32 base = t * TSORT_PER_THREAD;
-    static_assert(TSORT_PER_THREAD == 8, "flag scan reads one 8-byte word per thread");
-    const uint2 raw = *reinterpret_cast<const uint2*>(flag + base);
-    const u32 words[2] = {raw.x, raw.y};
+    static_assert(TSORT_PER_THREAD == 4, "flag scan reads one 4-byte word per thread");
+    const u32 words[1] = {*reinterpret_cast<const u32*>(flag + base)};
     u32 loc[TSORT_PER_THREAD];
     u32 run = 0;
 #pragma unroll

@@ -221,3 +221,32 @@ def test_package_level_api(tmp_path):
     with pytest.raises(genomics.FASTAError):
         genomics.read_nucleotide_fasta(os.path.join(GOLD, "messy.fasta"))
     assert genomics.factorize_dna_w_reference_seq("ACGTACGT", "ACGTACGT")[0] == (9, 8, 0, False)
+
+
+def test_multi_record_fasta_config3_style(tmp_path):
+    """configs[2] in miniature: many records, per-sequence RC factorization, counts, per-record files, and the
+    same records sharded over 2 'ranks' by nolzss_b200.sharding.assign_records."""
+    from nolzss_b200.sharding import assign_records
+
+    recs = wl.c3_records(40, 3000, seed=3)
+    fa = tmp_path / "many.fasta"
+    with open(fa, "w") as f:
+        for rid, s in recs:
+            f.write(f">{rid} synthetic\n")
+            for k in range(0, len(s), 70):
+                f.write(s[k:k + 70].decode() + "\n")
+    per, ids = ext.factorize_fasta_dna_w_rc_per_sequence(str(fa))
+    assert ids == [r for r, _ in recs]
+    for got, (_, s) in zip(per, recs):
+        assert got == _rc4(orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s)))
+    counts, _, total = ext.count_factors_fasta_dna_w_rc_per_sequence(str(fa))
+    assert counts == [len(p) for p in per] and total == sum(counts)
+    out = tmp_path / "bins"
+    assert ext.parallel_write_factors_binary_file_fasta_dna_w_rc_per_sequence(str(fa), str(out), 8) == total
+    assert sorted(os.listdir(out)) == sorted(f"{r}.bin" for r, _ in recs)
+    shares = assign_records([len(s) for _, s in recs], 2)
+    merged = {}
+    for share in shares:                      # what each rank would compute, gathered by record index
+        for i in share:
+            merged[i] = ext.factorize_dna_w_rc(recs[i][1])
+    assert [merged[i] for i in range(len(recs))] == per

@@ -191,3 +191,44 @@ def test_group_sort_fallback_paths():
                 assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s), e), flags
     finally:
         L.check(L.load().nlz_set_debug_flags(L.context(), 0))
+
+
+def _check_cover_and_valid(x, f, samples=4000, seed=0):
+    n = len(x)
+    st, ln, rf = f[:, 0].astype(np.int64), f[:, 1].astype(np.int64), f[:, 2]
+    assert st[0] == 0 and np.all(st[1:] == st[:-1] + ln[:-1]) and st[-1] + ln[-1] == n
+    rng = np.random.default_rng(seed)
+    for k in rng.integers(0, len(f), samples):
+        s0, l0, r0 = int(st[k]), int(ln[k]), int(rf[k])
+        if r0 >> 63:
+            r0 &= (1 << 63) - 1
+            assert r0 + l0 <= s0 and np.array_equal(wl.revcomp(x[r0:r0 + l0]), x[s0:s0 + l0])
+        elif r0 == s0:
+            assert l0 == 1
+        else:
+            assert r0 + l0 <= s0 and np.array_equal(x[r0:r0 + l0], x[s0:s0 + l0])
+
+
+def test_chromosome_scale_properties_single_gpu():
+    """configs[3] at N=1 (scaled repeat recipe, 64-bit sort keys, radix fallback rounds, hard positions):
+    too large for the oracle in test time, so the size-independent properties are checked: the factors
+    tile the text in order and every sampled factor is a genuine non-overlapping (reverse-complement)
+    match; RC and general mode on the same text; count == number of triples."""
+    x = wl.planted_dna(60_000_000, 4, scale=10.0)
+    t = x.tobytes()
+    f = L.factorize_array(L.MODE_DNA_RC, t)
+    _check_cover_and_valid(x, f)
+    assert L.count(L.MODE_DNA_RC, t) == len(f)
+    assert L.stats()["key_bits"] == 64
+    g = L.factorize_array(L.MODE_GENERAL, t)
+    _check_cover_and_valid(x, g, seed=1)
+    assert not np.any(g[:, 2] >> np.uint64(63))
+    # RC candidates can only lengthen factors on average: never more factors than 1.02x the forward-only count
+    assert len(f) <= len(g) * 1.02
+
+
+def test_mid_scale_parity_64bit_keys():
+    """20 Mbp planted text: 64-bit initial keys + radix-sorted doubling rounds, full parity with the oracle."""
+    t = wl.planted_dna(20_000_000, 11, scale=4.0).tobytes()
+    assert np.array_equal(L.factorize_array(L.MODE_GENERAL, t), orc.factorize(t))
+    assert L.stats()["key_bits"] == 64
