@@ -63,6 +63,7 @@ typedef struct nlz_stats {
 /* ---- context ---------------------------------------------------------------------------- */
 int nlz_ctx_create(int device, nlz_ctx** out);
 void nlz_ctx_destroy(nlz_ctx* ctx);
+int nlz_ctx_device(nlz_ctx* ctx);
 const char* nlz_last_error(void);
 void nlz_free(void* p);
 int nlz_get_stats(nlz_ctx* ctx, nlz_stats* out);
@@ -162,8 +163,10 @@ int nlz_factorize_fasta(nlz_ctx* ctx, const char* ref_fasta, const char* fasta_p
                         uint64_t* n_sentinel_idx, nlz_fasta** ids_out);
 /* factorize_/count_factors_/write_factors_binary_file_fasta_dna_{w,no}_rc_per_sequence (+ parallel_ writers)
  *                                 src/cpp/fasta_processor.cpp:428-561, src/cpp/parallel_fasta_processor.cpp:268-465 */
+/* num_threads host threads (0 = min(records, 8)) pull records from a queue, each with its own stream and workspace on
+ * ctx's device -- the reference's worker pool over an atomic record index (parallel_fasta_processor.cpp:360-385) */
 int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int with_rc, int sanitize_mode,
-                                     const char* out_dir, int want_factors, uint64_t** out_triples,
+                                     const char* out_dir, int want_factors, int num_threads, uint64_t** out_triples,
                                      uint64_t** per_seq_counts, uint64_t* total_count, nlz_fasta** ids_out);
 
 /* ---- stage probes used by the parity tests (device results copied to host arrays) -------- */

@@ -43,6 +43,7 @@ class Stats(ctypes.Structure):
 SIGNATURES = {
     "nlz_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
     "nlz_ctx_destroy": (None, [_vp]),
+    "nlz_ctx_device": (ctypes.c_int, [_vp]),
     "nlz_last_error": (ctypes.c_char_p, []),
     "nlz_free": (None, [_vp]),
     "nlz_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
@@ -80,7 +81,8 @@ SIGNATURES = {
     "nlz_factorize_fasta": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
                                             _u64pp, _u64p, _u64pp, _u64p, ctypes.POINTER(_vp)]),
     "nlz_factorize_fasta_per_sequence": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
-                                                         ctypes.c_int, _u64pp, _u64pp, _u64p, ctypes.POINTER(_vp)]),
+                                                         ctypes.c_int, ctypes.c_int, _u64pp, _u64pp, _u64p,
+                                                         ctypes.POINTER(_vp)]),
     "nlz_debug_index": (ctypes.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "nlz_debug_sort_pairs_u64": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int, ctypes.c_int]),
     "nlz_debug_sort_pairs_u32": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int, ctypes.c_int]),

@@ -391,13 +391,13 @@ def parallel_write_factors_dna_w_reference_fasta_files_to_binary(reference_fasta
 
 
 # ----------------------------------------------------------------------------- per-sequence FASTA (:1215-1510)
-def _per_sequence(fasta_path, with_rc: bool, sanitize_mode: str, out_dir=None, want_factors=False):
+def _per_sequence(fasta_path, with_rc: bool, sanitize_mode: str, out_dir=None, want_factors=False, num_threads=0):
     flag = _mode_flag(sanitize_mode)
     out, counts, total = _U64P(), _U64P(), _U64(0)
     ids = ctypes.c_void_p()
     L.check(L.load().nlz_factorize_fasta_per_sequence(
         L.context(), _path(fasta_path), 1 if with_rc else 0, flag, None if out_dir is None else _path(out_dir),
-        1 if want_factors else 0, ctypes.byref(out) if want_factors else None, ctypes.byref(counts),
+        1 if want_factors else 0, int(num_threads), ctypes.byref(out) if want_factors else None, ctypes.byref(counts),
         ctypes.byref(total), ctypes.byref(ids)))
     names = _ids_of(ids)
     cnts = _take_u64(counts, len(names))
@@ -437,9 +437,9 @@ def write_factors_binary_file_fasta_dna_no_rc_per_sequence(fasta_path, out_dir, 
 
 def parallel_write_factors_binary_file_fasta_dna_w_rc_per_sequence(fasta_path, out_dir, num_threads=0,
                                                                    sanitize_mode="remove_ambiguous"):
-    return _per_sequence(fasta_path, True, sanitize_mode, out_dir=out_dir)[3]
+    return _per_sequence(fasta_path, True, sanitize_mode, out_dir=out_dir, num_threads=num_threads)[3]
 
 
 def parallel_write_factors_binary_file_fasta_dna_no_rc_per_sequence(fasta_path, out_dir, num_threads=0,
                                                                     sanitize_mode="remove_ambiguous"):
-    return _per_sequence(fasta_path, False, sanitize_mode, out_dir=out_dir)[3]
+    return _per_sequence(fasta_path, False, sanitize_mode, out_dir=out_dir, num_threads=num_threads)[3]

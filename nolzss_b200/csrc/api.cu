@@ -720,6 +720,8 @@ void nlz_ctx_destroy(nlz_ctx* c) {
     delete c;
 }
 
+int nlz_ctx_device(nlz_ctx* c) { return c ? c->device : -1; }
+
 int nlz_get_stats(nlz_ctx* c, nlz_stats* out) {
     if (!c || !out) { set_error("null argument"); return ERR_INVALID; }
     std::lock_guard<std::mutex> lock(c->mu);

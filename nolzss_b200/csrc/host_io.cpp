@@ -13,7 +13,9 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <sys/stat.h>
@@ -23,6 +25,7 @@
 namespace nlz {
 void set_error(const char* fmt, ...);   // api.cu
 }
+extern "C" const char* nlz_last_error(void);
 using nlz::set_error;
 
 namespace {
@@ -453,9 +456,13 @@ int nlz_factorize_fasta(nlz_ctx* ctx, const char* ref_fasta, const char* fasta_p
 // per-sequence FASTA (fasta_processor.cpp:428-561, parallel_fasta_processor.cpp:268-465).  Results are returned as one
 // concatenated triple array plus per-record counts; out_dir != NULL also writes <out_dir>/<sanitized id>.bin (V8).
 // The no-RC variants drop the last nucleotide of every record, like the reference (fasta_processor.cpp:469-471).
+// Records are independent, so -- like the reference's worker pool over an atomic record index
+// (parallel_fasta_processor.cpp:360-385) -- `num_threads` host threads pull records from a queue; each owns a context
+// (its own CUDA stream and workspace) on the same device, so the small per-record kernels of different records
+// overlap on the GPU.  num_threads = 0 picks min(records, 8).
 int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int with_rc, int sanitize_mode, const char* out_dir,
-                                     int want_factors, uint64_t** out, uint64_t** per_seq_counts, uint64_t* total,
-                                     nlz_fasta** ids_out) {
+                                     int want_factors, int num_threads, uint64_t** out, uint64_t** per_seq_counts,
+                                     uint64_t* total, nlz_fasta** ids_out) {
     if (!total) { set_error("null argument"); return NLZ_ERR_INVALID; }
     nlz_fasta* fa = nullptr;
     int rc = nlz_fasta_parse(fasta_path, sanitize_mode, &fa);
@@ -466,43 +473,71 @@ int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int w
             if (i == d.size() || d[i] == '/') { std::string sub = d.substr(0, i); if (!sub.empty()) mkdir(sub.c_str(), 0777); }
     }
     const size_t k = fa->seqs.size();
-    std::vector<uint64_t> counts(k, 0), all;
-    uint64_t sum = 0;
-    for (size_t i = 0; i < k; ++i) {
-        Triples t;
-        const std::string& q = fa->seqs[i];
-        const bool need_triples = want_factors || out_dir;
-        if (with_rc) {
-            if (need_triples) rc = nlz_factorize_mode(ctx, NLZ_MODE_DNA_RC, reinterpret_cast<const uint8_t*>(q.data()), q.size(), 0, &t.p, &t.n);
-            else rc = nlz_count_mode(ctx, NLZ_MODE_DNA_RC, reinterpret_cast<const uint8_t*>(q.data()), q.size(), 0, &t.n);
-        } else {
-            const uint64_t n = q.size() - 1;
-            if (need_triples) rc = nlz_factorize_mode(ctx, NLZ_MODE_GENERAL, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.p, &t.n);
-            else rc = nlz_count_mode(ctx, NLZ_MODE_GENERAL, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.n);
+    std::vector<uint64_t> counts(k, 0);
+    std::vector<std::vector<uint64_t>> per(want_factors ? k : 0);
+    size_t nthreads = num_threads > 0 ? (size_t)num_threads : 8;
+    if (nthreads > k) nthreads = k;
+    if (nthreads < 1) nthreads = 1;
+    const int device = nlz_ctx_device(ctx);
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(NLZ_OK);
+    std::vector<std::string> errors(nthreads);
+    auto worker = [&](size_t tix, nlz_ctx* my) {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= k || failed.load() != NLZ_OK) break;
+            Triples t;
+            const std::string& q = fa->seqs[i];
+            const bool need_triples = want_factors || out_dir;
+            int r;
+            const int mode = with_rc ? NLZ_MODE_DNA_RC : NLZ_MODE_GENERAL;
+            const uint64_t n = with_rc ? q.size() : q.size() - 1;
+            if (need_triples) r = nlz_factorize_mode(my, mode, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.p, &t.n);
+            else r = nlz_count_mode(my, mode, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.n);
+            if (r == NLZ_OK && out_dir) {
+                std::string safe = fa->ids[i];                         // parallel_fasta_processor.cpp:307-317
+                for (char& c : safe)
+                    if (c == '/' || c == '\\' || c == ':' || c == '*' || c == '?' || c == '"' || c == '<' || c == '>' || c == '|' || c == ' ') c = '_';
+                std::string path = std::string(out_dir) + "/" + safe + ".bin";
+                std::string meta = fa->ids[i];
+                meta.push_back('\0');
+                r = write_factor_file(path.c_str(), t.p, t.n, meta, 1, 0, sum_lengths(t.p, t.n));   // :268-297
+            }
+            if (r != NLZ_OK) { errors[tix] = nlz_last_error(); failed.store(r); break; }
+            counts[i] = t.n;
+            if (want_factors && t.n) per[i].assign(t.p, t.p + 3 * t.n);
         }
+    };
+    if (nthreads == 1) {
+        worker(0, ctx);
+    } else {
+        std::vector<nlz_ctx*> ctxs(nthreads, nullptr);
+        ctxs[0] = ctx;
+        for (size_t t = 1; t < nthreads && rc == NLZ_OK; ++t) rc = nlz_ctx_create(device, &ctxs[t]);
+        if (rc == NLZ_OK) {
+            std::vector<std::thread> pool;
+            for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(worker, t, ctxs[t]);
+            for (auto& th : pool) th.join();
+        }
+        for (size_t t = 1; t < nthreads; ++t) nlz_ctx_destroy(ctxs[t]);
         if (rc != NLZ_OK) { delete fa; return rc; }
-        counts[i] = t.n;
-        sum += t.n;
-        if (out_dir) {
-            std::string safe = fa->ids[i];                             // parallel_fasta_processor.cpp:307-317
-            for (char& c : safe)
-                if (c == '/' || c == '\\' || c == ':' || c == '*' || c == '?' || c == '"' || c == '<' || c == '>' || c == '|' || c == ' ') c = '_';
-            std::string path = std::string(out_dir) + "/" + safe + ".bin";
-            std::string meta = fa->ids[i];
-            meta.push_back('\0');
-            rc = write_factor_file(path.c_str(), t.p, t.n, meta, 1, 0, sum_lengths(t.p, t.n));   // :268-297
-            if (rc != NLZ_OK) { delete fa; return rc; }
-        }
-        if (want_factors && t.n) all.insert(all.end(), t.p, t.p + 3 * t.n);
     }
+    if (failed.load() != NLZ_OK) {
+        for (const auto& e : errors) if (!e.empty()) { set_error("%s", e.c_str()); break; }
+        delete fa;
+        return failed.load();
+    }
+    uint64_t sum = 0;
+    for (uint64_t c : counts) sum += c;
     *total = sum;
     if (per_seq_counts) {
         *per_seq_counts = static_cast<uint64_t*>(malloc((k + 1) * 8));
         memcpy(*per_seq_counts, counts.data(), k * 8);
     }
     if (out) {
-        *out = static_cast<uint64_t*>(malloc((all.size() + 1) * 8));
-        if (!all.empty()) memcpy(*out, all.data(), all.size() * 8);
+        *out = static_cast<uint64_t*>(malloc((sum * 3 + 1) * 8));
+        uint64_t* w = *out;
+        for (const auto& v : per) { if (!v.empty()) memcpy(w, v.data(), v.size() * 8); w += v.size(); }
     }
     if (ids_out) *ids_out = fa; else delete fa;
     return NLZ_OK;
