@@ -45,6 +45,20 @@ def _text_for_rank(rank: int) -> bytes:
     return wl.c2_text(N_BASES, 2 + rank)
 
 
+def _traffic(kernel_class: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    --set full capture (profiles/r1_traffic.json, written by scripts/summarize_profiles.py); None if not captured."""
+    names = {"tile_sort": "k_tile_sort", "gather_rank": "k_gather_rank", "lpnf_rank": "k_lpnf_rank",
+             "lcp_kasai": "k_lcp_kasai", "radix_scatter": "k_rs_scatter", "node_tables": "k_node_tables"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(names.get(kernel_class, ""))
+        return (e["dram_bytes_per_launch"], e["launches_captured"]) if e else (None, 0)
+    except Exception:
+        return (None, 0)
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -263,6 +277,7 @@ def run_ours(args):
     dom = max(ksum, key=lambda k: ksum[k]["ms"])
     d = ksum[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    traffic, traffic_launches = _traffic(dom)
     total_kernel_ms = sum(v["ms"] for v in ksum.values())
     classes = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] // prof_steps,
                    "alg_GB_per_step": v["bytes"] / prof_steps / 1e9,
@@ -280,7 +295,9 @@ def run_ours(args):
                 "ms_per_step": e2e_ms_max / args.steps},
         "gpu_launches": int(launches_per_step) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": (f"ncu --set full, mean of {traffic_launches} captured launches "
+                                        "(profiles/r1_full.md, profiles/r1_traffic.json)") if traffic else None,
                      "kernel_share_of_step": d["ms"] / total_kernel_ms if total_kernel_ms else None,
                      "alg_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
                      "avg_launch_us": 1e3 * d["ms"] / max(d["launches"], 1)},
