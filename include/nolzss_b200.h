@@ -92,6 +92,15 @@ int nlz_count_mode(nlz_ctx* ctx, int mode, const uint8_t* text, uint64_t n, uint
 int nlz_factorize_device(nlz_ctx* ctx, int mode, const void* d_text, uint64_t n, uint64_t start_pos,
                          void* cuda_stream, void* d_out_triples, uint64_t capacity, uint64_t* out_count);
 
+/* ---- batch of independent records in ONE pipeline run (segmented suffix array: the record id is the leading
+ * sort-key field) -- the per-record loops of factorize_fasta_dna_{w,no}_rc_per_sequence and their count_/write_
+ * variants, src/cpp/fasta_processor.cpp:428-476, :505-561, src/cpp/parallel_fasta_processor.cpp:360-465.
+ * Record b is concat[offsets[b], offsets[b] + lens[b]); with_rc != 0 runs nolzss_dna_w_rc on every record, else
+ * nolzss.  Factors come back concatenated in record order, in record-local coordinates; per_record_counts
+ * (k entries, caller-provided) receives the number of factors of each record.  out_triples == NULL: count only. */
+int nlz_factorize_batch(nlz_ctx* ctx, int with_rc, const uint8_t* concat, const uint64_t* offsets, const uint64_t* lens,
+                        uint64_t k, uint64_t** out_triples, uint64_t* per_record_counts, uint64_t* total);
+
 /* ---- named entry points: one per reference function on the path ------------------------- */
 /* noLZSS::factorize(std::string_view, start_pos)                 src/cpp/factorizer.cpp:378-384 */
 int nlz_factorize(nlz_ctx* ctx, const uint8_t* text, uint64_t n, uint64_t start_pos,

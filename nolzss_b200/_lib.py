@@ -58,6 +58,7 @@ SIGNATURES = {
     "nlz_factorize_mode_into": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _vp, _u64, _u64p]),
     "nlz_count_mode": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _u64p]),
     "nlz_factorize_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _vp, _vp, _u64, _u64p]),
+    "nlz_factorize_batch": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _u64, _u64pp, _vp, _u64p]),
     "nlz_factorize": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64pp, _u64p]),
     "nlz_count_factors": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64p]),
     "nlz_factorize_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64pp, _u64p]),
@@ -166,6 +167,36 @@ def factorize_array(mode: int, data, start_pos: int = 0, device: int | None = No
     finally:
         L.nlz_free(out)
     return arr
+
+
+def factorize_batch(records, with_rc: bool, want_factors: bool = True, device: int | None = None):
+    """Independent records in one segmented pipeline run (nlz_factorize_batch).
+
+    Returns (triples, counts): record-local (z, 3) uint64 triples concatenated in record order (None when
+    want_factors is False) and the per-record factor counts."""
+    L = load()
+    lens = np.array([len(r) for r in records], dtype=np.uint64)
+    offs = np.zeros(len(records), dtype=np.uint64)
+    if len(records):
+        offs[1:] = np.cumsum(lens)[:-1]
+    concat = np.frombuffer(b"".join(bytes(r) for r in records), dtype=np.uint8)
+    counts = np.zeros(max(len(records), 1), dtype=np.uint64)
+    out = _u64p()
+    total = _u64(0)
+    check(L.nlz_factorize_batch(context(device), 1 if with_rc else 0, concat.ctypes.data if concat.size else None,
+                                offs.ctypes.data, lens.ctypes.data, len(records),
+                                ctypes.byref(out) if want_factors else None, counts.ctypes.data, ctypes.byref(total)))
+    counts = counts[:len(records)]
+    if not want_factors:
+        return None, counts
+    z = total.value
+    if z == 0:
+        return np.zeros((0, 3), dtype=np.uint64), counts
+    try:
+        arr = np.ctypeslib.as_array(out, shape=(z * 3,)).copy().reshape(z, 3)
+    finally:
+        L.nlz_free(out)
+    return arr, counts
 
 
 def count(mode: int, data, start_pos: int = 0, device: int | None = None) -> int:

@@ -61,6 +61,8 @@ struct Workspace {
     u32* tf[TREE_MAX_LEVELS] = {};
     u32* tr[TREE_MAX_LEVELS] = {};
     u32 *PSV = nullptr, *NSV = nullptr, *MINF = nullptr;   // per-node tables of stage 3
+    // batch mode only: record id per text position, record geometry, factor index of every record's sentinel
+    u32 *REC = nullptr, *FSTART = nullptr, *FLEN = nullptr, *INOFF = nullptr, *SENTIDX = nullptr;
 };
 
 }  // namespace nlz
@@ -84,7 +86,7 @@ struct nlz_ctx {
 
 namespace nlz {
 
-static size_t workspace_bytes_for(u64 n1) {
+static size_t workspace_bytes_for(u64 n1, u64 nrec) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
     t += al(n1 + 192);               // X
@@ -100,11 +102,12 @@ static size_t workspace_bytes_for(u64 n1) {
         c = (c + 31) / 32;
         t += al((c + 72) * 4) * 3;
     }
+    if (nrec) t += al((n1 + 72) * 4) + al((nrec + 1) * 4) * 4;   // REC, FSTART, FLEN, INOFF, SENTIDX
     return t + 4096;
 }
 
-static int ensure_workspace(nlz_ctx* c, u64 n1) {
-    size_t need = workspace_bytes_for(n1);
+static int ensure_workspace(nlz_ctx* c, u64 n1, u64 nrec = 0) {
+    size_t need = workspace_bytes_for(n1, nrec);
     if (need > c->arena.cap) {
         if (c->arena.base) {
             NLZ_CK(cudaDeviceSynchronize());
@@ -152,6 +155,13 @@ static int ensure_workspace(nlz_ctx* c, u64 n1) {
         w.tf[lev] = a.take<u32>(cnt + 72);
         w.tr[lev] = a.take<u32>(cnt + 72);
     }
+    if (nrec) {
+        w.REC = a.take<u32>(n1 + 72);
+        w.FSTART = a.take<u32>(nrec + 1);
+        w.FLEN = a.take<u32>(nrec + 1);
+        w.INOFF = a.take<u32>(nrec + 1);
+        w.SENTIDX = a.take<u32>(nrec + 1);
+    }
     c->stats.workspace_bytes = c->arena.cap;
     return OK;
 }
@@ -184,6 +194,49 @@ __global__ void k_zero_pad(u8* __restrict__ X, u64 L) {
 
 __global__ void k_set_u32(u32* p, u32 v) { *p = v; }
 
+// Batch mode (per-sequence FASTA entry points, fasta_processor.cpp:428-561): k independent records in
+// ONE indexed text.  Forward half  T1 s T2 s .. Tk s  at [0, N]; with RC the rc half
+// rc(Tk) s .. rc(T1) s  at [N+1, 2N+1] -- the record order of prepare_multiple_dna_sequences_w_rc
+// (factorizer.cpp:150-169), so the mirror e = 2N - p of the single-text path holds for every record.
+// All sentinels carry BATCH_SENT; REC[p] (record id, the leading sort-key field) keeps the records apart.
+constexpr u8 BATCH_SENT = 1;
+__global__ void __launch_bounds__(256)
+k_prepare_batch(const u8* __restrict__ T, const u32* __restrict__ inoff, const u32* __restrict__ fstart,
+                const u32* __restrict__ flen, u32 k, u32 N, bool rc, u8* __restrict__ X, u32* __restrict__ REC,
+                u32* __restrict__ first_bad) {
+    const u32 p = blockIdx.x * 256 + threadIdx.x;
+    if (p > N) return;
+    u32 lo = 0, hi = k - 1;                      // largest b with fstart[b] <= p
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (fstart[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    const u32 b = lo, fs = fstart[b], off = p - fs;
+    REC[p] = b;
+    if (off == flen[b]) { X[p] = BATCH_SENT; }
+    else {
+        const u8 c = T[(u64)inoff[b] + off];
+        u8 u = c, m = BATCH_SENT;
+        switch (c) {
+            case 'A': case 'a': u = 'A'; m = 'T'; break;
+            case 'C': case 'c': u = 'C'; m = 'G'; break;
+            case 'G': case 'g': u = 'G'; m = 'C'; break;
+            case 'T': case 't': u = 'T'; m = 'A'; break;
+            default: atomicMin(first_bad, p); break;
+        }
+        X[p] = u;
+        if (rc) {
+            X[2 * (u64)N - p] = m;
+            REC[2 * (u64)N - p] = b;
+            if (off == 0) {                       // sentinel that ends rc(T_b): mirror of the sentinel before T_b
+                X[2 * (u64)N - fs + 1] = BATCH_SENT;
+                REC[2 * (u64)N - fs + 1] = b;
+            }
+        }
+    }
+    if (p == 0) REC[rc ? 2 * (u64)N + 2 : (u64)N + 1] = k;   // terminator sorts after every record
+}
+
 // ---------------------------------------------------------------- pipeline
 struct Problem {
     int mode;
@@ -194,7 +247,16 @@ struct Problem {
     u32 N;          // RC: |S|/2-1
     u64 start_pos;
     bool rc;
+    // batch mode (records are independent; see k_prepare_batch)
+    u32 nrec = 0;
+    const u32 *h_inoff = nullptr, *h_fstart = nullptr, *h_flen = nullptr;
 };
+
+static int bits_for(u32 maxval) {
+    int nb = 1;
+    while (nb < 32 && (maxval >> nb) != 0) ++nb;
+    return nb;
+}
 
 static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout& lay) {
     int sigma = 0;
@@ -214,19 +276,13 @@ static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout
         use32 = space >= 16.0 * (double)n1;
     }
     if (use32) {
-        lay.key_bits = 32; lay.b = b; lay.W = w32; lay.D = 4;
+        lay.key_bits = 32; lay.b = b; lay.W = w32; lay.D = 4; lay.R = 0;
     } else {
         int w64 = 59 / b;
         if (w64 > 29) w64 = 29;
-        lay.key_bits = 64; lay.b = b; lay.W = w64; lay.D = 5;
+        lay.key_bits = 64; lay.b = b; lay.W = w64; lay.D = 5; lay.R = 0;
     }
     return OK;
-}
-
-static int bits_for(u32 maxval) {
-    int nb = 1;
-    while (nb < 32 && (maxval >> nb) != 0) ++nb;
-    return nb;
 }
 
 template <typename KeyT>
@@ -239,10 +295,11 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     KeyT* k[2] = {reinterpret_cast<KeyT*>(w.KEY[0]), reinterpret_cast<KeyT*>(w.KEY[1])};
     u32* v[2] = {w.VAL[0], w.VAL[1]};
     KL(P, KC_KEYS, (u64)n1 * (1 + kb + 4), st,
-       (k_build_keys<KeyT><<<ceil_div_u32(n1, 2048), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, k[0], v[0])));
+       (k_build_keys<KeyT><<<ceil_div_u32(n1, 2048), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pb.nrec ? w.REC : nullptr,
+                                                                   k[0], v[0])));
     NLZ_CK(cudaEventRecord(c->ev[EV_KEYS], st));
     DigitPlan plan;
-    const int used_lo = lay.key_bits - lay.W * lay.b;   // lowest symbol bit
+    const int used_lo = lay.key_bits - lay.R - lay.W * lay.b;   // lowest symbol bit
     if (used_lo - lay.D >= 6) {                         // wide unused gap: skip it
         plan_add_range(plan, 0, lay.D);                 // sentinel-offset field
         plan_add_range(plan, used_lo, lay.key_bits);    // symbols
@@ -283,7 +340,17 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     // ---- S0: text into X
     P.begin(st);
     u32 prep_launches = 2;
-    if (pb.mode == NLZ_MODE_DNA_RC) {
+    if (pb.nrec) {
+        u8* tmp = reinterpret_cast<u8*>(w.KEY[1]);
+        NLZ_CK(cudaMemcpyAsync(tmp, src, pb.n_in, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.INOFF, pb.h_inoff, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.FSTART, pb.h_fstart, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.FLEN, pb.h_flen, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
+        k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, 0xFFFFFFFFu);
+        k_prepare_batch<<<ceil_div_u32((u64)pb.N + 1, 256), 256, 0, st>>>(tmp, w.INOFF, w.FSTART, w.FLEN, pb.nrec, pb.N,
+                                                                        pb.rc, w.X, w.REC, w.CTR + 8);
+        prep_launches += 2;
+    } else if (pb.mode == NLZ_MODE_DNA_RC) {
         const u8* dT = static_cast<const u8*>(src);
         if (src_on_host) {
             u8* tmp = reinterpret_cast<u8*>(w.KEY[1]);
@@ -307,11 +374,18 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     }
     P.end(KC_PREPARE, pb.n_in + 2 * pb.L, st, prep_launches);
     NLZ_CK(cudaMemcpyAsync(c->h_pinned + 16, w.BYTEHIST, 256 * 4, cudaMemcpyDeviceToHost, st));
-    if (pb.mode == NLZ_MODE_DNA_RC) NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
+    if (pb.mode == NLZ_MODE_DNA_RC || pb.nrec) NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaEventRecord(c->ev[EV_PREP], st));
     NLZ_CK(cudaStreamSynchronize(st));
     S.host_syncs += 1;
-    if (pb.mode == NLZ_MODE_DNA_RC && c->h_pinned[8] != 0xFFFFFFFFu) {
+    if (pb.nrec && c->h_pinned[8] != 0xFFFFFFFFu) {
+        u32 bad = c->h_pinned[8], b = 0;
+        while (b + 1 < pb.nrec && pb.h_fstart[b + 1] <= bad) ++b;
+        set_error("Invalid nucleotide '%c' found in sequence %u",
+                  (char)static_cast<const u8*>(src)[(u64)pb.h_inoff[b] + (bad - pb.h_fstart[b])], b);
+        return ERR_RUNTIME;
+    }
+    if (pb.mode == NLZ_MODE_DNA_RC && !pb.nrec && c->h_pinned[8] != 0xFFFFFFFFu) {
         u32 bad = c->h_pinned[8];
         u8 ch = 0;
         if (src_on_host) ch = static_cast<const u8*>(src)[bad];
@@ -324,7 +398,16 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     // ---- S1: suffix array
     ClassTable tab;
     KeyLayout lay;
-    choose_layout(c->h_pinned + 16, n1, tab, lay);
+    if (pb.nrec) {
+        // records are told apart by the leading record-id field; every byte but ACGT is a sentinel
+        for (int ch = 0; ch < 256; ++ch) tab.cls[ch] = (u8)SENT_CLASS;
+        tab.cls['A'] = 0; tab.cls['C'] = 1; tab.cls['G'] = 2; tab.cls['T'] = 3;
+        lay.key_bits = 64; lay.b = 2; lay.D = 5; lay.R = bits_for(pb.nrec);
+        lay.W = (59 - lay.R) / 2;
+        if (lay.W > 29) lay.W = 29;
+    } else {
+        choose_layout(c->h_pinned + 16, n1, tab, lay);
+    }
     S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
     int cur = 0;
     u32 m = 0, maxg = 0;
@@ -398,8 +481,14 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
     // ---- S2: LCP
-    KL(P, KC_LCP, (u64)n1 * 28, st,
-       (k_lcp_kasai<<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP)));
+    BatchView bv;
+    bv.REC = w.REC; bv.fstart = w.FSTART; bv.flen = w.FLEN; bv.k = pb.nrec; bv.N = pb.rc ? pb.N : 0xFFFFFFFFu;
+    if (pb.nrec)
+        KL(P, KC_LCP, (u64)n1 * 36, st,
+           (k_lcp_kasai<true><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv)));
+    else
+        KL(P, KC_LCP, (u64)n1 * 28, st,
+           (k_lcp_kasai<false><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv)));
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
     if (stop_after_index) {
         NLZ_CK(cudaGetLastError());
@@ -522,9 +611,10 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     }
     *out_count = z;
     S.n_factors = z;
-    if (!count_only) {
+    if (!count_only || pb.nrec) {   // batch mode always runs the emit pass: it publishes the per-record boundaries
         u64* dst = d_out;
-        if (!dst) {   // host-buffer entry points: library-owned device output
+        if (count_only) { dst = nullptr; capacity = 0; }
+        else if (!dst) {   // host-buffer entry points: library-owned device output
             if (z > c->d_out_cap) {
                 if (c->d_out) NLZ_CK(cudaFree(c->d_out));
                 c->d_out = nullptr; c->d_out_cap = 0;
@@ -535,14 +625,19 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
             dst = c->d_out;
             capacity = c->d_out_cap;
         }
-        if (z > capacity) {
+        if (!count_only && z > capacity) {
             set_error("output capacity %llu factors is too small for %llu factors",
                       (unsigned long long)capacity, (unsigned long long)z);
             return ERR_RUNTIME;
         }
         P.begin(st);
-        if (pb.rc) k_chain_emit<true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity);
-        else k_chain_emit<false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity);
+        if (pb.nrec) {
+            if (pb.rc) k_chain_emit<true, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
+            else k_chain_emit<false, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
+        } else {
+            if (pb.rc) k_chain_emit<true, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
+            else k_chain_emit<false, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
+        }
         P.end(KC_CHAIN, (u64)nfac / 8 + z * 32, st);
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
@@ -789,6 +884,69 @@ int nlz_factorize_device(nlz_ctx* c, int mode, const void* d_text, uint64_t n, u
     NLZ_CK(cudaStreamSynchronize(st));
     finish_stats(c, pb);
     *out_count = z;
+    return OK;
+}
+
+int nlz_factorize_batch(nlz_ctx* c, int with_rc, const uint8_t* concat, const uint64_t* offsets, const uint64_t* lens,
+                        uint64_t k, uint64_t** out_triples, uint64_t* per_record_counts, uint64_t* total) {
+    if (!c || !total || !per_record_counts || (k && (!offsets || !lens))) { set_error("null argument"); return ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    *total = 0;
+    if (out_triples) *out_triples = nullptr;
+    std::vector<u32> rec, inoff, fstart, flen;     // non-empty records only (empty ones yield no factors)
+    u64 fwd = 0, hi = 0;
+    for (u64 b = 0; b < k; ++b) {
+        per_record_counts[b] = 0;
+        if (lens[b] == 0) continue;
+        if (offsets[b] + lens[b] > 0xFFFFFFF0ull || fwd + lens[b] + 1 > 0x7FFFFFF0ull) {
+            set_error("batch of %llu records exceeds the 32-bit index path; split it", (unsigned long long)k);
+            return ERR_INVALID;
+        }
+        rec.push_back((u32)b);
+        inoff.push_back((u32)offsets[b]);
+        fstart.push_back((u32)fwd);
+        flen.push_back((u32)lens[b]);
+        fwd += lens[b] + 1;
+        if (offsets[b] + lens[b] > hi) hi = offsets[b] + lens[b];
+    }
+    reset_stats(c);
+    if (rec.empty()) return OK;
+    if (rec.size() >= (1u << 24)) { set_error("batch of %zu records is too large; split it", rec.size()); return ERR_INVALID; }
+    Problem pb;
+    pb.mode = with_rc ? NLZ_MODE_RC_PREPARED : NLZ_MODE_GENERAL;
+    pb.rc = with_rc != 0;
+    pb.n_in = hi;
+    pb.N = (u32)(fwd - 1);
+    pb.nfac = pb.N;                    // every position but the last forward sentinel (factorizer_core.hpp:195, :241)
+    pb.L = with_rc ? 2 * fwd : fwd;
+    pb.start_pos = 0;
+    if (pb.L + 1 >= 0xFFFFFFF0ull) { set_error("batch exceeds the 32-bit index path; split it"); return ERR_INVALID; }
+    pb.n1 = (u32)(pb.L + 1);
+    pb.nrec = (u32)rec.size();
+    pb.h_inoff = inoff.data(); pb.h_fstart = fstart.data(); pb.h_flen = flen.data();
+    NLZ_TRY(ensure_workspace(c, pb.n1, pb.nrec));
+    cudaStream_t st = c->own_stream;
+    u64 z = 0;
+    NLZ_TRY(run_pipeline(c, pb, concat, true, st, nullptr, 0, out_triples == nullptr, false, false, &z));
+    std::vector<u32> sentidx(pb.nrec, 0);
+    if (pb.nrec > 1) NLZ_CK(cudaMemcpyAsync(sentidx.data(), c->ws.SENTIDX, (size_t)(pb.nrec - 1) * 4, cudaMemcpyDeviceToHost, st));
+    const u64 zout = z - (pb.nrec - 1);
+    if (out_triples && zout) {
+        u64* dst = static_cast<u64*>(malloc((size_t)zout * 24));
+        if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)zout); return ERR_RUNTIME; }
+        *out_triples = dst;
+        NLZ_CK(cudaMemcpyAsync(dst, c->d_out, (size_t)zout * 24, cudaMemcpyDeviceToHost, st));
+    }
+    NLZ_CK(cudaStreamSynchronize(st));
+    finish_stats(c, pb);
+    u64 prev = 0;                      // index (sentinel factors included) of the record's first factor
+    for (u32 j = 0; j < pb.nrec; ++j) {
+        const u64 end = (j + 1 < pb.nrec) ? sentidx[j] : z;
+        per_record_counts[rec[j]] = end - prev;
+        prev = end + 1;
+    }
+    *total = zout;
     return OK;
 }
 

@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "lpnf.cuh"
+#include "sa.cuh"
 
 namespace nlz {
 
@@ -136,10 +137,14 @@ k_chain_mark(const u64* __restrict__ LR, u32 nfac, const u8* __restrict__ REACH,
     }
 }
 
-template <bool RC>
+// BATCH: positions are translated to record-local coordinates; the literal factor of every interior
+// sentinel (one per record but the last) is dropped -- record b's factors are preceded by exactly b of
+// them, so the output index is idx - b -- and its index is published so that the host can derive the
+// per-record factor counts.
+template <bool RC, bool BATCH>
 __global__ void __launch_bounds__(CH_THREADS)
 k_chain_emit(const u64* __restrict__ LR, u32 nfac, const u32* __restrict__ MASK, const u32* __restrict__ OFF,
-             u64* __restrict__ out, u64 out_capacity) {
+             u64* __restrict__ out, u64 out_capacity, BatchView bv, u32* __restrict__ sentidx) {
     __shared__ u32 wpre[CH_CHUNK / 32];
     const u32 base = blockIdx.x * CH_CHUNK;
     const u32 lane = threadIdx.x & 31;
@@ -163,9 +168,17 @@ k_chain_emit(const u64* __restrict__ LR, u32 nfac, const u32* __restrict__ MASK,
         if ((wbits >> lane) & 1u) {
             u32 pos = base + o;
             u64 idx = off + wpre[wi] + __popc(wbits & lanemask_lt());
+            u32 shift = 0;
+            if (BATCH) {
+                const u32 b = bv.REC[pos];
+                shift = bv.fstart[b];
+                if (pos == shift + bv.flen[b]) { sentidx[b] = (u32)idx; continue; }
+                idx -= b;
+            }
             if (idx < out_capacity) {
                 u64 lr = LR[pos];
                 u32 ref32 = (u32)(lr >> 32);
+                if (BATCH) { ref32 -= shift; pos -= shift; }
                 u64 ref = RC ? ((u64)(ref32 & ~LR_RC_FLAG) | ((ref32 & LR_RC_FLAG) ? (1ULL << 63) : 0ULL))
                              : (u64)ref32;
                 out[3 * idx + 0] = pos;

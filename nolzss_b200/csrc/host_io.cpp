@@ -456,10 +456,9 @@ int nlz_factorize_fasta(nlz_ctx* ctx, const char* ref_fasta, const char* fasta_p
 // per-sequence FASTA (fasta_processor.cpp:428-561, parallel_fasta_processor.cpp:268-465).  Results are returned as one
 // concatenated triple array plus per-record counts; out_dir != NULL also writes <out_dir>/<sanitized id>.bin (V8).
 // The no-RC variants drop the last nucleotide of every record, like the reference (fasta_processor.cpp:469-471).
-// Records are independent, so -- like the reference's worker pool over an atomic record index
-// (parallel_fasta_processor.cpp:360-385) -- `num_threads` host threads pull records from a queue; each owns a context
-// (its own CUDA stream and workspace) on the same device, so the small per-record kernels of different records
-// overlap on the GPU.  num_threads = 0 picks min(records, 8).
+// Records are independent: instead of the reference's worker pool of per-record index builds
+// (parallel_fasta_processor.cpp:360-385) the records are concatenated and run through ONE segmented pipeline per chunk
+// (nlz_factorize_batch); `num_threads` host threads (0 = 8) only write the per-record files.
 int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int with_rc, int sanitize_mode, const char* out_dir,
                                      int want_factors, int num_threads, uint64_t** out, uint64_t** per_seq_counts,
                                      uint64_t* total, nlz_fasta** ids_out) {
@@ -473,71 +472,76 @@ int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int w
             if (i == d.size() || d[i] == '/') { std::string sub = d.substr(0, i); if (!sub.empty()) mkdir(sub.c_str(), 0777); }
     }
     const size_t k = fa->seqs.size();
+    const bool need_triples = want_factors || out_dir;
     std::vector<uint64_t> counts(k, 0);
-    std::vector<std::vector<uint64_t>> per(want_factors ? k : 0);
-    size_t nthreads = num_threads > 0 ? (size_t)num_threads : 8;
-    if (nthreads > k) nthreads = k;
-    if (nthreads < 1) nthreads = 1;
-    const int device = nlz_ctx_device(ctx);
-    std::atomic<size_t> next(0);
-    std::atomic<int> failed(NLZ_OK);
-    std::vector<std::string> errors(nthreads);
-    auto worker = [&](size_t tix, nlz_ctx* my) {
-        for (;;) {
-            const size_t i = next.fetch_add(1);
-            if (i >= k || failed.load() != NLZ_OK) break;
-            Triples t;
-            const std::string& q = fa->seqs[i];
-            const bool need_triples = want_factors || out_dir;
-            int r;
-            const int mode = with_rc ? NLZ_MODE_DNA_RC : NLZ_MODE_GENERAL;
-            const uint64_t n = with_rc ? q.size() : q.size() - 1;
-            if (need_triples) r = nlz_factorize_mode(my, mode, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.p, &t.n);
-            else r = nlz_count_mode(my, mode, reinterpret_cast<const uint8_t*>(q.data()), n, 0, &t.n);
-            if (r == NLZ_OK && out_dir) {
+    std::vector<uint64_t> all;                                     // concatenated record-local triples, record order
+    constexpr uint64_t kChunkSuffixes = 1ull << 28, kChunkRecords = 1ull << 20;
+    size_t i0 = 0;
+    while (i0 < k && rc == NLZ_OK) {
+        std::string concat;
+        std::vector<uint64_t> offs, lens;
+        uint64_t suffixes = 0;
+        size_t i1 = i0;
+        while (i1 < k && (i1 == i0 || (suffixes < kChunkSuffixes && i1 - i0 < kChunkRecords))) {
+            const std::string& q = fa->seqs[i1];
+            const uint64_t n = with_rc ? q.size() : q.size() - 1;  // fasta_processor.cpp:469-471 (no-RC drops the last base)
+            offs.push_back(concat.size());
+            lens.push_back(n);
+            concat.append(q.data(), n);
+            suffixes += (n + 1) * (with_rc ? 2 : 1);
+            ++i1;
+        }
+        Triples t;
+        rc = nlz_factorize_batch(ctx, with_rc, reinterpret_cast<const uint8_t*>(concat.data()), offs.data(), lens.data(),
+                                 i1 - i0, need_triples ? &t.p : nullptr, counts.data() + i0, &t.n);
+        if (rc == NLZ_OK && need_triples && t.n) all.insert(all.end(), t.p, t.p + 3 * t.n);
+        i0 = i1;
+    }
+    if (rc != NLZ_OK) { delete fa; return rc; }
+    std::vector<uint64_t> first(k + 1, 0);                         // first factor of every record in `all`
+    for (size_t i = 0; i < k; ++i) first[i + 1] = first[i] + counts[i];
+    if (out_dir) {
+        size_t nthreads = num_threads > 0 ? (size_t)num_threads : 8;
+        if (nthreads > k) nthreads = k;
+        if (nthreads < 1) nthreads = 1;
+        std::atomic<size_t> next(0);
+        std::atomic<int> failed(NLZ_OK);
+        std::vector<std::string> errors(nthreads);
+        auto writer = [&](size_t tix) {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= k || failed.load() != NLZ_OK) break;
                 std::string safe = fa->ids[i];                         // parallel_fasta_processor.cpp:307-317
                 for (char& c : safe)
                     if (c == '/' || c == '\\' || c == ':' || c == '*' || c == '?' || c == '"' || c == '<' || c == '>' || c == '|' || c == ' ') c = '_';
                 std::string path = std::string(out_dir) + "/" + safe + ".bin";
                 std::string meta = fa->ids[i];
                 meta.push_back('\0');
-                r = write_factor_file(path.c_str(), t.p, t.n, meta, 1, 0, sum_lengths(t.p, t.n));   // :268-297
+                const uint64_t* tp = all.data() + 3 * first[i];
+                int r = write_factor_file(path.c_str(), tp, counts[i], meta, 1, 0, sum_lengths(tp, counts[i]));   // :268-297
+                if (r != NLZ_OK) { errors[tix] = nlz_last_error(); failed.store(r); break; }
             }
-            if (r != NLZ_OK) { errors[tix] = nlz_last_error(); failed.store(r); break; }
-            counts[i] = t.n;
-            if (want_factors && t.n) per[i].assign(t.p, t.p + 3 * t.n);
-        }
-    };
-    if (nthreads == 1) {
-        worker(0, ctx);
-    } else {
-        std::vector<nlz_ctx*> ctxs(nthreads, nullptr);
-        ctxs[0] = ctx;
-        for (size_t t = 1; t < nthreads && rc == NLZ_OK; ++t) rc = nlz_ctx_create(device, &ctxs[t]);
-        if (rc == NLZ_OK) {
+        };
+        if (nthreads == 1) writer(0);
+        else {
             std::vector<std::thread> pool;
-            for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(worker, t, ctxs[t]);
+            for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(writer, t);
             for (auto& th : pool) th.join();
         }
-        for (size_t t = 1; t < nthreads; ++t) nlz_ctx_destroy(ctxs[t]);
-        if (rc != NLZ_OK) { delete fa; return rc; }
+        if (failed.load() != NLZ_OK) {
+            for (const auto& e : errors) if (!e.empty()) { set_error("%s", e.c_str()); break; }
+            delete fa;
+            return failed.load();
+        }
     }
-    if (failed.load() != NLZ_OK) {
-        for (const auto& e : errors) if (!e.empty()) { set_error("%s", e.c_str()); break; }
-        delete fa;
-        return failed.load();
-    }
-    uint64_t sum = 0;
-    for (uint64_t c : counts) sum += c;
-    *total = sum;
+    *total = first[k];
     if (per_seq_counts) {
         *per_seq_counts = static_cast<uint64_t*>(malloc((k + 1) * 8));
         memcpy(*per_seq_counts, counts.data(), k * 8);
     }
     if (out) {
-        *out = static_cast<uint64_t*>(malloc((sum * 3 + 1) * 8));
-        uint64_t* w = *out;
-        for (const auto& v : per) { if (!v.empty()) memcpy(w, v.data(), v.size() * 8); w += v.size(); }
+        *out = static_cast<uint64_t*>(malloc((all.size() + 1) * 8));
+        if (!all.empty()) memcpy(*out, all.data(), all.size() * 8);
     }
     if (ids_out) *ids_out = fa; else delete fa;
     return NLZ_OK;

@@ -10,6 +10,7 @@
 // raw-byte match can never run across one.
 #pragma once
 #include "common.cuh"
+#include "sa.cuh"
 
 namespace nlz {
 
@@ -53,9 +54,12 @@ __device__ __forceinline__ u32 warp_extend_match(const u64* __restrict__ xw, u64
 //    costs the warp one long comparison instead of 32.
 //  * inside a run (k > 0): the lane continues from l-1 on its own; a lane whose match still outlasts
 //    LCP_LOCAL_WORDS words hands the comparison to its warp.
+// BATCH: suffixes of different records share nothing, and a match stops at the sentinel that ends
+// either segment (batch sentinels all carry the same byte, so the raw compare alone would run on).
+template <bool BATCH>
 __global__ void __launch_bounds__(256)
 k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
-            const u32* __restrict__ RANK, u32* __restrict__ LCP) {
+            const u32* __restrict__ RANK, u32* __restrict__ LCP, BatchView bv) {
     const u64* xw = reinterpret_cast<const u64*>(x);
     const u32 lane = threadIdx.x & 31;
     const u64 c = (u64)blockIdx.x * 256 + threadIdx.x;
@@ -74,6 +78,10 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
             else {
                 j = SA[r - 1];
                 maxl = (u32)(L - (i > j ? i : (u64)j));
+                if (BATCH) {
+                    if (bv.REC[i] != bv.REC[j]) maxl = 0;
+                    else maxl = min(maxl, min(batch_cap(bv, (u32)i), batch_cap(bv, j)));
+                }
                 if (l > maxl) l = maxl;
                 need = true;
             }

@@ -32,7 +32,26 @@ struct KeyLayout {
     int b;          // bits per symbol
     int W;          // symbols per key
     int D;          // bits of the sentinel-offset field
+    int R;          // bits of the record-id prefix (batch mode: suffixes are grouped by record first)
 };
+
+// Batch mode (many independent records in one text): record id of every text position and the
+// geometry needed to stop matches at record boundaries (all sentinels carry the same byte there).
+struct BatchView {
+    const u32* REC;      // record id per position (forward half, rc half and their sentinels); k for the terminator
+    const u32* fstart;   // start of record b in the forward half
+    const u32* flen;     // its length
+    u32 k;               // number of records
+    u32 N;               // RC layout: |S|/2 - 1 (positions > N are the rc half); 0xFFFFFFFF when there is no rc half
+};
+// symbols of position p up to (excluding) the sentinel that ends its segment
+__device__ __forceinline__ u32 batch_cap(const BatchView& bv, u32 p) {
+    const u32 b = bv.REC[p];
+    if (b >= bv.k) return 0;
+    const u32 fs = bv.fstart[b];
+    if (p <= bv.N) return fs + bv.flen[b] - p;          // forward half (0 at the sentinel itself)
+    return 2 * bv.N - fs + 1 - p;                         // rc half: its segment ends at the mirror of the sentinel before fs
+}
 
 // ---------------------------------------------------------------- byte histogram
 __global__ void __launch_bounds__(256) k_byte_hist(const u8* __restrict__ x, u64 L, u32* __restrict__ hist) {
@@ -61,7 +80,7 @@ __global__ void __launch_bounds__(256) k_byte_hist(const u8* __restrict__ x, u64
 // One thread per suffix; the CTA stages its text window in shared memory (coalesced 4-byte loads).
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay,
+k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay, const u32* __restrict__ REC,
              KeyT* __restrict__ keys, u32* __restrict__ vals) {
     constexpr int TP = 2048;            // suffixes per CTA
     constexpr int HALO = 32;            // >= max W
@@ -86,7 +105,8 @@ k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout 
         if (p >= n1) break;
         KeyT key = 0;
         KeyT dist = dist_none;
-        int sh = kb - b;
+        int sh = kb - lay.R - b;
+        if (lay.R) key = (KeyT)REC[p] << (kb - lay.R);
         for (int t = 0; t < W; ++t, sh -= b) {
             u32 c = (p + t < L) ? (u32)cls[tile[o + t]] : SENT_CLASS;
             if (c == SENT_CLASS) { dist = (KeyT)t; break; }

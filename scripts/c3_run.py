@@ -1,7 +1,7 @@
 """configs[2]: 10 000 records x 10 kbp multi-record FASTA, per-sequence RC factorization (count + files)."""
 import os, sys, time, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from nolzss_b200 import _noLZSS as ext, workloads as wl
+from nolzss_b200 import _lib as L, _noLZSS as ext, workloads as wl
 
 nrec = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000
 recs = wl.c3_records(nrec, 10_000, seed=3)
@@ -21,3 +21,14 @@ t0 = time.perf_counter()
 counts, ids, total2 = ext.count_factors_fasta_dna_w_rc_per_sequence(fa)
 print(f"count only (8 threads): {time.perf_counter()-t0:.2f} s, total {total2}")
 assert total2 == total
+st = L.stats()
+print("last batch device stages:", {k: (round(v, 2) if isinstance(v, float) else v) for k, v in st.items()})
+# device-only view of the same batch (records already parsed)
+t0 = time.perf_counter()
+_, cnts = L.factorize_batch([s for _, s in recs], True, want_factors=False)
+dt = time.perf_counter() - t0
+st = L.stats()
+print(f"nlz_factorize_batch count-only: wall {dt*1e3:.0f} ms, device {st['ms_total']:.1f} ms -> {nb/st['ms_total']/1e3:.1f} Mbases/s on the device; "
+      f"rounds={st['doubling_rounds']} key_syms={st['key_syms']} stages: prep {st['ms_prepare']:.1f} keys {st['ms_keys']:.1f} sort0 {st['ms_sort0']:.1f} "
+      f"doubling {st['ms_doubling']:.1f} lcp {st['ms_lcp']:.1f} lpnf {st['ms_lpnf']:.1f} chain {st['ms_chain']:.1f}")
+assert int(cnts.sum()) == total

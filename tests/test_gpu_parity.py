@@ -232,3 +232,54 @@ def test_mid_scale_parity_64bit_keys():
     t = wl.planted_dna(20_000_000, 11, scale=4.0).tobytes()
     assert np.array_equal(L.factorize_array(L.MODE_GENERAL, t), orc.factorize(t))
     assert L.stats()["key_bits"] == 64
+
+
+def _batch_expected(records, with_rc):
+    exp = []
+    for s in records:
+        if len(s) == 0:
+            exp.append(np.zeros((0, 3), dtype=np.uint64))
+        elif with_rc:
+            exp.append(orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s)))
+        else:
+            exp.append(orc.factorize(s))
+    return exp
+
+
+@pytest.mark.parametrize("with_rc", [True, False])
+def test_batch_records_vs_oracle_per_record(with_rc):
+    """Segmented pipeline (nlz_factorize_batch): every record must factorize exactly as if it were alone."""
+    rng = random.Random(11 + with_rc)
+    records = [b"A", b"", b"ACGT", b"AAAAAAAAAAAAAAAA", b"ACGTACGTACGTACGT", b"TTTTTTTTAAAAAAAA", b"GATTACA" * 9]
+    for _ in range(300):
+        n = rng.choice([1, 2, 3, 5, 8, 13, 40, 100, 333])
+        sigma = rng.choice([1, 2, 4, 4])
+        records.append(bytes(rng.choice(b"ACGT"[:sigma]) for _ in range(n)))
+    # identical records and records that are reverse complements of each other must not see one another
+    records += [records[10], records[10], wl.revcomp(np.frombuffer(records[10], dtype=np.uint8)).tobytes()]
+    for seed in range(4):
+        records.append(wl.planted_dna(20_000, 40 + seed, scale=0.05).tobytes())
+    records.append(b"AC" * 3000)
+    records.append(b"A" * 5000)
+    got, counts = L.factorize_batch(records, with_rc)
+    exp = _batch_expected(records, with_rc)
+    assert counts.tolist() == [len(e) for e in exp]
+    at = 0
+    for j, e in enumerate(exp):
+        assert np.array_equal(got[at:at + len(e)], e), (j, records[j][:40])
+        at += len(e)
+    assert at == len(got)
+    _, counts2 = L.factorize_batch(records, with_rc, want_factors=False)
+    assert counts2.tolist() == counts.tolist()
+
+
+def test_batch_config3_sample():
+    """configs[2] recipe (10 kbp records with a planted copy), 200 records, RC mode."""
+    recs = [s for _, s in wl.c3_records(200, 10_000, seed=3)]
+    got, counts = L.factorize_batch(recs, True)
+    at = 0
+    for j, s in enumerate(recs):
+        e = orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s))
+        assert counts[j] == len(e)
+        assert np.array_equal(got[at:at + len(e)], e), j
+        at += len(e)
