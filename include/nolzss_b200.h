@@ -101,6 +101,22 @@ int nlz_factorize_device(nlz_ctx* ctx, int mode, const void* d_text, uint64_t n,
 int nlz_factorize_batch(nlz_ctx* ctx, int with_rc, const uint8_t* concat, const uint64_t* offsets, const uint64_t* lens,
                         uint64_t k, uint64_t** out_triples, uint64_t* per_record_counts, uint64_t* total);
 
+/* ---- ONE text across the GPUs of a box (replaces the single serial index build of the reference's parallel mode,
+ * src/cpp/parallel_factorizer.cpp:78-84; see csrc/dist.cuh).  One nlz_dist per rank (GPU).  Every rank calls
+ * nlz_dist_factorize with the same text; rank 0 receives the factors, every rank the count.  The ranks exchange
+ * data through peer memory: either all ranks live in one process (nlz_dist_attach_local) or one process per GPU
+ * exchanges the CUDA IPC handles of the shared segments (nlz_dist_export / nlz_dist_attach; e.g. all-gathered
+ * with torch.distributed).  max_text_bytes / max_mode size the shared segment (mode as in nlz_factorize_mode). */
+typedef struct nlz_dist nlz_dist;
+int nlz_dist_create(nlz_ctx* ctx, int rank, int world, uint64_t max_text_bytes, int max_mode, nlz_dist** out);
+void nlz_dist_destroy(nlz_dist* d);
+int nlz_dist_ipc_handle_bytes(void);
+int nlz_dist_export(nlz_dist* d, uint8_t* handle_out);
+int nlz_dist_attach(nlz_dist* d, const uint8_t* all_handles /* world x nlz_dist_ipc_handle_bytes() */);
+int nlz_dist_attach_local(nlz_dist* const* ranks, int world);
+int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples,
+                       uint64_t* out_count);
+
 /* ---- named entry points: one per reference function on the path ------------------------- */
 /* noLZSS::factorize(std::string_view, start_pos)                 src/cpp/factorizer.cpp:378-384 */
 int nlz_factorize(nlz_ctx* ctx, const uint8_t* text, uint64_t n, uint64_t start_pos,

@@ -59,6 +59,13 @@ SIGNATURES = {
     "nlz_count_mode": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _u64p]),
     "nlz_factorize_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64, _vp, _vp, _u64, _u64p]),
     "nlz_factorize_batch": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _u64, _u64pp, _vp, _u64p]),
+    "nlz_dist_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _u64, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "nlz_dist_destroy": (None, [_vp]),
+    "nlz_dist_ipc_handle_bytes": (ctypes.c_int, []),
+    "nlz_dist_export": (ctypes.c_int, [_vp, _vp]),
+    "nlz_dist_attach": (ctypes.c_int, [_vp, _vp]),
+    "nlz_dist_attach_local": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
+    "nlz_dist_factorize": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64pp, _u64p]),
     "nlz_factorize": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64pp, _u64p]),
     "nlz_count_factors": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64p]),
     "nlz_factorize_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64pp, _u64p]),

@@ -10,6 +10,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -17,6 +19,7 @@
 #include "../../include/nolzss_b200.h"
 #include "chain.cuh"
 #include "common.cuh"
+#include "dist.cuh"
 #include "lcp.cuh"
 #include "lpnf.cuh"
 #include "prof.cuh"
@@ -63,11 +66,14 @@ struct Workspace {
     u32 *PSV = nullptr, *NSV = nullptr, *MINF = nullptr;   // per-node tables of stage 3
     // batch mode only: record id per text position, record geometry, factor index of every record's sentinel
     u32 *REC = nullptr, *FSTART = nullptr, *FLEN = nullptr, *INOFF = nullptr, *SENTIDX = nullptr;
+    u32* DCNT = nullptr;     // distributed runs: per-CTA counts / offsets of the key compaction
 };
 
 }  // namespace nlz
 
 using namespace nlz;
+
+struct nlz_dist;
 
 struct nlz_ctx {
     int device = 0;
@@ -81,6 +87,7 @@ struct nlz_ctx {
     cudaEvent_t ev[EV_COUNT];
     nlz_stats stats;
     Profiler prof;
+    Trees trees;                // summary trees of the last stage_lpnf call
     int debug_flags = 0;        // test hook: 1 force the bitonic tile path, 2 disable the pivot fast path, 4 force counting
 };
 
@@ -285,19 +292,43 @@ static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout
     return OK;
 }
 
+// ---- distributed runs: per-call state (nullptr on the single-GPU path) ---------------------------
+struct DistRt {
+    nlz_dist* d = nullptr;
+    int G = 1, me = 0;
+    int pbits = 0;                       // leading key bits the bucket histogram is taken over
+    u32 split[MAX_PEERS + 1] = {};       // bucket ranges
+    u32 base[MAX_PEERS + 1] = {};        // rank ranges: GPU g owns global ranks [base[g], base[g+1])
+    u32 m_loc = 0;                       // suffixes this GPU owns
+    u32 chunk = 0;                       // text positions per GPU (Kasai slices)
+};
+static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all);
+
+static RankDst rank_dst(nlz_ctx* c, DistRt* dr);
+
 template <typename KeyT>
 static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay,
-                                    cudaStream_t st, int* cur_out, u32* m_out, u32* maxg_out) {
+                                    cudaStream_t st, DistRt* dr, u32 cnt, int* cur_out, u32* m_out, u32* maxg_out) {
     Workspace& w = c->ws;
     Profiler& P = c->prof;
     const u32 n1 = pb.n1;
     const u64 kb = sizeof(KeyT);
     KeyT* k[2] = {reinterpret_cast<KeyT*>(w.KEY[0]), reinterpret_cast<KeyT*>(w.KEY[1])};
     u32* v[2] = {w.VAL[0], w.VAL[1]};
-    KL(P, KC_KEYS, (u64)n1 * (1 + kb + 4), st,
-       (k_build_keys<KeyT><<<ceil_div_u32(n1, 2048), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pb.nrec ? w.REC : nullptr,
-                                                                   k[0], v[0])));
+    if (!dr) {
+        KL(P, KC_KEYS, (u64)n1 * (1 + kb + 4), st,
+           (k_build_keys<KeyT><<<ceil_div_u32(n1, KB_TP), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pb.nrec ? w.REC : nullptr,
+                                                                       k[0], v[0])));
+    } else {
+        // ordered compaction of the suffixes of this GPU's bucket range (per-CTA offsets in DCNT, scanned in dist_partition)
+        KL(P, KC_KEYS, (u64)n1 + (u64)cnt * (kb + 4), st,
+           (k_keys_partition<KeyT, 2><<<ceil_div_u32(n1, KB_TP), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, dr->pbits,
+                                                                              dr->split[dr->me], dr->split[dr->me + 1],
+                                                                              w.DCNT, k[0], v[0])));
+    }
     NLZ_CK(cudaEventRecord(c->ev[EV_KEYS], st));
+    *cur_out = 1; *m_out = 0; *maxg_out = 0;
+    if (cnt == 0) { NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st)); return OK; }
     DigitPlan plan;
     const int used_lo = lay.key_bits - lay.R - lay.W * lay.b;   // lowest symbol bit
     if (used_lo - lay.D >= 6) {                         // wide unused gap: skip it
@@ -307,41 +338,286 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
         plan_add_range(plan, 0, lay.key_bits);
     }
     int res = 0;
-    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, n1, plan, w.HIST, st, &res, P));
+    NLZ_TRY(radix_sort_pairs<KeyT>(k, v, cnt, plan, w.HIST, st, &res, P));
     NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
     const KeyT dist_mask = ((KeyT)1 << lay.D) - 1;
-    const u32 tiles = ceil_div_u32(n1, RG_TILE);
+    const u32 tiles = ceil_div_u32(cnt, RG_TILE);
     // compaction target must not alias the sorted buffers: use the other KEY/VAL pair
     P.begin(st);
-    k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], n1, dist_mask, w.PMAX, w.PSUM);
+    k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
     k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
-    k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, n1, dist_mask, w.PMAX,
-                                                              w.PSUM, w.SA, w.RANK, w.KEY[res ^ 1],
+    k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, cnt, dist_mask, w.PMAX,
+                                                              w.PSUM, w.SA, rank_dst(c, dr), w.KEY[res ^ 1],
                                                               w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
-    P.end(KC_REGROUP, (u64)n1 * (2 * kb + 4 + 8), st, 3);
+    P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8), st, 3);
+    *cur_out = res ^ 1;
+    if (dr) return OK;                                  // the counts travel with the next barrier
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     c->stats.host_syncs += 1;
     *m_out = c->h_pinned[0];
     *maxg_out = c->h_pinned[3];
-    *cur_out = res ^ 1;
     return OK;
 }
 
-static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host, cudaStream_t st,
-                        u64* d_out, u64 capacity, bool count_only, bool stop_after_index,
-                        bool stop_after_lpnf, u64* out_count) {
+// ---- S1: suffix array of the `cnt` suffixes this GPU sorts (all n1 on one GPU).  Results: w.SA (local
+// rank order), RANK (= ISA; every replica in a distributed run).
+static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay, cudaStream_t st,
+                    DistRt* dr, u32 cnt) {
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
     Profiler& P = c->prof;
     const u32 n1 = pb.n1;
-    NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
+    S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
+    int cur = 0;
+    u32 m = 0, maxg = 0;
+    if (dr) NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));
+    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, dr, cnt, &cur, &m, &maxg));
+    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, dr, cnt, &cur, &m, &maxg));
+    const RankDst rdst = rank_dst(c, dr);
+    const int nb = bits_for(n1 - 1);
+    DigitPlan plan;
+    plan_add_range(plan, 0, nb);
+    plan_add_range(plan, 32, 32 + nb);
+    u64 h = (u64)lay.W;
+    int sc = 0;
+    u32 gm = m;                                          // largest active count over all GPUs
+    std::vector<u32> all((size_t)MAX_PEERS * 4);
+    for (;;) {
+        if (dr) {
+            // all refined ranks of the previous step are in every replica; learn every GPU's (m, maxg)
+            NLZ_TRY(dist_barrier(dr, st, w.CTR, 4, all.data()));
+            m = all[(size_t)dr->me * 4 + 0];
+            maxg = all[(size_t)dr->me * 4 + 3];
+            gm = 0;
+            for (int g = 0; g < dr->G; ++g) gm = gm > all[(size_t)g * 4] ? gm : all[(size_t)g * 4];
+        }
+        if (gm == 0) break;
+        S.doubling_rounds += 1;
+        S.active_sum += m;
+        static const bool trace = getenv("NLZ_TRACE") != nullptr;
+        cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+        if (trace) { cudaEventCreate(&tev0); cudaEventCreate(&tev1); cudaEventRecord(tev0, st); }
+        int rb = cur;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
+        const bool fused = maxg <= (u32)TSORT_SLOTS / 2;
+        if (m > 0)
+            KL(P, KC_GATHER, (u64)m * 24, st,
+               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1,
+                                                                     fused ? w.CTR : nullptr)));
+        else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));
+        if (dr) NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));   // every GPU has read its snapshot of RANK
+        if (m > 0 && fused) {
+            // every tie group fits in shared memory: segmented sort + regroup in one pass
+            u32 cap = 32;
+            while (cap < maxg) cap <<= 1;
+            const u32 tile = TSORT_SLOTS - cap;
+            KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
+               (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                   w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
+                   w.SLOT[sc ^ 1], w.CTR, c->debug_flags)));
+            rb = cur;                       // next round's lists were written to the cur^1 buffers
+            S.tile_sort_rounds += 1;
+            if (trace) cudaEventRecord(tev1, st);
+        } else if (m > 0) {
+            u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
+            u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
+            int res = 0;
+            NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
+            rb = res == 0 ? cur : (cur ^ 1);
+            if (trace) cudaEventRecord(tev1, st);
+            const u32 tiles = ceil_div_u32(m, RG_TILE);
+            P.begin(st);
+            k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
+            k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
+            k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
+                                                                    w.PMAX, w.PSUM, w.SA, rdst, w.KEY[rb ^ 1],
+                                                                    w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
+            P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
+        }
+        if (!dr) {
+            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
+            NLZ_CK(cudaStreamSynchronize(st));
+            S.host_syncs += 1;
+            if (trace) {
+                float tms = 0.f;
+                cudaEventElapsedTime(&tms, tev0, tev1);
+                fprintf(stderr, "[nlz] round %u h=%llu m=%u maxg=%u sort_ms=%.3f -> m'=%u maxg'=%u\n", S.doubling_rounds,
+                        (unsigned long long)h, m, maxg, tms, c->h_pinned[0], c->h_pinned[3]);
+            }
+            m = c->h_pinned[0];
+            maxg = c->h_pinned[3];
+            gm = m;
+        }
+        if (trace) { cudaEventDestroy(tev0); cudaEventDestroy(tev1); }
+        cur = rb ^ 1;
+        sc ^= 1;
+        h *= 2;
+        if (S.doubling_rounds > 40) { set_error("prefix doubling did not converge"); return ERR_RUNTIME; }
+    }
+    return OK;
+}
 
-    // ---- S0: text into X
+// ---- S3: per-position factor rule over the rank-ordered arrays (SA, LCP) of `cnt` ranks; in a
+// distributed run these hold virtual ranks around the real ones [wp.real_lo, wp.real_hi).
+static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32* SA, const u32* LCP, WalkParams wp,
+                      const u32* RANK, u64* LR, u8* HARDF) {
+    Workspace& w = c->ws;
+    Profiler& P = c->prof;
+    const u32 n1 = wp.n1;
+    Trees T;
+    memset(&T, 0, sizeof(T));
+    T.lcp[0] = LCP; T.cntL[0] = n1 + 1;
+    T.f[0] = SA; T.r[0] = SA; T.cntS[0] = n1;
+    int lev = 0;
+    P.begin(st);
+    while (T.cntL[lev] > 32 && lev + 1 < TREE_MAX_LEVELS) {
+        u32 cl = (T.cntL[lev] + 31) / 32, cs = (T.cntS[lev] + 31) / 32;
+        u32 nodes = cl > cs ? cl : cs;
+        u32 grid = ceil_div_u32((u64)nodes * 32, 256);
+        if (lev == 0) {
+            if (pb.rc) k_tree_level1<true><<<grid, 256, 0, st>>>(LCP, T.cntL[0], SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
+            else k_tree_level1<false><<<grid, 256, 0, st>>>(LCP, T.cntL[0], SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
+        } else {
+            if (pb.rc) k_tree_level_up<true><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
+            else k_tree_level_up<false><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
+        }
+        ++lev;
+        T.lcp[lev] = w.tl[lev]; T.f[lev] = w.tf[lev]; T.r[lev] = w.tr[lev];
+        T.cntL[lev] = cl; T.cntS[lev] = cs;
+    }
+    T.nlev = lev + 1;
+    P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
+    c->trees = T;
+    if (!LR) return OK;                                  // trees only (edge staircases of a distributed run)
+    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 12), st,
+       (pb.rc ? k_node_tables<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)
+              : k_node_tables<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)));
+    RNear rn;
+    memset(&rn, 0, sizeof(rn));
+    if (pb.rc) {
+        // nearest rc(T) rank on either side of every rank + LCP minimum on the way (two segmented scans)
+        u32* PR = reinterpret_cast<u32*>(w.KEY[1]);
+        u32* ML = PR + n1;
+        u32* NR = w.VAL[0];
+        u32* MR = w.VAL[1];
+        const u32 tiles = ceil_div_u32(n1, RN_TILE);
+        P.begin(st);
+        k_rnear_reduce<0><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM);
+        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
+        k_rnear_apply<0><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM, PR, ML);
+        k_rnear_reduce<1><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM);
+        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
+        k_rnear_apply<1><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM, NR, MR);
+        P.end(KC_RNEAR, (u64)n1 * (4 * 8 + 4 * 4), st, 6);
+        rn.PR = PR; rn.ML = ML; rn.NR = NR; rn.MR = MR;
+    }
+    unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);   // [0] probes, [1] hard
+    NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 16, st));
+    // algorithmic bytes: SA[r] for every rank; per factorized position the two LCP neighbours, the
+    // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
+    P.begin(st);
+    static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
+    NodeTables nt;
+    nt.PSV = w.PSV; nt.NSV = w.NSV; nt.MINF = w.MINF;
+    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
+    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
+    P.end(KC_WALK, (u64)n1 * 4 + (u64)(wp.real_hi - wp.real_lo) * 17, st);
+    {
+        const u32 grid = ceil_div_u32((u64)ceil_div_u32(pb.nfac, WALK_Q) * 8, 256);   // one 8-lane tile per run
+        P.begin(st);
+        if (pb.rc) k_lpnf_hard<true><<<grid, 256, 0, st>>>(T, wp, RANK, LR, HARDF, visit_ctr);
+        else k_lpnf_hard<false><<<grid, 256, 0, st>>>(T, wp, RANK, LR, HARDF, visit_ctr);
+        P.end(KC_WALK_HARD, (u64)pb.nfac, st);
+    }
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 4, visit_ctr, 16, cudaMemcpyDeviceToHost, st));
+    return OK;
+}
+
+// ---- S4: chain extraction over LR[0, nfac) and emission of the triples.  Scratch: EXIT, J2, alist
+// (u32 x nfac), REACH (u8 x nfac), MASK (u32 x (33 x chunks)).
+struct ChainScratch { u32 *EXIT, *J2, *alist; u8* REACH; u32* MASK; };
+static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64* LR, const ChainScratch& cs,
+                       u64* d_out, u64 capacity, bool count_only, u64* out_count) {
+    Workspace& w = c->ws;
+    nlz_stats& S = c->stats;
+    Profiler& P = c->prof;
+    const u32 nfac = pb.nfac;
+    const u32 nchunks = ceil_div_u32(nfac, CH_CHUNK);
+    u32* EXIT = cs.EXIT;
+    u32* J2 = cs.J2;
+    u32* alist = cs.alist;
+    u8* REACH = cs.REACH;
+    u32* MASK = cs.MASK;
+    u32* CNT = MASK + (size_t)nchunks * 32;
+    u32* acount = w.CTR + 1;
+    P.begin(st);
+    NLZ_CK(cudaMemsetAsync(REACH, 0, nfac, st));
+    k_chain_init<<<1, 1, 0, st>>>(alist, acount, REACH, (u32)pb.start_pos);
+    k_chain_exit<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, EXIT, alist, acount);
+    int rounds = bits_for(nchunks) + 1;
+    {
+        u32* Ja = EXIT;
+        u32* Jb = J2;
+        u32 grid = nchunks < (u32)kNumSM * 2 ? (nchunks ? nchunks : 1) : kNumSM * 2;
+        for (int r = 0; r < rounds; ++r) {
+            k_chain_double<<<grid, 256, 0, st>>>(alist, acount, Ja, Jb, REACH, nfac);
+            u32* t = Ja; Ja = Jb; Jb = t;
+        }
+    }
+    k_chain_mark<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, REACH, MASK, CNT);
+    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(CNT, nchunks, w.CTR + 2);
+    P.end(KC_CHAIN, (u64)nfac * (8 + 4 + 1 + 8 + 1), st, (u32)(4 + rounds));
+    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 2, w.CTR + 2, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaStreamSynchronize(st));
+    S.host_syncs += 1;
+    const u64 z = c->h_pinned[2];
+    *out_count = z;
+    S.n_factors = z;
+    BatchView bv;
+    bv.REC = w.REC; bv.fstart = w.FSTART; bv.flen = w.FLEN; bv.k = pb.nrec; bv.N = pb.rc ? pb.N : 0xFFFFFFFFu;
+    if (!count_only || pb.nrec) {   // batch mode always runs the emit pass: it publishes the per-record boundaries
+        u64* dst = d_out;
+        if (count_only) { dst = nullptr; capacity = 0; }
+        else if (!dst) {   // host-buffer entry points: library-owned device output
+            if (z > c->d_out_cap) {
+                if (c->d_out) NLZ_CK(cudaFree(c->d_out));
+                c->d_out = nullptr; c->d_out_cap = 0;
+                size_t want = z + z / 4 + 1024;
+                NLZ_CK(cudaMalloc(&c->d_out, want * 24));
+                c->d_out_cap = want;
+            }
+            dst = c->d_out;
+            capacity = c->d_out_cap;
+        }
+        if (!count_only && z > capacity) {
+            set_error("output capacity %llu factors is too small for %llu factors",
+                      (unsigned long long)capacity, (unsigned long long)z);
+            return ERR_RUNTIME;
+        }
+        P.begin(st);
+        if (pb.nrec) {
+            if (pb.rc) k_chain_emit<true, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
+            else k_chain_emit<false, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
+        } else {
+            if (pb.rc) k_chain_emit<true, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
+            else k_chain_emit<false, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
+        }
+        P.end(KC_CHAIN, (u64)nfac / 8 + z * 32, st);
+    }
+    return OK;
+}
+
+// ---- S0: text into X (validated / reverse-complemented on the device), byte histogram, key layout
+static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host, cudaStream_t st,
+                         u8* staging, ClassTable& tab, KeyLayout& lay) {
+    Workspace& w = c->ws;
+    nlz_stats& S = c->stats;
+    Profiler& P = c->prof;
+    const u32 n1 = pb.n1;
     P.begin(st);
     u32 prep_launches = 2;
     if (pb.nrec) {
-        u8* tmp = reinterpret_cast<u8*>(w.KEY[1]);
+        u8* tmp = staging;
         NLZ_CK(cudaMemcpyAsync(tmp, src, pb.n_in, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
         NLZ_CK(cudaMemcpyAsync(w.INOFF, pb.h_inoff, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
         NLZ_CK(cudaMemcpyAsync(w.FSTART, pb.h_fstart, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
@@ -353,7 +629,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     } else if (pb.mode == NLZ_MODE_DNA_RC) {
         const u8* dT = static_cast<const u8*>(src);
         if (src_on_host) {
-            u8* tmp = reinterpret_cast<u8*>(w.KEY[1]);
+            u8* tmp = staging;
             NLZ_CK(cudaMemcpyAsync(tmp, src, pb.n_in, cudaMemcpyHostToDevice, st));
             dT = tmp;
         }
@@ -394,10 +670,6 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
         set_error("Invalid nucleotide '%c' found in sequence 0", (char)ch);
         return ERR_RUNTIME;
     }
-
-    // ---- S1: suffix array
-    ClassTable tab;
-    KeyLayout lay;
     if (pb.nrec) {
         // records are told apart by the leading record-id field; every byte but ACGT is a sentinel
         for (int ch = 0; ch < 256; ++ch) tab.cls[ch] = (u8)SENT_CLASS;
@@ -408,162 +680,55 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     } else {
         choose_layout(c->h_pinned + 16, n1, tab, lay);
     }
-    S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
-    int cur = 0;
-    u32 m = 0, maxg = 0;
-    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, &cur, &m, &maxg));
-    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, &cur, &m, &maxg));
+    return OK;
+}
 
-    {
-        const int nb = bits_for(n1 - 1);
-        DigitPlan plan;
-        plan_add_range(plan, 0, nb);
-        plan_add_range(plan, 32, 32 + nb);
-        u64 h = (u64)lay.W;
-        int sc = 0;
-        while (m > 0) {
-            S.doubling_rounds += 1;
-            S.active_sum += m;
-            static const bool trace = getenv("NLZ_TRACE") != nullptr;
-            cudaEvent_t tev0 = nullptr, tev1 = nullptr;
-            if (trace) { cudaEventCreate(&tev0); cudaEventCreate(&tev1); cudaEventRecord(tev0, st); }
-            int rb;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
-            const bool fused = maxg <= (u32)TSORT_SLOTS / 2;
-            KL(P, KC_GATHER, (u64)m * 24, st,
-               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1,
-                                                                     fused ? w.CTR : nullptr)));
-            if (fused) {
-                // every tie group fits in shared memory: segmented sort + regroup in one pass
-                u32 cap = 32;
-                while (cap < maxg) cap <<= 1;
-                const u32 tile = TSORT_SLOTS - cap;
-                KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
-                   (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
-                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, tile, cap, w.SA, w.RANK, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
-                       w.SLOT[sc ^ 1], w.CTR, c->debug_flags)));
-                rb = cur;                       // next round's lists were written to the cur^1 buffers
-                S.tile_sort_rounds += 1;
-                if (trace) cudaEventRecord(tev1, st);
-            } else {
-                u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
-                u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
-                int res = 0;
-                NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
-                rb = res == 0 ? cur : (cur ^ 1);
-                if (trace) cudaEventRecord(tev1, st);
-                const u32 tiles = ceil_div_u32(m, RG_TILE);
-                P.begin(st);
-                k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
-                k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
-                k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
-                                                                        w.PMAX, w.PSUM, w.SA, w.RANK, w.KEY[rb ^ 1],
-                                                                        w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
-                P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
-            }
-            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
-            NLZ_CK(cudaStreamSynchronize(st));
-            S.host_syncs += 1;
-            if (trace) {
-                float tms = 0.f;
-                cudaEventElapsedTime(&tms, tev0, tev1);
-                fprintf(stderr, "[nlz] round %u h=%llu m=%u maxg=%u sort_ms=%.3f -> m'=%u maxg'=%u\n", S.doubling_rounds,
-                        (unsigned long long)h, m, maxg, tms, c->h_pinned[0], c->h_pinned[3]);
-                cudaEventDestroy(tev0); cudaEventDestroy(tev1);
-            }
-            m = c->h_pinned[0];
-            maxg = c->h_pinned[3];
-            cur = rb ^ 1;
-            sc ^= 1;
-            h *= 2;
-            if (S.doubling_rounds > 40) { set_error("prefix doubling did not converge"); return ERR_RUNTIME; }
-        }
-    }
+static void account_walk(nlz_ctx* c) {
+    unsigned long long visits[2] = {0, 0};
+    memcpy(visits, c->h_pinned + 4, 16);
+    c->stats.walk_nodes = visits[0];
+    c->stats.hard_positions = visits[1];
+    c->prof.bytes[KC_WALK] += (u64)visits[0] * 16;
+    c->prof.bytes[KC_WALK_HARD] += (u64)visits[1] * (4 + 8 + 8 + 8);
+}
+
+static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host, cudaStream_t st,
+                        u64* d_out, u64 capacity, bool count_only, bool stop_after_index,
+                        bool stop_after_lpnf, u64* out_count) {
+    Workspace& w = c->ws;
+    Profiler& P = c->prof;
+    const u32 n1 = pb.n1;
+    NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
+    ClassTable tab;
+    KeyLayout lay;
+    NLZ_TRY(stage_prepare(c, pb, src, src_on_host, st, reinterpret_cast<u8*>(w.KEY[1]), tab, lay));
+    NLZ_TRY(stage_sa(c, pb, tab, lay, st, nullptr, n1));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
     // ---- S2: LCP
     BatchView bv;
     bv.REC = w.REC; bv.fstart = w.FSTART; bv.flen = w.FLEN; bv.k = pb.nrec; bv.N = pb.rc ? pb.N : 0xFFFFFFFFu;
+    LcpDist nold;
+    memset(&nold, 0, sizeof(nold));
     if (pb.nrec)
         KL(P, KC_LCP, (u64)n1 * 36, st,
-           (k_lcp_kasai<true><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv)));
+           (k_lcp_kasai<true, false><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv, nold)));
     else
         KL(P, KC_LCP, (u64)n1 * 28, st,
-           (k_lcp_kasai<false><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv)));
+           (k_lcp_kasai<false, false><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv, nold)));
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
     if (stop_after_index) {
         NLZ_CK(cudaGetLastError());
         return OK;
     }
 
-    // ---- S3: summary trees + per-rank walk
-    Trees T;
-    memset(&T, 0, sizeof(T));
+    // ---- S3: summary trees, node tables, per-rank walk
     WalkParams wp;
     wp.n1 = n1; wp.nfac = pb.nfac; wp.N = pb.N; wp.twoN = 2 * pb.N;
-    T.lcp[0] = w.LCP; T.cntL[0] = n1 + 1;
-    T.f[0] = w.SA; T.r[0] = w.SA; T.cntS[0] = n1;
-    int lev = 0;
-    P.begin(st);
-    while (T.cntL[lev] > 32 && lev + 1 < TREE_MAX_LEVELS) {
-        u32 cl = (T.cntL[lev] + 31) / 32, cs = (T.cntS[lev] + 31) / 32;
-        u32 nodes = cl > cs ? cl : cs;
-        u32 grid = ceil_div_u32((u64)nodes * 32, 256);
-        if (lev == 0) {
-            if (pb.rc) k_tree_level1<true><<<grid, 256, 0, st>>>(w.LCP, T.cntL[0], w.SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
-            else k_tree_level1<false><<<grid, 256, 0, st>>>(w.LCP, T.cntL[0], w.SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
-        } else {
-            if (pb.rc) k_tree_level_up<true><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
-            else k_tree_level_up<false><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
-        }
-        ++lev;
-        T.lcp[lev] = w.tl[lev]; T.f[lev] = w.tf[lev]; T.r[lev] = w.tr[lev];
-        T.cntL[lev] = cl; T.cntS[lev] = cs;
-    }
-    T.nlev = lev + 1;
-    P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
-    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 12), st,
-       (pb.rc ? k_node_tables<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)
-              : k_node_tables<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)));
+    wp.real_lo = 0; wp.real_hi = n1; wp.rank_add = 0;
     u64* LR = w.KEY[0];
     u8* HARDF = reinterpret_cast<u8*>(w.SLOT[0]);
-    RNear rn;
-    memset(&rn, 0, sizeof(rn));
-    if (pb.rc) {
-        // nearest rc(T) rank on either side of every rank + LCP minimum on the way (two segmented scans)
-        u32* PR = reinterpret_cast<u32*>(w.KEY[1]);
-        u32* ML = PR + n1;
-        u32* NR = w.VAL[0];
-        u32* MR = w.VAL[1];
-        const u32 tiles = ceil_div_u32(n1, RN_TILE);
-        P.begin(st);
-        k_rnear_reduce<0><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM);
-        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
-        k_rnear_apply<0><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM, PR, ML);
-        k_rnear_reduce<1><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM);
-        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
-        k_rnear_apply<1><<<tiles, RN_THREADS, 0, st>>>(w.SA, w.LCP, wp, w.PMAX, w.PSUM, NR, MR);
-        P.end(KC_RNEAR, (u64)n1 * (4 * 8 + 4 * 4), st, 6);
-        rn.PR = PR; rn.ML = ML; rn.NR = NR; rn.MR = MR;
-    }
-    unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);   // [0] probes, [1] hard
-    NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 16, st));
-    // algorithmic bytes: SA[r] for every rank; per factorized position the two LCP neighbours, the
-    // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
-    P.begin(st);
-    static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
-    NodeTables nt;
-    nt.PSV = w.PSV; nt.NSV = w.NSV; nt.MINF = w.MINF;
-    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
-    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
-    P.end(KC_WALK, (u64)n1 * 4 + (u64)pb.nfac * 17, st);
-    {
-        const u32 grid = ceil_div_u32((u64)ceil_div_u32(pb.nfac, WALK_Q) * 8, 256);   // one 8-lane tile per run
-        P.begin(st);
-        if (pb.rc) k_lpnf_hard<true><<<grid, 256, 0, st>>>(T, wp, w.RANK, LR, HARDF, visit_ctr);
-        else k_lpnf_hard<false><<<grid, 256, 0, st>>>(T, wp, w.RANK, LR, HARDF, visit_ctr);
-        P.end(KC_WALK_HARD, (u64)pb.nfac, st);
-    }
-    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 4, visit_ctr, 16, cudaMemcpyDeviceToHost, st));
+    NLZ_TRY(stage_lpnf(c, pb, st, w.SA, w.LCP, wp, w.RANK, LR, HARDF));
     NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
     if (stop_after_lpnf) {
         NLZ_CK(cudaGetLastError());
@@ -571,77 +736,384 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     }
 
     // ---- S4: chain
-    const u32 nfac = pb.nfac;
-    const u32 nchunks = ceil_div_u32(nfac, CH_CHUNK);
-    u32* EXIT = w.VAL[0];
-    u32* J2 = w.VAL[1];
-    u32* alist = w.SLOT[0];
-    u8* REACH = reinterpret_cast<u8*>(w.SLOT[1]);
-    u32* MASK = reinterpret_cast<u32*>(w.KEY[1]);
-    u32* CNT = MASK + (size_t)nchunks * 32;
-    u32* acount = w.CTR + 1;
-    P.begin(st);
-    NLZ_CK(cudaMemsetAsync(REACH, 0, nfac, st));
-    k_chain_init<<<1, 1, 0, st>>>(alist, acount, REACH, (u32)pb.start_pos);
-    k_chain_exit<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, EXIT, alist, acount);
-    int rounds = bits_for(nchunks) + 1;
-    {
-        u32* Ja = EXIT;
-        u32* Jb = J2;
-        u32 grid = nchunks < (u32)kNumSM * 2 ? (nchunks ? nchunks : 1) : kNumSM * 2;
-        for (int r = 0; r < rounds; ++r) {
-            k_chain_double<<<grid, 256, 0, st>>>(alist, acount, Ja, Jb, REACH, nfac);
-            u32* t = Ja; Ja = Jb; Jb = t;
-        }
-    }
-    k_chain_mark<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, REACH, MASK, CNT);
-    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(CNT, nchunks, w.CTR + 2);
-    P.end(KC_CHAIN, (u64)nfac * (8 + 4 + 1 + 8 + 1), st, (u32)(4 + rounds));
-    NLZ_CK(cudaMemcpyAsync(c->h_pinned + 2, w.CTR + 2, 4, cudaMemcpyDeviceToHost, st));
-    NLZ_CK(cudaStreamSynchronize(st));
-    S.host_syncs += 1;
-    const u64 z = c->h_pinned[2];
-    {
-        unsigned long long visits[2] = {0, 0};
-        memcpy(visits, c->h_pinned + 4, 16);
-        S.walk_nodes = visits[0];
-        S.hard_positions = visits[1];
-        P.bytes[KC_WALK] += (u64)visits[0] * 16;
-        P.bytes[KC_WALK_HARD] += (u64)visits[1] * (4 + 8 + 8 + 8);
-    }
-    *out_count = z;
-    S.n_factors = z;
-    if (!count_only || pb.nrec) {   // batch mode always runs the emit pass: it publishes the per-record boundaries
-        u64* dst = d_out;
-        if (count_only) { dst = nullptr; capacity = 0; }
-        else if (!dst) {   // host-buffer entry points: library-owned device output
-            if (z > c->d_out_cap) {
-                if (c->d_out) NLZ_CK(cudaFree(c->d_out));
-                c->d_out = nullptr; c->d_out_cap = 0;
-                size_t want = z + z / 4 + 1024;
-                NLZ_CK(cudaMalloc(&c->d_out, want * 24));
-                c->d_out_cap = want;
-            }
-            dst = c->d_out;
-            capacity = c->d_out_cap;
-        }
-        if (!count_only && z > capacity) {
-            set_error("output capacity %llu factors is too small for %llu factors",
-                      (unsigned long long)capacity, (unsigned long long)z);
-            return ERR_RUNTIME;
-        }
-        P.begin(st);
-        if (pb.nrec) {
-            if (pb.rc) k_chain_emit<true, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
-            else k_chain_emit<false, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
-        } else {
-            if (pb.rc) k_chain_emit<true, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
-            else k_chain_emit<false, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
-        }
-        P.end(KC_CHAIN, (u64)nfac / 8 + z * 32, st);
-    }
+    ChainScratch cs;
+    cs.EXIT = w.VAL[0]; cs.J2 = w.VAL[1]; cs.alist = w.SLOT[0];
+    cs.REACH = reinterpret_cast<u8*>(w.SLOT[1]);
+    cs.MASK = reinterpret_cast<u32*>(w.KEY[1]);
+    NLZ_TRY(stage_chain(c, pb, st, LR, cs, d_out, capacity, count_only, out_count));
+    account_walk(c);
     NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
     NLZ_CK(cudaGetLastError());
+    return OK;
+}
+
+// =================================================================== one text across G GPUs (dist.cuh)
+struct HostBarrier {          // in-process groups only (several ranks of one process, e.g. sharing a GPU in tests)
+    std::mutex mu;
+    std::condition_variable cv;
+    int world = 0, waiting = 0;
+    unsigned gen = 0;
+    void arrive() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned g = gen;
+        if (++waiting == world) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+}  // namespace nlz
+
+struct nlz_dist {
+    nlz_ctx* ctx = nullptr;
+    int rank = 0, world = 1;
+    u64 max_n1 = 0;
+    u8* seg = nullptr;                 // shared segment: DistCtl | RANK replica | local LCP | Phi slice | LR (rank 0)
+    size_t seg_bytes = 0, off_rank = 0, off_lcp = 0, off_phi = 0, off_lr = 0;
+    u8* peer[MAX_PEERS] = {};
+    bool ipc_opened[MAX_PEERS] = {};
+    bool attached = false;
+    u32 epoch = 0;
+    int xparity = 0;
+    HostBarrier* hb = nullptr;
+    bool owns_hb = false;
+    u32* h_pin = nullptr;              // pinned: exchange readback
+    // persistent device buffers sized by max_n1
+    u8* Xbuf = nullptr;
+    u32 *DCNT = nullptr, *HISTP = nullptr, *SMALL = nullptr;   // SMALL: CTR[64] | BYTEHIST[256] | SPLIT[16] | BASE[16] | PAYLOAD[512]
+    Arena arena;                       // per-call private workspace
+};
+
+namespace nlz {
+
+static RankDst rank_dst(nlz_ctx* c, DistRt* dr) {
+    RankDst r;
+    memset(&r, 0, sizeof(r));
+    if (!dr) { r.p[0] = c->ws.RANK; r.n = 1; r.base = 0; return r; }
+    nlz_dist* d = dr->d;
+    for (int g = 0; g < dr->G; ++g) r.p[g] = reinterpret_cast<u32*>(d->peer[g] + d->off_rank);
+    r.n = dr->G;
+    r.base = dr->base[dr->me];
+    return r;
+}
+
+// Stream-ordered barrier over all ranks; optionally every rank contributes `nwords` words (device
+// buffer d_src) and receives everybody's words in h_all[g * nwords ..] (host sync).
+static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all) {
+    nlz_dist* d = dr->d;
+    DistPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    for (int g = 0; g < dr->G; ++g) peers.ctl[g] = reinterpret_cast<DistCtl*>(d->peer[g]);
+    peers.n = dr->G; peers.me = dr->me;
+    d->epoch += 1;
+    if (nwords) d->xparity ^= 1;
+    k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords);
+    d->ctx->prof.launches[KC_PREPARE] += 1;
+    if (!h_all) return OK;
+    DistCtl* mine = reinterpret_cast<DistCtl*>(d->seg);
+    for (int g = 0; g < dr->G; ++g)
+        NLZ_CK(cudaMemcpyAsync(d->h_pin + (size_t)g * nwords, &mine->xch[d->xparity][g][0], (size_t)nwords * 4,
+                               cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaMemcpyAsync(d->h_pin + (size_t)MAX_PEERS * DIST_XCH_WORDS, &mine->error, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaStreamSynchronize(st));
+    d->ctx->stats.host_syncs += 1;
+    if (d->h_pin[(size_t)MAX_PEERS * DIST_XCH_WORDS] != 0) {
+        set_error("distributed barrier %u timed out on rank %d (a peer failed or never arrived)", d->epoch, dr->me);
+        return ERR_RUNTIME;
+    }
+    memcpy(h_all, d->h_pin, (size_t)dr->G * nwords * 4);
+    return OK;
+}
+
+static size_t dist_private_bytes(u64 cap, u64 nfac, bool rank0) {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t t = 0;
+    t += al((cap + 72) * 4) * 4;          // SA, PSV, NSV, MINF
+    t += al(cap * 8) * 2 + al(cap * 4) * 4;
+    t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
+    size_t tiles = (cap + RG_TILE - 1) / RG_TILE + 1;
+    t += al(tiles * 4) * 2;
+    u64 cnt = cap + 1;
+    for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; t += al((cnt + 72) * 4) * 3; }
+    t += al(nfac * 8) + al(nfac + 64);    // LRloc, HARD
+    if (rank0) t += al(nfac * 4) * 3 + al(nfac + 64) + al(((nfac + CH_CHUNK - 1) / CH_CHUNK + 1) * 33 * 4);
+    return t + 4096;
+}
+
+struct VirtBlock { u32 cnt = 0, F = NONE_MIN, R = 0; };
+
+// Factorizes one text with all ranks of the group (every rank passes the same text).  Rank 0 receives
+// the factors; every rank learns the count.
+static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_alloc, u64* out_count) {
+    nlz_ctx* c = d->ctx;
+    Workspace& w = c->ws;
+    Profiler& P = c->prof;
+    cudaStream_t st = c->own_stream;
+    const u32 n1 = pb.n1;
+    const int G = d->world, me = d->rank;
+    DistRt rt;
+    rt.d = d; rt.G = G; rt.me = me;
+    DistRt* dr = &rt;
+    w = Workspace();
+    w.n1 = n1;
+    w.X = d->Xbuf;
+    w.DCNT = d->DCNT;
+    w.CTR = d->SMALL; w.BYTEHIST = d->SMALL + 64;
+    u32* d_split = d->SMALL + 320;
+    u32* d_base = d->SMALL + 336;
+    u32* d_pay = d->SMALL + 352;
+    w.RANK = reinterpret_cast<u32*>(d->seg + d->off_rank);
+    u32* LCPbuf = reinterpret_cast<u32*>(d->seg + d->off_lcp);     // [DIST_VIRT virtual | real | virtual | guard]
+    u32* PHI = reinterpret_cast<u32*>(d->seg + d->off_phi);
+    NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
+
+    // ---- S0 (replicated) + bucket histogram -> rank ranges
+    ClassTable tab;
+    KeyLayout lay;
+    NLZ_TRY(stage_prepare(c, pb, text, true, st, w.X, tab, lay));
+    int pbits = lay.W * lay.b;
+    if (pbits > 24) pbits = 24;
+    { int lim = bits_for(n1) + 2; if (pbits > lim) pbits = lim; }
+    pbits -= pbits % lay.b;
+    if (pbits < lay.b) pbits = lay.b;
+    const int K = pbits / lay.b;                                     // crossing nodes are shallower than K symbols
+    rt.pbits = pbits;
+    const u32 nb = 1u << pbits;
+    const u32 nctas = ceil_div_u32(n1, KB_TP);
+    P.begin(st);
+    NLZ_CK(cudaMemsetAsync(d->HISTP, 0, (size_t)nb * 4, st));
+    if (lay.key_bits == 32) k_keys_partition<u32, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, 0, 0, d->HISTP, nullptr, nullptr);
+    else k_keys_partition<u64, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, 0, 0, d->HISTP, nullptr, nullptr);
+    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d->HISTP, nb, nullptr);
+    k_dist_splitters<<<1, 32, 0, st>>>(d->HISTP, nb, n1, G, d_split, d_base);
+    P.end(KC_KEYS, (u64)n1 + (u64)nb * 8, st, 3);
+    NLZ_CK(cudaMemcpyAsync(d->h_pin, d_split, 32 * 4, cudaMemcpyDeviceToHost, st));   // SPLIT[16] | BASE[16]
+    NLZ_CK(cudaStreamSynchronize(st));
+    for (int g = 0; g <= G; ++g) { rt.split[g] = d->h_pin[g]; rt.base[g] = d->h_pin[16 + g]; }
+    rt.m_loc = rt.base[me + 1] - rt.base[me];
+    rt.chunk = (u32)(((u64)ceil_div_u32(n1, G) + 1023) / 1024 * 1024);
+    const u32 m_loc = rt.m_loc;
+    P.begin(st);
+    if (lay.key_bits == 32) k_keys_partition<u32, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
+    else k_keys_partition<u64, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
+    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.DCNT, nctas, nullptr);
+    P.end(KC_KEYS, (u64)n1, st, 2);
+
+    // ---- private workspace for this GPU's share (allocated before the first barrier: cudaFree synchronises the device)
+    const u64 cap = (u64)m_loc + 2 * DIST_VIRT + 8;
+    {
+        const size_t need = dist_private_bytes(cap, pb.nfac, me == 0);
+        if (need > d->arena.cap) {
+            NLZ_CK(cudaStreamSynchronize(st));
+            if (d->arena.base) { NLZ_CK(cudaFree(d->arena.base)); d->arena.base = nullptr; d->arena.cap = 0; }
+            const size_t want = need + need / 8;
+            cudaError_t e = cudaMalloc(&d->arena.base, want);
+            if (e != cudaSuccess) { set_error("cudaMalloc of %zu workspace bytes failed: %s", want, cudaGetErrorString(e)); return ERR_CUDA; }
+            d->arena.cap = want;
+        }
+        if (d->hb) d->hb->arrive();
+        Arena& a = d->arena;
+        a.off = 0;
+        u32* SAbuf = a.take<u32>(cap + 72);
+        w.SA = SAbuf + DIST_VIRT;
+        w.PSV = a.take<u32>(cap + 72);
+        w.NSV = a.take<u32>(cap + 72);
+        w.MINF = a.take<u32>(cap + 72);
+        for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(cap);
+        for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(cap);
+        for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(cap);
+        w.HIST = a.take<u32>((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS);
+        size_t tiles = (cap + RG_TILE - 1) / RG_TILE + 1;
+        w.PMAX = a.take<u32>(tiles);
+        w.PSUM = a.take<u32>(tiles);
+        u64 cnt = cap + 1;
+        for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
+            cnt = (cnt + 31) / 32;
+            w.tl[lev] = a.take<u32>(cnt + 72);
+            w.tf[lev] = a.take<u32>(cnt + 72);
+            w.tr[lev] = a.take<u32>(cnt + 72);
+        }
+        c->stats.workspace_bytes = d->arena.cap + d->seg_bytes;
+    }
+    u32* SAbuf = w.SA - DIST_VIRT;
+    u64* LRloc = d->arena.take<u64>(pb.nfac);
+    u8* HARDF = d->arena.take<u8>(pb.nfac + 64);
+    ChainScratch cs;
+    memset(&cs, 0, sizeof(cs));
+    if (me == 0) {
+        cs.EXIT = d->arena.take<u32>(pb.nfac); cs.J2 = d->arena.take<u32>(pb.nfac); cs.alist = d->arena.take<u32>(pb.nfac);
+        cs.REACH = d->arena.take<u8>(pb.nfac + 64);
+        cs.MASK = d->arena.take<u32>((size_t)(ceil_div_u32(pb.nfac, CH_CHUNK) + 1) * 33);
+    }
+    w.LCP = LCPbuf + DIST_VIRT;
+
+    // ---- S1: rank-range-local suffix sorting; refined ranks go to every replica
+    NLZ_TRY(stage_sa(c, pb, tab, lay, st, dr, m_loc));
+    NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
+
+    // ---- S2: Phi to the position owners, Kasai per position slice, LCP back to the rank owners
+    std::vector<u32> all((size_t)MAX_PEERS * DIST_XCH_WORDS);
+    if (m_loc) NLZ_CK(cudaMemcpyAsync(d_pay, w.SA + (m_loc - 1), 4, cudaMemcpyDeviceToDevice, st));
+    else k_set_u32<<<1, 1, 0, st>>>(d_pay, NONE_MIN);
+    NLZ_TRY(dist_barrier(dr, st, d_pay, 1, all.data()));
+    {
+        u32 left_sa = NONE_MIN;
+        for (int g = me - 1; g >= 0; --g)
+            if (rt.base[g + 1] > rt.base[g]) { left_sa = all[g]; break; }
+        PosDst pd;
+        memset(&pd, 0, sizeof(pd));
+        for (int g = 0; g < G; ++g) pd.p[g] = reinterpret_cast<u32*>(d->peer[g] + d->off_phi);
+        pd.chunk = rt.chunk;
+        if (m_loc) KL(P, KC_LCP, (u64)m_loc * 12, st, (k_dist_phi<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(w.SA, m_loc, left_sa, pd)));
+        NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+        LcpDist ld;
+        memset(&ld, 0, sizeof(ld));
+        ld.PHI = PHI;
+        ld.pos0 = (u32)std::min<u64>((u64)me * rt.chunk, n1);
+        ld.pos1 = (u32)std::min<u64>((u64)(me + 1) * rt.chunk, n1);
+        for (int g = 0; g < G; ++g) { ld.lcp[g] = reinterpret_cast<u32*>(d->peer[g] + d->off_lcp) + DIST_VIRT; ld.base[g] = rt.base[g]; }
+        ld.base[G] = rt.base[G];
+        ld.G = G;
+        BatchView bv;
+        memset(&bv, 0, sizeof(bv));
+        const u32 npos = ld.pos1 - ld.pos0;
+        if (npos)
+            KL(P, KC_LCP, (u64)npos * 28, st,
+               (k_lcp_kasai<false, true><<<ceil_div_u32(ceil_div_u32(npos, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, nullptr, w.RANK, nullptr, bv, ld)));
+        NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+    }
+    NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
+
+    // ---- S3a: boundary exchange.  Edge staircases of the local range (trees over the real ranks, guards at both ends)
+    WalkParams wp;
+    wp.n1 = m_loc; wp.nfac = pb.nfac; wp.N = pb.N; wp.twoN = 2 * pb.N;
+    wp.real_lo = 0; wp.real_hi = m_loc; wp.rank_add = 0;
+    NLZ_CK(cudaMemsetAsync(d_pay, 0, DIST_XCH_WORDS * 4, st));
+    if (m_loc) {
+        NLZ_CK(cudaMemcpyAsync(d_pay, w.LCP, 4, cudaMemcpyDeviceToDevice, st));          // c0 = lcp(previous GPU's last, my first)
+        NLZ_CK(cudaMemsetAsync(w.LCP, 0, 4, st));
+        NLZ_CK(cudaMemsetAsync(w.LCP + m_loc, 0, 4, st));
+        k_set_u32<<<1, 1, 0, st>>>(d_pay + 1, m_loc);
+        NLZ_TRY(stage_lpnf(c, pb, st, w.SA, w.LCP, wp, nullptr, nullptr, nullptr));
+        if (pb.rc) k_dist_edges<true><<<1, 64, 0, st>>>(c->trees, wp, m_loc, K, d_pay + 4);
+        else k_dist_edges<false><<<1, 64, 0, st>>>(c->trees, wp, m_loc, K, d_pay + 4);
+    }
+    const u32 pay_words = 4 + 8 * (u32)K;
+    NLZ_TRY(dist_barrier(dr, st, d_pay, pay_words, all.data()));
+    u32 n_ext = 0;
+    if (m_loc) {
+        auto C0 = [&](int g) { return all[(size_t)g * pay_words + 0]; };
+        auto M = [&](int g) { return all[(size_t)g * pay_words + 1]; };
+        auto E = [&](int g, int side, int v) { return &all[(size_t)g * pay_words + 4 + (size_t)(side * K + v - 1) * 4]; };
+        auto minint = [&](int g) { u32 r = 0; for (int v = 1; v <= K; ++v) if (E(g, 0, v)[3]) r = (u32)v; return r; };
+        auto prev_ne = [&](int g) { for (--g; g >= 0; --g) if (M(g)) return g; return -1; };
+        auto next_ne = [&](int g) { for (++g; g < G; ++g) if (M(g)) return g; return -1; };
+        auto merge = [&](std::vector<VirtBlock>& blk, int g, int side, u32 cur) {
+            for (int v = 1; v <= K; ++v) {
+                const u32* e = E(g, side, v);
+                if (!e[0]) continue;
+                const u32 eff = (u32)v < cur ? (u32)v : cur;
+                VirtBlock& b = blk[eff];
+                b.cnt += e[0];
+                if (e[1] < b.F) b.F = e[1];
+                if (e[2] > b.R) b.R = e[2];
+            }
+        };
+        std::vector<VirtBlock> left(K + 1), right(K + 1);
+        const u32 c0 = C0(me);
+        {
+            u32 cur = c0 < (u32)K ? c0 : (u32)K;
+            for (int g = prev_ne(me); g >= 0 && cur > 0; g = prev_ne(g)) {
+                merge(left, g, 0, cur);
+                cur = std::min(cur, std::min(minint(g), C0(g)));
+            }
+        }
+        {
+            int g = next_ne(me);
+            u32 cur = g >= 0 ? std::min<u32>(C0(g), (u32)K) : 0u;
+            while (g >= 0 && cur > 0) {
+                merge(right, g, 1, cur);
+                cur = std::min(cur, minint(g));
+                g = next_ne(g);
+                if (g >= 0) cur = std::min(cur, C0(g));
+            }
+        }
+        // virtual ranks: per block one representative per class (min forward start / max rc start), or a null leaf
+        u32* hv = d->h_pin;                                  // [SA left 64 | LCP left 64 | SA right 64 | LCP right 64 + guard]
+        u32 *sl = hv, *ll = hv + 64, *sr = hv + 128, *lr = hv + 192;
+        for (int i = 0; i < 64; ++i) { sl[i] = NONE_MIN; ll[i] = 0; sr[i] = NONE_MIN; lr[i] = 0; }
+        lr[64] = 0;
+        auto reps_of = [&](const VirtBlock& b, u32 reps[2]) {
+            int k = 0;
+            if (b.F != NONE_MIN) reps[k++] = b.F;
+            if (b.R != 0) reps[k++] = b.R;
+            if (!k) reps[k++] = NONE_MIN;
+            return k;
+        };
+        u32 vl = 0;
+        for (int eff = 1; eff <= K; ++eff) if (left[eff].cnt) { u32 r2[2]; vl += (u32)reps_of(left[eff], r2); }
+        {
+            u32 idx = DIST_VIRT - vl, prev_eff = 0;
+            for (int eff = 1; eff <= K; ++eff) {
+                if (!left[eff].cnt) continue;
+                u32 r2[2];
+                const int k = reps_of(left[eff], r2);
+                for (int j = 0; j < k; ++j) { sl[idx] = r2[j]; ll[idx] = j == 0 ? prev_eff : (u32)eff; ++idx; }
+                prev_eff = (u32)eff;
+            }
+        }
+        u32 vr = 0;
+        for (int eff = K; eff >= 1; --eff) {
+            if (!right[eff].cnt) continue;
+            u32 r2[2];
+            const int k = reps_of(right[eff], r2);
+            for (int j = 0; j < k; ++j) { sr[vr] = r2[j]; lr[vr] = (u32)eff; ++vr; }
+        }
+        lr[vr] = 0;                                          // right guard
+        NLZ_CK(cudaMemcpyAsync(SAbuf, sl, 64 * 4, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(LCPbuf, ll, 64 * 4, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.SA + m_loc, sr, 64 * 4, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.LCP + m_loc, lr, 65 * 4, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.LCP, &all[(size_t)me * pay_words], 4, cudaMemcpyHostToDevice, st));   // restore c0
+        n_ext = DIST_VIRT + m_loc + vr;
+
+        // ---- S3b: factor rule in rank space over [virtual | real | virtual]
+        wp.n1 = n_ext;
+        wp.real_lo = DIST_VIRT; wp.real_hi = DIST_VIRT + m_loc;
+        wp.rank_add = (u32)DIST_VIRT - rt.base[me];
+        NLZ_CK(cudaMemsetAsync(HARDF, 0, pb.nfac, st));
+        NLZ_TRY(stage_lpnf(c, pb, st, SAbuf, LCPbuf, wp, w.RANK, LRloc, HARDF));
+        u64* LR0 = reinterpret_cast<u64*>(d->peer[0] + d->off_lr);
+        KL(P, KC_WALK, (u64)m_loc * 20, st, (k_dist_push_lr<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(w.SA, m_loc, pb.nfac, LRloc, LR0)));
+    }
+    NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+    NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
+
+    // ---- S4: chain on rank 0; the count travels with the closing barrier
+    u64 z = 0;
+    NLZ_CK(cudaMemsetAsync(d_pay, 0, 8, st));
+    // in-process groups may share a device: rank 0's output (re)allocation synchronises that device, so no
+    // other rank may sit in a spinning barrier kernel meanwhile -> host rendezvous around the chain stage
+    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); d->hb->arrive(); }
+    if (me == 0) {
+        const u64* LR0 = reinterpret_cast<const u64*>(d->seg + d->off_lr);
+        NLZ_TRY(stage_chain(c, pb, st, LR0, cs, nullptr, 0, out_alloc == nullptr, &z));
+        k_set_u32<<<1, 1, 0, st>>>(d_pay, (u32)z);
+    }
+    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); d->hb->arrive(); }
+    NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
+    NLZ_TRY(dist_barrier(dr, st, d_pay, 2, all.data()));
+    if (m_loc) account_walk(c);
+    z = all[0];
+    c->stats.n_factors = z;
+    if (me == 0 && out_alloc && z) {
+        u64* dst = static_cast<u64*>(malloc((size_t)z * 24));
+        if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)z); return ERR_RUNTIME; }
+        *out_alloc = dst;
+        NLZ_CK(cudaMemcpyAsync(dst, c->d_out, (size_t)z * 24, cudaMemcpyDeviceToHost, st));
+    }
+    NLZ_CK(cudaStreamSynchronize(st));
+    NLZ_CK(cudaGetLastError());
+    *out_count = z;
     return OK;
 }
 
@@ -947,6 +1419,137 @@ int nlz_factorize_batch(nlz_ctx* c, int with_rc, const uint8_t* concat, const ui
         prev = end + 1;
     }
     *total = zout;
+    return OK;
+}
+
+// ---- one text across G GPUs ------------------------------------------------------------------
+static size_t dist_al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int nlz_dist_create(nlz_ctx* c, int rank, int world, uint64_t max_text_bytes, int max_mode, nlz_dist** out) {
+    if (!c || !out) { set_error("null argument"); return ERR_INVALID; }
+    *out = nullptr;
+    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) { set_error("bad rank %d / world %d (at most %d ranks)", rank, world, MAX_PEERS); return ERR_INVALID; }
+    const u64 max_n1 = (max_mode == NLZ_MODE_DNA_RC ? 2 * max_text_bytes + 2 : max_text_bytes) + 1;
+    if (max_n1 >= 0xFFFFFFF0ull) { set_error("text of %llu symbols exceeds the 32-bit index path of this build", (unsigned long long)max_n1); return ERR_RUNTIME; }
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    nlz_dist* d = new nlz_dist();
+    d->ctx = c; d->rank = rank; d->world = world; d->max_n1 = max_n1;
+    d->off_rank = dist_al(sizeof(DistCtl));
+    d->off_lcp = d->off_rank + dist_al((max_n1 + 72) * 4);
+    d->off_phi = d->off_lcp + dist_al((max_n1 + 2 * DIST_VIRT + 200) * 4);
+    d->off_lr = d->off_phi + dist_al((max_n1 / world + 4096) * 4);
+    d->seg_bytes = d->off_lr + (rank == 0 ? dist_al(max_n1 * 8) : 0);
+    cudaError_t e = cudaMalloc(&d->seg, d->seg_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d->Xbuf, max_n1 + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&d->DCNT, (max_n1 / KB_TP + 8) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->HISTP, ((size_t)(1u << 24) + 1024) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->SMALL, 1024 * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&d->h_pin, ((size_t)MAX_PEERS * DIST_XCH_WORDS + 64) * 4);
+    if (e == cudaSuccess) e = cudaMemset(d->seg, 0, d->off_rank);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error("allocating the distributed workspace (%zu bytes shared) failed: %s", d->seg_bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        nlz_dist_destroy(d);
+        return ERR_CUDA;
+    }
+    d->peer[rank] = d->seg;
+    *out = d;
+    return OK;
+}
+
+void nlz_dist_destroy(nlz_dist* d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < MAX_PEERS; ++g) if (d->ipc_opened[g]) cudaIpcCloseMemHandle(d->peer[g]);
+    if (d->seg) cudaFree(d->seg);
+    if (d->Xbuf) cudaFree(d->Xbuf);
+    if (d->DCNT) cudaFree(d->DCNT);
+    if (d->HISTP) cudaFree(d->HISTP);
+    if (d->SMALL) cudaFree(d->SMALL);
+    if (d->arena.base) cudaFree(d->arena.base);
+    if (d->h_pin) cudaFreeHost(d->h_pin);
+    if (d->owns_hb) delete d->hb;
+    cudaGetLastError();
+    delete d;
+}
+
+int nlz_dist_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int nlz_dist_export(nlz_dist* d, uint8_t* handle_out) {
+    if (!d || !handle_out) { set_error("null argument"); return ERR_INVALID; }
+    NLZ_CK(cudaSetDevice(d->ctx->device));
+    cudaIpcMemHandle_t h;
+    NLZ_CK(cudaIpcGetMemHandle(&h, d->seg));
+    memcpy(handle_out, &h, sizeof(h));
+    return OK;
+}
+
+int nlz_dist_attach(nlz_dist* d, const uint8_t* all_handles) {
+    if (!d || !all_handles) { set_error("null argument"); return ERR_INVALID; }
+    NLZ_CK(cudaSetDevice(d->ctx->device));
+    for (int g = 0; g < d->world; ++g) {
+        if (g == d->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)g * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        NLZ_CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        d->peer[g] = static_cast<u8*>(p);
+        d->ipc_opened[g] = true;
+    }
+    d->attached = true;
+    return OK;
+}
+
+int nlz_dist_attach_local(nlz_dist* const* ranks, int world) {
+    if (!ranks || world < 1 || world > MAX_PEERS) { set_error("bad local group"); return ERR_INVALID; }
+    HostBarrier* hb = new HostBarrier();
+    hb->world = world;
+    for (int a = 0; a < world; ++a) {
+        nlz_dist* d = ranks[a];
+        if (!d || d->rank != a || d->world != world) { set_error("local group: rank %d is missing or misnumbered", a); delete hb; return ERR_INVALID; }
+        NLZ_CK(cudaSetDevice(d->ctx->device));
+        for (int g = 0; g < world; ++g) {
+            d->peer[g] = ranks[g]->seg;
+            const int dev = ranks[g]->ctx->device;
+            if (dev != d->ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    set_error("cannot enable peer access %d -> %d: %s", d->ctx->device, dev, cudaGetErrorString(e));
+                    delete hb;
+                    return ERR_CUDA;
+                }
+                cudaGetLastError();
+            }
+        }
+        d->hb = hb;
+        d->owns_hb = a == 0;
+        d->attached = true;
+    }
+    return OK;
+}
+
+int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples, uint64_t* out_count) {
+    if (!d || !out_count) { set_error("null argument"); return ERR_INVALID; }
+    if (n && !text) { set_error("null text"); return ERR_INVALID; }
+    if (!d->attached && d->world > 1) { set_error("distributed group is not attached"); return ERR_INVALID; }
+    nlz_ctx* c = d->ctx;
+    std::lock_guard<std::mutex> lock(c->mu);
+    NLZ_CK(cudaSetDevice(c->device));
+    *out_count = 0;
+    if (out_triples) *out_triples = nullptr;
+    Problem pb;
+    bool empty = false;
+    NLZ_TRY(make_problem(mode, n, 0, pb, &empty));
+    reset_stats(c);
+    if (empty) return OK;
+    if (pb.n1 > d->max_n1) { set_error("text of %llu suffixes exceeds the group's capacity of %llu", (unsigned long long)pb.n1, (unsigned long long)d->max_n1); return ERR_INVALID; }
+    u64 z = 0;
+    NLZ_TRY(run_dist(d, pb, text, d->rank == 0 ? out_triples : nullptr, &z));
+    finish_stats(c, pb);
+    *out_count = z;
     return OK;
 }
 

@@ -56,16 +56,32 @@ __device__ __forceinline__ u32 warp_extend_match(const u64* __restrict__ xw, u64
 //    LCP_LOCAL_WORDS words hands the comparison to its warp.
 // BATCH: suffixes of different records share nothing, and a match stops at the sentinel that ends
 // either segment (batch sentinels all carry the same byte, so the raw compare alone would run on).
-template <bool BATCH>
+// DIST (one text across GPUs, dist.cuh): this GPU owns the text positions [pos0, pos1); Phi arrives from
+// the owners of the ranks (PHI[i - pos0] = SA[RANK[i] - 1]) and LCP[r] is stored to the owner of rank r.
+struct LcpDist {
+    const u32* PHI;
+    u32 pos0, pos1;
+    u32* lcp[MAX_PEERS];       // local LCP arrays of all GPUs (entry 0 = first rank the GPU owns)
+    u32 base[MAX_PEERS + 1];   // rank ranges
+    int G;
+    __device__ __forceinline__ void store(u32 r, u32 l) const {
+        int g = 0;
+        while (g + 1 < G && r >= base[g + 1]) ++g;
+        lcp[g][r - base[g]] = l;
+    }
+};
+
+template <bool BATCH, bool DIST>
 __global__ void __launch_bounds__(256)
 k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
-            const u32* __restrict__ RANK, u32* __restrict__ LCP, BatchView bv) {
+            const u32* __restrict__ RANK, u32* __restrict__ LCP, BatchView bv, LcpDist ld) {
     const u64* xw = reinterpret_cast<const u64*>(x);
     const u32 lane = threadIdx.x & 31;
     const u64 c = (u64)blockIdx.x * 256 + threadIdx.x;
-    const u64 i0 = c * LCP_Q;
-    if ((c - lane) * LCP_Q >= n1) return;          // whole warp out of range (warp-uniform)
-    if (c == 0) LCP[n1] = 0;                       // right guard used by the interval walks
+    const u64 i0 = (DIST ? (u64)ld.pos0 : 0ull) + c * LCP_Q;
+    if (DIST) n1 = ld.pos1;
+    if (i0 - (u64)lane * LCP_Q >= n1) return;      // whole warp out of range (warp-uniform)
+    if (!DIST && c == 0) LCP[n1] = 0;              // right guard used by the interval walks
     u32 l = 0;
 #pragma unroll 1
     for (int k = 0; k < LCP_Q; ++k) {
@@ -74,9 +90,9 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
         bool need = false;
         if (i < n1) {
             r = RANK[i];
-            if (r == 0) { LCP[0] = 0; l = 0; }
+            if (r == 0) { if (DIST) ld.store(0, 0); else LCP[0] = 0; l = 0; }
             else {
-                j = SA[r - 1];
+                j = DIST ? ld.PHI[i - ld.pos0] : SA[r - 1];
                 maxl = (u32)(L - (i > j ? i : (u64)j));
                 if (BATCH) {
                     if (bv.REC[i] != bv.REC[j]) maxl = 0;
@@ -139,7 +155,7 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
             }
         }
         if (need) {
-            LCP[r] = l;
+            if (DIST) ld.store(r, l); else LCP[r] = l;
             if (l) --l;
         }
     }

@@ -62,6 +62,10 @@ struct WalkParams {
     u32 nfac;      // positions [0, nfac) are factorized (general: L, RC: N)
     u32 N;         // RC: |S|/2 - 1
     u32 twoN;      // RC: 2N
+    // distributed runs (dist.cuh): the arrays hold virtual ranks around the real ones; only ranks in
+    // [real_lo, real_hi) are evaluated, and a global rank r lives at index r + rank_add (mod 2^32).
+    // Single GPU: real_lo = 0, real_hi = n1, rank_add = 0.
+    u32 real_lo, real_hi, rank_add;
 };
 
 template <bool RC> __device__ __forceinline__ u32 f_value(u32 s, const WalkParams& p) {
@@ -692,7 +696,7 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, NodeTables nt, int max_nodes, u64* 
     const u32* LCP = T.lcp[0];
     const u32* SA = T.f[0];
     u32 i = 0xFFFFFFFFu;
-    if (r < p.n1) i = SA[r];
+    if (r >= p.real_lo && r < p.real_hi) i = SA[r];
     if (i < p.nfac) {
         bool have_f = false, at_root = false;
         u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
@@ -794,7 +798,7 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict
         if (k != prev_k + 1) prevF = 0;                          // the carry only links consecutive positions
         prev_k = k;
         const u32 i = (u32)(i0 + k);
-        const u32 r = __ldg(RANK + i);
+        const u32 r = __ldg(RANK + i) + p.rank_add;
         NodeState leaf;
         leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
         const u32 Dtop = max(__ldg(LCP + r), __ldg(LCP + r + 1)) + 1;   // deeper than the leaf's parent nothing matches

@@ -53,6 +53,20 @@ __device__ __forceinline__ u32 batch_cap(const BatchView& bv, u32 p) {
     return 2 * bv.N - fs + 1 - p;                         // rc half: its segment ends at the mirror of the sentinel before fs
 }
 
+// Where refined ranks are written.  One GPU: its RANK array.  Distributed (one rank-range of the suffix
+// array per GPU): the replica of every GPU, through peer pointers over NVLink, and `base` = the first
+// global rank this GPU owns (slots and ranks are global, the local SA array starts at rank `base`).
+constexpr int MAX_PEERS = 8;
+struct RankDst {
+    u32* p[MAX_PEERS];
+    int n;
+    u32 base;
+    __device__ __forceinline__ void store(u32 s, u32 r) const {
+#pragma unroll 1
+        for (int g = 0; g < n; ++g) p[g][s] = r;
+    }
+};
+
 // ---------------------------------------------------------------- byte histogram
 __global__ void __launch_bounds__(256) k_byte_hist(const u8* __restrict__ x, u64 L, u32* __restrict__ hist) {
     __shared__ u32 h[8][256];
@@ -78,42 +92,111 @@ __global__ void __launch_bounds__(256) k_byte_hist(const u8* __restrict__ x, u64
 
 // ---------------------------------------------------------------- key construction
 // One thread per suffix; the CTA stages its text window in shared memory (coalesced 4-byte loads).
-template <typename KeyT>
-__global__ void __launch_bounds__(256)
-k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay, const u32* __restrict__ REC,
-             KeyT* __restrict__ keys, u32* __restrict__ vals) {
-    constexpr int TP = 2048;            // suffixes per CTA
-    constexpr int HALO = 32;            // >= max W
-    __shared__ u8 cls[256];
-    __shared__ __align__(16) u8 tile[TP + HALO];
+constexpr int KB_TP = 2048;            // suffixes per CTA
+constexpr int KB_HALO = 32;            // >= max W
+
+__device__ __forceinline__ void kb_stage(const u8* __restrict__ x, u64 L, const ClassTable& tab, u8* cls, u8* tile) {
     cls[threadIdx.x] = tab.cls[threadIdx.x];
-    const u64 base = (u64)blockIdx.x * TP;
+    const u64 base = (u64)blockIdx.x * KB_TP;
     // x is padded with >= 64 readable bytes past L (workspace contract)
     const u32* xw = reinterpret_cast<const u32*>(x + base);
     u32* tw = reinterpret_cast<u32*>(tile);
-    for (int i = threadIdx.x; i < (TP + HALO) / 4; i += 256) {
+    for (int i = threadIdx.x; i < (KB_TP + KB_HALO) / 4; i += 256) {
         u64 byte0 = base + (u64)i * 4;
         tw[i] = (byte0 < L + 64) ? xw[i] : 0u;
     }
     __syncthreads();
+}
+
+template <typename KeyT>
+__device__ __forceinline__ KeyT kb_key(const u8* cls, const u8* tile, int o, u64 p, u64 L, const KeyLayout& lay,
+                                       const u32* __restrict__ REC) {
     const int kb = lay.key_bits, b = lay.b, W = lay.W;
-    const KeyT dist_none = ((KeyT)1 << lay.D) - 1;
+    KeyT key = 0;
+    KeyT dist = ((KeyT)1 << lay.D) - 1;
+    int sh = kb - lay.R - b;
+    if (lay.R) key = (KeyT)REC[p] << (kb - lay.R);
+    for (int t = 0; t < W; ++t, sh -= b) {
+        u32 c = (p + t < L) ? (u32)cls[tile[o + t]] : SENT_CLASS;
+        if (c == SENT_CLASS) { dist = (KeyT)t; break; }
+        key |= (KeyT)c << sh;
+    }
+    return key | dist;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay, const u32* __restrict__ REC,
+             KeyT* __restrict__ keys, u32* __restrict__ vals) {
+    __shared__ u8 cls[256];
+    __shared__ __align__(16) u8 tile[KB_TP + KB_HALO];
+    kb_stage(x, L, tab, cls, tile);
+    const u64 base = (u64)blockIdx.x * KB_TP;
 #pragma unroll 1
-    for (int r = 0; r < TP / 256; ++r) {
+    for (int r = 0; r < KB_TP / 256; ++r) {
         const int o = r * 256 + threadIdx.x;
         const u64 p = base + o;
         if (p >= n1) break;
-        KeyT key = 0;
-        KeyT dist = dist_none;
-        int sh = kb - lay.R - b;
-        if (lay.R) key = (KeyT)REC[p] << (kb - lay.R);
-        for (int t = 0; t < W; ++t, sh -= b) {
-            u32 c = (p + t < L) ? (u32)cls[tile[o + t]] : SENT_CLASS;
-            if (c == SENT_CLASS) { dist = (KeyT)t; break; }
-            key |= (KeyT)c << sh;
-        }
-        keys[p] = key | dist;
+        keys[p] = kb_key<KeyT>(cls, tile, o, p, L, lay, REC);
         vals[p] = (u32)p;
+    }
+}
+
+// Distributed suffix array: every GPU scans the whole (replicated) text but keeps only the suffixes whose
+// key prefix (top `pbits` bits) falls into its bucket range [plo, phi).
+//   MODE 0: histogram of the key prefixes (atomicAdd into hist[2^pbits]);
+//   MODE 1: number of kept suffixes per CTA;
+//   MODE 2: ordered (position order = stable) compaction of the kept (key, suffix) pairs.
+template <typename KeyT, int MODE>
+__global__ void __launch_bounds__(256)
+k_keys_partition(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay, int pbits, u32 plo, u32 phi,
+                 u32* __restrict__ hist_or_counts, KeyT* __restrict__ keys, u32* __restrict__ vals) {
+    __shared__ u8 cls[256];
+    __shared__ __align__(16) u8 tile[KB_TP + KB_HALO];
+    __shared__ u32 wcnt[8];
+    __shared__ u32 s_run;
+    kb_stage(x, L, tab, cls, tile);
+    const u64 base = (u64)blockIdx.x * KB_TP;
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 run = (MODE == 2) ? hist_or_counts[blockIdx.x] : 0u;    // MODE 2: exclusive prefix of the CTA counts
+    u32 mine = 0;
+#pragma unroll 1
+    for (int r = 0; r < KB_TP / 256; ++r) {
+        const int o = r * 256 + threadIdx.x;
+        const u64 p = base + o;
+        KeyT key = 0;
+        bool keep = false;
+        if (p < n1) {
+            key = kb_key<KeyT>(cls, tile, o, p, L, lay, nullptr);
+            const u32 pre = (u32)(key >> (lay.key_bits - pbits));
+            if (MODE == 0) atomicAdd(&hist_or_counts[pre], 1u);
+            keep = pre >= plo && pre < phi;
+        }
+        if (MODE == 1) mine += keep ? 1u : 0u;
+        if (MODE == 2) {
+            const u32 bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) wcnt[w] = __popc(bal);
+            __syncthreads();
+            u32 before = 0, tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const u32 c = wcnt[i]; if (i < (int)w) before += c; tot += c; }
+            if (keep) {
+                const u32 dst = run + before + __popc(bal & lanemask_lt());
+                keys[dst] = key;
+                vals[dst] = (u32)p;
+            }
+            run += tot;
+            __syncthreads();
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (threadIdx.x == 0) s_run = 0;
+        __syncthreads();
+        if (lane == 0 && mine) atomicAdd(&s_run, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) hist_or_counts[blockIdx.x] = s_run;
     }
 }
 
@@ -208,7 +291,7 @@ template <typename KeyT, bool INITIAL>
 __global__ void __launch_bounds__(RG_THREADS)
 k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ slots,
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
-                u32* __restrict__ SA, u32* __restrict__ RANK, u64* __restrict__ key_next,
+                u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
                 u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out) {
     __shared__ u8 sh_head[RG_TILE + 8];
     __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
@@ -265,11 +348,11 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
         if (idx < valid) {
             u32 e = (u32)(tile_start + idx);
             u32 hj = max(hm[q], cm) - 1;          // index (in this sorted list) of the group head
-            u32 newrank = INITIAL ? hj : slots[hj];
+            u32 newrank = INITIAL ? hj + RANK.base : slots[hj];
             u32 s = vals[e];
-            u32 slot = INITIAL ? e : slots[e];
-            RANK[s] = newrank;
-            SA[slot] = s;
+            u32 slot = INITIAL ? e + RANK.base : slots[e];
+            RANK.store(s, newrank);
+            SA[slot - RANK.base] = s;
             if (act[q]) {
                 u32 pos = cs + ps[q];
                 key_next[pos] = (u64)newrank << 32;

@@ -24,6 +24,7 @@
 // reservation per tile; the order of groups in that list is irrelevant).
 #pragma once
 #include "common.cuh"
+#include "sa.cuh"
 
 namespace nlz {
 
@@ -84,7 +85,7 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
 
 __global__ void __launch_bounds__(TSORT_THREADS)
 k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in, u32 m,
-            u32 tile, u32 maxg, u32* __restrict__ SA, u32* __restrict__ RANK, u64* __restrict__ key_next,
+            u32 tile, u32 maxg, u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
             u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ ctr /* [0] m', [3] max group */,
             int dbg) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
@@ -277,8 +278,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         const u32 s = sval[o];
         const u32 slot = sslot[o];
         const u32 newrank = sslot[sgs[o]];
-        RANK[s] = newrank;
-        SA[slot] = s;
+        RANK.store(s, newrank);
+        SA[slot - RANK.base] = s;
         if (act[o]) {
             const u32 pos = base + seq[o];
             key_next[pos] = (u64)newrank << 32;

@@ -1,0 +1,77 @@
+"""One text across several ranks (csrc/dist.cuh).  The ranks of these tests share cuda:0 -- every exchange
+step (rank replicas, Phi / LCP delivery, edge staircases, virtual ranks, LR push, barriers) runs exactly as it
+does across GPUs, only the peer pointers are local; the multi-GPU launch is covered by bench.py --gpus N."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from nolzss_b200 import _lib as L
+from nolzss_b200 import dist as nd
+from nolzss_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _expected(mode, s):
+    if mode == L.MODE_GENERAL:
+        return orc.factorize(s)
+    if mode == L.MODE_DNA_RC:
+        return orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s))
+    return orc.factorize_multiple_dna_w_rc(s)
+
+
+def _cases():
+    rng = random.Random(5)
+    cases = [b"ACGT" * 8, b"A" * 300, b"AC" * 200, b"GATTACA" * 30, b"ACGTTGCAACGTTGCA", b"T" + b"A" * 99 + b"C" + b"A" * 99]
+    for _ in range(40):
+        n = rng.choice([2, 3, 7, 33, 100, 500, 2000])
+        sigma = rng.choice([1, 2, 4, 4, 4])
+        cases.append(bytes(rng.choice(b"ACGT"[:sigma]) for _ in range(n)))
+    cases.append(wl.planted_dna(60_000, 7, scale=0.1).tobytes())
+    cases.append(wl.uniform_dna(50_000, 8).tobytes())
+    return cases
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+def test_dist_small_cases_vs_oracle(world):
+    grp = nd.LocalGroup([0] * world, 200_000, L.MODE_DNA_RC)
+    try:
+        for s in _cases():
+            for mode in (L.MODE_DNA_RC, L.MODE_GENERAL):
+                got, _ = grp.factorize(mode, s)
+                assert np.array_equal(got, _expected(mode, s)), (world, mode, s[:60], len(s))
+    finally:
+        grp.close()
+
+
+def test_dist_general_bytes_and_prepared():
+    rng = np.random.default_rng(3)
+    text = bytes(rng.integers(97, 123, 30_000, dtype=np.uint8))          # 26-letter alphabet: 8-bit symbols
+    words = [b"lorem", b"ipsum", b"dolor", b"sit", b"amet", b"consectetur"]
+    prose = b" ".join(words[i] for i in rng.integers(0, len(words), 8000))
+    from treewalk_model import prepare_multiple_dna_sequences_w_rc
+    S, _, _ = prepare_multiple_dna_sequences_w_rc([wl.uniform_dna(3000, 1).tobytes(), wl.planted_dna(5000, 2, scale=0.02).tobytes(), b"ACGTACGTAC"])
+    grp = nd.LocalGroup([0, 0, 0], 100_000, L.MODE_GENERAL)
+    try:
+        for s in (text, prose):
+            got, _ = grp.factorize(L.MODE_GENERAL, s)
+            assert np.array_equal(got, orc.factorize(s))
+        got, _ = grp.factorize(L.MODE_RC_PREPARED, S)
+        assert np.array_equal(got, orc.factorize_multiple_dna_w_rc(S))
+    finally:
+        grp.close()
+
+
+def test_dist_matches_single_gpu_5mbp_rc():
+    """configs[1] text on 4 ranks: identical triples to the single-GPU pipeline (itself oracle-checked)."""
+    s = wl.c2_text()
+    single = L.factorize_array(L.MODE_DNA_RC, s)
+    grp = nd.LocalGroup([0, 0, 0, 0], len(s), L.MODE_DNA_RC)
+    try:
+        got, stats = grp.factorize(L.MODE_DNA_RC, s)
+    finally:
+        grp.close()
+    assert np.array_equal(got, single)
+    assert sum(st["active_sum"] for st in stats) > 0
