@@ -305,6 +305,8 @@ struct DistRt {
 static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all);
 
 static RankDst rank_dst(nlz_ctx* c, DistRt* dr);
+static int dist_push_updates(DistRt* dr, cudaStream_t st, u32 cnt);
+static int dist_apply_updates(DistRt* dr, cudaStream_t st, const u32* cnts);
 
 template <typename KeyT>
 static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay,
@@ -351,7 +353,7 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
                                                               w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
     P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8), st, 3);
     *cur_out = res ^ 1;
-    if (dr) return OK;                                  // the counts travel with the next barrier
+    if (dr) return dist_push_updates(dr, st, cnt);      // the counts travel with the next barrier
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     c->stats.host_syncs += 1;
@@ -383,10 +385,14 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     int sc = 0;
     u32 gm = m;                                          // largest active count over all GPUs
     std::vector<u32> all((size_t)MAX_PEERS * 4);
+    u32 sent[MAX_PEERS];                                 // records every GPU pushed in the step before the barrier
+    if (dr) for (int g = 0; g < dr->G; ++g) sent[g] = dr->base[g + 1] - dr->base[g];
     for (;;) {
         if (dr) {
-            // all refined ranks of the previous step are in every replica; learn every GPU's (m, maxg)
+            // every GPU has pushed the ranks it refined; learn every GPU's (m, maxg), then apply their records
             NLZ_TRY(dist_barrier(dr, st, w.CTR, 4, all.data()));
+            NLZ_TRY(dist_apply_updates(dr, st, sent));
+            for (int g = 0; g < dr->G; ++g) sent[g] = all[(size_t)g * 4];
             m = all[(size_t)dr->me * 4 + 0];
             maxg = all[(size_t)dr->me * 4 + 3];
             gm = 0;
@@ -405,7 +411,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1,
                                                                      fused ? w.CTR : nullptr)));
         else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));
-        if (dr) NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));   // every GPU has read its snapshot of RANK
+        if (dr) NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));   // every GPU has applied its inbox: it may be overwritten
         if (m > 0 && fused) {
             // every tie group fits in shared memory: segmented sort + regroup in one pass
             u32 cap = 32;
@@ -434,6 +440,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                                                                     w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
             P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
         }
+        if (dr) NLZ_TRY(dist_push_updates(dr, st, m));
         if (!dr) {
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
             NLZ_CK(cudaStreamSynchronize(st));
@@ -768,7 +775,7 @@ struct nlz_dist {
     int rank = 0, world = 1;
     u64 max_n1 = 0;
     u8* seg = nullptr;                 // shared segment: DistCtl | RANK replica | local LCP | Phi slice | LR (rank 0)
-    size_t seg_bytes = 0, off_rank = 0, off_lcp = 0, off_phi = 0, off_lr = 0;
+    size_t seg_bytes = 0, off_rank = 0, off_lcp = 0, off_phi = 0, off_upd = 0, off_lr = 0, off_pos = 0;
     u8* peer[MAX_PEERS] = {};
     bool ipc_opened[MAX_PEERS] = {};
     bool attached = false;
@@ -787,13 +794,39 @@ namespace nlz {
 
 static RankDst rank_dst(nlz_ctx* c, DistRt* dr) {
     RankDst r;
-    memset(&r, 0, sizeof(r));
-    if (!dr) { r.p[0] = c->ws.RANK; r.n = 1; r.base = 0; return r; }
-    nlz_dist* d = dr->d;
-    for (int g = 0; g < dr->G; ++g) r.p[g] = reinterpret_cast<u32*>(d->peer[g] + d->off_rank);
-    r.n = dr->G;
-    r.base = dr->base[dr->me];
+    r.rank = c->ws.RANK; r.upd = nullptr; r.base = 0;
+    if (dr) {
+        r.base = dr->base[dr->me];
+        if (dr->G > 1) r.upd = reinterpret_cast<u64*>(dr->d->seg + dr->d->off_upd) + r.base;
+    }
     return r;
+}
+
+// The (suffix, rank) records of the `cnt` list elements this GPU just processed -> every other GPU's inbox
+// (bulk copies over NVLink; each source owns the inbox slice [base[src], base[src+1])).
+static int dist_push_updates(DistRt* dr, cudaStream_t st, u32 cnt) {
+    nlz_dist* d = dr->d;
+    if (!cnt) return OK;
+    const u64* mine = reinterpret_cast<const u64*>(d->seg + d->off_upd) + dr->base[dr->me];
+    for (int g = 0; g < dr->G; ++g) {
+        if (g == dr->me) continue;
+        u64* theirs = reinterpret_cast<u64*>(d->peer[g] + d->off_upd) + dr->base[dr->me];
+        NLZ_CK(cudaMemcpyAsync(theirs, mine, (size_t)cnt * 8, cudaMemcpyDefault, st));
+    }
+    d->ctx->prof.bytes[KC_BARRIER] += (u64)cnt * 8 * (dr->G - 1);
+    return OK;
+}
+// after the barrier: apply what the other GPUs sent (cnts[g] records from GPU g)
+static int dist_apply_updates(DistRt* dr, cudaStream_t st, const u32* cnts) {
+    nlz_dist* d = dr->d;
+    Profiler& P = d->ctx->prof;
+    for (int g = 0; g < dr->G; ++g) {
+        if (g == dr->me || !cnts[g]) continue;
+        const u64* inbox = reinterpret_cast<const u64*>(d->seg + d->off_upd) + dr->base[g];
+        KL(P, KC_REGROUP, (u64)cnts[g] * 12, st,
+           (k_dist_apply_ranks<<<ceil_div_u32(cnts[g], 256), 256, 0, st>>>(inbox, cnts[g], d->ctx->ws.RANK)));
+    }
+    return OK;
 }
 
 // Stream-ordered barrier over all ranks; optionally every rank contributes `nwords` words (device
@@ -806,8 +839,8 @@ static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nword
     peers.n = dr->G; peers.me = dr->me;
     d->epoch += 1;
     if (nwords) d->xparity ^= 1;
-    k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords);
-    d->ctx->prof.launches[KC_PREPARE] += 1;
+    KL(d->ctx->prof, KC_BARRIER, (u64)nwords * 4 * dr->G, st,
+       (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords)));
     if (!h_all) return OK;
     DistCtl* mine = reinterpret_cast<DistCtl*>(d->seg);
     for (int g = 0; g < dr->G; ++g)
@@ -883,7 +916,17 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     NLZ_CK(cudaMemsetAsync(d->HISTP, 0, (size_t)nb * 4, st));
     if (lay.key_bits == 32) k_keys_partition<u32, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, 0, 0, d->HISTP, nullptr, nullptr);
     else k_keys_partition<u64, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, 0, 0, d->HISTP, nullptr, nullptr);
-    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d->HISTP, nb, nullptr);
+    {
+        const u32 nt = ceil_div_u32(nb, SCAN_TILE);
+        u32* tsum = d->HISTP + (size_t)(1u << 24) + 16;             // tile sums live behind the histogram
+        if (nt > 1) {
+            k_scan_tiles<false><<<nt, 1024, 0, st>>>(d->HISTP, nb, tsum);
+            k_scan_u32_single_cta<<<1, 1024, 0, st>>>(tsum, nt, nullptr);
+            k_scan_tiles<true><<<nt, 1024, 0, st>>>(d->HISTP, nb, tsum);
+        } else {
+            k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d->HISTP, nb, nullptr);
+        }
+    }
     k_dist_splitters<<<1, 32, 0, st>>>(d->HISTP, nb, n1, G, d_split, d_base);
     P.end(KC_KEYS, (u64)n1 + (u64)nb * 8, st, 3);
     NLZ_CK(cudaMemcpyAsync(d->h_pin, d_split, 32 * 4, cudaMemcpyDeviceToHost, st));   // SPLIT[16] | BASE[16]
@@ -1082,10 +1125,22 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
         wp.rank_add = (u32)DIST_VIRT - rt.base[me];
         NLZ_CK(cudaMemsetAsync(HARDF, 0, pb.nfac, st));
         NLZ_TRY(stage_lpnf(c, pb, st, SAbuf, LCPbuf, wp, w.RANK, LRloc, HARDF));
-        u64* LR0 = reinterpret_cast<u64*>(d->peer[0] + d->off_lr);
-        KL(P, KC_WALK, (u64)m_loc * 20, st, (k_dist_push_lr<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(w.SA, m_loc, pb.nfac, LRloc, LR0)));
+        // results to GPU 0: (SA, LR[SA]) of the local ranks in rank order, bulk-copied into its inboxes
+        u64* lval = reinterpret_cast<u64*>(d->seg + d->off_upd) + rt.base[me];
+        KL(P, KC_WALK, (u64)m_loc * 20, st, (k_dist_pack_lr<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(w.SA, m_loc, pb.nfac, LRloc, lval)));
+        if (me != 0) {
+            NLZ_CK(cudaMemcpyAsync(reinterpret_cast<u64*>(d->peer[0] + d->off_upd) + rt.base[me], lval, (size_t)m_loc * 8, cudaMemcpyDefault, st));
+            NLZ_CK(cudaMemcpyAsync(reinterpret_cast<u32*>(d->peer[0] + d->off_pos) + rt.base[me], w.SA, (size_t)m_loc * 4, cudaMemcpyDefault, st));
+        }
     }
     NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+    if (me == 0) {
+        u64* LR0 = reinterpret_cast<u64*>(d->seg + d->off_lr);
+        const u64* lval = reinterpret_cast<const u64*>(d->seg + d->off_upd);
+        u32* pos = reinterpret_cast<u32*>(d->seg + d->off_pos);
+        if (m_loc) NLZ_CK(cudaMemcpyAsync(pos, w.SA, (size_t)m_loc * 4, cudaMemcpyDeviceToDevice, st));   // base[0] = 0
+        KL(P, KC_WALK, (u64)n1 * 20, st, (k_dist_apply_lr<<<ceil_div_u32(n1, 256), 256, 0, st>>>(pos, lval, n1, pb.nfac, LR0)));
+    }
     NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
 
     // ---- S4: chain on rank 0; the count travels with the closing barrier
@@ -1438,12 +1493,14 @@ int nlz_dist_create(nlz_ctx* c, int rank, int world, uint64_t max_text_bytes, in
     d->off_rank = dist_al(sizeof(DistCtl));
     d->off_lcp = d->off_rank + dist_al((max_n1 + 72) * 4);
     d->off_phi = d->off_lcp + dist_al((max_n1 + 2 * DIST_VIRT + 200) * 4);
-    d->off_lr = d->off_phi + dist_al((max_n1 / world + 4096) * 4);
-    d->seg_bytes = d->off_lr + (rank == 0 ? dist_al(max_n1 * 8) : 0);
+    d->off_upd = d->off_phi + dist_al((max_n1 / world + 4096) * 4);
+    d->off_lr = d->off_upd + dist_al((max_n1 + 64) * 8);
+    d->off_pos = d->off_lr + dist_al((max_n1 + 64) * 8);
+    d->seg_bytes = rank == 0 ? d->off_pos + dist_al((max_n1 + 64) * 4) : d->off_lr;
     cudaError_t e = cudaMalloc(&d->seg, d->seg_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&d->Xbuf, max_n1 + 256);
     if (e == cudaSuccess) e = cudaMalloc(&d->DCNT, (max_n1 / KB_TP + 8) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d->HISTP, ((size_t)(1u << 24) + 1024) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->HISTP, ((size_t)(1u << 24) + 8192) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d->SMALL, 1024 * 4);
     if (e == cudaSuccess) e = cudaMallocHost(&d->h_pin, ((size_t)MAX_PEERS * DIST_XCH_WORDS + 64) * 4);
     if (e == cudaSuccess) e = cudaMemset(d->seg, 0, d->off_rank);

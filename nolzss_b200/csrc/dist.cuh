@@ -146,13 +146,66 @@ __global__ void k_dist_edges(Trees T, WalkParams p, u32 m, int K, u32* __restric
     o[0] = cnt; o[1] = fmin; o[2] = rmax; o[3] = whole;
 }
 
-// final LR of the positions whose rank is local -> GPU 0
+// (suffix, rank) records received from another GPU -> local RANK replica
 __global__ void __launch_bounds__(256)
-k_dist_push_lr(const u32* __restrict__ SA, u32 m, u32 nfac, const u64* __restrict__ LRloc, u64* __restrict__ LR0) {
+k_dist_apply_ranks(const u64* __restrict__ upd, u32 cnt, u32* __restrict__ RANK) {
+    const u32 e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= cnt) return;
+    const u64 u = upd[e];
+    RANK[(u32)u] = (u32)(u >> 32);
+}
+
+// per-position results of the local ranks, in rank order (bulk-copied to GPU 0 together with SA)
+__global__ void __launch_bounds__(256)
+k_dist_pack_lr(const u32* __restrict__ SA, u32 m, u32 nfac, const u64* __restrict__ LRloc, u64* __restrict__ lval) {
     const u32 r = blockIdx.x * 256 + threadIdx.x;
     if (r >= m) return;
     const u32 i = SA[r];
-    if (i < nfac) LR0[i] = LRloc[i];
+    lval[r] = i < nfac ? LRloc[i] : 0ull;
+}
+// GPU 0: LR[pos[r]] = lval[r]
+__global__ void __launch_bounds__(256)
+k_dist_apply_lr(const u32* __restrict__ pos, const u64* __restrict__ lval, u32 cnt, u32 nfac, u64* __restrict__ LR) {
+    const u32 r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= cnt) return;
+    const u32 i = pos[r];
+    if (i < nfac) LR[i] = lval[r];
+}
+
+// Exclusive scan of a large u32 array in three launches: per-tile sums, single-CTA scan of the tile
+// sums (k_scan_u32_single_cta), per-tile scan with the tile offset.  Tile = 4096 words, 1024 threads.
+constexpr int SCAN_TILE = 4096;
+template <bool APPLY>
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(u32* __restrict__ data, u32 count, u32* __restrict__ tile_sums) {
+    __shared__ u32 wsum[32];
+    const u32 base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    u32 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (base + j < count) ? data[base + j] : 0u;
+    const u32 s = v[0] + v[1] + v[2] + v[3];
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    u32 carry = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const u32 x = wsum[i]; if (i < (int)w) carry += x; tot += x; }
+    if (!APPLY) {
+        if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+        return;
+    }
+    u32 run = tile_sums[blockIdx.x] + carry + inc - s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (base + j < count) data[base + j] = run;
+        run += v[j];
+    }
 }
 
 __global__ void k_copy_words(const u32* __restrict__ a, u32* __restrict__ b, u32 n) {

@@ -23,12 +23,13 @@ enum KClass : int {
     KC_WALK,          // factor rule, rank order (bounded climb + direct RC candidate)
     KC_WALK_HARD,     // factor rule, text order over deep-nesting positions (depth search + carry)
     KC_CHAIN,         // chain extraction (exit, doubling, mark, scan, emit)
+    KC_BARRIER,       // distributed runs: flag barrier in peer memory (time = waiting for the slowest GPU)
     KC_COUNT
 };
 
 static const char* const kClassNames[KC_COUNT] = {
     "prepare", "build_keys", "radix_hist", "radix_scan", "radix_scatter", "gather_rank",
-    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain"};
+    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain", "dist_barrier"};
 
 struct Profiler {
     bool timing = false;

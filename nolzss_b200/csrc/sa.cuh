@@ -53,19 +53,21 @@ __device__ __forceinline__ u32 batch_cap(const BatchView& bv, u32 p) {
     return 2 * bv.N - fs + 1 - p;                         // rc half: its segment ends at the mirror of the sentinel before fs
 }
 
-// Where refined ranks are written.  One GPU: its RANK array.  Distributed (one rank-range of the suffix
-// array per GPU): the replica of every GPU, through peer pointers over NVLink, and `base` = the first
-// global rank this GPU owns (slots and ranks are global, the local SA array starts at rank `base`).
-constexpr int MAX_PEERS = 8;
+// Where refined ranks are written.  One GPU: its RANK array.  Distributed (one rank range of the suffix
+// array per GPU, dist.cuh): the local replica of RANK, plus one (suffix, rank) record per processed list
+// element in `upd` -- a contiguous list that is bulk-copied to the other GPUs over NVLink and applied to
+// their replicas there (scattered peer stores collapse beyond ~1 GB of span; bulk copies do not).
+// `base` = the first global rank this GPU owns: slots and ranks are global, the local SA array starts at `base`.
 struct RankDst {
-    u32* p[MAX_PEERS];
-    int n;
+    u32* rank;
+    u64* upd;
     u32 base;
-    __device__ __forceinline__ void store(u32 s, u32 r) const {
-#pragma unroll 1
-        for (int g = 0; g < n; ++g) p[g][s] = r;
+    __device__ __forceinline__ void store(u32 e, u32 s, u32 r) const {
+        rank[s] = r;
+        if (upd) upd[e] = ((u64)r << 32) | (u64)s;
     }
 };
+constexpr int MAX_PEERS = 8;
 
 // ---------------------------------------------------------------- byte histogram
 __global__ void __launch_bounds__(256) k_byte_hist(const u8* __restrict__ x, u64 L, u32* __restrict__ hist) {
@@ -351,7 +353,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
             u32 newrank = INITIAL ? hj + RANK.base : slots[hj];
             u32 s = vals[e];
             u32 slot = INITIAL ? e + RANK.base : slots[e];
-            RANK.store(s, newrank);
+            RANK.store(e, s, newrank);
             SA[slot - RANK.base] = s;
             if (act[q]) {
                 u32 pos = cs + ps[q];

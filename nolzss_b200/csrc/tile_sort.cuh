@@ -278,7 +278,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         const u32 s = sval[o];
         const u32 slot = sslot[o];
         const u32 newrank = sslot[sgs[o]];
-        RANK.store(s, newrank);
+        RANK.store(first + o, s, newrank);
         SA[slot - RANK.base] = s;
         if (act[o]) {
             const u32 pos = base + seq[o];
