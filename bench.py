@@ -266,6 +266,11 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = times.tolist()
+    one_text = None
+    if not args.no_single_text:
+        del d_text, d_out, flush
+        torch.cuda.empty_cache()
+        one_text = single_text_leg(world, rank, local, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -307,6 +312,8 @@ def run_ours(args):
                                            "walk_nodes", "host_syncs", "workspace_bytes")},
         "wall_s_timed_region": t_wall,
     }
+    if one_text is not None:
+        line["single_text_all_gpus"] = one_text
 
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -330,6 +337,52 @@ def run_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------- configs[3]: one text, all GPUs
+C3_BASES = 250_000_000
+
+
+def single_text_leg(world, rank, local, dist, steps=2):
+    """configs[3]: ONE 250 Mbp chromosome-sized text (planted repeats scaled x50), RC mode, across all `world` GPUs
+    (nolzss_b200.dist: rank-range-partitioned suffix array over peer memory); at N = 1 the ordinary single-GPU
+    pipeline.  Count-only calls from pageable host text; time = CUDA events inside the call, max over ranks."""
+    import torch
+
+    from nolzss_b200 import _lib as L
+    from nolzss_b200 import dist as nd
+    from nolzss_b200 import workloads as wl
+
+    text = wl.planted_dna(C3_BASES, 4, scale=50.0).tobytes()
+    out = {"workload": "configs[3]: one 250 Mbp synthetic text with planted tandem/interspersed repeats, RC mode "
+                       "(n' = 500 000 003 suffixes), partitioned over all GPUs", "n_bases": C3_BASES, "n_gpus": world}
+    times = []
+    if world == 1:
+        for it in range(steps + 1):
+            z = L.count(L.MODE_DNA_RC, text, device=local)
+            st = L.stats(local)
+            if it:
+                times.append(st["ms_total"])
+    else:
+        grp = nd.ProcessGroup(C3_BASES, L.MODE_DNA_RC, device=local)
+        lib = L.load()
+        addr, n, keep = L._as_buffer(text)
+        for it in range(steps + 1):
+            dist.barrier()
+            cnt = ctypes.c_uint64(0)
+            L.check(lib.nlz_dist_factorize(grp.dist, L.MODE_DNA_RC, addr, n, None, ctypes.byref(cnt)))
+            z = cnt.value
+            st = grp.stats()
+            t = torch.tensor([st["ms_total"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it:
+                times.append(t.item())
+        grp.close()
+    ms = sum(times) / len(times)
+    out.update(ms_per_text=ms, value=C3_BASES / ms / 1e3, unit=UNIT, factors=int(z),
+               stages_ms_rank0={k: st[k] for k in st if k.startswith("ms_")}, doubling_rounds=st["doubling_rounds"],
+               workspace_bytes_rank0=st["workspace_bytes"])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +390,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-text", action="store_true", help="skip the configs[3] leg (one 250 Mbp text over all GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

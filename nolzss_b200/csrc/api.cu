@@ -912,10 +912,12 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     rt.pbits = pbits;
     const u32 nb = 1u << pbits;
     const u32 nctas = ceil_div_u32(n1, KB_TP);
+    KeyLayout lay_top = lay;                                         // the bucket of a suffix only needs its first K symbols
+    lay_top.W = K;
     P.begin(st);
     NLZ_CK(cudaMemsetAsync(d->HISTP, 0, (size_t)nb * 4, st));
-    if (lay.key_bits == 32) k_keys_partition<u32, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, 0, 0, d->HISTP, nullptr, nullptr);
-    else k_keys_partition<u64, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, 0, 0, d->HISTP, nullptr, nullptr);
+    if (lay.key_bits == 32) k_keys_partition<u32, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, 0, 0, d->HISTP, nullptr, nullptr);
+    else k_keys_partition<u64, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, 0, 0, d->HISTP, nullptr, nullptr);
     {
         const u32 nt = ceil_div_u32(nb, SCAN_TILE);
         u32* tsum = d->HISTP + (size_t)(1u << 24) + 16;             // tile sums live behind the histogram
@@ -936,8 +938,8 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     rt.chunk = (u32)(((u64)ceil_div_u32(n1, G) + 1023) / 1024 * 1024);
     const u32 m_loc = rt.m_loc;
     P.begin(st);
-    if (lay.key_bits == 32) k_keys_partition<u32, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
-    else k_keys_partition<u64, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
+    if (lay.key_bits == 32) k_keys_partition<u32, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
+    else k_keys_partition<u64, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
     k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.DCNT, nctas, nullptr);
     P.end(KC_KEYS, (u64)n1, st, 2);
 
