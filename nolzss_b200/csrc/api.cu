@@ -67,7 +67,9 @@ struct Workspace {
     // batch mode only: record id per text position, record geometry, factor index of every record's sentinel
     u32 *REC = nullptr, *FSTART = nullptr, *FLEN = nullptr, *INOFF = nullptr, *SENTIDX = nullptr;
     u32* DCNT = nullptr;     // distributed runs: per-CTA counts / offsets of the key compaction
+    u32* RING = nullptr;     // pipelined doubling rounds: (list length, largest group) entering every round
 };
+constexpr int RING_ROUNDS = 48;
 
 }  // namespace nlz
 
@@ -85,6 +87,7 @@ struct nlz_ctx {
     u32* h_pinned = nullptr;    // 4 KB pinned readback area
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[EV_COUNT];
+    cudaEvent_t ring_ev[48];    // pipelined doubling rounds: count readback of every round
     nlz_stats stats;
     Profiler prof;
     Trees trees;                // summary trees of the last stage_lpnf call
@@ -103,7 +106,7 @@ static size_t workspace_bytes_for(u64 n1, u64 nrec) {
     t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
     size_t tiles = (n1 + RG_TILE - 1) / RG_TILE + 1;
     t += al(tiles * 4) * 2;
-    t += al(64 * 4) + al(256 * 4);
+    t += al(64 * 4) + al(256 * 4) + al(2 * RING_ROUNDS * 4);
     u64 c = n1 + 1;
     for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
         c = (c + 31) / 32;
@@ -155,6 +158,7 @@ static int ensure_workspace(nlz_ctx* c, u64 n1, u64 nrec = 0) {
     w.PSUM = a.take<u32>(tiles);
     w.CTR = a.take<u32>(64);
     w.BYTEHIST = a.take<u32>(256);
+    w.RING = a.take<u32>(2 * RING_ROUNDS);
     u64 cnt = n1 + 1;
     for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
         cnt = (cnt + 31) / 32;
@@ -387,6 +391,47 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     std::vector<u32> all((size_t)MAX_PEERS * 4);
     u32 sent[MAX_PEERS];                                 // records every GPU pushed in the step before the barrier
     if (dr) for (int g = 0; g < dr->G; ++g) sent[g] = dr->base[g + 1] - dr->base[g];
+    static const bool no_pipeline = getenv("NLZ_TRACE") != nullptr || getenv("NLZ_NO_PIPELINE") != nullptr;
+    if (!dr && !no_pipeline && m > 0 && maxg <= (u32)TSORT_SLOTS / 2) {
+        // Every remaining round is a fused one (groups only shrink).  The host runs one round AHEAD of the device:
+        // round r is launched with grids sized from the counts of round r-1 and reads its true list length from
+        // RING[r] on the device, so the per-round count readback no longer leaves the GPU idle.
+        u32* RING = w.RING;                              // RING[2r] = m_r, RING[2r+1] = largest group entering round r
+        u32* hring = c->h_pinned + 512;
+        NLZ_CK(cudaMemsetAsync(RING, 0, 2 * RING_ROUNDS * 4, st));
+        hring[0] = m; hring[1] = maxg;
+        NLZ_CK(cudaMemcpyAsync(RING, hring, 8, cudaMemcpyHostToDevice, st));
+        u32 bm = m, bg = maxg;                           // upper bounds for the round being launched
+        for (int r = 0;; ++r) {
+            if (r + 1 >= RING_ROUNDS) { set_error("prefix doubling did not converge"); return ERR_RUNTIME; }
+            u32 cap = 32;
+            while (cap < bg) cap <<= 1;
+            const u32 tile = TSORT_SLOTS - cap;
+            KL(P, KC_GATHER, (u64)bm * 24, st,
+               (k_gather_rank<<<ceil_div_u32(bm, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], bm, RING + 2 * r, w.RANK, h, n1, nullptr)));
+            KL(P, KC_TILE_SORT, (u64)bm * (12 + 4 + 8 + 16), st,
+               (k_tile_sort<<<ceil_div_u32(bm, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                   w.KEY[cur], w.VAL[cur], w.SLOT[sc], bm, RING + 2 * r, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
+                   w.SLOT[sc ^ 1], RING + 2 * (r + 1), RING + 2 * (r + 1) + 1, c->debug_flags)));
+            NLZ_CK(cudaMemcpyAsync(hring + 2 * (r + 1), RING + 2 * (r + 1), 8, cudaMemcpyDeviceToHost, st));
+            NLZ_CK(cudaEventRecord(c->ring_ev[r + 1], st));
+            cur ^= 1; sc ^= 1; h *= 2;
+            if (r == 0) { S.doubling_rounds += 1; S.tile_sort_rounds += 1; S.active_sum += m; continue; }
+            // the counts entering round r (produced by round r-1, which ran while round r was being launched)
+            NLZ_CK(cudaEventSynchronize(c->ring_ev[r]));
+            S.host_syncs += 1;
+            const u32 mr = hring[2 * r], gr = hring[2 * r + 1];
+            if (mr == 0) {                               // round r found nothing to do: r rounds did the work
+                P.bytes[KC_GATHER] -= (u64)bm * 24; P.bytes[KC_TILE_SORT] -= (u64)bm * 40;
+                break;
+            }
+            // algorithmic bytes were booked with the bound; correct them to the true list length
+            P.bytes[KC_GATHER] -= (u64)(bm - mr) * 24; P.bytes[KC_TILE_SORT] -= (u64)(bm - mr) * 40;
+            S.doubling_rounds += 1; S.tile_sort_rounds += 1; S.active_sum += mr;
+            bm = mr; bg = gr;
+        }
+        return OK;
+    }
     for (;;) {
         if (dr) {
             // every GPU has pushed the ranks it refined; learn every GPU's (m, maxg), then apply their records
@@ -408,7 +453,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
         const bool fused = maxg <= (u32)TSORT_SLOTS / 2;
         if (m > 0)
             KL(P, KC_GATHER, (u64)m * 24, st,
-               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, w.RANK, h, n1,
+               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, nullptr, w.RANK, h, n1,
                                                                      fused ? w.CTR : nullptr)));
         else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));
         if (dr) NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));   // every GPU has applied its inbox: it may be overwritten
@@ -419,8 +464,8 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
             const u32 tile = TSORT_SLOTS - cap;
             KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
                (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
-                   w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
-                   w.SLOT[sc ^ 1], w.CTR, c->debug_flags)));
+                   w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, nullptr, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
+                   w.SLOT[sc ^ 1], w.CTR, w.CTR + 3, c->debug_flags)));
             rb = cur;                       // next round's lists were written to the cur^1 buffers
             S.tile_sort_rounds += 1;
             if (trace) cudaEventRecord(tev1, st);
@@ -649,6 +694,18 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         NLZ_CK(cudaMemcpyAsync(w.X, src, pb.n_in, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
     }
     k_zero_pad<<<1, 128, 0, st>>>(w.X, pb.L);
+    if (pb.mode == NLZ_MODE_DNA_RC && !pb.nrec) {
+        // the alphabet is known (A C G T + two unique sentinels): no byte histogram and no host round trip; the
+        // validity flag is read back with the first count readback of the suffix sort (check_dna_deferred)
+        P.end(KC_PREPARE, pb.n_in + 2 * pb.L, st, prep_launches - 1);
+        NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
+        NLZ_CK(cudaEventRecord(c->ev[EV_PREP], st));
+        u32 hist[256];
+        for (int ch = 0; ch < 256; ++ch) hist[ch] = 0;
+        hist['A'] = hist['C'] = hist['G'] = hist['T'] = 2;
+        choose_layout(hist, n1, tab, lay);
+        return OK;
+    }
     NLZ_CK(cudaMemsetAsync(w.BYTEHIST, 0, 256 * 4, st));
     {
         u32 grid = ceil_div_u32(pb.L / 4 + 1, 256 * 8);
@@ -657,7 +714,7 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
     }
     P.end(KC_PREPARE, pb.n_in + 2 * pb.L, st, prep_launches);
     NLZ_CK(cudaMemcpyAsync(c->h_pinned + 16, w.BYTEHIST, 256 * 4, cudaMemcpyDeviceToHost, st));
-    if (pb.mode == NLZ_MODE_DNA_RC || pb.nrec) NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
+    if (pb.nrec) NLZ_CK(cudaMemcpyAsync(c->h_pinned + 8, w.CTR + 8, 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaEventRecord(c->ev[EV_PREP], st));
     NLZ_CK(cudaStreamSynchronize(st));
     S.host_syncs += 1;
@@ -666,15 +723,6 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         while (b + 1 < pb.nrec && pb.h_fstart[b + 1] <= bad) ++b;
         set_error("Invalid nucleotide '%c' found in sequence %u",
                   (char)static_cast<const u8*>(src)[(u64)pb.h_inoff[b] + (bad - pb.h_fstart[b])], b);
-        return ERR_RUNTIME;
-    }
-    if (pb.mode == NLZ_MODE_DNA_RC && !pb.nrec && c->h_pinned[8] != 0xFFFFFFFFu) {
-        u32 bad = c->h_pinned[8];
-        u8 ch = 0;
-        if (src_on_host) ch = static_cast<const u8*>(src)[bad];
-        else NLZ_CK(cudaMemcpy(&ch, static_cast<const u8*>(src) + bad, 1, cudaMemcpyDeviceToHost));
-        // message of prepare_multiple_dna_sequences_w_rc, factorizer.cpp:91-92
-        set_error("Invalid nucleotide '%c' found in sequence 0", (char)ch);
         return ERR_RUNTIME;
     }
     if (pb.nrec) {
@@ -688,6 +736,18 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         choose_layout(c->h_pinned + 16, n1, tab, lay);
     }
     return OK;
+}
+
+// DNA_RC mode: the invalid-nucleotide flag of k_prepare_dna_rc, checked after the first host sync of the suffix sort
+static int check_dna_deferred(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host) {
+    if (pb.mode != NLZ_MODE_DNA_RC || pb.nrec || c->h_pinned[8] == 0xFFFFFFFFu) return OK;
+    const u32 bad = c->h_pinned[8];
+    u8 ch = 0;
+    if (src_on_host) ch = static_cast<const u8*>(src)[bad];
+    else NLZ_CK(cudaMemcpy(&ch, static_cast<const u8*>(src) + bad, 1, cudaMemcpyDeviceToHost));
+    // message of prepare_multiple_dna_sequences_w_rc, factorizer.cpp:91-92
+    set_error("Invalid nucleotide '%c' found in sequence 0", (char)ch);
+    return ERR_RUNTIME;
 }
 
 static void account_walk(nlz_ctx* c) {
@@ -710,6 +770,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     KeyLayout lay;
     NLZ_TRY(stage_prepare(c, pb, src, src_on_host, st, reinterpret_cast<u8*>(w.KEY[1]), tab, lay));
     NLZ_TRY(stage_sa(c, pb, tab, lay, st, nullptr, n1));
+    NLZ_TRY(check_dna_deferred(c, pb, src, src_on_host));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
     // ---- S2: LCP
@@ -993,6 +1054,7 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
 
     // ---- S1: rank-range-local suffix sorting; refined ranks go to every replica
     NLZ_TRY(stage_sa(c, pb, tab, lay, st, dr, m_loc));
+    NLZ_TRY(check_dna_deferred(c, pb, text, true));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
     // ---- S2: Phi to the position owners, Kasai per position slice, LCP back to the rank owners
@@ -1324,9 +1386,10 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     memset(&c->stats, 0, sizeof(c->stats));
     c->prof.reset();
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));
+    NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));   // words [0, 512): readbacks; [512, 1024): pipelined round counts
     NLZ_CK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 48; ++i) NLZ_CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
     *out = c;
     return OK;
 }
@@ -1339,6 +1402,7 @@ void nlz_ctx_destroy(nlz_ctx* c) {
     if (c->d_out) cudaFree(c->d_out);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 48; ++i) cudaEventDestroy(c->ring_ev[i]);
     c->prof.destroy();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;

@@ -369,10 +369,12 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
     if (lane == 0 && gmax > 1) atomicMax(maxg_out, gmax);
 }
 
-// KEY[j] |= RANK[VAL[j] + h]   (second half of the doubling key)
+// KEY[j] |= RANK[VAL[j] + h]   (second half of the doubling key).  The list length is `m`, or *m_dev when the
+// host runs ahead of the device (pipelined rounds: the grid is sized from an upper bound).
 __global__ void __launch_bounds__(256)
-k_gather_rank(u64* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ RANK, u64 h, u32 n1,
-              u32* __restrict__ ctr) {
+k_gather_rank(u64* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ m_dev,
+              const u32* __restrict__ RANK, u64 h, u32 n1, u32* __restrict__ ctr) {
+    if (m_dev) m = *m_dev;
     u32 j = blockIdx.x * 256 + threadIdx.x;
     if (j == 0 && ctr) { ctr[0] = 0; ctr[3] = 0; }   // next round's active count / largest group (fused regroup)
     if (j >= m) return;

@@ -85,9 +85,10 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
 
 __global__ void __launch_bounds__(TSORT_THREADS)
 k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in, u32 m,
+            const u32* __restrict__ m_dev /* overrides m when the host runs ahead (pipelined rounds) */,
             u32 tile, u32 maxg, u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
-            u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ ctr /* [0] m', [3] max group */,
-            int dbg) {
+            u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ out_m /* m' */,
+            u32* __restrict__ out_maxg /* largest new group */, int dbg) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
     u64* skey = reinterpret_cast<u64*>(tsort_smem + TSORT_OFF_KEY);
     u32* sval = reinterpret_cast<u32*>(tsort_smem + TSORT_OFF_VAL);
@@ -106,7 +107,9 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     u32* wscratch = misc + 8;   // one word per warp
 
     const u32 tid = threadIdx.x, lane = tid & 31;
+    if (m_dev) m = *m_dev;
     const u32 a = blockIdx.x * tile;
+    if (a >= m) return;                // grid sized from an upper bound of m
     u32 b = a + tile;
     if (b > m) b = m;
     u32 load_end = b + maxg;          // a group headed before b ends before b + maxg
@@ -115,13 +118,24 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     if (tid == 0) { s_first = 0xFFFFFFFFu; s_end = load_end; s_cost = 0; }
     __syncthreads();
     // pass 1: find the first owned head (>= a) and the first foreign head (>= b)
-    for (u32 o = tid; o < nload; o += TSORT_THREADS) {
-        const u32 j = a + o;
-        const u32 g = (u32)(key_in[j] >> 32);
-        const bool head = (j == 0) || ((u32)(key_in[j - 1] >> 32) != g);
-        if (head) {
-            if (j < b) atomicMin(&s_first, j);
-            else atomicMin(&s_end, j);
+    // (one shared-memory atomic per warp: thousands of heads hitting one address would serialise the CTA)
+    for (u32 ob = 0; ob < nload; ob += TSORT_THREADS) {
+        const u32 o = ob + tid;
+        u32 fo = 0xFFFFFFFFu, fe = 0xFFFFFFFFu;
+        if (o < nload) {
+            const u32 j = a + o;
+            const u32 g = (u32)(key_in[j] >> 32);
+            const bool head = (j == 0) || ((u32)(key_in[j - 1] >> 32) != g);
+            if (head) {
+                if (j < b) fo = j;
+                else fe = j;
+            }
+        }
+        fo = __reduce_min_sync(0xffffffffu, fo);
+        fe = __reduce_min_sync(0xffffffffu, fe);
+        if (lane == 0) {
+            if (fo != 0xFFFFFFFFu) atomicMin(&s_first, fo);
+            if (fe != 0xFFFFFFFFu) atomicMin(&s_end, fe);
         }
     }
     __syncthreads();
@@ -131,11 +145,10 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     // pass 2: composite keys (group head slot, RANK[s+h]) of the owned elements
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS) {
         u64 k = ~0ull;
-        u32 v = 0, sl = 0;
-        if (o < cnt) { k = key_in[first + o]; v = val_in[first + o]; sl = slot_in[first + o]; }
+        u32 v = 0;
+        if (o < cnt) { k = key_in[first + o]; v = val_in[first + o]; }
         skey[o] = k;
         sval[o] = v;
-        sslot[o] = sl;
     }
     __syncthreads();
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
@@ -178,14 +191,24 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     }
     __syncthreads();
     tsort_scan_flags<false>(flag, seq, wscratch);                 // seq[o] = pivot-equal members before o (tile-wide)
-    // all-pairs budget: sum over groups of outliers x size
-    for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
-        if (o == 0 || sgs[o] != sgs[o - 1]) {
-            const u32 e = gle[o >> 1] >> 16, size = e - o;
-            const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
-            const u32 outl = size - eqc;
-            if (outl) atomicAdd(&s_cost, outl * size);
+    // Outliers (members that differ from their group's pivot) are compacted, 32-bit ranks only, into `outk` (the
+    // slot table's shared memory, which is loaded after the sort): outlier o lands at o - seq[o], so the outliers of a
+    // group are contiguous and in member order.  An outlier then ranks itself among its group's OUTLIERS only --
+    // the pivot block is accounted for in one step -- so a group costs outliers^2 compares, not outliers x size.
+    u32* outk = sslot;
+    for (u32 ob = 0; ob < cnt; ob += TSORT_THREADS) {
+        const u32 o = ob + tid;
+        u32 cost = 0;
+        if (o < cnt) {
+            if (!flag[o]) outk[o - (u32)seq[o]] = (u32)skey[o];
+            if (o == 0 || sgs[o] != sgs[o - 1]) {
+                const u32 e = gle[o >> 1] >> 16, size = e - o;
+                const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
+                cost = (size - eqc) * (size - eqc);
+            }
         }
+        cost = __reduce_add_sync(0xffffffffu, cost);
+        if (lane == 0 && cost) atomicAdd(&s_cost, cost);
     }
     __syncthreads();
     if ((s_cost <= TSORT_ALLPAIRS_BUDGET || (dbg & 4)) && !(dbg & 1)) {
@@ -206,12 +229,15 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
                     pos = gs + (ge & 0xFFFFu) + ((u32)seq[o] - (u32)seq[gs]);
                 } else {
                     const u32 e = ge >> 16;
+                    const u32 xb = gs - (u32)seq[gs];                               // outliers of the group: outk[xb, xe)
+                    const u32 xe = e - ((u32)seq[e - 1] + flag[e - 1]);
+                    const u32 me = o - (u32)seq[o];
+                    const u32 k32 = (u32)k;
                     u32 smaller = 0;
-                    for (u32 x = gs; x < e; ++x) {
-                        const u64 kx = skey[x];
-                        smaller += (kx < k || (kx == k && x < o)) ? 1u : 0u;
-                    }
-                    pos = gs + smaller;
+                    for (u32 x = xb; x < me; ++x) smaller += outk[x] <= k32 ? 1u : 0u;       // earlier members win ties
+                    for (u32 x = me + 1; x < xe; ++x) smaller += outk[x] < k32 ? 1u : 0u;
+                    const u32 eqc = (e - gs) - (xe - xb);
+                    pos = gs + smaller + (k32 > gpiv[gs >> 1] ? eqc : 0u);
                 }
                 rk[q] = k; rv[q] = sval[o]; rp[q] = (unsigned short)pos;
             }
@@ -247,8 +273,10 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         }
     }
     // ---- regroup: the tile's members are sorted by (group, rank); sub-groups = runs of equal keys
-    for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
+    for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS) {
         flag[o] = (o < cnt && (o == 0 || skey[o] != skey[o - 1])) ? 1 : 0;
+        sslot[o] = o < cnt ? slot_in[first + o] : 0u;      // suffix-array slots of the owned range (outk is dead now)
+    }
     __syncthreads();
     tsort_scan_flags<true>(flag, sgs, wscratch);                  // sgs[o] = start of o's new sub-group
     // still-tied members: not (head and next is head); flags reused: bit0 head, bit1 active
@@ -265,12 +293,12 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    if (lane == 0 && gmax > 1) atomicMax(&ctr[3], gmax);
+    if (lane == 0 && gmax > 1) atomicMax(out_maxg, gmax);
     __syncthreads();
     tsort_scan_flags<false>(act, seq, wscratch);                  // seq[o] = still-tied members before o
     if (tid == 0) {
         const u32 total = (u32)seq[cnt - 1] + act[cnt - 1];
-        s_base = total ? atomicAdd(&ctr[0], total) : 0u;
+        s_base = total ? atomicAdd(out_m, total) : 0u;
     }
     __syncthreads();
     const u32 base = s_base;
