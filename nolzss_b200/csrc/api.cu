@@ -63,7 +63,7 @@ struct Workspace {
     u32* tl[TREE_MAX_LEVELS] = {};
     u32* tf[TREE_MAX_LEVELS] = {};
     u32* tr[TREE_MAX_LEVELS] = {};
-    u32 *PSV = nullptr, *NSV = nullptr, *MINF = nullptr;   // per-node tables of stage 3
+    uint4* NODE = nullptr;   // per-node table of stage 3: {parent, min forward start, depth, -}
     // batch mode only: record id per text position, record geometry, factor index of every record's sentinel
     u32 *REC = nullptr, *FSTART = nullptr, *FLEN = nullptr, *INOFF = nullptr, *SENTIDX = nullptr;
     u32* DCNT = nullptr;     // distributed runs: per-CTA counts / offsets of the key compaction
@@ -100,7 +100,8 @@ static size_t workspace_bytes_for(u64 n1, u64 nrec) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
     t += al(n1 + 192);               // X
-    t += al((n1 + 72) * 4) * 6;      // SA, RANK, LCP, PSV, NSV, MINF (+ one padded line for whole-line reads)
+    t += al((n1 + 72) * 4) * 3;      // SA, RANK, LCP (+ one padded line for whole-line reads)
+    t += al((n1 + 72) * 16);         // NODE
     t += al(n1 * 8) * 2;             // KEY
     t += al(n1 * 4) * 4;             // VAL, SLOT
     t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
@@ -146,9 +147,7 @@ static int ensure_workspace(nlz_ctx* c, u64 n1, u64 nrec = 0) {
     w.SA = a.take<u32>(n1 + 72);
     w.RANK = a.take<u32>(n1 + 72);
     w.LCP = a.take<u32>(n1 + 72);
-    w.PSV = a.take<u32>(n1 + 72);
-    w.NSV = a.take<u32>(n1 + 72);
-    w.MINF = a.take<u32>(n1 + 72);
+    w.NODE = a.take<uint4>(n1 + 72);
     for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(n1);
     for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(n1);
     for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(n1);
@@ -541,9 +540,9 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
     P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
     c->trees = T;
     if (!LR) return OK;                                  // trees only (edge staircases of a distributed run)
-    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 12), st,
-       (pb.rc ? k_node_tables<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)
-              : k_node_tables<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, w.PSV, w.NSV, w.MINF)));
+    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
+       (pb.rc ? k_node_tables<true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
+              : k_node_tables<false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
     RNear rn;
     memset(&rn, 0, sizeof(rn));
     if (pb.rc) {
@@ -569,10 +568,8 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
     // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
     static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
-    NodeTables nt;
-    nt.PSV = w.PSV; nt.NSV = w.NSV; nt.MINF = w.MINF;
-    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
-    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, nt, walk_nodes, LR, HARDF, visit_ctr);
+    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, walk_nodes, LR, HARDF, visit_ctr);
+    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, walk_nodes, LR, HARDF, visit_ctr);
     P.end(KC_WALK, (u64)n1 * 4 + (u64)(wp.real_hi - wp.real_lo) * 17, st);
     {
         const u32 grid = ceil_div_u32((u64)ceil_div_u32(pb.nfac, WALK_Q) * 8, 256);   // one 8-lane tile per run
@@ -921,7 +918,7 @@ static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nword
 static size_t dist_private_bytes(u64 cap, u64 nfac, bool rank0) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
-    t += al((cap + 72) * 4) * 4;          // SA, PSV, NSV, MINF
+    t += al((cap + 72) * 4) + al((cap + 72) * 16);   // SA, NODE
     t += al(cap * 8) * 2 + al(cap * 4) * 4;
     t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
     size_t tiles = (cap + RG_TILE - 1) / RG_TILE + 1;
@@ -1021,9 +1018,7 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
         a.off = 0;
         u32* SAbuf = a.take<u32>(cap + 72);
         w.SA = SAbuf + DIST_VIRT;
-        w.PSV = a.take<u32>(cap + 72);
-        w.NSV = a.take<u32>(cap + 72);
-        w.MINF = a.take<u32>(cap + 72);
+        w.NODE = a.take<uint4>(cap + 72);
         for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(cap);
         for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(cap);
         for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(cap);

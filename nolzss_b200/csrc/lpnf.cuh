@@ -660,36 +660,32 @@ __device__ __forceinline__ u64 select_factor(const Trees& T, const WalkParams& p
     return ((u64)ref << 32) | (u64)len;
 }
 
-// ---- per-node tables ---------------------------------------------------------------------------
-// Every rank k with LCP[k] > 0 names the LCP interval ("node") [PSV[k], NSV[k]-1] of string depth
-// LCP[k] (PSV/NSV = nearest strictly smaller LCP value to the left / right).  With the F-min of each
-// node tabulated once (MINF), a leaf climbs to its parent with five word loads and no search:
-// parent of [a, b] is the node named by a if LCP[a] >= LCP[b+1], else by b+1.  Rank order, scalar
-// probes: neighbouring lanes name nested or identical nodes and share the cache lines.
+// ---- per-node table ----------------------------------------------------------------------------
+// Every rank k with LCP[k] > 0 names the LCP interval ("node") [a, b1-1] of string depth LCP[k] (a / b1 =
+// nearest strictly smaller LCP value to the left / right).  NODE[k] = {rank that names the parent node, minimum
+// forward start inside the node, string depth, -}: the suffix tree's internal nodes, tabulated once, so that
+// a leaf climbs to the root with ONE 16-byte load per ancestor.  The parent of [a, b1-1] is named by a if
+// LCP[a] >= LCP[b1], else by b1.  Ranks with LCP 0 (and the guard entry n1) name the root: depth 0.
+// Rank order, scalar probes: neighbouring lanes name nested or identical nodes and share the cache lines.
 template <bool RC>
 __global__ void __launch_bounds__(256)
-k_node_tables(Trees T, WalkParams p, u32* __restrict__ PSV, u32* __restrict__ NSV, u32* __restrict__ MINF) {
+k_node_tables(Trees T, WalkParams p, uint4* __restrict__ NODE) {
     const u32 k = blockIdx.x * 256 + threadIdx.x;
-    if (k == 0 || k >= p.n1) return;
-    const u32 d = T.lcp[0][k];
-    if (d == 0) return;                              // names the root: never looked up
+    if (k > p.n1) return;
+    const u32 d = (k == 0 || k == p.n1) ? 0u : T.lcp[0][k];
+    if (d == 0) { NODE[k] = make_uint4(k, NONE_MIN, 0u, 0u); return; }
     const u32 a = find_prev_less<false>(T, k - 1, d);
     const u32 b1 = find_next_less<false>(T, k + 1, d);
     u32 fmin = NONE_MIN, rmax = 0;
     agg_range<RC, false, false>(T, p, (i64)a, (i64)b1 - 1, fmin, rmax);
-    PSV[k] = a;
-    NSV[k] = b1;
-    MINF[k] = fmin;
+    const u32 la = T.lcp[0][a], lb = T.lcp[0][b1];
+    NODE[k] = make_uint4(la >= lb ? a : b1, fmin, d, 0u);
 }
-
-struct NodeTables {
-    const u32* PSV; const u32* NSV; const u32* MINF;
-};
 
 // ---- kernel 1: rank order ---------------------------------------------------------------------
 template <bool RC>
 __global__ void __launch_bounds__(256)
-k_lpnf_rank(Trees T, WalkParams p, RNear rn, NodeTables nt, int max_nodes, u64* __restrict__ LR,
+k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, int max_nodes, u64* __restrict__ LR,
             u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
     const u32 r = blockIdx.x * 256 + threadIdx.x;
     u32 visited = 0, hard = 0;
@@ -704,22 +700,20 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, NodeTables nt, int max_nodes, u64* 
         {
             const u32 dl = LCP[r], dh = LCP[r + 1];
             u32 k = dl >= dh ? r : r + 1;            // names the parent of the leaf
-            u32 d = max(dl, dh);
 #pragma unroll 1
             for (int step = 0;; ++step) {
+                const uint4 nd = __ldg(NODE + k);    // {parent, min forward start, depth}
+                const u32 d = nd.z;
                 if (d == 0) { at_root = true; break; }
                 if (step == max_nodes) break;
                 ++visited;
-                const u32 m = nt.MINF[k];
+                const u32 m = nd.y;
                 if (m != NONE_MIN && (u64)m + d <= (u64)i) {          // factorizer_core.hpp:75 / :266
                     have_f = true; dF = d; jF = m; belowF = childF;
                     break;
                 }
                 childF = m;
-                const u32 a = nt.PSV[k], b1 = nt.NSV[k];
-                const u32 la = LCP[a], lb = LCP[b1];
-                k = la >= lb ? a : b1;
-                d = max(la, lb);
+                k = nd.x;
             }
         }
         u32 dR = 0;

@@ -43,8 +43,10 @@ constexpr size_t TSORT_OFF_GS = TSORT_OFF_GLE + (size_t)TSORT_SLOTS * 2;     // 
 constexpr size_t TSORT_OFF_EQ = TSORT_OFF_GS + (size_t)TSORT_SLOTS * 2;      // u16[SLOTS]   exclusive prefix counts
 constexpr size_t TSORT_OFF_FLAG = TSORT_OFF_EQ + (size_t)TSORT_SLOTS * 2;    // u8 [SLOTS]   head / pivot-equal flags
 constexpr size_t TSORT_OFF_ACT = TSORT_OFF_FLAG + (size_t)TSORT_SLOTS;       // u8 [SLOTS]   still-tied flags
-constexpr size_t TSORT_OFF_MISC = TSORT_OFF_ACT + (size_t)TSORT_SLOTS;       // u32[64]
-constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 256;
+constexpr size_t TSORT_OFF_POS = TSORT_OFF_ACT + (size_t)TSORT_SLOTS;        // u16[SLOTS]   sorted position of every member
+constexpr size_t TSORT_OFF_MISC = TSORT_OFF_POS + (size_t)TSORT_SLOTS * 2;   // u32[128]
+constexpr size_t TSORT_SMEM = TSORT_OFF_MISC + 512;
+constexpr u32 TSORT_BIG_OUTLIERS = 64;     // groups with more outliers are ranked by whole warps (one warp per outlier)
 
 // Scans over the SLOTS one-byte flags, 4 consecutive flags per thread.
 // MAXPOS: out[o] = index of the last set flag at or before o (flag[0] must be set).
@@ -83,7 +85,7 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TSORT_THREADS)
+__global__ void __launch_bounds__(TSORT_THREADS, 2)
 k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in, u32 m,
             const u32* __restrict__ m_dev /* overrides m when the host runs ahead (pipelined rounds) */,
             u32 tile, u32 maxg, u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
@@ -104,7 +106,10 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     u32& s_end = misc[1];
     u32& s_cost = misc[2];
     u32& s_base = misc[3];
+    u32& s_nbig = misc[4];
     u32* wscratch = misc + 8;   // one word per warp
+    unsigned short* biglist = reinterpret_cast<unsigned short*>(misc + 64);   // starts of the groups with many outliers
+    unsigned short* spos = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_POS);
 
     const u32 tid = threadIdx.x, lane = tid & 31;
     if (m_dev) m = *m_dev;
@@ -115,7 +120,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     u32 load_end = b + maxg;          // a group headed before b ends before b + maxg
     if (load_end > m) load_end = m;
     const u32 nload = load_end - a;   // <= TSORT_SLOTS
-    if (tid == 0) { s_first = 0xFFFFFFFFu; s_end = load_end; s_cost = 0; }
+    if (tid == 0) { s_first = 0xFFFFFFFFu; s_end = load_end; s_cost = 0; s_nbig = 0; }
     __syncthreads();
     // pass 1: find the first owned head (>= a) and the first foreign head (>= b)
     // (one shared-memory atomic per warp: thousands of heads hitting one address would serialise the CTA)
@@ -195,6 +200,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     // slot table's shared memory, which is loaded after the sort): outlier o lands at o - seq[o], so the outliers of a
     // group are contiguous and in member order.  An outlier then ranks itself among its group's OUTLIERS only --
     // the pivot block is accounted for in one step -- so a group costs outliers^2 compares, not outliers x size.
+    // Groups with many outliers (the far end of a tandem array late in the doubling) would make a few threads loop
+    // long while the CTA waits at the barrier: their outliers are ranked afterwards by whole warps.
     u32* outk = sslot;
     for (u32 ob = 0; ob < cnt; ob += TSORT_THREADS) {
         const u32 o = ob + tid;
@@ -204,7 +211,13 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
             if (o == 0 || sgs[o] != sgs[o - 1]) {
                 const u32 e = gle[o >> 1] >> 16, size = e - o;
                 const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
-                cost = (size - eqc) * (size - eqc);
+                const u32 outl = size - eqc;
+                if (outl > TSORT_BIG_OUTLIERS) {
+                    cost = outl * outl / 16;
+                    biglist[atomicAdd(&s_nbig, 1u)] = (unsigned short)o;     // at most SLOTS / 65 groups
+                } else {
+                    cost = outl * outl;
+                }
             }
         }
         cost = __reduce_add_sync(0xffffffffu, cost);
@@ -212,35 +225,63 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     }
     __syncthreads();
     if ((s_cost <= TSORT_ALLPAIRS_BUDGET || (dbg & 4)) && !(dbg & 1)) {
-        // every thread computes the sorted positions of its members, then the tile is permuted in place
-        u64 rk[TSORT_PER_THREAD];
-        u32 rv[TSORT_PER_THREAD];
-        unsigned short rp[TSORT_PER_THREAD];
+        // sorted positions: pivot-equal members by prefix counts, outliers of small groups by their own thread
 #pragma unroll 1
         for (int q = 0; q < TSORT_PER_THREAD; ++q) {
             const u32 o = q * TSORT_THREADS + tid;
-            rk[q] = 0; rv[q] = 0; rp[q] = 0xFFFF;
             if (o < cnt) {
                 const u32 gs = sgs[o];
-                const u64 k = skey[o];
-                u32 pos;
                 const u32 ge = gle[gs >> 1];
                 if (flag[o]) {
-                    pos = gs + (ge & 0xFFFFu) + ((u32)seq[o] - (u32)seq[gs]);
+                    spos[o] = (unsigned short)(gs + (ge & 0xFFFFu) + ((u32)seq[o] - (u32)seq[gs]));
                 } else {
                     const u32 e = ge >> 16;
                     const u32 xb = gs - (u32)seq[gs];                               // outliers of the group: outk[xb, xe)
                     const u32 xe = e - ((u32)seq[e - 1] + flag[e - 1]);
-                    const u32 me = o - (u32)seq[o];
-                    const u32 k32 = (u32)k;
-                    u32 smaller = 0;
-                    for (u32 x = xb; x < me; ++x) smaller += outk[x] <= k32 ? 1u : 0u;       // earlier members win ties
-                    for (u32 x = me + 1; x < xe; ++x) smaller += outk[x] < k32 ? 1u : 0u;
-                    const u32 eqc = (e - gs) - (xe - xb);
-                    pos = gs + smaller + (k32 > gpiv[gs >> 1] ? eqc : 0u);
+                    if (xe - xb <= TSORT_BIG_OUTLIERS) {
+                        const u32 me = o - (u32)seq[o];
+                        const u32 k32 = (u32)skey[o];
+                        u32 smaller = 0;
+                        for (u32 x = xb; x < me; ++x) smaller += outk[x] <= k32 ? 1u : 0u;       // earlier members win ties
+                        for (u32 x = me + 1; x < xe; ++x) smaller += outk[x] < k32 ? 1u : 0u;
+                        const u32 eqc = (e - gs) - (xe - xb);
+                        spos[o] = (unsigned short)(gs + smaller + (k32 > gpiv[gs >> 1] ? eqc : 0u));
+                    }
                 }
-                rk[q] = k; rv[q] = sval[o]; rp[q] = (unsigned short)pos;
             }
+        }
+        // outliers of the big groups: one warp per outlier, lanes stride over the group's outliers
+        const u32 nbig = s_nbig, warp = tid >> 5;
+        for (u32 gi = 0; gi < nbig; ++gi) {
+            const u32 gs = biglist[gi];
+            const u32 ge = gle[gs >> 1], e = ge >> 16;
+            const u32 xb = gs - (u32)seq[gs];
+            const u32 xe = e - ((u32)seq[e - 1] + flag[e - 1]);
+            const u32 eqc = (e - gs) - (xe - xb);
+            const u32 piv = gpiv[gs >> 1];
+            for (u32 o = gs + warp; o < e; o += TSORT_THREADS / 32) {
+                if (flag[o]) continue;                                              // warp-uniform
+                const u32 me = o - (u32)seq[o];
+                const u32 k32 = (u32)skey[o];
+                u32 smaller = 0;
+                for (u32 x = xb + lane; x < xe; x += 32) {
+                    const u32 kx = outk[x];
+                    smaller += (kx < k32 || (kx == k32 && x < me)) ? 1u : 0u;
+                }
+                smaller = __reduce_add_sync(0xffffffffu, smaller);
+                if (lane == 0) spos[o] = (unsigned short)(gs + smaller + (k32 > piv ? eqc : 0u));
+            }
+        }
+        __syncthreads();
+        // permute the tile in place
+        u64 rk[TSORT_PER_THREAD];
+        u32 rv[TSORT_PER_THREAD];
+        unsigned short rp[TSORT_PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < TSORT_PER_THREAD; ++q) {
+            const u32 o = q * TSORT_THREADS + tid;
+            rk[q] = 0; rv[q] = 0; rp[q] = 0xFFFF;
+            if (o < cnt) { rk[q] = skey[o]; rv[q] = sval[o]; rp[q] = spos[o]; }
         }
         __syncthreads();
 #pragma unroll
