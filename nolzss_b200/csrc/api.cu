@@ -568,9 +568,19 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
     // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
     static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
-    if (pb.rc) k_lpnf_rank<true><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, walk_nodes, LR, HARDF, visit_ctr);
-    else k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, walk_nodes, LR, HARDF, visit_ctr);
-    P.end(KC_WALK, (u64)n1 * 4 + (u64)(wp.real_hi - wp.real_lo) * 17, st);
+    if (pb.rc) {
+        // compact the ranks that hold a forward suffix (about half): no idle lanes in the walk
+        u32* list = w.SLOT[1];
+        const u32 tiles = ceil_div_u32(n1, FR_TILE);
+        k_forward_ranks<1><<<tiles, 256, 0, st>>>(SA, wp, w.PMAX, nullptr);
+        k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.PMAX, tiles, w.CTR + 5);
+        k_forward_ranks<2><<<tiles, 256, 0, st>>>(SA, wp, w.PMAX, list);
+        const u32 bound = wp.real_hi - wp.real_lo < pb.nfac ? wp.real_hi - wp.real_lo : pb.nfac;
+        k_lpnf_rank<true><<<ceil_div_u32(bound, 256), 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, HARDF, visit_ctr);
+    } else {
+        k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, HARDF, visit_ctr);
+    }
+    P.end(KC_WALK, (u64)n1 * (pb.rc ? 12 : 4) + (u64)(wp.real_hi - wp.real_lo) * 17, st, pb.rc ? 4 : 1);
     {
         const u32 grid = ceil_div_u32((u64)ceil_div_u32(pb.nfac, WALK_Q) * 8, 256);   // one 8-lane tile per run
         P.begin(st);

@@ -682,17 +682,47 @@ k_node_tables(Trees T, WalkParams p, uint4* __restrict__ NODE) {
     NODE[k] = make_uint4(la >= lb ? a : b1, fmin, d, 0u);
 }
 
+// ---- ranks to evaluate ---------------------------------------------------------------------------
+// RC mode: half of the ranks hold rc(T) suffixes and have no factor to compute.  The ranks that do
+// (real rank, suffix start < nfac) are compacted, in rank order, so that every lane of k_lpnf_rank works.
+// MODE 1: per-CTA counts; MODE 2: ordered write (cta_off = exclusive scan of the counts).
+constexpr int FR_TILE = 2048;
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_forward_ranks(const u32* __restrict__ SA, WalkParams p, u32* __restrict__ cta_off, u32* __restrict__ list) {
+    __shared__ u32 wcnt[8];
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 run = MODE == 2 ? cta_off[blockIdx.x] : 0u;
+#pragma unroll 1
+    for (int t = 0; t < FR_TILE / 256; ++t) {
+        const u32 r = blockIdx.x * FR_TILE + t * 256 + threadIdx.x;
+        const bool keep = r >= p.real_lo && r < p.real_hi && SA[r] < p.nfac;
+        const u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[w] = __popc(bal);
+        __syncthreads();
+        u32 before = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const u32 c = wcnt[i]; if (i < (int)w) before += c; tot += c; }
+        if (MODE == 2 && keep) list[run + before + __popc(bal & lanemask_lt())] = r;
+        run += tot;
+        __syncthreads();
+    }
+    if (MODE == 1 && threadIdx.x == 0) cta_off[blockIdx.x] = run;
+}
+
 // ---- kernel 1: rank order ---------------------------------------------------------------------
 template <bool RC>
 __global__ void __launch_bounds__(256)
-k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, int max_nodes, u64* __restrict__ LR,
-            u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
-    const u32 r = blockIdx.x * 256 + threadIdx.x;
+k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, const u32* __restrict__ list,
+            const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
+            unsigned long long* __restrict__ counters) {
+    u32 r = blockIdx.x * 256 + threadIdx.x;
+    if (list) r = r < *nlist ? list[r] : 0xFFFFFFFFu;       // compacted forward ranks (RC mode)
     u32 visited = 0, hard = 0;
     const u32* LCP = T.lcp[0];
     const u32* SA = T.f[0];
     u32 i = 0xFFFFFFFFu;
-    if (r >= p.real_lo && r < p.real_hi) i = SA[r];
+    if (r >= p.real_lo && r < p.real_hi) i = SA[r];         // r = 0xFFFFFFFF: no work
     if (i < p.nfac) {
         bool have_f = false, at_root = false;
         u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
