@@ -31,7 +31,7 @@ namespace nlz {
 constexpr int TSORT_THREADS = 1024;
 constexpr int TSORT_SLOTS = 4096;
 constexpr int TSORT_PER_THREAD = TSORT_SLOTS / TSORT_THREADS;   // 4
-constexpr u32 TSORT_ALLPAIRS_BUDGET = 384u * 1024u;             // compare steps a tile may spend on counting
+constexpr u32 TSORT_ALLPAIRS_BUDGET = 320u * 1024u;             // compare steps a tile may spend on counting (beyond: bitonic network)
 // shared memory layout (dynamic).  Groups of the active list have >= 2 members, so group start / 2 is
 // a unique per-group index: the per-group tables need SLOTS/2 entries.
 constexpr size_t TSORT_OFF_KEY = 0;                                          // u64[SLOTS]
@@ -212,12 +212,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
                 const u32 e = gle[o >> 1] >> 16, size = e - o;
                 const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
                 const u32 outl = size - eqc;
-                if (outl > TSORT_BIG_OUTLIERS) {
-                    cost = outl * outl / 16;
-                    biglist[atomicAdd(&s_nbig, 1u)] = (unsigned short)o;     // at most SLOTS / 65 groups
-                } else {
-                    cost = outl * outl;
-                }
+                cost = outl * outl;
+                if (outl > TSORT_BIG_OUTLIERS) biglist[atomicAdd(&s_nbig, 1u)] = (unsigned short)o;   // at most SLOTS / 65 groups
             }
         }
         cost = __reduce_add_sync(0xffffffffu, cost);

@@ -57,5 +57,24 @@ def full(src, dst):
             f.write("\n")
 
 
+def traffic(src, dst):
+    """mean dram__bytes_read.sum + dram__bytes_write.sum per captured launch of every kernel -> JSON (bench.py's roofline.traffic)"""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].replace("void ", "").split("<")[0].replace("nlz::", "")
+        b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+        a = acc.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += b
+    with open(dst, "w") as f:
+        json.dump({k: {"launches_captured": v[0], "dram_bytes_per_launch": v[1] / v[0]} for k, v in acc.items()}, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
