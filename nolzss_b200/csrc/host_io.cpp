@@ -18,7 +18,10 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/nolzss_b200.h"
 
@@ -206,10 +209,29 @@ int nlz_fasta_parse(const char* path, int sanitize_mode, nlz_fasta** out) {
         set_error("Invalid sanitize_mode. Expected 'remove_ambiguous' or 'strict'.");   // bindings.cpp:29-37
         return NLZ_ERR_INVALID;
     }
-    std::ifstream file(path);
-    if (!file.is_open()) { set_error("Cannot open FASTA file: %s", path); return NLZ_ERR_RUNTIME; }
+    // The file is mapped and scanned line by line with memchr; a sequence line made only of upper-case ACGT (the
+    // common case) is appended with one memcpy -- the reference parses byte by byte into a std::string
+    // (fasta_processor.cpp:85-96), which becomes the wall-time floor once the GPU stages take 100 ms.
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_error("Cannot open FASTA file: %s", path); return NLZ_ERR_RUNTIME; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { close(fd); set_error("Cannot open FASTA file: %s", path); return NLZ_ERR_RUNTIME; }
+    const size_t fsize = (size_t)sb.st_size;
+    const char* map = nullptr;
+    if (fsize) {
+        void* m = mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); set_error("Cannot open FASTA file: %s", path); return NLZ_ERR_RUNTIME; }
+        map = static_cast<const char*>(m);
+        madvise(m, fsize, MADV_SEQUENTIAL);
+    }
+    struct Unmap { const char* m; size_t n; int fd; ~Unmap() { if (m) munmap(const_cast<char*>(m), n); close(fd); } } unmap{map, fsize, fd};
+    static const struct Kind { unsigned char k[256]; Kind() {
+        for (int c = 0; c < 256; ++c) k[c] = std::isspace(c) ? 2 : 3;          // 0 ACGT, 1 acgt, 2 whitespace, 3 other
+        for (const char* u = "ACGT"; *u; ++u) k[(unsigned char)*u] = 0;
+        for (const char* l = "acgt"; *l; ++l) k[(unsigned char)*l] = 1;
+    } } kind;
     nlz_fasta* fa = new nlz_fasta();
-    std::string line, cur_seq, cur_id;
+    std::string cur_seq, cur_id;
     size_t empty_count = 0, removed = 0;
     auto flush = [&]() {
         if (cur_id.empty()) return;
@@ -217,28 +239,44 @@ int nlz_fasta_parse(const char* path, int sanitize_mode, nlz_fasta** out) {
         else { std::cerr << "Warning: Skipping empty sequence with ID: " << cur_id << std::endl; ++empty_count; }
         cur_seq.clear();
     };
-    while (std::getline(file, line)) {
-        while (!line.empty() && std::isspace((unsigned char)line.back())) line.pop_back();
-        if (line.empty()) continue;
-        if (line[0] == '>') {
+    const char* p = map;
+    const char* const end = map + fsize;
+    while (p < end) {
+        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+        const char* le = nl ? nl : end;                         // line = [p, le)
+        const char* next = nl ? nl + 1 : end;
+        while (le > p && std::isspace((unsigned char)le[-1])) --le;
+        if (le == p) { p = next; continue; }
+        if (*p == '>') {
             flush();
-            size_t a = 1;
-            while (a < line.size() && std::isspace((unsigned char)line[a])) ++a;
-            size_t b = a;
-            while (b < line.size() && !std::isspace((unsigned char)line[b])) ++b;
-            if (a < line.size()) cur_id = line.substr(a, b - a);
+            const char* a = p + 1;
+            while (a < le && std::isspace((unsigned char)*a)) ++a;
+            const char* b = a;
+            while (b < le && !std::isspace((unsigned char)*b)) ++b;
+            if (a < le) cur_id.assign(a, b);
             else { delete fa; set_error("Empty sequence header in FASTA file"); return NLZ_ERR_RUNTIME; }
         } else {
-            for (unsigned char c : line) {
-                if (std::isspace(c)) continue;
-                if (is_acgt_any_case(c)) cur_seq.push_back((char)upper_ascii(c));
-                else if (sanitize_mode == 1) {
-                    set_error("Invalid nucleotide '%c' found in sequence with ID: %s", (char)c, cur_id.c_str());
-                    delete fa;
-                    return NLZ_ERR_RUNTIME;
-                } else ++removed;
+            const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+            const unsigned char* qe = reinterpret_cast<const unsigned char*>(le);
+            while (q < qe) {
+                const unsigned char* r = q;
+                while (r < qe && kind.k[*r] == 0) ++r;           // run of clean bases
+                if (r > q) cur_seq.append(reinterpret_cast<const char*>(q), (size_t)(r - q));
+                if (r == qe) break;
+                const unsigned char c = *r;
+                if (kind.k[c] == 1) cur_seq.push_back((char)upper_ascii(c));
+                else if (kind.k[c] == 3) {
+                    if (sanitize_mode == 1) {
+                        set_error("Invalid nucleotide '%c' found in sequence with ID: %s", (char)c, cur_id.c_str());
+                        delete fa;
+                        return NLZ_ERR_RUNTIME;
+                    }
+                    ++removed;
+                }
+                q = r + 1;
             }
         }
+        p = next;
     }
     flush();
     if (empty_count > 0) std::cerr << "Warning: Skipped " << empty_count << " empty sequence(s) in FASTA file" << std::endl;
