@@ -940,6 +940,52 @@ static size_t dist_private_bytes(u64 cap, u64 nfac, bool rank0) {
     return t + 4096;
 }
 
+// Buckets this GPU's pairs by destination, ships every bucket with one bulk copy into the destination's inbox
+// slice [base[me], ...) and scatters what arrived from everybody into `dst` (see k_dist_bucket_pairs).
+// Collective: 2 barriers.  `staging` holds ps.count pairs; `all` receives the count matrix.
+template <int SRC>
+static int dist_exchange_pairs(DistRt* dr, cudaStream_t st, const PairSrc& ps, u64* staging, u32* dst, std::vector<u32>& all) {
+    nlz_dist* d = dr->d;
+    Profiler& P = d->ctx->prof;
+    const int G = dr->G, me = dr->me;
+    u32* cnts = d->SMALL + 352;          // payload area: counts[G]
+    u32* cursor = d->SMALL + 352 + 16;
+    NLZ_CK(cudaMemsetAsync(cnts, 0, 32 * 4, st));
+    if (ps.count) {
+        const u32 grid = ceil_div_u32(ps.count, 256);
+        P.begin(st);
+        k_dist_bucket_pairs<SRC, 0><<<grid, 256, 0, st>>>(ps, cnts, nullptr);
+        k_dist_bucket_starts<<<1, 32, 0, st>>>(cnts, cursor, G);
+        k_dist_bucket_pairs<SRC, 1><<<grid, 256, 0, st>>>(ps, cursor, staging);
+        P.end(KC_LCP, (u64)ps.count * 24, st, 3);
+    }
+    NLZ_TRY(dist_barrier(dr, st, cnts, (u32)G, all.data()));          // all[g * G + dst] = pairs g sends to dst
+    // receiver d lays the buckets out in sender order: the bucket of sender g starts at sum_{g' < g} cnt(g' -> d)
+    auto inbox_off = [&](int g, int dst_gpu) { u64 o = 0; for (int q = 0; q < g; ++q) o += all[(size_t)q * G + dst_gpu]; return o; };
+    u64 start = 0;
+    for (int g = 0; g < G; ++g) {
+        const u32 cnt = all[(size_t)me * G + g];
+        if (g != me && cnt) {
+            u64* theirs = reinterpret_cast<u64*>(d->peer[g] + d->off_upd) + inbox_off(me, g);
+            NLZ_CK(cudaMemcpyAsync(theirs, staging + start, (size_t)cnt * 8, cudaMemcpyDefault, st));
+            P.bytes[KC_BARRIER] += (u64)cnt * 8;
+        }
+        start += cnt;
+    }
+    NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+    start = 0;
+    for (int g = 0; g < G; ++g) {
+        const u32 mine = all[(size_t)me * G + g];
+        const u32 cnt = all[(size_t)g * G + me];
+        if (cnt) {
+            const u64* src = g == me ? staging + start : reinterpret_cast<const u64*>(d->seg + d->off_upd) + inbox_off(g, me);
+            KL(P, KC_LCP, (u64)cnt * 12, st, (k_dist_apply_pairs<<<ceil_div_u32(cnt, 256), 256, 0, st>>>(src, cnt, dst)));
+        }
+        start += mine;
+    }
+    return OK;
+}
+
 struct VirtBlock { u32 cnt = 0, F = NONE_MIN, R = 0; };
 
 // Factorizes one text with all ranks of the group (every rank passes the same text).  Rank 0 receives
@@ -1012,7 +1058,8 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     P.end(KC_KEYS, (u64)n1, st, 2);
 
     // ---- private workspace for this GPU's share (allocated before the first barrier: cudaFree synchronises the device)
-    const u64 cap = (u64)m_loc + 2 * DIST_VIRT + 8;
+    // (sort buffers double as staging of the pair exchanges: at least one position slice)
+    const u64 cap = (u64)std::max(m_loc, rt.chunk) + 2 * DIST_VIRT + 8;
     {
         const size_t need = dist_private_bytes(cap, pb.nfac, me == 0);
         if (need > d->arena.cap) {
@@ -1071,27 +1118,28 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
         u32 left_sa = NONE_MIN;
         for (int g = me - 1; g >= 0; --g)
             if (rt.base[g + 1] > rt.base[g]) { left_sa = all[g]; break; }
-        PosDst pd;
-        memset(&pd, 0, sizeof(pd));
-        for (int g = 0; g < G; ++g) pd.p[g] = reinterpret_cast<u32*>(d->peer[g] + d->off_phi);
-        pd.chunk = rt.chunk;
-        if (m_loc) KL(P, KC_LCP, (u64)m_loc * 12, st, (k_dist_phi<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(w.SA, m_loc, left_sa, pd)));
-        NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+        const u32 pos0 = (u32)std::min<u64>((u64)me * rt.chunk, n1);
+        const u32 pos1 = (u32)std::min<u64>((u64)(me + 1) * rt.chunk, n1);
+        const u32 npos = pos1 - pos0;
+        PairSrc ps;
+        memset(&ps, 0, sizeof(ps));
+        ps.SA = w.SA; ps.left_sa = left_sa; ps.chunk = rt.chunk;
+        ps.RANK = w.RANK; ps.PLCP = PHI; ps.pos0 = pos0;
+        for (int g = 0; g <= G; ++g) ps.base[g] = rt.base[g];
+        ps.G = G;
+        // Phi: rank owners -> position owners
+        ps.count = m_loc;
+        NLZ_TRY((dist_exchange_pairs<0>(dr, st, ps, w.KEY[0], PHI, all)));
         LcpDist ld;
-        memset(&ld, 0, sizeof(ld));
-        ld.PHI = PHI;
-        ld.pos0 = (u32)std::min<u64>((u64)me * rt.chunk, n1);
-        ld.pos1 = (u32)std::min<u64>((u64)(me + 1) * rt.chunk, n1);
-        for (int g = 0; g < G; ++g) { ld.lcp[g] = reinterpret_cast<u32*>(d->peer[g] + d->off_lcp) + DIST_VIRT; ld.base[g] = rt.base[g]; }
-        ld.base[G] = rt.base[G];
-        ld.G = G;
+        ld.PHI = PHI; ld.pos0 = pos0; ld.pos1 = pos1;
         BatchView bv;
         memset(&bv, 0, sizeof(bv));
-        const u32 npos = ld.pos1 - ld.pos0;
         if (npos)
             KL(P, KC_LCP, (u64)npos * 28, st,
                (k_lcp_kasai<false, true><<<ceil_div_u32(ceil_div_u32(npos, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, nullptr, w.RANK, nullptr, bv, ld)));
-        NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
+        // LCP: position owners -> rank owners (PLCP sits in the Phi slice, text order)
+        ps.count = npos;
+        NLZ_TRY((dist_exchange_pairs<1>(dr, st, ps, w.KEY[0], w.LCP, all)));
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
 

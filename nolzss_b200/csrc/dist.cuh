@@ -97,20 +97,66 @@ __global__ void k_dist_splitters(const u32* __restrict__ cum, u32 nb, u32 n1, in
     base[g] = cum[lo];
 }
 
-// Phi[SA[r]] = SA[r-1], delivered to the GPU that owns text position SA[r] (positions are dealt in
-// slices of `chunk`).  `left_sa` = SA of the rank just before this GPU's range (NONE_MIN for rank 0).
-struct PosDst {
-    u32* p[MAX_PEERS];
-    u32 chunk;
+// ---- bucketed pair exchange -----------------------------------------------------------------------
+// Phi and LCP change owners (rank owner <-> position owner).  Scattered peer stores collapse when most of
+// them are remote, so every GPU first buckets its (destination-local index, value) pairs by destination
+// GPU into a contiguous staging list (order inside a bucket is irrelevant), the buckets travel as bulk
+// copies, and the receiver scatters them locally (k_dist_apply_pairs).
+//   SRC 0 (Phi):  item = local rank r;      index = SA[r] - owner * chunk, value = SA[r-1]   (left_sa for r = 0)
+//   SRC 1 (LCP):  item = local position t;  index = RANK[pos0 + t] - base[owner], value = PLCP[t]
+struct PairSrc {
+    const u32* SA; u32 left_sa; u32 chunk;            // SRC 0
+    const u32* RANK; const u32* PLCP; u32 pos0;      // SRC 1
+    u32 base[MAX_PEERS + 1];
+    int G;
+    u32 count;                                        // items
 };
+template <int SRC>
+__device__ __forceinline__ u64 pair_of(const PairSrc& ps, u32 t, u32& dest) {
+    if (SRC == 0) {
+        const u32 s = ps.SA[t];
+        const u32 prev = t ? ps.SA[t - 1] : ps.left_sa;
+        dest = s / ps.chunk;
+        return ((u64)prev << 32) | (u64)(s - dest * ps.chunk);
+    }
+    const u32 r = ps.RANK[ps.pos0 + t];
+    u32 g = 0;
+    while ((int)g + 1 < ps.G && r >= ps.base[g + 1]) ++g;
+    dest = g;
+    return ((u64)ps.PLCP[t] << 32) | (u64)(r - ps.base[g]);
+}
+// PASS 0: counts[dest] += ...;  PASS 1: staging[cursor[dest]++] = pair (cursor initialised to the bucket starts)
+template <int SRC, int PASS>
 __global__ void __launch_bounds__(256)
-k_dist_phi(const u32* __restrict__ SA, u32 m, u32 left_sa, PosDst phi) {
-    const u32 r = blockIdx.x * 256 + threadIdx.x;
-    if (r >= m) return;
-    const u32 s = SA[r];
-    const u32 prev = r ? SA[r - 1] : left_sa;
-    const u32 g = s / phi.chunk;
-    phi.p[g][s - g * phi.chunk] = prev;
+k_dist_bucket_pairs(PairSrc ps, u32* __restrict__ counts_or_cursor, u64* __restrict__ staging) {
+    __shared__ u32 cnt[MAX_PEERS], basev[MAX_PEERS];
+    if (threadIdx.x < MAX_PEERS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = t < ps.count;
+    u32 dest = 0xFFu;
+    u64 pr = 0;
+    if (valid) pr = pair_of<SRC>(ps, t, dest);
+    const u32 same = __match_any_sync(0xffffffffu, dest);
+    const u32 leader = __ffs(same) - 1, lane = threadIdx.x & 31;
+    u32 off = 0;
+    if (valid && lane == leader) off = atomicAdd(&cnt[dest], __popc(same));
+    off = __shfl_sync(0xffffffffu, off, leader) + __popc(same & lanemask_lt());
+    __syncthreads();
+    if (threadIdx.x < MAX_PEERS && cnt[threadIdx.x]) basev[threadIdx.x] = atomicAdd(&counts_or_cursor[threadIdx.x], cnt[threadIdx.x]);
+    if (PASS == 0) return;
+    __syncthreads();
+    if (valid) staging[basev[dest] + off] = pr;
+}
+__global__ void k_dist_bucket_starts(const u32* __restrict__ counts, u32* __restrict__ cursor, int G) {
+    if (threadIdx.x == 0) { u32 run = 0; for (int g = 0; g < G; ++g) { cursor[g] = run; run += counts[g]; } }
+}
+__global__ void __launch_bounds__(256)
+k_dist_apply_pairs(const u64* __restrict__ pairs, u32 cnt, u32* __restrict__ dst) {
+    const u32 e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= cnt) return;
+    const u64 u = pairs[e];
+    dst[(u32)u] = (u32)(u >> 32);
 }
 
 // Edge staircases of the local rank range (real ranks [0, m) of the arrays in T, with LCP[0] and LCP[m]

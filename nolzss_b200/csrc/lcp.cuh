@@ -56,19 +56,13 @@ __device__ __forceinline__ u32 warp_extend_match(const u64* __restrict__ xw, u64
 //    LCP_LOCAL_WORDS words hands the comparison to its warp.
 // BATCH: suffixes of different records share nothing, and a match stops at the sentinel that ends
 // either segment (batch sentinels all carry the same byte, so the raw compare alone would run on).
-// DIST (one text across GPUs, dist.cuh): this GPU owns the text positions [pos0, pos1); Phi arrives from
-// the owners of the ranks (PHI[i - pos0] = SA[RANK[i] - 1]) and LCP[r] is stored to the owner of rank r.
+// DIST (one text across GPUs, dist.cuh): this GPU owns the text positions [pos0, pos1).  PHI[i - pos0] =
+// SA[RANK[i] - 1] arrives from the owners of the ranks; the result overwrites it in place (PLCP, text order)
+// and is sent to the owners of the ranks afterwards (bucketed pair exchange).
 struct LcpDist {
-    const u32* PHI;
+    u32* PHI;
     u32 pos0, pos1;
-    u32* lcp[MAX_PEERS];       // local LCP arrays of all GPUs (entry 0 = first rank the GPU owns)
-    u32 base[MAX_PEERS + 1];   // rank ranges
-    int G;
-    __device__ __forceinline__ void store(u32 r, u32 l) const {
-        int g = 0;
-        while (g + 1 < G && r >= base[g + 1]) ++g;
-        lcp[g][r - base[g]] = l;
-    }
+    __device__ __forceinline__ void store(u64 i, u32 l) const { PHI[i - pos0] = l; }
 };
 
 template <bool BATCH, bool DIST>
@@ -90,7 +84,7 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
         bool need = false;
         if (i < n1) {
             r = RANK[i];
-            if (r == 0) { if (DIST) ld.store(0, 0); else LCP[0] = 0; l = 0; }
+            if (r == 0) { if (DIST) ld.store(i, 0); else LCP[0] = 0; l = 0; }
             else {
                 j = DIST ? ld.PHI[i - ld.pos0] : SA[r - 1];
                 maxl = (u32)(L - (i > j ? i : (u64)j));
@@ -155,7 +149,7 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
             }
         }
         if (need) {
-            if (DIST) ld.store(r, l); else LCP[r] = l;
+            if (DIST) ld.store(i, l); else LCP[r] = l;
             if (l) --l;
         }
     }
