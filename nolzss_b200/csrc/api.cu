@@ -356,7 +356,10 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
                                                               w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
     P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8), st, 3);
     *cur_out = res ^ 1;
-    if (dr) return dist_push_updates(dr, st, cnt);      // the counts travel with the next barrier
+    if (dr) {                                           // every rank is new: cnt records; the counts travel with the next barrier
+        k_set_u32<<<1, 1, 0, st>>>(w.CTR + 4, cnt);
+        return dist_push_updates(dr, st, cnt);
+    }
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     c->stats.host_syncs += 1;
@@ -376,7 +379,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
     int cur = 0;
     u32 m = 0, maxg = 0;
-    if (dr) NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));
+    if (dr) NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
     if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, dr, cnt, &cur, &m, &maxg));
     else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, dr, cnt, &cur, &m, &maxg));
     const RankDst rdst = rank_dst(c, dr);
@@ -387,7 +390,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     u64 h = (u64)lay.W;
     int sc = 0;
     u32 gm = m;                                          // largest active count over all GPUs
-    std::vector<u32> all((size_t)MAX_PEERS * 4);
+    std::vector<u32> all((size_t)MAX_PEERS * 8);
     u32 sent[MAX_PEERS];                                 // records every GPU pushed in the step before the barrier
     if (dr) for (int g = 0; g < dr->G; ++g) sent[g] = dr->base[g + 1] - dr->base[g];
     static const bool no_pipeline = getenv("NLZ_TRACE") != nullptr || getenv("NLZ_NO_PIPELINE") != nullptr;
@@ -434,13 +437,13 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     for (;;) {
         if (dr) {
             // every GPU has pushed the ranks it refined; learn every GPU's (m, maxg), then apply their records
-            NLZ_TRY(dist_barrier(dr, st, w.CTR, 4, all.data()));
+            NLZ_TRY(dist_barrier(dr, st, w.CTR, 8, all.data()));        // CTR: [0] m', [3] largest group, [4] records pushed
+            for (int g = 0; g < dr->G; ++g) sent[g] = all[(size_t)g * 8 + 4];
             NLZ_TRY(dist_apply_updates(dr, st, sent));
-            for (int g = 0; g < dr->G; ++g) sent[g] = all[(size_t)g * 4];
-            m = all[(size_t)dr->me * 4 + 0];
-            maxg = all[(size_t)dr->me * 4 + 3];
+            m = all[(size_t)dr->me * 8 + 0];
+            maxg = all[(size_t)dr->me * 8 + 3];
             gm = 0;
-            for (int g = 0; g < dr->G; ++g) gm = gm > all[(size_t)g * 4] ? gm : all[(size_t)g * 4];
+            for (int g = 0; g < dr->G; ++g) gm = gm > all[(size_t)g * 8] ? gm : all[(size_t)g * 8];
         }
         if (gm == 0) break;
         S.doubling_rounds += 1;
@@ -454,8 +457,8 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
             KL(P, KC_GATHER, (u64)m * 24, st,
                (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, nullptr, w.RANK, h, n1,
                                                                      fused ? w.CTR : nullptr)));
-        else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));
-        if (dr) NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));   // every GPU has applied its inbox: it may be overwritten
+        else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
+        if (dr) { NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 4, st)); NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr)); }   // every GPU has applied its inbox: it may be overwritten
         if (m > 0 && fused) {
             // every tie group fits in shared memory: segmented sort + regroup in one pass
             u32 cap = 32;
@@ -862,7 +865,7 @@ namespace nlz {
 
 static RankDst rank_dst(nlz_ctx* c, DistRt* dr) {
     RankDst r;
-    r.rank = c->ws.RANK; r.upd = nullptr; r.base = 0;
+    r.rank = c->ws.RANK; r.upd = nullptr; r.upd_count = c->ws.CTR + 4; r.base = 0;
     if (dr) {
         r.base = dr->base[dr->me];
         if (dr->G > 1) r.upd = reinterpret_cast<u64*>(dr->d->seg + dr->d->off_upd) + r.base;
@@ -870,18 +873,19 @@ static RankDst rank_dst(nlz_ctx* c, DistRt* dr) {
     return r;
 }
 
-// The (suffix, rank) records of the `cnt` list elements this GPU just processed -> every other GPU's inbox
-// (bulk copies over NVLink; each source owns the inbox slice [base[src], base[src+1])).
-static int dist_push_updates(DistRt* dr, cudaStream_t st, u32 cnt) {
+// The (suffix, rank) records this GPU produced in the step (CTR[4] of them, at most `bound`) -> every other GPU's
+// inbox (bulk stores over NVLink; each source owns the inbox slice [base[src], base[src+1])).
+static int dist_push_updates(DistRt* dr, cudaStream_t st, u32 bound) {
     nlz_dist* d = dr->d;
-    if (!cnt) return OK;
-    const u64* mine = reinterpret_cast<const u64*>(d->seg + d->off_upd) + dr->base[dr->me];
-    for (int g = 0; g < dr->G; ++g) {
-        if (g == dr->me) continue;
-        u64* theirs = reinterpret_cast<u64*>(d->peer[g] + d->off_upd) + dr->base[dr->me];
-        NLZ_CK(cudaMemcpyAsync(theirs, mine, (size_t)cnt * 8, cudaMemcpyDefault, st));
-    }
-    d->ctx->prof.bytes[KC_BARRIER] += (u64)cnt * 8 * (dr->G - 1);
+    if (!bound || dr->G == 1) return OK;
+    UpdDst ud;
+    memset(&ud, 0, sizeof(ud));
+    for (int g = 0; g < dr->G; ++g) ud.p[g] = reinterpret_cast<u64*>(d->peer[g] + d->off_upd) + dr->base[dr->me];
+    ud.n = dr->G; ud.me = dr->me;
+    u32 grid = ceil_div_u32(bound, 256 * 4);
+    if (grid > (u32)kNumSM * 8) grid = kNumSM * 8;
+    KL(d->ctx->prof, KC_BARRIER, (u64)bound * 8 * (dr->G - 1), st,
+       (k_dist_push_ranks<<<grid, 256, 0, st>>>(ud.p[dr->me], d->ctx->ws.CTR + 4, ud)));
     return OK;
 }
 // after the barrier: apply what the other GPUs sent (cnts[g] records from GPU g)

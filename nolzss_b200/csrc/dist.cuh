@@ -192,6 +192,21 @@ __global__ void k_dist_edges(Trees T, WalkParams p, u32 m, int K, u32* __restric
     o[0] = cnt; o[1] = fmin; o[2] = rmax; o[3] = whole;
 }
 
+// this GPU's (suffix, rank) records of the round (*cnt of them) -> the inbox slice of every other GPU
+struct UpdDst {
+    u64* p[MAX_PEERS];
+    int n, me;
+};
+__global__ void __launch_bounds__(256)
+k_dist_push_ranks(const u64* __restrict__ src, const u32* __restrict__ cnt, UpdDst dst) {
+    const u32 m = *cnt;
+    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < m; e += gridDim.x * 256) {
+        const u64 u = src[e];
+        for (int g = 0; g < dst.n; ++g)
+            if (g != dst.me) dst.p[g][e] = u;
+    }
+}
+
 // (suffix, rank) records received from another GPU -> local RANK replica
 __global__ void __launch_bounds__(256)
 k_dist_apply_ranks(const u64* __restrict__ upd, u32 cnt, u32* __restrict__ RANK) {

@@ -54,19 +54,35 @@ __device__ __forceinline__ u32 batch_cap(const BatchView& bv, u32 p) {
 }
 
 // Where refined ranks are written.  One GPU: its RANK array.  Distributed (one rank range of the suffix
-// array per GPU, dist.cuh): the local replica of RANK, plus one (suffix, rank) record per processed list
-// element in `upd` -- a contiguous list that is bulk-copied to the other GPUs over NVLink and applied to
-// their replicas there (scattered peer stores collapse beyond ~1 GB of span; bulk copies do not).
+// array per GPU, dist.cuh): the local replica of RANK, plus one (suffix, rank) record per CHANGED rank in
+// `upd` -- a contiguous list (appended with one atomic range reservation per CTA, *upd_count entries) that is
+// bulk-copied to the other GPUs over NVLink and applied to their replicas there (scattered peer stores collapse
+// beyond ~1 GB of span; bulk copies do not).  A member that stays in the first sub-group of its group keeps its
+// rank (= the group's head slot): neither a store nor a record.
 // `base` = the first global rank this GPU owns: slots and ranks are global, the local SA array starts at `base`.
 struct RankDst {
     u32* rank;
     u64* upd;
+    u32* upd_count;
     u32 base;
-    __device__ __forceinline__ void store(u32 e, u32 s, u32 r) const {
-        rank[s] = r;
-        if (upd) upd[e] = ((u64)r << 32) | (u64)s;
-    }
 };
+// CTA-wide exclusive prefix of one count per thread (blockDim.x <= 1024); `ws` holds 33 words.
+__device__ __forceinline__ u32 cta_excl_scan(u32 v, u32* ws, u32& total) {
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    u32 carry = 0, tot = 0;
+    for (u32 i = 0; i < nw; ++i) { const u32 x = ws[i]; if (i < w) carry += x; tot += x; }
+    total = tot;
+    return carry + inc - v;
+}
 constexpr int MAX_PEERS = 8;
 
 // ---------------------------------------------------------------- byte histogram
@@ -314,6 +330,8 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
     bool act[RG_ITEMS];
     u32 gmax = 0;
     u32 run_max = 0, run_sum = 0;
+    u64 upd_rec[RG_ITEMS];
+    u32 nupd = 0;
 #pragma unroll
     for (int q = 0; q < RG_ITEMS; ++q) {
         u32 idx = i0 + q;
@@ -353,7 +371,15 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
             u32 newrank = INITIAL ? hj + RANK.base : slots[hj];
             u32 s = vals[e];
             u32 slot = INITIAL ? e + RANK.base : slots[e];
-            RANK.store(e, s, newrank);
+            // the old rank of a member is its group's head slot = the high half of its doubling key
+            const bool changed = INITIAL || newrank != (u32)((u64)keys[e] >> 32);
+            if (changed) {
+                RANK.rank[s] = newrank;
+                if (RANK.upd) {
+                    if (INITIAL) RANK.upd[e] = ((u64)newrank << 32) | (u64)s;      // every rank is new: dense list
+                    else { upd_rec[nupd] = ((u64)newrank << 32) | (u64)s; ++nupd; }
+                }
+            }
             SA[slot - RANK.base] = s;
             if (act[q]) {
                 u32 pos = cs + ps[q];
@@ -367,6 +393,15 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
 #pragma unroll
     for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if (lane == 0 && gmax > 1) atomicMax(maxg_out, gmax);
+    if (!INITIAL && RANK.upd) {                      // append this CTA's records of changed ranks
+        __shared__ u32 ws[33];
+        __shared__ u32 s_ubase;
+        u32 total;
+        const u32 off = cta_excl_scan(nupd, ws, total);
+        if (threadIdx.x == 0) s_ubase = total ? atomicAdd(RANK.upd_count, total) : 0u;
+        __syncthreads();
+        for (u32 j = 0; j < nupd; ++j) RANK.upd[s_ubase + off + j] = upd_rec[j];
+    }
 }
 
 // KEY[j] |= RANK[VAL[j] + h]   (second half of the doubling key).  The list length is `m`, or *m_dev when the

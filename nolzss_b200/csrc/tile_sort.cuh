@@ -220,7 +220,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         if (lane == 0 && cost) atomicAdd(&s_cost, cost);
     }
     __syncthreads();
-    if ((s_cost <= TSORT_ALLPAIRS_BUDGET || (dbg & 4)) && !(dbg & 1)) {
+    const bool used_bitonic = !((s_cost <= TSORT_ALLPAIRS_BUDGET || (dbg & 4)) && !(dbg & 1));
+    if (!used_bitonic) {
         // sorted positions: pivot-equal members by prefix counts, outliers of small groups by their own thread
 #pragma unroll 1
         for (int q = 0; q < TSORT_PER_THREAD; ++q) {
@@ -339,18 +340,37 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     }
     __syncthreads();
     const u32 base = s_base;
-    for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
-        const u32 s = sval[o];
-        const u32 slot = sslot[o];
-        const u32 newrank = sslot[sgs[o]];
-        RANK.store(first + o, s, newrank);
-        SA[slot - RANK.base] = s;
-        if (act[o]) {
-            const u32 pos = base + seq[o];
-            key_next[pos] = (u64)newrank << 32;
-            val_next[pos] = s;
-            slot_next[pos] = slot;
+    u64 upd_rec[TSORT_PER_THREAD];
+    u32 nupd = 0;
+#pragma unroll
+    for (int q = 0; q < TSORT_PER_THREAD; ++q) {
+        const u32 o = q * TSORT_THREADS + tid;
+        if (o < cnt) {
+            const u32 s = sval[o];
+            const u32 slot = sslot[o];
+            const u32 newrank = sslot[sgs[o]];
+            // old rank = head slot of the member's group (the bitonic path keyed the members by their group's tile position)
+            const u32 gid = (u32)(skey[o] >> 32);
+            const u32 oldrank = used_bitonic ? sslot[gid] : gid;
+            if (newrank != oldrank) {
+                RANK.rank[s] = newrank;
+                if (RANK.upd) { upd_rec[nupd] = ((u64)newrank << 32) | (u64)s; ++nupd; }
+            }
+            SA[slot - RANK.base] = s;
+            if (act[o]) {
+                const u32 pos = base + seq[o];
+                key_next[pos] = (u64)newrank << 32;
+                val_next[pos] = s;
+                slot_next[pos] = slot;
+            }
         }
+    }
+    if (RANK.upd) {                                   // append this tile's records of changed ranks
+        u32 total;
+        const u32 off = cta_excl_scan(nupd, wscratch, total);
+        if (tid == 0) s_base = total ? atomicAdd(RANK.upd_count, total) : 0u;
+        __syncthreads();
+        for (u32 j = 0; j < nupd; ++j) RANK.upd[s_base + off + j] = upd_rec[j];
     }
 }
 
