@@ -407,9 +407,10 @@ def _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo):
     return rc_len, (e - rc_len + 1) | LR_RC_FLAG
 
 
-def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16):
+def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16, real=None):
     """Stage 3 = k_lpnf_rank (rank order, bounded climb, direct RC candidate; marks `hard` positions)
-    followed by k_lpnf_hard (text order over hard positions with a Kasai-style carry)."""
+    followed by k_lpnf_hard (text order over hard positions with a Kasai-style carry).
+    real = (lo, hi): only these ranks are evaluated (distributed runs: the others are virtual ranks)."""
     SA, LCP = T.f[0], T.lcp[0]
     rc, twoN = T.rc, T.twoN
     LR = [None] * nfac
@@ -420,7 +421,7 @@ def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16):
         return st[2] != NONE_MIN and st[2] + D <= i
 
     # ---- kernel 1: rank order
-    for r in range(n1):
+    for r in (range(n1) if real is None else range(real[0], real[1])):
         i = SA[r]
         if i >= nfac:
             continue
