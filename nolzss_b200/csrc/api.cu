@@ -198,6 +198,30 @@ k_prepare_dna_rc(const u8* __restrict__ T, u32 n, u8* __restrict__ S, u32* __res
     }
 }
 
+// Distributed runs: every GPU uploads and prepares only its slice [lo, hi) of T (staged in place in its own X) and
+// stores both strands into the X of EVERY GPU (coalesced peer stores), instead of G uploads of the whole text.
+struct XDst {
+    u8* p[MAX_PEERS];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+k_prepare_dna_rc_slice(const u8* T, u32 n, u32 lo, u32 hi, XDst X, bool write_sentinels, u32* __restrict__ first_bad) {
+    for (u32 i = lo + blockIdx.x * 256 + threadIdx.x; i < hi; i += gridDim.x * 256) {
+        u8 c = T[i];
+        u8 u = c, k = 0;
+        switch (c) {
+            case 'A': case 'a': u = 'A'; k = 'T'; break;
+            case 'C': case 'c': u = 'C'; k = 'G'; break;
+            case 'G': case 'g': u = 'G'; k = 'C'; break;
+            case 'T': case 't': u = 'T'; k = 'A'; break;
+            default: atomicMin(first_bad, i); k = c; break;
+        }
+        for (int g = 0; g < X.n; ++g) { X.p[g][i] = u; X.p[g][2 * (u64)n - i] = k; }
+    }
+    if (write_sentinels && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int g = 0; g < X.n; ++g) { X.p[g][n] = 1; X.p[g][2 * (u64)n + 1] = 2; }
+}
+
 __global__ void k_zero_pad(u8* __restrict__ X, u64 L) {
     if (threadIdx.x < 128) X[L + threadIdx.x] = 0;
 }
@@ -670,8 +694,12 @@ static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64
 }
 
 // ---- S0: text into X (validated / reverse-complemented on the device), byte histogram, key layout
+struct DistRt;
+static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all);
+static int dist_prepare_sliced(DistRt* dr, nlz_ctx* c, const Problem& pb, const void* src, cudaStream_t st);
+
 static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host, cudaStream_t st,
-                         u8* staging, ClassTable& tab, KeyLayout& lay) {
+                         u8* staging, ClassTable& tab, KeyLayout& lay, DistRt* dr = nullptr) {
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
     Profiler& P = c->prof;
@@ -687,6 +715,9 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, 0xFFFFFFFFu);
         k_prepare_batch<<<ceil_div_u32((u64)pb.N + 1, 256), 256, 0, st>>>(tmp, w.INOFF, w.FSTART, w.FLEN, pb.nrec, pb.N,
                                                                         pb.rc, w.X, w.REC, w.CTR + 8);
+        prep_launches += 2;
+    } else if (pb.mode == NLZ_MODE_DNA_RC && dr) {
+        NLZ_TRY(dist_prepare_sliced(dr, c, pb, src, st));
         prep_launches += 2;
     } else if (pb.mode == NLZ_MODE_DNA_RC) {
         const u8* dT = static_cast<const u8*>(src);
@@ -846,7 +877,7 @@ struct nlz_dist {
     int rank = 0, world = 1;
     u64 max_n1 = 0;
     u8* seg = nullptr;                 // shared segment: DistCtl | RANK replica | local LCP | Phi slice | LR (rank 0)
-    size_t seg_bytes = 0, off_rank = 0, off_lcp = 0, off_phi = 0, off_upd = 0, off_lr = 0, off_pos = 0;
+    size_t seg_bytes = 0, off_x = 0, off_rank = 0, off_lcp = 0, off_phi = 0, off_upd = 0, off_lr = 0, off_pos = 0;
     u8* peer[MAX_PEERS] = {};
     bool ipc_opened[MAX_PEERS] = {};
     bool attached = false;
@@ -856,7 +887,6 @@ struct nlz_dist {
     bool owns_hb = false;
     u32* h_pin = nullptr;              // pinned: exchange readback
     // persistent device buffers sized by max_n1
-    u8* Xbuf = nullptr;
     u32 *DCNT = nullptr, *HISTP = nullptr, *SMALL = nullptr;   // SMALL: CTR[64] | BYTEHIST[256] | SPLIT[16] | BASE[16] | PAYLOAD[512]
     Arena arena;                       // per-call private workspace
 };
@@ -926,6 +956,36 @@ static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nword
         return ERR_RUNTIME;
     }
     memcpy(h_all, d->h_pin, (size_t)dr->G * nwords * 4);
+    return OK;
+}
+
+// DNA_RC text of a distributed run: slice upload + peer stores into every replica of X, then a barrier that also
+// agrees on the first invalid nucleotide (every GPU must take the same exit).
+static int dist_prepare_sliced(DistRt* dr, nlz_ctx* c, const Problem& pb, const void* src, cudaStream_t st) {
+    nlz_dist* d = dr->d;
+    Workspace& w = c->ws;
+    const u32 n = (u32)pb.n_in;
+    const u32 per = (u32)(((u64)ceil_div_u32(n, dr->G) + 255) / 256 * 256);
+    const u32 lo = (u32)std::min<u64>((u64)dr->me * per, n), hi = (u32)std::min<u64>((u64)(dr->me + 1) * per, n);
+    XDst xd;
+    memset(&xd, 0, sizeof(xd));
+    for (int g = 0; g < dr->G; ++g) xd.p[g] = d->peer[g] + d->off_x;
+    xd.n = dr->G;
+    k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, 0xFFFFFFFFu);
+    if (hi > lo) {
+        NLZ_CK(cudaMemcpyAsync(w.X + lo, static_cast<const u8*>(src) + lo, hi - lo, cudaMemcpyHostToDevice, st));
+        u32 grid = ceil_div_u32(hi - lo, 256);
+        if (grid > (u32)kNumSM * 16) grid = kNumSM * 16;
+        k_prepare_dna_rc_slice<<<grid, 256, 0, st>>>(w.X, n, lo, hi, xd, dr->me == 0, w.CTR + 8);
+    } else if (dr->me == 0) {
+        k_prepare_dna_rc_slice<<<1, 256, 0, st>>>(w.X, n, 0, 0, xd, true, w.CTR + 8);
+    }
+    std::vector<u32> all(MAX_PEERS);
+    NLZ_TRY(dist_barrier(dr, st, w.CTR + 8, 1, all.data()));
+    u32 bad = 0xFFFFFFFFu;
+    for (int g = 0; g < dr->G; ++g) bad = std::min(bad, all[g]);
+    c->h_pinned[8] = bad;                               // read by check_dna_deferred on every GPU
+    k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, bad);
     return OK;
 }
 
@@ -1006,7 +1066,7 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     DistRt* dr = &rt;
     w = Workspace();
     w.n1 = n1;
-    w.X = d->Xbuf;
+    w.X = d->seg + d->off_x;
     w.DCNT = d->DCNT;
     w.CTR = d->SMALL; w.BYTEHIST = d->SMALL + 64;
     u32* d_split = d->SMALL + 320;
@@ -1020,7 +1080,7 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     // ---- S0 (replicated) + bucket histogram -> rank ranges
     ClassTable tab;
     KeyLayout lay;
-    NLZ_TRY(stage_prepare(c, pb, text, true, st, w.X, tab, lay));
+    NLZ_TRY(stage_prepare(c, pb, text, true, st, w.X, tab, lay, G > 1 ? dr : nullptr));
     int pbits = lay.W * lay.b;
     if (pbits > 24) pbits = 24;
     { int lim = bits_for(n1) + 2; if (pbits > lim) pbits = lim; }
@@ -1613,7 +1673,8 @@ int nlz_dist_create(nlz_ctx* c, int rank, int world, uint64_t max_text_bytes, in
     NLZ_CK(cudaSetDevice(c->device));
     nlz_dist* d = new nlz_dist();
     d->ctx = c; d->rank = rank; d->world = world; d->max_n1 = max_n1;
-    d->off_rank = dist_al(sizeof(DistCtl));
+    d->off_x = dist_al(sizeof(DistCtl));
+    d->off_rank = d->off_x + dist_al(max_n1 + 512);
     d->off_lcp = d->off_rank + dist_al((max_n1 + 72) * 4);
     d->off_phi = d->off_lcp + dist_al((max_n1 + 2 * DIST_VIRT + 200) * 4);
     d->off_upd = d->off_phi + dist_al((max_n1 / world + 4096) * 4);
@@ -1621,12 +1682,11 @@ int nlz_dist_create(nlz_ctx* c, int rank, int world, uint64_t max_text_bytes, in
     d->off_pos = d->off_lr + dist_al((max_n1 + 64) * 8);
     d->seg_bytes = rank == 0 ? d->off_pos + dist_al((max_n1 + 64) * 4) : d->off_lr;
     cudaError_t e = cudaMalloc(&d->seg, d->seg_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&d->Xbuf, max_n1 + 256);
     if (e == cudaSuccess) e = cudaMalloc(&d->DCNT, (max_n1 / KB_TP + 8) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d->HISTP, ((size_t)(1u << 24) + 8192) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d->SMALL, 1024 * 4);
     if (e == cudaSuccess) e = cudaMallocHost(&d->h_pin, ((size_t)MAX_PEERS * DIST_XCH_WORDS + 64) * 4);
-    if (e == cudaSuccess) e = cudaMemset(d->seg, 0, d->off_rank);
+    if (e == cudaSuccess) e = cudaMemset(d->seg, 0, d->off_x);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error("allocating the distributed workspace (%zu bytes shared) failed: %s", d->seg_bytes, cudaGetErrorString(e));
@@ -1645,7 +1705,6 @@ void nlz_dist_destroy(nlz_dist* d) {
     cudaDeviceSynchronize();
     for (int g = 0; g < MAX_PEERS; ++g) if (d->ipc_opened[g]) cudaIpcCloseMemHandle(d->peer[g]);
     if (d->seg) cudaFree(d->seg);
-    if (d->Xbuf) cudaFree(d->Xbuf);
     if (d->DCNT) cudaFree(d->DCNT);
     if (d->HISTP) cudaFree(d->HISTP);
     if (d->SMALL) cudaFree(d->SMALL);

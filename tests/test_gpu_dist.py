@@ -75,3 +75,16 @@ def test_dist_matches_single_gpu_5mbp_rc():
         grp.close()
     assert np.array_equal(got, single)
     assert sum(st["active_sum"] for st in stats) > 0
+
+
+def test_dist_invalid_nucleotide_is_reported_by_every_rank():
+    grp = nd.LocalGroup([0, 0, 0], 10_000, L.MODE_DNA_RC)
+    try:
+        s = wl.uniform_dna(5000, 3).tobytes()
+        bad = s[:4100] + b"N" + s[4101:]
+        with pytest.raises(RuntimeError, match="Invalid nucleotide 'N' found in sequence 0"):
+            grp.factorize(L.MODE_DNA_RC, bad)
+        got, _ = grp.factorize(L.MODE_DNA_RC, s)          # the group stays usable
+        assert np.array_equal(got, _expected(L.MODE_DNA_RC, s))
+    finally:
+        grp.close()
