@@ -941,8 +941,15 @@ static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nword
     peers.n = dr->G; peers.me = dr->me;
     d->epoch += 1;
     if (nwords) d->xparity ^= 1;
+    static const u32 timeout_s = getenv("NLZ_BARRIER_TIMEOUT_S") ? (u32)atoi(getenv("NLZ_BARRIER_TIMEOUT_S")) : 60u;
+    static const bool trace = getenv("NLZ_TRACE_DIST") != nullptr;
+    if (trace) fprintf(stderr, "[nlz dist] rank %d barrier %u (%u payload words)\n", dr->me, d->epoch, nwords);
     KL(d->ctx->prof, KC_BARRIER, (u64)nwords * 4 * dr->G, st,
-       (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords)));
+       (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords, timeout_s)));
+    // In-process groups may share ONE device (tests): a copy or memset queued behind a spinning barrier kernel
+    // blocks its hardware copy queue for the other ranks' copies, which then never reach their barrier.  There the
+    // host waits for the barrier before it enqueues anything else; one process per GPU needs no such care.
+    if (d->hb) NLZ_CK(cudaStreamSynchronize(st));
     if (!h_all) return OK;
     DistCtl* mine = reinterpret_cast<DistCtl*>(d->seg);
     for (int g = 0; g < dr->G; ++g)
@@ -956,6 +963,11 @@ static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nword
         return ERR_RUNTIME;
     }
     memcpy(h_all, d->h_pin, (size_t)dr->G * nwords * 4);
+    if (trace) {
+        fprintf(stderr, "[nlz dist] rank %d passed %u:", dr->me, d->epoch);
+        for (u32 i = 0; i < (u32)dr->G * nwords && i < 32; ++i) fprintf(stderr, " %u", h_all[i]);
+        fprintf(stderr, "\n");
+    }
     return OK;
 }
 

@@ -52,7 +52,7 @@ struct DistPeers {
 // rest: everything this rank launched before the barrier has completed (its peer stores are performed),
 // and nothing launched after it starts before all ranks have arrived.
 __global__ void __launch_bounds__(256)
-k_dist_barrier(DistPeers peers, u32 epoch, int parity, const u32* __restrict__ src, u32 nwords) {
+k_dist_barrier(DistPeers peers, u32 epoch, int parity, const u32* __restrict__ src, u32 nwords, u32 timeout_s) {
     const int G = peers.n, me = peers.me;
     for (u32 i = threadIdx.x; i < nwords * (u32)G; i += blockDim.x) {
         const int g = (int)(i / nwords);
@@ -72,7 +72,7 @@ k_dist_barrier(DistPeers peers, u32 epoch, int parity, const u32* __restrict__ s
         while ((int)(*mine - epoch) < 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 60ull * 1000000000ull) { peers.ctl[me]->error = epoch; break; }   // a peer died: do not hang the GPU
+            if (t1 - t0 > (unsigned long long)timeout_s * 1000000000ull) { peers.ctl[me]->error = epoch; break; }   // a peer died: do not hang the GPU
             __nanosleep(200);
         }
     }

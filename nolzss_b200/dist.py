@@ -73,9 +73,13 @@ class LocalGroup:
             t.start()
         for t in threads:
             t.join()
-        for g, e in enumerate(errors):
-            if e is not None:
-                raise (ValueError if e[0] == L.NLZ_ERR_INVALID else RuntimeError)(f"rank {g}: {e[1]}")
+        failed = [(g, e) for g, e in enumerate(errors) if e is not None]
+        if failed:
+            # a rank that fails leaves the others waiting in a barrier until it times out: report the root cause first
+            failed.sort(key=lambda ge: "timed out" in ge[1][1])
+            g, e = failed[0]
+            msg = "; ".join(f"rank {gg}: {ee[1]}" for gg, ee in failed)
+            raise (ValueError if e[0] == L.NLZ_ERR_INVALID else RuntimeError)(msg)
         counts = {r[1] for r in results}
         assert len(counts) == 1, f"ranks disagree on the factor count: {counts}"
         return results[0][0], [_ctx_stats(c) for c in self.ctxs]
