@@ -25,3 +25,4 @@ from .sequences import (  # noqa: F401
     is_dna_sequence,
     is_protein_sequence,
 )
+from .shuffle_control import factorize_with_shuffled_control, shuffle_fasta_sequences  # noqa: F401,E402

@@ -187,3 +187,29 @@ def test_golden_vectors_agree_with_oracle():
         assert [[int(x) for x in r] for r in got] == c["factors"]
     for text, exp in GENERAL_KATS.items():
         assert any(c["text"].encode("latin-1") == text and [tuple(r) for r in c["factors"]] == exp for c in cases)
+
+
+def test_shuffle_control_matches_reference_algorithm(tmp_path):
+    """shuffle_fasta_sequences(method="reference") = batch_factorize.py:209-270: random.seed(seed), one
+    random.shuffle per record in file order, 80-character lines, headers kept."""
+    import random
+
+    from nolzss_b200.genomics import shuffle_fasta_sequences
+
+    recs = {"chr1 some description": "ACGT" * 50 + "GATTACA", "chr2": "TTTTGGGGCCCCAAAA" * 11, "chr3": "A"}
+    src = tmp_path / "in.fasta"
+    src.write_text("".join(f">{k}\n{v[:70]}\n{v[70:]}\n" for k, v in recs.items()))
+    assert shuffle_fasta_sequences(src, tmp_path / "o" / "ref.fasta", seed=5)
+    random.seed(5)
+    exp = ""
+    for k, v in recs.items():
+        lst = list(v)
+        random.shuffle(lst)
+        sh = "".join(lst)
+        exp += f">{k.split()[0]}\n" + "".join(sh[i:i + 80] + "\n" for i in range(0, len(sh), 80))
+    assert (tmp_path / "o" / "ref.fasta").read_text() == exp
+    assert shuffle_fasta_sequences(src, tmp_path / "np.fasta", seed=5, method="numpy")
+    from nolzss_b200.genomics.fasta import _parse_fasta_content
+    got = _parse_fasta_content((tmp_path / "np.fasta").read_text())
+    assert list(got) == [k.split()[0] for k in recs] and all(sorted(got[k.split()[0]]) == sorted(recs[k]) for k in recs)
+    assert not shuffle_fasta_sequences(tmp_path / "missing.fasta", tmp_path / "x.fasta")
