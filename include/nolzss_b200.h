@@ -58,6 +58,8 @@ typedef struct nlz_stats {
     uint32_t host_syncs;
     /* device time per stage (CUDA events on the call's stream), milliseconds */
     float ms_total, ms_prepare, ms_keys, ms_sort0, ms_doubling, ms_lcp, ms_lpnf, ms_chain;
+    /* distributed runs: (suffix, rank) records this GPU received from the others and applied to its replica */
+    uint64_t rank_records_applied;
 } nlz_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -862,11 +863,18 @@ struct HostBarrier {          // in-process groups only (several ranks of one pr
     std::condition_variable cv;
     int world = 0, waiting = 0;
     unsigned gen = 0;
-    void arrive() {
+    bool broken = false;      // a rank gave up waiting (a peer failed earlier): the group is unusable
+    bool arrive() {
         std::unique_lock<std::mutex> lk(mu);
+        if (broken) return false;
         const unsigned g = gen;
-        if (++waiting == world) { waiting = 0; ++gen; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        if (++waiting == world) { waiting = 0; ++gen; cv.notify_all(); return true; }
+        if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g || broken; }) || broken) {
+            broken = true;
+            cv.notify_all();
+            return false;
+        }
+        return true;
     }
 };
 
@@ -924,6 +932,7 @@ static int dist_apply_updates(DistRt* dr, cudaStream_t st, const u32* cnts) {
     Profiler& P = d->ctx->prof;
     for (int g = 0; g < dr->G; ++g) {
         if (g == dr->me || !cnts[g]) continue;
+        d->ctx->stats.rank_records_applied += cnts[g];
         const u64* inbox = reinterpret_cast<const u64*>(d->seg + d->off_upd) + dr->base[g];
         KL(P, KC_REGROUP, (u64)cnts[g] * 12, st,
            (k_dist_apply_ranks<<<ceil_div_u32(cnts[g], 256), 256, 0, st>>>(inbox, cnts[g], d->ctx->ws.RANK)));
@@ -1146,7 +1155,7 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
             if (e != cudaSuccess) { set_error("cudaMalloc of %zu workspace bytes failed: %s", want, cudaGetErrorString(e)); return ERR_CUDA; }
             d->arena.cap = want;
         }
-        if (d->hb) d->hb->arrive();
+        if (d->hb && !d->hb->arrive()) { set_error("a rank of the in-process group failed before the workspace rendezvous"); return ERR_RUNTIME; }
         Arena& a = d->arena;
         a.off = 0;
         u32* SAbuf = a.take<u32>(cap + 72);
@@ -1341,13 +1350,13 @@ static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_al
     NLZ_CK(cudaMemsetAsync(d_pay, 0, 8, st));
     // in-process groups may share a device: rank 0's output (re)allocation synchronises that device, so no
     // other rank may sit in a spinning barrier kernel meanwhile -> host rendezvous around the chain stage
-    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); d->hb->arrive(); }
+    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); if (!d->hb->arrive()) { set_error("a rank of the in-process group failed before the chain stage"); return ERR_RUNTIME; } }
     if (me == 0) {
         const u64* LR0 = reinterpret_cast<const u64*>(d->seg + d->off_lr);
         NLZ_TRY(stage_chain(c, pb, st, LR0, cs, nullptr, 0, out_alloc == nullptr, &z));
         k_set_u32<<<1, 1, 0, st>>>(d_pay, (u32)z);
     }
-    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); d->hb->arrive(); }
+    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); if (!d->hb->arrive()) { set_error("rank 0 of the in-process group failed in the chain stage"); return ERR_RUNTIME; } }
     NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
     NLZ_TRY(dist_barrier(dr, st, d_pay, 2, all.data()));
     if (m_loc) account_walk(c);

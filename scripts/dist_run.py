@@ -31,7 +31,7 @@ for it in range(3):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     line = (f"rank {rank} it {it}: z={z} wall={dt*1e3:.1f} ms dev={st['ms_total']:.1f} (prep {st['ms_prepare']:.1f} keys {st['ms_keys']:.1f} sort0 {st['ms_sort0']:.1f} "
             f"doubling {st['ms_doubling']:.1f} lcp {st['ms_lcp']:.1f} lpnf {st['ms_lpnf']:.1f} chain {st['ms_chain']:.1f}) rounds={st['doubling_rounds']} "
-            f"active_sum={st['active_sum']} suffixes={st['n_suffixes']} ws={st['workspace_bytes']/2**30:.1f} GiB")
+            f"active_sum={st['active_sum']} records_applied={st['rank_records_applied']} suffixes={st['n_suffixes']} ws={st['workspace_bytes']/2**30:.1f} GiB")
     print(line, flush=True)
     if rank == 0: print(f"[dist_run] it {it}: max-over-ranks device time {ms.item():.1f} ms -> {n/ms.item()/1e3:.1f} Mbases/s on {world} GPUs", flush=True)
 L.check(L.load().nlz_set_profiling(grp.ctx, 1))
