@@ -27,6 +27,7 @@
 #include "radix_sort.cuh"
 #include "sa.cuh"
 #include "tile_sort.cuh"
+#include "big_groups.cuh"
 
 namespace nlz {
 
@@ -419,7 +420,11 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     u32 sent[MAX_PEERS];                                 // records every GPU pushed in the step before the barrier
     if (dr) for (int g = 0; g < dr->G; ++g) sent[g] = dr->base[g + 1] - dr->base[g];
     static const bool no_pipeline = getenv("NLZ_TRACE") != nullptr || getenv("NLZ_NO_PIPELINE") != nullptr;
-    if (!dr && !no_pipeline && m > 0 && maxg <= (u32)TSORT_SLOTS / 2) {
+    // largest tie group the shared-memory tile sort takes (test hook: debug flags >> 8 lower it so that small texts
+    // reach the hybrid rounds)
+    u32 gcap = (u32)TSORT_SLOTS / 2;
+    if ((c->debug_flags >> 8) >= 64 && (u32)(c->debug_flags >> 8) < gcap) gcap = (u32)(c->debug_flags >> 8);
+    if (!dr && !no_pipeline && m > 0 && maxg <= gcap) {
         // Every remaining round is a fused one (groups only shrink).  The host runs one round AHEAD of the device:
         // round r is launched with grids sized from the counts of round r-1 and reads its true list length from
         // RING[r] on the device, so the per-round count readback no longer leaves the GPU idle.
@@ -459,73 +464,181 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
         }
         return OK;
     }
+    // Hybrid rounds (big_groups.cuh): once a tie group exceeds the tile-sort capacity the list is split into
+    // S (groups <= gcap, left-aligned, k_tile_sort) and B (larger groups, right-aligned, k_group_stream).
+    struct { bool on = false, off = false; u32 mS = 0, mB = 0, maxgS = 0; int fallbacks = 0; } hy;
+    static const bool no_hybrid = getenv("NLZ_NO_HYBRID") != nullptr;
+    hy.off = no_hybrid;
+    const u32 END = cnt;                                 // capacity of the active lists (B grows down from here)
+    static const bool trace = getenv("NLZ_TRACE") != nullptr;
+    // radix sort + regroup of the unified list [0, m) held in the `cur` buffers (keys already gathered)
+    auto radix_round = [&](u32 mm, int* rb_out, cudaEvent_t tev1) -> int {
+        u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
+        u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
+        int res = 0;
+        NLZ_TRY(radix_sort_pairs<u64>(k, v, mm, plan, w.HIST, st, &res, P));
+        const int rb = res == 0 ? cur : (cur ^ 1);
+        if (tev1) cudaEventRecord(tev1, st);
+        const u32 tiles = ceil_div_u32(mm, RG_TILE);
+        P.begin(st);
+        k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], mm, 0ull, w.PMAX, w.PSUM);
+        k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
+        k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], mm, 0ull,
+                                                                w.PMAX, w.PSUM, w.SA, rdst, w.KEY[rb ^ 1],
+                                                                w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
+        P.end(KC_REGROUP, (u64)mm * (16 + 4 + 4 + 8 + 16), st, 3);
+        *rb_out = rb;
+        return OK;
+    };
     for (;;) {
         if (dr) {
             // every GPU has pushed the ranks it refined; learn every GPU's (m, maxg), then apply their records
-            NLZ_TRY(dist_barrier(dr, st, w.CTR, 8, all.data()));        // CTR: [0] m', [3] largest group, [4] records pushed
+            NLZ_TRY(dist_barrier(dr, st, w.CTR, 8, all.data()));        // CTR: [0] m' (S), [3] largest group, [4] records pushed, [6] m' (B)
             for (int g = 0; g < dr->G; ++g) sent[g] = all[(size_t)g * 8 + 4];
             NLZ_TRY(dist_apply_updates(dr, st, sent));
-            m = all[(size_t)dr->me * 8 + 0];
-            maxg = all[(size_t)dr->me * 8 + 3];
+            const u32* mine = &all[(size_t)dr->me * 8];
+            if (hy.on) { hy.mS = mine[0]; hy.maxgS = mine[3]; hy.mB = mine[6]; m = hy.mS + hy.mB; }
+            else { m = mine[0]; maxg = mine[3]; }
             gm = 0;
-            for (int g = 0; g < dr->G; ++g) gm = gm > all[(size_t)g * 8] ? gm : all[(size_t)g * 8];
+            for (int g = 0; g < dr->G; ++g) gm = std::max(gm, all[(size_t)g * 8] + all[(size_t)g * 8 + 6]);
         }
         if (gm == 0) break;
         S.doubling_rounds += 1;
         S.active_sum += m;
-        static const bool trace = getenv("NLZ_TRACE") != nullptr;
         cudaEvent_t tev0 = nullptr, tev1 = nullptr;
         if (trace) { cudaEventCreate(&tev0); cudaEventCreate(&tev1); cudaEventRecord(tev0, st); }
-        int rb = cur;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
-        const bool fused = maxg <= (u32)TSORT_SLOTS / 2;
-        if (m > 0)
-            KL(P, KC_GATHER, (u64)m * 24, st,
-               (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, nullptr, w.RANK, h, n1,
-                                                                     fused ? w.CTR : nullptr)));
-        else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
-        if (dr) { NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 4, st)); NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr)); }   // every GPU has applied its inbox: it may be overwritten
-        if (m > 0 && fused) {
-            // every tie group fits in shared memory: segmented sort + regroup in one pass
-            u32 cap = 32;
-            while (cap < maxg) cap <<= 1;
-            const u32 tile = TSORT_SLOTS - cap;
-            KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
-               (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
-                   w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, nullptr, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
-                   w.SLOT[sc ^ 1], w.CTR, w.CTR + 3, c->debug_flags)));
-            rb = cur;                       // next round's lists were written to the cur^1 buffers
-            S.tile_sort_rounds += 1;
-            if (trace) cudaEventRecord(tev1, st);
-        } else if (m > 0) {
-            u64* k[2] = {w.KEY[cur], w.KEY[cur ^ 1]};
-            u32* v[2] = {w.VAL[cur], w.VAL[cur ^ 1]};
-            int res = 0;
-            NLZ_TRY(radix_sort_pairs<u64>(k, v, m, plan, w.HIST, st, &res, P));
-            rb = res == 0 ? cur : (cur ^ 1);
-            if (trace) cudaEventRecord(tev1, st);
+        if (!hy.on && !hy.off && m > 0 && maxg > gcap) {
+            // split the list once: small groups to the left, big groups to the right end of the other buffers
             const u32 tiles = ceil_div_u32(m, RG_TILE);
             P.begin(st);
-            k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], m, 0ull, w.PMAX, w.PSUM);
-            k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
-            k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], m, 0ull,
-                                                                    w.PMAX, w.PSUM, w.SA, rdst, w.KEY[rb ^ 1],
-                                                                    w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
-            P.end(KC_REGROUP, (u64)m * (16 + 4 + 4 + 8 + 16), st, 3);
-        }
-        if (dr) NLZ_TRY(dist_push_updates(dr, st, m));
-        if (!dr) {
-            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
+            k_split_count<<<tiles, RG_THREADS, 0, st>>>(w.KEY[cur], w.SLOT[sc], m, gcap, w.PSUM);
+            k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.PSUM, tiles, w.CTR + 6);
+            k_split_apply<<<tiles, RG_THREADS, 0, st>>>(w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, gcap, w.PSUM, w.CTR + 6, END,
+                                                        w.KEY[cur ^ 1], w.VAL[cur ^ 1], w.SLOT[sc ^ 1]);
+            P.end(KC_REGROUP, (u64)m * 40, st, 3);
+            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
             NLZ_CK(cudaStreamSynchronize(st));
             S.host_syncs += 1;
-            if (trace) {
-                float tms = 0.f;
-                cudaEventElapsedTime(&tms, tev0, tev1);
-                fprintf(stderr, "[nlz] round %u h=%llu m=%u maxg=%u sort_ms=%.3f -> m'=%u maxg'=%u\n", S.doubling_rounds,
-                        (unsigned long long)h, m, maxg, tms, c->h_pinned[0], c->h_pinned[3]);
+            hy.on = true;
+            hy.mB = c->h_pinned[6]; hy.mS = m - hy.mB; hy.maxgS = gcap;
+            cur ^= 1; sc ^= 1;
+            if (trace) fprintf(stderr, "[nlz] hybrid rounds from here: S=%u B=%u (groups > %u)\n", hy.mS, hy.mB, gcap);
+        }
+        int rb = cur;   // physical index of the buffers that hold this round's sorted (key, suffix) pairs
+        if (hy.on) {
+            const u32 mS = hy.mS, mB = hy.mB, b0 = END - mB;
+            NLZ_CK(cudaMemsetAsync(w.CTR, 0, 16, st));                  // [0] next S length, [3] its largest group
+            NLZ_CK(cudaMemsetAsync(w.CTR + 6, 0, 8, st));               // [6] next B length, [7] fallback flag
+            if (mS) KL(P, KC_GATHER, (u64)mS * 24, st,
+                       (k_gather_rank<<<ceil_div_u32(mS, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], mS, nullptr, w.RANK, h, n1, nullptr)));
+            if (mB) KL(P, KC_GATHER, (u64)mB * 24, st,
+                       (k_gather_rank<<<ceil_div_u32(mB, 256), 256, 0, st>>>(w.KEY[cur] + b0, w.VAL[cur] + b0, mB, nullptr, w.RANK, h, n1, nullptr)));
+            if (dr) { NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 4, st)); NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr)); }
+            if (mS) {
+                u32 cap = 32;
+                while (cap < hy.maxgS) cap <<= 1;
+                const u32 tile = TSORT_SLOTS - cap;
+                KL(P, KC_TILE_SORT, (u64)mS * 40, st,
+                   (k_tile_sort<<<ceil_div_u32(mS, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], mS, nullptr, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
+                       w.SLOT[sc ^ 1], w.CTR, w.CTR + 3, c->debug_flags)));
             }
-            m = c->h_pinned[0];
-            maxg = c->h_pinned[3];
-            gm = m;
+            if (mB) {
+                StreamOut so;
+                so.key_next = w.KEY[cur ^ 1]; so.val_next = w.VAL[cur ^ 1]; so.slot_next = w.SLOT[sc ^ 1];
+                so.end = END; so.mS = w.CTR; so.maxgS = w.CTR + 3; so.mB = w.CTR + 6; so.fallback = w.CTR + 7;
+                const int dbg = (c->debug_flags & 8) && S.doubling_rounds >= 3 ? 8 : 0;   // test hook: fail the third round
+                KL(P, KC_STREAM, (u64)mB * 44, st,
+                   (k_group_stream<<<ceil_div_u32(mB, gcap), GS_THREADS, GS_SMEM, st>>>(
+                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], b0, mB, gcap, w.SA, rdst, so, dbg)));
+            }
+            S.tile_sort_rounds += 1;
+            if (trace) cudaEventRecord(tev1, st);
+            NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
+            NLZ_CK(cudaStreamSynchronize(st));
+            S.host_syncs += 1;
+            if (c->h_pinned[7]) {
+                // a group had more outliers than fit in shared memory: unify the lists and redo the round with the
+                // radix path (the keys are gathered; ranks and slots written so far are rewritten with equal values)
+                if (mB) {
+                    NLZ_CK(cudaMemcpyAsync(w.KEY[cur ^ 1], w.KEY[cur] + b0, (size_t)mB * 8, cudaMemcpyDeviceToDevice, st));
+                    NLZ_CK(cudaMemcpyAsync(w.KEY[cur] + mS, w.KEY[cur ^ 1], (size_t)mB * 8, cudaMemcpyDeviceToDevice, st));
+                    NLZ_CK(cudaMemcpyAsync(w.VAL[cur ^ 1], w.VAL[cur] + b0, (size_t)mB * 4, cudaMemcpyDeviceToDevice, st));
+                    NLZ_CK(cudaMemcpyAsync(w.VAL[cur] + mS, w.VAL[cur ^ 1], (size_t)mB * 4, cudaMemcpyDeviceToDevice, st));
+                    NLZ_CK(cudaMemcpyAsync(w.SLOT[sc ^ 1], w.SLOT[sc] + b0, (size_t)mB * 4, cudaMemcpyDeviceToDevice, st));
+                    NLZ_CK(cudaMemcpyAsync(w.SLOT[sc] + mS, w.SLOT[sc ^ 1], (size_t)mB * 4, cudaMemcpyDeviceToDevice, st));
+                }
+                {
+                    // The hybrid lists hold their groups in no particular order, but the radix path pairs sorted list
+                    // positions with slots BY POSITION, which needs ascending slots: sort the slot list (the groups'
+                    // slot intervals are disjoint, so ascending slots line up with the groups in ascending rank order).
+                    u32* k[2] = {w.SLOT[sc], w.SLOT[sc ^ 1]};
+                    u32* v[2] = {reinterpret_cast<u32*>(w.KEY[cur ^ 1]), reinterpret_cast<u32*>(w.KEY[cur ^ 1]) + END};   // carried along, unused
+                    DigitPlan p32;
+                    plan_add_range(p32, 0, nb);
+                    int res = 0;
+                    NLZ_TRY(radix_sort_pairs<u32>(k, v, mS + mB, p32, w.HIST, st, &res, P));
+                    if (res) NLZ_CK(cudaMemcpyAsync(w.SLOT[sc], w.SLOT[sc ^ 1], (size_t)(mS + mB) * 4, cudaMemcpyDeviceToDevice, st));
+                }
+                NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 16, st));          // records pushed so far are dropped, B is gone
+                hy.on = false; hy.off = ++hy.fallbacks >= 2;            // one more try from a fresh split after this round
+                if (trace) fprintf(stderr, "[nlz] round %u: outliers exceed the stream kernel, back to radix rounds\n", S.doubling_rounds);
+                NLZ_TRY(radix_round(mS + mB, &rb, nullptr));
+                if (!dr) {
+                    NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
+                    NLZ_CK(cudaStreamSynchronize(st));
+                    S.host_syncs += 1;
+                    m = c->h_pinned[0]; maxg = c->h_pinned[3]; gm = m;
+                }
+            } else if (!dr) {
+                hy.mS = c->h_pinned[0]; hy.maxgS = c->h_pinned[3]; hy.mB = c->h_pinned[6];
+                if (trace) {
+                    float tms = 0.f;
+                    cudaEventElapsedTime(&tms, tev0, tev1);
+                    fprintf(stderr, "[nlz] round %u h=%llu S=%u B=%u sort_ms=%.3f -> S'=%u (maxg %u) B'=%u\n", S.doubling_rounds,
+                            (unsigned long long)h, mS, mB, tms, hy.mS, hy.maxgS, hy.mB);
+                }
+                m = hy.mS + hy.mB; gm = m;
+            }
+            if (dr) NLZ_TRY(dist_push_updates(dr, st, mS + mB));
+        } else {
+            const bool fused = maxg <= gcap;
+            if (m > 0)
+                KL(P, KC_GATHER, (u64)m * 24, st,
+                   (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, nullptr, w.RANK, h, n1,
+                                                                         fused ? w.CTR : nullptr)));
+            else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
+            if (dr) { NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 4, st)); NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr)); }   // every GPU has applied its inbox: it may be overwritten
+            if (m > 0 && fused) {
+                // every tie group fits in shared memory: segmented sort + regroup in one pass
+                u32 cap = 32;
+                while (cap < maxg) cap <<= 1;
+                const u32 tile = TSORT_SLOTS - cap;
+                KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
+                   (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, nullptr, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
+                       w.SLOT[sc ^ 1], w.CTR, w.CTR + 3, c->debug_flags)));
+                rb = cur;                       // next round's lists were written to the cur^1 buffers
+                S.tile_sort_rounds += 1;
+                if (trace) cudaEventRecord(tev1, st);
+            } else if (m > 0) {
+                NLZ_TRY(radix_round(m, &rb, tev1));
+            }
+            if (dr) NLZ_TRY(dist_push_updates(dr, st, m));
+            if (!dr) {
+                NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
+                NLZ_CK(cudaStreamSynchronize(st));
+                S.host_syncs += 1;
+                if (trace) {
+                    float tms = 0.f;
+                    cudaEventElapsedTime(&tms, tev0, tev1);
+                    fprintf(stderr, "[nlz] round %u h=%llu m=%u maxg=%u sort_ms=%.3f -> m'=%u maxg'=%u\n", S.doubling_rounds,
+                            (unsigned long long)h, m, maxg, tms, c->h_pinned[0], c->h_pinned[3]);
+                }
+                m = c->h_pinned[0];
+                maxg = c->h_pinned[3];
+                gm = m;
+            }
         }
         if (trace) { cudaEventDestroy(tev0); cudaEventDestroy(tev1); }
         cur = rb ^ 1;
@@ -1526,6 +1639,7 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));   // words [0, 512): readbacks; [512, 1024): pipelined round counts
     NLZ_CK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 48; ++i) NLZ_CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
     *out = c;

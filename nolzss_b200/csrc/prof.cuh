@@ -24,12 +24,13 @@ enum KClass : int {
     KC_WALK_HARD,     // factor rule, text order over deep-nesting positions (depth search + carry)
     KC_CHAIN,         // chain extraction (exit, doubling, mark, scan, emit)
     KC_BARRIER,       // distributed runs: flag barrier in peer memory (time = waiting for the slowest GPU)
+    KC_STREAM,        // doubling: tie groups beyond the tile, one CTA streaming each (pivot partition + outlier sort)
     KC_COUNT
 };
 
 static const char* const kClassNames[KC_COUNT] = {
     "prepare", "build_keys", "radix_hist", "radix_scan", "radix_scatter", "gather_rank",
-    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain", "dist_barrier"};
+    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain", "dist_barrier", "group_stream"};
 
 struct Profiler {
     bool timing = false;

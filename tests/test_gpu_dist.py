@@ -77,6 +77,26 @@ def test_dist_matches_single_gpu_5mbp_rc():
     assert sum(st["active_sum"] for st in stats) > 0
 
 
+def test_dist_hybrid_rounds_big_tie_groups():
+    """The hybrid doubling rounds (big_groups.cuh) inside the distributed loop: tile capacity lowered to 64 members on
+    every rank's context, with and without the forced redo of a round."""
+    from test_gpu_parity import _hybrid_cases
+    cases = _hybrid_cases()
+    for world in (2, 3):
+        grp = nd.LocalGroup([0] * world, 400_000, L.MODE_DNA_RC)
+        try:
+            for flags in ((64 << 8), (64 << 8) | 8):
+                for c in grp.ctxs:
+                    L.check(L.load().nlz_set_debug_flags(c, flags))
+                for s in cases:
+                    modes = (L.MODE_GENERAL, L.MODE_DNA_RC) if set(s) <= set(b"ACGT") else (L.MODE_GENERAL,)
+                    for mode in modes:
+                        got, _ = grp.factorize(mode, s)
+                        assert np.array_equal(got, _expected(mode, s)), (world, hex(flags), mode, len(s))
+        finally:
+            grp.close()
+
+
 def test_dist_invalid_nucleotide_is_reported_by_every_rank():
     grp = nd.LocalGroup([0, 0, 0], 10_000, L.MODE_DNA_RC)
     try:

@@ -193,6 +193,42 @@ def test_group_sort_fallback_paths():
         L.check(L.load().nlz_set_debug_flags(L.context(), 0))
 
 
+def _hybrid_cases():
+    rnd = random.Random(7)
+    out = [b"AC" * 1500 + b"G" + b"AC" * 700, b"A" * 3000, b"ACG" * 900 + b"T" + b"ACG" * 400 + b"GATTACA" * 300,
+           wl.planted_dna(200_000, 5, scale=1.0, families=3, tandems=25).tobytes(),
+           (b"the quick brown fox jumps over the lazy dog " * 300) + b"!"]
+    for _ in range(4):
+        parts = []
+        for _p in range(rnd.randint(2, 6)):
+            unit = bytes(rnd.choice(b"ACGT") for _u in range(rnd.randint(1, 9)))
+            parts.append(unit * rnd.randint(50, 2500))
+            parts.append(bytes(rnd.choice(b"ACGT") for _u in range(rnd.randint(0, 40))))
+        out.append(b"".join(parts))
+    return out
+
+
+def test_hybrid_rounds_big_tie_groups():
+    """Doubling rounds with tie groups beyond the tile sort (big_groups.cuh): the debug flags lower the tile
+    capacity to 64 / 256 members so that small texts run the split, the group-stream kernel and (flag 8) the
+    redo of a round through the radix path; factors against the oracle in general and RC mode."""
+    cases = _hybrid_cases()
+    exp_g = [orc.factorize(s) for s in cases]
+    exp_r = [orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s)) if set(s) <= set(b"ACGT") else None for s in cases]
+    try:
+        for flags in ((64 << 8), (64 << 8) | 8, (256 << 8), (1024 << 8) | 8):
+            L.check(L.load().nlz_set_debug_flags(L.context(), flags))
+            for s, eg, er in zip(cases, exp_g, exp_r):
+                assert np.array_equal(L.factorize_array(L.MODE_GENERAL, s), eg), (hex(flags), len(s))
+                if er is not None:
+                    assert np.array_equal(L.factorize_array(L.MODE_DNA_RC, s), er), (hex(flags), len(s))
+        L.check(L.load().nlz_set_debug_flags(L.context(), 64 << 8))
+        _index_case(cases[0])
+        _index_case(cases[3])
+    finally:
+        L.check(L.load().nlz_set_debug_flags(L.context(), 0))
+
+
 def _check_cover_and_valid(x, f, samples=4000, seed=0):
     n = len(x)
     st, ln, rf = f[:, 0].astype(np.int64), f[:, 1].astype(np.int64), f[:, 2]
