@@ -1066,6 +1066,17 @@ static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nword
     static const u32 timeout_s = getenv("NLZ_BARRIER_TIMEOUT_S") ? (u32)atoi(getenv("NLZ_BARRIER_TIMEOUT_S")) : 60u;
     static const bool trace = getenv("NLZ_TRACE_DIST") != nullptr;
     if (trace) fprintf(stderr, "[nlz dist] rank %d barrier %u (%u payload words)\n", dr->me, d->epoch, nwords);
+    if (d->hb) {
+        // In-process groups (ranks that may share ONE device): the ranks first meet on the host, so that no barrier
+        // kernel spins on the device while another rank still has work to launch.  A kernel launched for the first
+        // time is loaded lazily by the CUDA runtime, and that load waits for running kernels -- behind a spinning
+        // barrier it would wait for ever (and the barrier for it).  One process per GPU needs no such care.
+        NLZ_CK(cudaStreamSynchronize(st));
+        if (!d->hb->arrive()) {
+            set_error("distributed barrier %u: a rank of the in-process group failed or never arrived (rank %d waited)", d->epoch, dr->me);
+            return ERR_RUNTIME;
+        }
+    }
     KL(d->ctx->prof, KC_BARRIER, (u64)nwords * 4 * dr->G, st,
        (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords, timeout_s)));
     // In-process groups may share ONE device (tests): a copy or memset queued behind a spinning barrier kernel
@@ -1640,6 +1651,20 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));   // words [0, 512): readbacks; [512, 1024): pipelined round counts
     NLZ_CK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
     NLZ_CK(cudaFuncSetAttribute(k_group_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    {
+        // First launches of these kernels now, while nothing else runs: the CUDA runtime loads a kernel lazily at
+        // its first launch, and that load waits for running kernels.  Inside a distributed doubling round a peer
+        // rank of an in-process group (several ranks sharing one device) may already spin in its flag barrier --
+        // the load would wait for the barrier and the barrier for this rank (seen as a barrier timeout).
+        StreamOut so;
+        memset(&so, 0, sizeof(so));
+        RankDst rd;
+        memset(&rd, 0, sizeof(rd));
+        k_group_stream<<<1, GS_THREADS, GS_SMEM, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_split_count<<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, 0, 64, nullptr);
+        k_split_apply<<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 64, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
+        NLZ_CK(cudaStreamSynchronize(c->own_stream));
+    }
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 48; ++i) NLZ_CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
     *out = c;

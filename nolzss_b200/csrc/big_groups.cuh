@@ -58,7 +58,7 @@ k_split_count(const u64* __restrict__ key, const u32* __restrict__ slot, u32 m, 
     }
     u32 total;
     cta_excl_scan(c, ws, total);
-    if (threadIdx.x == 0) psum[blockIdx.x] = total;
+    if (threadIdx.x == 0 && psum) psum[blockIdx.x] = total;
 }
 
 // stable partition: small-group members to [0, mS), big-group members to [end - mB, end); mB = *mB_dev
@@ -67,6 +67,7 @@ k_split_apply(const u64* __restrict__ key, const u32* __restrict__ val, const u3
               const u32* __restrict__ psum, const u32* __restrict__ mB_dev, u32 end,
               u64* __restrict__ key_out, u32* __restrict__ val_out, u32* __restrict__ slot_out) {
     __shared__ u32 ws[33];
+    if (m == 0) return;                                          // warm-up launch (api.cu: nlz_ctx_create)
     const u32 tile_start = blockIdx.x * RG_TILE;
     const u32 i0 = tile_start + threadIdx.x * RG_ITEMS;          // RG_ITEMS consecutive members per thread
     bool big[RG_ITEMS];

@@ -242,6 +242,68 @@ int nlzo_factorize(const uint8_t *x, uint64_t n, uint64_t start_pos, uint64_t **
 }
 
 /* ------------------------------------------------------------------ RC mode */
+typedef struct { const index_t *ix; const uint8_t *S; uint64_t len_S, N; } rc_ctx_t;
+
+/* One iteration of the reference's main loop (factorizer_core.hpp:241-379): the factor that starts at i. */
+static void rc_factor_at(const rc_ctx_t *c, uint64_t i, uint64_t *out_len, uint64_t *out_ref) {
+    const index_t *ixp = c->ix;
+    const uint8_t *S = c->S;
+    const uint64_t len_S = c->len_S, N = c->N;
+    const idx_t n1 = ixp->n1;
+    const uint64_t INF = UINT64_MAX / 2;
+    const uint64_t T_end = N, R_beg = N + 1, R_end = len_S - 1; /* :215-217 */
+#define FWD_START(k) ((uint64_t)ixp->sa[k] < T_end ? (uint64_t)ixp->sa[k] : INF)                 /* :221-223 */
+#define RC_END(k) (((uint64_t)ixp->sa[k] >= R_beg && (uint64_t)ixp->sa[k] < R_end)                \
+                       ? N - ((uint64_t)ixp->sa[k] - R_beg) - 1 : INF)                           /* :224-229 */
+    idx_t lo = ixp->isa[i], hi = lo;
+    uint64_t jF = FWD_START(lo), eR = RC_END(lo), pR = (uint64_t)ixp->sa[lo];
+    int have_fwd = 0, have_rc = 0;
+    uint64_t best_fwd_start = 0, best_rc_end = 0, best_rc_posS = 0;
+    for (;;) {
+        idx_t d = ixp->lcp[lo] > ixp->lcp[hi + 1] ? ixp->lcp[lo] : ixp->lcp[hi + 1];
+        if (d <= 0) break;                                 /* :259 root */
+        while (ixp->lcp[lo] >= d) {
+            --lo;
+            uint64_t f = FWD_START(lo), e = RC_END(lo);
+            if (f < jF) jF = f;
+            if (e < eR) { eR = e; pR = (uint64_t)ixp->sa[lo]; }
+        }
+        while (hi + 1 < n1 && ixp->lcp[hi + 1] >= d) {
+            ++hi;
+            uint64_t f = FWD_START(hi), e = RC_END(hi);
+            if (f < jF) jF = f;
+            if (e < eR) { eR = e; pR = (uint64_t)ixp->sa[hi]; }
+        }
+        int okF = (jF != INF) && (jF + (uint64_t)d - 1 < i);   /* :266 */
+        int okR = (eR != INF) && (eR < i);                     /* :271 */
+        if (okF && !have_fwd) { have_fwd = 1; best_fwd_start = jF; }              /* deepest okF: :280-287 */
+        if (okR && !have_rc) { have_rc = 1; best_rc_end = eR; best_rc_posS = pR; } /* deepest okR: :290-299 */
+        if (have_fwd && have_rc) break;
+    }
+#undef FWD_START
+#undef RC_END
+    uint64_t emit_len = 1, emit_ref = i;                   /* :302-303 */
+    if (have_fwd || have_rc) {
+        uint64_t fwd_true_len = 0, rc_true_len = 0;
+        if (have_fwd) {                                    /* :322-326 */
+            uint64_t cap = i - best_fwd_start;
+            uint64_t L = direct_lcp(S, len_S, i, best_fwd_start, cap);
+            fwd_true_len = L < cap ? L : cap;
+        }
+        if (have_rc) rc_true_len = direct_lcp(S, len_S, i, best_rc_posS, UINT64_MAX); /* :328-330 */
+        int use_fwd = 0, use_literal = 0;                  /* :335-352 */
+        if (have_fwd && fwd_true_len >= 1) {
+            use_fwd = !(have_rc && rc_true_len > fwd_true_len);
+        } else {
+            if (have_rc && rc_true_len > 1) use_fwd = 0; else use_literal = 1;
+        }
+        if (use_literal) { emit_len = 1; emit_ref = i; }   /* :354-365 */
+        else if (use_fwd) { emit_len = fwd_true_len; emit_ref = best_fwd_start; }
+        else { emit_len = rc_true_len; emit_ref = RC_MASK | (best_rc_end - emit_len + 1); }
+    }
+    *out_len = emit_len; *out_ref = emit_ref;
+}
+
 /* factorizer_core.hpp:177-383.  Returns 1 for the start_pos error (std::invalid_argument, :203). */
 int nlzo_factorize_multiple_dna_w_rc(const uint8_t *S, uint64_t len_S, uint64_t start_pos,
                                      uint64_t **out, uint64_t *count) {
@@ -256,66 +318,125 @@ int nlzo_factorize_multiple_dna_w_rc(const uint8_t *S, uint64_t len_S, uint64_t 
     int rc = index_build(S, len_S, &ix);                       /* :208 */
     if (rc) return rc;
     double t1 = now_s();
-    const idx_t n1 = ix.n1;
-    const uint64_t INF = UINT64_MAX / 2;
-    const uint64_t T_end = N, R_beg = N + 1, R_end = len_S - 1; /* :215-217 */
-#define FWD_START(k) ((uint64_t)ix.sa[k] < T_end ? (uint64_t)ix.sa[k] : INF)                   /* :221-223 */
-#define RC_END(k) (((uint64_t)ix.sa[k] >= R_beg && (uint64_t)ix.sa[k] < R_end)                  \
-                       ? N - ((uint64_t)ix.sa[k] - R_beg) - 1 : INF)                           /* :224-229 */
+    rc_ctx_t c = {&ix, S, len_S, N};
     sink_t sk = {0, 0, 0};
     uint64_t i = start_pos;
     while (i < N) {                                            /* :241 */
-        idx_t lo = ix.isa[i], hi = lo;
-        uint64_t jF = FWD_START(lo), eR = RC_END(lo), pR = (uint64_t)ix.sa[lo];
-        int have_fwd = 0, have_rc = 0;
-        uint64_t best_fwd_start = 0, best_rc_end = 0, best_rc_posS = 0;
-        for (;;) {
-            idx_t d = ix.lcp[lo] > ix.lcp[hi + 1] ? ix.lcp[lo] : ix.lcp[hi + 1];
-            if (d <= 0) break;                                 /* :259 root */
-            while (ix.lcp[lo] >= d) {
-                --lo;
-                uint64_t f = FWD_START(lo), e = RC_END(lo);
-                if (f < jF) jF = f;
-                if (e < eR) { eR = e; pR = (uint64_t)ix.sa[lo]; }
-            }
-            while (hi + 1 < n1 && ix.lcp[hi + 1] >= d) {
-                ++hi;
-                uint64_t f = FWD_START(hi), e = RC_END(hi);
-                if (f < jF) jF = f;
-                if (e < eR) { eR = e; pR = (uint64_t)ix.sa[hi]; }
-            }
-            int okF = (jF != INF) && (jF + (uint64_t)d - 1 < i);   /* :266 */
-            int okR = (eR != INF) && (eR < i);                     /* :271 */
-            if (okF && !have_fwd) { have_fwd = 1; best_fwd_start = jF; }              /* deepest okF: :280-287 */
-            if (okR && !have_rc) { have_rc = 1; best_rc_end = eR; best_rc_posS = pR; } /* deepest okR: :290-299 */
-            if (have_fwd && have_rc) break;
-        }
-        uint64_t emit_len = 1, emit_ref = i;                   /* :302-303 */
-        if (have_fwd || have_rc) {
-            uint64_t fwd_true_len = 0, rc_true_len = 0;
-            if (have_fwd) {                                    /* :322-326 */
-                uint64_t cap = i - best_fwd_start;
-                uint64_t L = direct_lcp(S, len_S, i, best_fwd_start, cap);
-                fwd_true_len = L < cap ? L : cap;
-            }
-            if (have_rc) rc_true_len = direct_lcp(S, len_S, i, best_rc_posS, UINT64_MAX); /* :328-330 */
-            int use_fwd = 0, use_literal = 0;                  /* :335-352 */
-            if (have_fwd && fwd_true_len >= 1) {
-                use_fwd = !(have_rc && rc_true_len > fwd_true_len);
-            } else {
-                if (have_rc && rc_true_len > 1) use_fwd = 0; else use_literal = 1;
-            }
-            if (use_literal) { emit_len = 1; emit_ref = i; }   /* :354-365 */
-            else if (use_fwd) { emit_len = fwd_true_len; emit_ref = best_fwd_start; }
-            else { emit_len = rc_true_len; emit_ref = RC_MASK | (best_rc_end - emit_len + 1); }
-        }
+        uint64_t emit_len, emit_ref;
+        rc_factor_at(&c, i, &emit_len, &emit_ref);
         if (sink_push(&sk, i, emit_len, emit_ref)) { index_free(&ix); free(sk.v); return -1; }
         i += emit_len;                                         /* :377-379 */
     }
-#undef FWD_START
-#undef RC_END
     index_free(&ix);
     g_last_index_s = t1 - t0; g_last_walk_s = now_s() - t1;
+    *out = sk.v; *count = sk.count;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ RC mode, the reference's CPU "parallel mode"
+ * src/cpp/parallel_factorizer.cpp:849-984 (parallel_factorize_dna_w_rc): ONE index built serially (:896-922 --
+ * construct_im, fwd_starts/rc_ends, the two RMQs), then the factorized range is cut into num_threads chunks
+ * (:86-144; at least MIN_CHARS_PER_THREAD = 100000 characters per thread, parallel_factorizer.hpp:55); every
+ * thread follows the factor chain from its chunk start and the chains are merged where they CONVERGE (:499-569):
+ * f(i) is a pure function of the text, so once two chains meet at a position they coincide from there on.  Here
+ * every thread walks its chunk into its own buffer; the merge keeps thread 0's chain, continues serially from the
+ * position where it leaves a chunk until that position is a factor start of the next thread's chain, then switches
+ * to that chain.  Output is identical to the serial function (asserted by the reference's
+ * tests/test_parallel_fasta.py:294-330 and by tests/test_oracle.py here). */
+#include <pthread.h>
+typedef struct {
+    const rc_ctx_t *c;
+    uint64_t begin, end;       /* chain starts at begin, stops at the first position >= end */
+    sink_t sk;
+    uint64_t exit_pos;
+    int rc;
+} rc_job_t;
+
+static void *rc_job_run(void *arg) {
+    rc_job_t *j = (rc_job_t *)arg;
+    uint64_t i = j->begin;
+    while (i < j->end) {
+        uint64_t l, r;
+        rc_factor_at(j->c, i, &l, &r);
+        if (sink_push(&j->sk, i, l, r)) { j->rc = -1; return NULL; }
+        i += l;
+    }
+    j->exit_pos = i;
+    return NULL;
+}
+
+/* index of the factor of job j that starts exactly at pos, or -1 */
+static int64_t job_find(const rc_job_t *j, uint64_t pos) {
+    int64_t lo = 0, hi = (int64_t)j->sk.count - 1;
+    while (lo <= hi) {
+        int64_t mid = (lo + hi) / 2;
+        uint64_t s = j->sk.v[3 * mid];
+        if (s == pos) return mid;
+        if (s < pos) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+int nlzo_parallel_factorize_dna_w_rc(const uint8_t *S, uint64_t len_S, uint64_t start_pos, int num_threads,
+                                     uint64_t **out, uint64_t *count, int *threads_used) {
+    *out = NULL; *count = 0;
+    if (threads_used) *threads_used = 0;
+    if (len_S < 4) return 0;
+    const uint64_t N = len_S / 2 - 1;
+    if (N == 0) return 0;
+    if (start_pos >= N) return 1;
+    index_t ix;
+    double t0 = now_s();
+    int rc = index_build(S, len_S, &ix);                       /* serial, as in the reference (:78-84, :896-922) */
+    if (rc) return rc;
+    double t1 = now_s();
+    rc_ctx_t c = {&ix, S, len_S, N};
+    uint64_t span = N - start_pos;
+    int T = num_threads > 0 ? num_threads : 1;
+    if ((uint64_t)T > span / 100000) T = (int)(span / 100000);  /* MIN_CHARS_PER_THREAD */
+    if (T < 1) T = 1;
+    if (threads_used) *threads_used = T;
+    rc_job_t *jobs = (rc_job_t *)calloc((size_t)T, sizeof(rc_job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+    if (!jobs || !th) { free(jobs); free(th); index_free(&ix); return -1; }
+    for (int t = 0; t < T; ++t) {
+        jobs[t].c = &c;
+        jobs[t].begin = start_pos + span * (uint64_t)t / (uint64_t)T;
+        jobs[t].end = t + 1 == T ? N : start_pos + span * (uint64_t)(t + 1) / (uint64_t)T;
+    }
+    for (int t = 1; t < T; ++t) pthread_create(&th[t], NULL, rc_job_run, &jobs[t]);
+    rc_job_run(&jobs[0]);
+    for (int t = 1; t < T; ++t) pthread_join(th[t], NULL);
+    sink_t sk = {0, 0, 0};
+    int fail = 0;
+    for (int t = 0; t < T; ++t) fail |= jobs[t].rc;
+    /* merge: chain position `pos`; `cur` = the job whose chain we are copying (from factor index `from`) */
+    if (!fail) {
+        uint64_t pos = start_pos;
+        int t = 0;
+        while (pos < N && !fail) {
+            /* the chunk that holds pos */
+            while (t + 1 < T && pos >= jobs[t + 1].begin) ++t;
+            int64_t k = job_find(&jobs[t], pos);
+            if (k >= 0) {                                      /* converged with job t: take the rest of its chain */
+                for (uint64_t q = (uint64_t)k; q < jobs[t].sk.count && !fail; ++q) {
+                    const uint64_t *f = jobs[t].sk.v + 3 * q;
+                    fail |= sink_push(&sk, f[0], f[1], f[2]);
+                }
+                pos = jobs[t].exit_pos;
+            } else {                                           /* not yet: one more factor of the incoming chain */
+                uint64_t l, r;
+                rc_factor_at(&c, pos, &l, &r);
+                fail |= sink_push(&sk, pos, l, r);
+                pos += l;
+            }
+        }
+    }
+    for (int t = 0; t < T; ++t) free(jobs[t].sk.v);
+    free(jobs); free(th);
+    index_free(&ix);
+    g_last_index_s = t1 - t0; g_last_walk_s = now_s() - t1;
+    if (fail) { free(sk.v); return -1; }
     *out = sk.v; *count = sk.count;
     return 0;
 }

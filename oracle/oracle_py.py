@@ -37,6 +37,9 @@ def lib():
             f = getattr(L, name)
             f.argtypes = [u8p, u64, u64, pp, ctypes.POINTER(u64)]
             f.restype = ctypes.c_int
+        L.nlzo_parallel_factorize_dna_w_rc.argtypes = [u8p, u64, u64, ctypes.c_int, pp, ctypes.POINTER(u64),
+                                                       ctypes.POINTER(ctypes.c_int)]
+        L.nlzo_parallel_factorize_dna_w_rc.restype = ctypes.c_int
         L.nlzo_free.argtypes = [ctypes.c_void_p]
         L.nlzo_free.restype = None
         L.nlzo_suffix_array_i32.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
@@ -76,6 +79,18 @@ def factorize(data: bytes, start_pos: int = 0) -> np.ndarray:
 def factorize_multiple_dna_w_rc(S: bytes, start_pos: int = 0) -> np.ndarray:
     """(z,3) uint64 triples with RC_MASK in ref (factorizer_core.hpp:177-383)."""
     return _run(lib().nlzo_factorize_multiple_dna_w_rc, S, start_pos)
+
+
+def parallel_factorize_multiple_dna_w_rc(S: bytes, num_threads: int, start_pos: int = 0):
+    """The reference's CPU parallel mode (parallel_factorizer.cpp:849-984): serial index build, chunked chain walk
+    on `num_threads` threads, convergence merge.  Returns ((z,3) triples, threads actually used)."""
+    used = ctypes.c_int(0)
+
+    def fn(data, n, sp, out, cnt):
+        return lib().nlzo_parallel_factorize_dna_w_rc(data, n, sp, int(num_threads), out, cnt, ctypes.byref(used))
+
+    arr = _run(fn, S, start_pos)
+    return arr, used.value
 
 
 def last_timing():

@@ -76,3 +76,19 @@ def test_prepare_functions():
     S, ol, sent = tm.prepare_multiple_dna_sequences_no_rc([b"ATCG", b"GGCC", b"TT"])
     assert S == b"ATCG\x01GGCC\x02TT" and ol == len(S) and sent == [4, 9]
     assert [tm.sentinel_byte(i) for i in (0, 63, 64, 65, 66)] == [1, 64, 66, 68, 69]
+
+
+def test_parallel_mode_equals_serial():
+    """The oracle's restatement of the reference's CPU parallel mode (parallel_factorizer.cpp:849-984: serial index,
+    chunked chain walk, convergence merge) must give the serial triples (the reference asserts the same in
+    tests/test_parallel_fasta.py:294-330), for any thread count and start position."""
+    from nolzss_b200 import workloads as wl
+    for seed, n, sp in ((50, 350_000, 0), (51, 420_000, 17), (52, 250_000, 100_001)):
+        S = wl.prepare_w_rc_single(wl.planted_dna(n, seed, scale=0.3).tobytes())
+        want = orc.factorize_multiple_dna_w_rc(S, sp)
+        for threads in (1, 2, 3, 8):
+            got, used = orc.parallel_factorize_multiple_dna_w_rc(S, threads, sp)
+            assert 1 <= used <= threads and used <= max(1, (n - sp) // 100_000)
+            assert np.array_equal(got, want), (seed, threads)
+    got, used = orc.parallel_factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(b"ACGTACGTTTGCA"), 8)
+    assert used == 1 and np.array_equal(got, orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(b"ACGTACGTTTGCA")))
