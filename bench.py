@@ -128,6 +128,39 @@ class ClockSampler:
         self.path = None
 
     def start(self):
+        # NVML from a thread of this process (first sample within a millisecond, one every 5 ms); the nvidia-smi
+        # loop below is the fallback -- on an 8-GPU box it needs longer to start than a 50 ms timed region lasts
+        self.nvml = None
+        try:
+            import threading
+
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.device).uuid))
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            state = {"stop": False, "clk": [], "reasons": 0, "smax": smax, "n": 0}
+
+            def loop():
+                while not state["stop"]:
+                    try:
+                        state["clk"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        state["reasons"] |= pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        state["n"] += 1
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            th = threading.Thread(target=loop, daemon=True)
+            th.start()
+            self.nvml = (pynvml, state, th)
+            return
+        except Exception:
+            self.nvml = None
         try:
             fd, self.path = tempfile.mkstemp(prefix="nlz_clocks_", suffix=".csv")
             os.close(fd)
@@ -140,6 +173,19 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if getattr(self, "nvml", None):
+            pynvml, state, th = self.nvml
+            state["stop"] = True
+            th.join(timeout=1.0)
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            if state["clk"]:
+                out.update(sm_mhz=float(statistics.median(state["clk"])), sm_max_mhz=float(state["smax"]),
+                           reasons=sorted(k for k, b in bits.items() if state["reasons"] & b), samples=state["n"],
+                           source="nvml, 5 ms period, during the timed regions")
+            return out
         if self.proc is None:
             return out
         try:

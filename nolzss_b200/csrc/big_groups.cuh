@@ -16,9 +16,11 @@
 // without knowing each other's size).  A group with more outliers than fit in shared memory raises a flag and
 // leaves everything untouched: the host redoes the round with the radix path (api.cu).
 //
-// Invariants used: a group's members are contiguous in the list, in suffix-array slot order, and the group's id
-// (high key half) is the slot of its head; every group of B has more than gcap members, so a chunk of gcap list
-// positions holds at most one group head and CTA c simply looks for a head in chunk c.
+// Invariants used: a group's members are contiguous in the list, in suffix-array slot order; the group's id (high
+// key half = its current rank) is a slot inside the group's slot range -- the head slot after a regroup or a tile
+// sort, possibly a middle slot after k_group_stream (see "Ranks" in the kernel); every group of B has more than
+// gcap members, so a chunk of gcap list positions holds at most one group head and CTA c simply looks for a head
+// in chunk c.
 #pragma once
 #include "common.cuh"
 #include "sa.cuh"
@@ -123,7 +125,6 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     u32& s_baseU = misc[8];
     u32& s_nbig = misc[9];
     u32& s_actS = misc[10];
-    u32& s_first_size = misc[11];
     u32* ws = misc + 32;       // 33 words of scan scratch
     u32* big_head = misc + 128;
     u32* big_base = misc + 128 + GS_MAX_BIGSUB;
@@ -141,7 +142,8 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     __syncthreads();
     const u32 head = s_head;
     if (head == 0xFFFFFFFFu) return;
-    const u32 g = gs_grp(key_in[head]);
+    const u32 g = gs_grp(key_in[head]);        // the group's rank: a slot inside the group's slot range (see below)
+    const u32 gbase = slot_in[head];            // first slot of the group
     // group end: first probe position (head + t * gcap) outside the group, then the exact end inside that stride
     for (u32 tb = 0;; tb += GS_THREADS) {
         const u64 p = (u64)head + (u64)(tb + tid + 1) * gcap;
@@ -293,17 +295,32 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
         actS_before = cta_excl_scan(mine, ws, total);
         gmax = __reduce_max_sync(0xffffffffu, gmax);
         if (lane == 0 && gmax) atomicMax(out.maxgS, gmax);
-        if (tid == 0) { s_actS = total; s_first_size = nlt ? osize[0] : 0u; }
+        if (tid == 0) s_actS = total;
         __syncthreads();
     } else if (tid == 0) {
-        s_actS = 0; s_first_size = 0;
+        s_actS = 0;
     }
     __syncthreads();
     // ---- reservations: S (outlier sub-groups, then the pivot block if it is small), B (pivot block / big sub-groups),
     // records of changed ranks
     const bool eq_act = neq >= 2, eq_big = neq > gcap;
-    // ranks that change: everything except the sub-group that stays at the group's head slot
-    const u32 unchanged = nlt ? s_first_size : neq;
+    // Ranks.  A group's rank only has to be a slot inside the group's own slot range [gbase, gbase + M): ranges of
+    // different groups are disjoint, so any such representative orders the groups correctly, and a singleton's
+    // rank is its slot (the inverse suffix array in the end).  Outlier sub-groups take their head slot.  The pivot
+    // block KEEPS the group's rank whenever that slot still lies inside the block's range, and otherwise takes the
+    // slot in the middle of its range -- a tandem-array group sheds outliers from the same side in every round,
+    // and with the head slot as its name all of its members (and, on several GPUs, one record each for every
+    // replica) would be renamed every round; named by a middle slot it is renamed O(log) times.
+    const u32 rel = g - gbase;
+    const u32 eq_rank = (rel >= nlt && rel < nlt + neq) ? g : gbase + nlt + (neq >> 1);
+    const bool eq_changed = eq_rank != g;
+    // the one outlier sub-group that keeps the rank: its head slot is the old rank
+    u32 qu = 0xFFFFFFFFu, usz = 0;
+    {
+        const u32 qc = rel < nlt ? rel : (rel >= nlt + neq ? rel - neq : 0xFFFFFFFFu);
+        if (qc < nout && ohead[qc] == qc) { qu = qc; usz = osize[qc]; }
+    }
+    const u32 n_changed = (eq_changed ? neq : 0u) + nout - usz;
     if (tid == 0) {
         const u32 toS = s_actS + ((eq_act && !eq_big) ? neq : 0u);
         s_baseS = toS ? atomicAdd(out.mS, toS) : 0u;
@@ -314,7 +331,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
             const u32 sz = osize[big_head[k]];
             big_base[k] = out.end - (atomicAdd(out.mB, sz) + sz);
         }
-        s_baseU = (RANK.upd && M > unchanged) ? atomicAdd(RANK.upd_count, M - unchanged) : 0u;
+        s_baseU = (RANK.upd && n_changed) ? atomicAdd(RANK.upd_count, n_changed) : 0u;
     }
     __syncthreads();
     const u32 baseS = s_baseS, baseU = s_baseU;
@@ -332,12 +349,12 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
             const u32 hq = ohead[q], sz = osize[hq];
             const u32 pos = q < nlt ? q : neq + q;                  // position inside the group
             const u32 hpos = hq < nlt ? hq : neq + hq;
-            const u32 slot = g + pos, newrank = g + hpos;
+            const u32 slot = gbase + pos, newrank = gbase + hpos;
             SA[slot - RANK.base] = s;
             if (newrank != g) {
                 RANK.rank[s] = newrank;
-                // record index: position among the changed members = pos minus the unchanged ones before it
-                if (RANK.upd) RANK.upd[baseU + (pos - (nlt ? s_first_size : neq))] = ((u64)newrank << 32) | (u64)s;
+                // record index: rank among the changed outliers (sorted order minus the sub-group that kept the rank)
+                if (RANK.upd) RANK.upd[baseU + (q - ((qu != 0xFFFFFFFFu && q >= qu + usz) ? usz : 0u))] = ((u64)newrank << 32) | (u64)s;
             }
             if (sz >= 2) {
                 u32 dst;
@@ -355,8 +372,9 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     }
     // ---- pass B: the pivot block (any order among its members is a valid order of equal keys)
     {
-        const u32 newrank = g + nlt;
-        const bool changed = nlt != 0;
+        const u32 newrank = eq_rank;
+        const bool changed = eq_changed;
+        const u32 slot0 = gbase + nlt;
         for (u32 jb = head; jb < gend; jb += GS_THREADS) {
             const u32 j = jb + tid;
             bool eq = false;
@@ -369,12 +387,12 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
             if (eq) {
                 const u32 e = base + __popc(em & lanemask_lt());
                 const u32 s = val_in[j];
-                const u32 slot = newrank + e;
+                const u32 slot = slot0 + e;
                 SA[slot - RANK.base] = s;
                 if (changed) {
                     RANK.rank[s] = newrank;
-                    // changed members in group order: [lt sub-groups after the first | pivot block | gt outliers]
-                    if (RANK.upd) RANK.upd[baseU + (nlt - s_first_size) + e] = ((u64)newrank << 32) | (u64)s;
+                    // records: [changed outliers | pivot block]
+                    if (RANK.upd) RANK.upd[baseU + (nout - usz) + e] = ((u64)newrank << 32) | (u64)s;
                 }
                 if (eq_act) {
                     const u32 dst = baseEq + e;

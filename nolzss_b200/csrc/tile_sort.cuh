@@ -349,9 +349,11 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
             const u32 s = sval[o];
             const u32 slot = sslot[o];
             const u32 newrank = sslot[sgs[o]];
-            // old rank = head slot of the member's group (the bitonic path keyed the members by their group's tile position)
+            // old rank = the high key half.  The bitonic path keyed the members by their group's tile position and has
+            // lost it; it cannot assume the head slot either (a group that comes from k_group_stream may be named by
+            // any slot of its range), so there every rank is stored.
             const u32 gid = (u32)(skey[o] >> 32);
-            const u32 oldrank = used_bitonic ? sslot[gid] : gid;
+            const u32 oldrank = used_bitonic ? 0xFFFFFFFFu : gid;
             if (newrank != oldrank) {
                 RANK.rank[s] = newrank;
                 if (RANK.upd) { upd_rec[nupd] = ((u64)newrank << 32) | (u64)s; ++nupd; }
