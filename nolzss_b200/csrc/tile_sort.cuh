@@ -348,7 +348,18 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         if (o < cnt) {
             const u32 s = sval[o];
             const u32 slot = sslot[o];
-            const u32 newrank = sslot[sgs[o]];
+            const u32 gid0 = (u32)(skey[o] >> 32);
+            // New rank of the member's sub-group: any slot inside the sub-group's slot range is a valid name (the
+            // ranges of different groups are disjoint; a singleton's range is its slot).  The sub-group that still
+            // holds the slot the old group was named by KEEPS that name -- a tandem-array group that sheds a few
+            // members per round is then renamed (one scattered store per member, one record per replica on several
+            // GPUs) only when its name falls out of its range -- every other sub-group takes its head slot.
+            // The old name's tile position follows from the slots being consecutive inside a group.
+            u32 newrank = sslot[sgs[o]];
+            if (!used_bitonic) {
+                const u32 pg = o + (gid0 - slot);                  // tile position of the member that holds slot gid0
+                if (pg < cnt && sgs[pg] == sgs[o]) newrank = gid0;
+            }
             // old rank = the high key half.  The bitonic path keyed the members by their group's tile position and has
             // lost it; it cannot assume the head slot either (a group that comes from k_group_stream may be named by
             // any slot of its range), so there every rank is stored.

@@ -29,9 +29,15 @@ def gen():
         return x.tobytes()
     x = np.repeat(np.frombuffer(b"ACGT", dtype=np.uint8)[r.integers(0, 4, n // 50 + 1)], r.integers(1, 100, n // 50 + 1))[:n]
     return x.tobytes()
+FLAG_CHOICES = [0, 0, 0, 64 << 8, (64 << 8) | 8, 128 << 8, (256 << 8) | 8, 1024 << 8, 1, 2, 4, (64 << 8) | 1, (512 << 8) | 2]
 while time.time() < t_end:
     s = gen()
-    print(f"case {n_cases}: n={len(s)} head={s[:24]!r}", flush=True)
+    # test hooks (nlz_set_debug_flags): tile capacity lowered so that small texts run the hybrid rounds of
+    # big_groups.cuh, forced redo of a hybrid round (8), forced tile-sort paths (1, 2, 4)
+    flags = rng.choice(FLAG_CHOICES)
+    for c in [L.context()] + list(grp.ctxs):
+        L.check(L.load().nlz_set_debug_flags(c, flags))
+    print(f"case {n_cases}: n={len(s)} flags={flags:#x} head={s[:24]!r}", flush=True)
     exp_rc = orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s))
     exp_g = orc.factorize(s)
     assert np.array_equal(L.factorize_array(L.MODE_DNA_RC, s), exp_rc), ("single rc", len(s))
