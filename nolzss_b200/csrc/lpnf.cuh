@@ -603,7 +603,8 @@ __device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p
 // LR[i] = (ref | rc_flag<<31) << 32 | len        for every factorized position i
 constexpr u32 LR_RC_FLAG = 0x80000000u;
 constexpr int WALK_MAX_NODES = 512;    // default: ancestors climbed in rank order before a position is "hard" (250 Mbp text: 2048 -> 512 saves 15 ms of failed climbs; the 5 Mbp text never exceeds 500)
-constexpr int WALK_Q = 8;              // consecutive text positions per 8-lane tile in k_lpnf_hard
+constexpr int WALK_Q = 32;             // consecutive text positions per 8-lane tile in k_lpnf_hard (the carried bound
+                                       // links them: the first one pays a full bisection, the others 2-3 probes)
 
 struct NodeState {
     u32 lo, hi;   // rank interval
@@ -791,6 +792,17 @@ template <bool RC>
 __device__ __forceinline__ u32 depth_search(const Trees& T, const WalkParams& p, u32 i, const NodeState& cur,
                                             u32 loD, u32 hiD, NodeState& U, NodeState& L, u32& probes) {
     L = cur;
+    // Gallop upwards from the known-true bound first: along consecutive positions the carried bound is within a few
+    // symbols of the answer (inside a tandem array the answer is constant over a period and the upper bound is the
+    // rest of the array: ~20 bisection probes, each a fresh interval search, against 2-3 galloping ones).
+    for (u32 step = 1; loD >= 1 && hiD - loD > 1; step <<= 1) {     // no carried bound (loD = 0): bisect at once
+        const u32 mid = loD + step;
+        if (mid >= hiD || step >= (1u << 30)) break;
+        const NodeState cand = extend_to<RC, false, true>(T, p, L, mid);
+        ++probes;
+        if (pred_f(cand, mid, i)) { loD = mid; U = cand; }
+        else { hiD = mid; L = cand; break; }
+    }
     while (hiD - loD > 1) {
         const u32 mid = loD + ((hiD - loD) >> 1);
         const NodeState cand = extend_to<RC, false, true>(T, p, L, mid);
@@ -810,7 +822,12 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict
     const u64 i0 = tile_id * WALK_Q;
     if (i0 >= p.nfac) return;                                   // tile-uniform
     const u32 q = t8.thread_rank();
-    u32 todo = t8.ballot((i0 + q < p.nfac) && HARD[i0 + q] != 0);
+    u32 todo = 0;                                               // bit k: position i0 + k is hard
+#pragma unroll
+    for (int j = 0; j < WALK_Q / 8; ++j) {
+        const u64 ii = i0 + (u64)(j * 8) + q;
+        todo |= t8.ballot(ii < p.nfac && HARD[ii] != 0) << (8 * j);
+    }
     if (!todo) return;
     const u32* LCP = T.lcp[0];
     u32 visited = 0;
