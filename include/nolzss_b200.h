@@ -75,7 +75,9 @@ const char* nlz_version(void); /* bindings.cpp:1513-1517 (__version__) */
 int nlz_set_profiling(nlz_ctx* ctx, int on);
 int nlz_kernel_class_count(void);
 /* test hook: forces the fallback paths of the shared-memory group sort (1 bitonic network, 2 no pivot fast path,
- * 4 counting only); 0 = normal operation */
+ * 4 counting only); 8 makes the group-stream kernel of the hybrid doubling rounds give up from the third round
+ * on (the round is redone through the radix path); flags >> 8, when in [64, 2048), lowers the largest tie group
+ * the tile sort takes, so that small texts run the hybrid rounds; 0 = normal operation */
 int nlz_set_debug_flags(nlz_ctx* ctx, int flags);
 int nlz_get_kernel_stats(nlz_ctx* ctx, int cls, const char** name, double* ms, uint64_t* bytes,
                          uint32_t* launches);
