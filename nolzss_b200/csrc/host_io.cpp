@@ -230,55 +230,109 @@ int nlz_fasta_parse(const char* path, int sanitize_mode, nlz_fasta** out) {
         for (const char* u = "ACGT"; *u; ++u) k[(unsigned char)*u] = 0;
         for (const char* l = "acgt"; *l; ++l) k[(unsigned char)*l] = 1;
     } } kind;
-    nlz_fasta* fa = new nlz_fasta();
-    std::string cur_seq, cur_id;
-    size_t empty_count = 0, removed = 0;
-    auto flush = [&]() {
-        if (cur_id.empty()) return;
-        if (!cur_seq.empty()) { fa->seqs.push_back(cur_seq); fa->ids.push_back(cur_id); }
-        else { std::cerr << "Warning: Skipping empty sequence with ID: " << cur_id << std::endl; ++empty_count; }
-        cur_seq.clear();
+    // The file is cut at header lines into one range per host thread; every range is parsed independently (a record
+    // never straddles a cut) and the results are concatenated in file order, so ids, sequences, warnings and the
+    // first error are exactly those of a serial scan.
+    struct Part {
+        std::vector<std::string> ids, seqs;
+        std::vector<std::string> skipped;        // ids of empty records, in order (warnings)
+        size_t removed = 0;
+        int err = NLZ_OK;
+        std::string msg;
     };
-    const char* p = map;
-    const char* const end = map + fsize;
-    while (p < end) {
-        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
-        const char* le = nl ? nl : end;                         // line = [p, le)
-        const char* next = nl ? nl + 1 : end;
-        while (le > p && std::isspace((unsigned char)le[-1])) --le;
-        if (le == p) { p = next; continue; }
-        if (*p == '>') {
-            flush();
-            const char* a = p + 1;
-            while (a < le && std::isspace((unsigned char)*a)) ++a;
-            const char* b = a;
-            while (b < le && !std::isspace((unsigned char)*b)) ++b;
-            if (a < le) cur_id.assign(a, b);
-            else { delete fa; set_error("Empty sequence header in FASTA file"); return NLZ_ERR_RUNTIME; }
-        } else {
-            const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
-            const unsigned char* qe = reinterpret_cast<const unsigned char*>(le);
-            while (q < qe) {
-                const unsigned char* r = q;
-                while (r < qe && kind.k[*r] == 0) ++r;           // run of clean bases
-                if (r > q) cur_seq.append(reinterpret_cast<const char*>(q), (size_t)(r - q));
-                if (r == qe) break;
-                const unsigned char c = *r;
-                if (kind.k[c] == 1) cur_seq.push_back((char)upper_ascii(c));
-                else if (kind.k[c] == 3) {
-                    if (sanitize_mode == 1) {
-                        set_error("Invalid nucleotide '%c' found in sequence with ID: %s", (char)c, cur_id.c_str());
-                        delete fa;
-                        return NLZ_ERR_RUNTIME;
-                    }
-                    ++removed;
-                }
-                q = r + 1;
+    auto parse_range = [&](const char* p, const char* const end, Part& out) {
+        std::string cur_seq, cur_id;
+        auto flush = [&]() {
+            if (cur_id.empty()) return;
+            if (!cur_seq.empty()) {
+                const size_t cap = cur_seq.size();
+                out.seqs.push_back(std::move(cur_seq));
+                out.ids.push_back(cur_id);
+                cur_seq = std::string();
+                cur_seq.reserve(cap);
+            } else {
+                out.skipped.push_back(cur_id);
             }
+            cur_seq.clear();
+        };
+        while (p < end) {
+            const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+            const char* le = nl ? nl : end;                         // line = [p, le)
+            const char* next = nl ? nl + 1 : end;
+            while (le > p && std::isspace((unsigned char)le[-1])) --le;
+            if (le == p) { p = next; continue; }
+            if (*p == '>') {
+                flush();
+                const char* a = p + 1;
+                while (a < le && std::isspace((unsigned char)*a)) ++a;
+                const char* b = a;
+                while (b < le && !std::isspace((unsigned char)*b)) ++b;
+                if (a < le) cur_id.assign(a, b);
+                else { out.err = NLZ_ERR_RUNTIME; out.msg = "Empty sequence header in FASTA file"; return; }
+            } else {
+                const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+                const unsigned char* qe = reinterpret_cast<const unsigned char*>(le);
+                while (q < qe) {
+                    const unsigned char* r = q;
+                    while (r < qe && kind.k[*r] == 0) ++r;           // run of clean bases
+                    if (r > q) cur_seq.append(reinterpret_cast<const char*>(q), (size_t)(r - q));
+                    if (r == qe) break;
+                    const unsigned char c = *r;
+                    if (kind.k[c] == 1) cur_seq.push_back((char)upper_ascii(c));
+                    else if (kind.k[c] == 3) {
+                        if (sanitize_mode == 1) {
+                            out.err = NLZ_ERR_RUNTIME;
+                            out.msg = std::string("Invalid nucleotide '") + (char)c + "' found in sequence with ID: " + cur_id;
+                            return;
+                        }
+                        ++out.removed;
+                    }
+                    q = r + 1;
+                }
+            }
+            p = next;
         }
-        p = next;
+        flush();
+    };
+    const char* const end = map + fsize;
+    size_t nparts = std::thread::hardware_concurrency();
+    if (nparts > 32) nparts = 32;
+    if (nparts > fsize / (4u << 20)) nparts = fsize / (4u << 20);        // at least 4 MiB per thread
+    if (nparts < 1) nparts = 1;
+    std::vector<const char*> cut(nparts + 1, end);
+    cut[0] = map;
+    for (size_t t = 1; t < nparts; ++t) {
+        const char* q = map + fsize / nparts * t;
+        if (q < cut[t - 1]) q = cut[t - 1];
+        const char* hit = end;                                            // next line that starts with '>'
+        while (q < end) {
+            const char* nl = static_cast<const char*>(memchr(q, '\n', (size_t)(end - q)));
+            if (!nl || nl + 1 >= end) break;
+            if (nl[1] == '>') { hit = nl + 1; break; }
+            q = nl + 1;
+        }
+        cut[t] = hit;
     }
-    flush();
+    std::vector<Part> parts(nparts);
+    if (nparts == 1) parse_range(cut[0], cut[1], parts[0]);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nparts; ++t)
+            pool.emplace_back([&, t] { if (cut[t] < cut[t + 1]) parse_range(cut[t], cut[t + 1], parts[t]); });
+        for (auto& th : pool) th.join();
+    }
+    nlz_fasta* fa = new nlz_fasta();
+    size_t empty_count = 0, removed = 0, total = 0;
+    for (const Part& pt : parts) total += pt.seqs.size();
+    fa->ids.reserve(total);
+    fa->seqs.reserve(total);
+    for (Part& pt : parts) {
+        // warnings and records of this range come before the first error of a later one, as in a serial scan
+        for (const std::string& id : pt.skipped) { std::cerr << "Warning: Skipping empty sequence with ID: " << id << std::endl; ++empty_count; }
+        if (pt.err != NLZ_OK) { set_error("%s", pt.msg.c_str()); delete fa; return pt.err; }
+        removed += pt.removed;
+        for (size_t i = 0; i < pt.seqs.size(); ++i) { fa->seqs.push_back(std::move(pt.seqs[i])); fa->ids.push_back(std::move(pt.ids[i])); }
+    }
     if (empty_count > 0) std::cerr << "Warning: Skipped " << empty_count << " empty sequence(s) in FASTA file" << std::endl;
     if (sanitize_mode == 0 && removed > 0)
         std::cerr << "Warning: Removed " << removed << " ambiguous nucleotide(s) from FASTA input" << std::endl;

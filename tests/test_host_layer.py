@@ -213,3 +213,76 @@ def test_shuffle_control_matches_reference_algorithm(tmp_path):
     got = _parse_fasta_content((tmp_path / "np.fasta").read_text())
     assert list(got) == [k.split()[0] for k in recs] and all(sorted(got[k.split()[0]]) == sorted(recs[k]) for k in recs)
     assert not shuffle_fasta_sequences(tmp_path / "missing.fasta", tmp_path / "x.fasta")
+
+
+def _py_fasta_model(data: bytes, strict: bool):
+    """Serial restatement of fasta_processor.cpp:28-128 (the semantics the threaded parser must keep)."""
+    recs, cur_id, cur = [], None, bytearray()
+
+    def flush():
+        nonlocal cur
+        if cur_id is None:
+            return
+        if cur:
+            recs.append((cur_id, bytes(cur)))
+        cur = bytearray()
+
+    for line in data.split(b"\n"):
+        line = line.rstrip(b" \t\r\n\v\f")
+        if not line:
+            continue
+        if line[:1] == b">":
+            flush()
+            toks = line[1:].split()
+            if not toks:
+                raise RuntimeError("Empty sequence header in FASTA file")
+            cur_id = toks[0].decode()
+        else:
+            for c in line:
+                ch = bytes([c])
+                if ch in b"ACGTacgt":
+                    cur += ch.upper()
+                elif ch.isspace():
+                    continue
+                elif strict:
+                    raise RuntimeError(f"Invalid nucleotide '{ch.decode()}' found in sequence with ID: {cur_id}")
+    flush()
+    return recs
+
+
+def test_threaded_fasta_parser_equals_serial_model(tmp_path):
+    """Files large enough to be cut into several ranges (>= 4 MiB per host thread): records, ids, dropped
+    characters, empty records and the first strict-mode error must be those of a serial scan."""
+    import random as _r
+    rnd = _r.Random(9)
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    chunks = []
+    for k in range(1500):
+        n = rnd.choice([0, 1, 50, 5_000, 40_000])
+        seq = acgt[rng.integers(0, 4, n)].tobytes()
+        if k % 7 == 0 and n:
+            seq = seq.lower()
+        if k % 11 == 0 and n > 10:
+            seq = seq[:7] + b"NN-" + seq[7:]
+        width = rnd.choice([60, 80, 10_000_000])
+        body = b"".join(seq[i:i + width] + rnd.choice([b"\n", b"\r\n", b" \n"]) for i in range(0, len(seq), width))
+        chunks.append(b">rec%d some description > with a bracket\n" % k + body + (b"\n" if k % 5 == 0 else b""))
+    data = b"".join(chunks)
+    assert len(data) > 12 * (1 << 20)
+    path = tmp_path / "big.fasta"
+    path.write_bytes(data)
+    assert _parse(str(path), 0) == _py_fasta_model(data, False)
+    with pytest.raises(RuntimeError) as e1:
+        _py_fasta_model(data, True)
+    with pytest.raises(RuntimeError) as e2:
+        _parse(str(path), 1)
+    assert str(e1.value) in str(e2.value)
+    # an error that only a late range sees
+    clean = b"".join(b">c%d\n" % k + acgt[rng.integers(0, 4, 30_000)].tobytes() + b"\n" for k in range(500))
+    late = clean + b">bad\nACGTXACGT\n" + b">after\nACGT\n"
+    path.write_bytes(late)
+    with pytest.raises(RuntimeError, match="Invalid nucleotide 'X' found in sequence with ID: bad"):
+        _parse(str(path), 1)
+    got = _parse(str(path), 0)
+    assert got[-2] == ("bad", b"ACGTACGT") and got[-1] == ("after", b"ACGT") and len(got) == 502
