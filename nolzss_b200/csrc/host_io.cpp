@@ -13,6 +13,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -572,16 +573,31 @@ int nlz_factorize_fasta_per_sequence(nlz_ctx* ctx, const char* fasta_path, int w
     while (i0 < k && rc == NLZ_OK) {
         std::string concat;
         std::vector<uint64_t> offs, lens;
-        uint64_t suffixes = 0;
+        uint64_t suffixes = 0, bytes = 0;
         size_t i1 = i0;
         while (i1 < k && (i1 == i0 || (suffixes < kChunkSuffixes && i1 - i0 < kChunkRecords))) {
             const std::string& q = fa->seqs[i1];
             const uint64_t n = with_rc ? q.size() : q.size() - 1;  // fasta_processor.cpp:469-471 (no-RC drops the last base)
-            offs.push_back(concat.size());
+            offs.push_back(bytes);
             lens.push_back(n);
-            concat.append(q.data(), n);
+            bytes += n;
             suffixes += (n + 1) * (with_rc ? 2 : 1);
             ++i1;
+        }
+        concat.resize(bytes);                                      // one allocation; records copied by a few threads
+        {
+            const size_t nrec = i1 - i0;
+            size_t nt = std::min<size_t>(8, std::max<size_t>(1, bytes >> 22));
+            if (nt > nrec) nt = nrec ? nrec : 1;
+            auto copy_range = [&](size_t a, size_t b) {
+                for (size_t j = a; j < b; ++j) memcpy(&concat[offs[j]], fa->seqs[i0 + j].data(), lens[j]);
+            };
+            if (nt <= 1) copy_range(0, nrec);
+            else {
+                std::vector<std::thread> pool;
+                for (size_t t = 0; t < nt; ++t) pool.emplace_back(copy_range, nrec * t / nt, nrec * (t + 1) / nt);
+                for (auto& th : pool) th.join();
+            }
         }
         Triples t;
         rc = nlz_factorize_batch(ctx, with_rc, reinterpret_cast<const uint8_t*>(concat.data()), offs.data(), lens.data(),
