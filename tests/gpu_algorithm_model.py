@@ -107,6 +107,135 @@ def suffix_array(data: bytes, force_bits=None):
     return SA, RANK, rounds
 
 
+def suffix_array_hybrid(data: bytes, gcap: int = 8, out_cap: int = 16, force_bits=None, rnd=None):
+    """Prefix doubling with the HYBRID rounds of csrc/big_groups.cuh + the representative ranks of tile_sort.cuh.
+
+    The active list is split once into S (groups of <= gcap members: k_tile_sort) and B (larger groups: one CTA of
+    k_group_stream each).  Modelled: the pivot partition of a big group (pivot = most frequent of 32 evenly spaced
+    samples; pivot-equal block in arbitrary member order, outliers sorted), sub-groups routed to S or B by size, ranks
+    as representatives (a sub-group that still holds the slot its group was named by keeps that name; the pivot block
+    otherwise takes its middle slot, every other sub-group its head slot), and the redo of a round through the radix
+    path when a group has more than `out_cap` outliers (lists unified, slot list sorted, ordinary regroup; one fresh
+    split is tried afterwards).  Returns (SA, RANK, rounds, stats)."""
+    import random as _random
+    rnd = rnd or _random.Random(1)
+    L = len(data)
+    n1 = L + 1
+    cls, lay = choose_layout(data, n1, force_bits)
+    keys = build_keys(data, cls, lay)
+    order = sorted(range(n1), key=lambda p: keys[p])
+    SA = [0] * n1
+    RANK = [0] * n1
+    act = regroup([keys[p] for p in order], order, None, (1 << lay["D"]) - 1, SA, RANK)
+    h = lay["W"]
+    stats = dict(rounds=0, hybrid_rounds=0, fallbacks=0, stream_groups=0, renamed=0, kept=0)
+
+    def groups_of(lst):                       # contiguous runs of equal rank
+        out, a = [], 0
+        for j in range(1, len(lst) + 1):
+            if j == len(lst) or lst[j][0] != lst[a][0]:
+                out.append(lst[a:j])
+                a = j
+        return out
+
+    def radix_round(lst):                     # the legacy path: global sort by (rank, rank[s+h]) + regroup
+        ck = [((g << 32) | RANK[s + h], s) for (g, s, _) in lst]
+        slots = sorted(slot for (_, _, slot) in lst)          # ascending slots line up with ascending ranks
+        perm = sorted(range(len(ck)), key=lambda j: ck[j][0])
+        return regroup([ck[j][0] for j in perm], [ck[j][1] for j in perm], slots, None, SA, RANK)
+
+    def emit(sub, base_slot, old_rank, is_pivot_block, nextS, nextB, writes):
+        """one sorted sub-group occupying slots [base_slot, base_slot + len(sub))"""
+        size = len(sub)
+        if base_slot <= old_rank < base_slot + size:
+            name = old_rank                                    # still holds the group's name: keeps it
+            stats["kept"] += size
+        else:
+            name = base_slot + (size >> 1) if is_pivot_block else base_slot
+            stats["renamed"] += size
+        for j, s in enumerate(sub):
+            writes.append((s, name, base_slot + j))
+        if size >= 2:
+            (nextS if size <= gcap else nextB).extend((name, s, base_slot + j) for j, s in enumerate(sub))
+
+    S, B, hybrid, fallbacks = [], [], False, 0
+    while act or S or B:
+        stats["rounds"] += 1
+        assert stats["rounds"] < 64
+        if not hybrid:
+            if fallbacks < 2 and any(len(g) > gcap for g in groups_of(act)):
+                gs = groups_of(act)
+                S = [e for g in gs if len(g) <= gcap for e in g]
+                B = [e for g in gs if len(g) > gcap for e in g]
+                act, hybrid = [], True
+            else:
+                act = radix_round(act)
+                h *= 2
+                continue
+        stats["hybrid_rounds"] += 1
+        # consistent snapshot of the second key half for both lists (k_gather_rank before any rank is written)
+        key2 = {s: RANK[s + h] for (_, s, _) in S + B}
+        nextS, nextB, writes, overflow = [], [], [], False
+        for grp in groups_of(S) + groups_of(B):
+            old_rank = grp[0][0]
+            base = min(slot for (_, _, slot) in grp)
+            members = [s for (_, s, _) in grp]
+            assert sorted(slot for (_, _, slot) in grp) == list(range(base, base + len(grp)))
+            assert base <= old_rank < base + len(grp)          # a rank is a slot inside the group's range
+            if len(grp) <= gcap:                               # k_tile_sort: full sort, sub-groups by equal key
+                members.sort(key=lambda s: key2[s])
+                subs = [[s for s in members if key2[s] == k] for k in sorted(set(key2[s] for s in members))]
+                at = base
+                for sub in subs:
+                    emit(sub, at, old_rank, False, nextS, nextB, writes)
+                    at += len(sub)
+                continue
+            stats["stream_groups"] += 1
+            M = len(members)
+            samples = [key2[members[(M * q) >> 5]] for q in range(32)]
+            piv = max(samples, key=lambda v: (samples.count(v), -samples.index(v)))
+            lt = sorted((s for s in members if key2[s] < piv), key=lambda s: (key2[s], s))
+            gt = sorted((s for s in members if key2[s] > piv), key=lambda s: (key2[s], s))
+            eq = [s for s in members if key2[s] == piv]
+            rnd.shuffle(eq)                                    # pass B places the block in no particular order
+            if len(lt) + len(gt) > out_cap:
+                overflow = True
+                break
+            at = base
+            for side in (lt, None, gt):
+                if side is None:
+                    emit(eq, at, old_rank, True, nextS, nextB, writes)
+                    at += len(eq)
+                    continue
+                a = 0
+                for j in range(1, len(side) + 1):
+                    if j == len(side) or key2[side[j]] != key2[side[a]]:
+                        emit(side[a:j], at, old_rank, False, nextS, nextB, writes)
+                        at += j - a
+                        a = j
+        if overflow:
+            # groups handled before the overflow have been written (a valid refinement); the round is redone
+            for s, name, slot in writes:
+                RANK[s] = name
+                SA[slot] = s
+            stats["fallbacks"] += 1
+            fallbacks += 1
+            # the unified list keeps the OLD ranks as sort keys (the keys were gathered before any write)
+            lst = S + B
+            ck = [((g << 32) | key2[s], s) for (g, s, _) in lst]
+            slots = sorted(slot for (_, _, slot) in lst)
+            perm = sorted(range(len(ck)), key=lambda j: ck[j][0])
+            act = regroup([ck[j][0] for j in perm], [ck[j][1] for j in perm], slots, None, SA, RANK)
+            S, B, hybrid = [], [], False
+        else:
+            for s, name, slot in writes:
+                RANK[s] = name
+                SA[slot] = s
+            S, B = nextS, nextB
+        h *= 2
+    return SA, RANK, stats["rounds"], stats
+
+
 # ------------------------------------------------------------------ stage 2: LCP (chunked Kasai)
 def lcp_array(data: bytes, SA, RANK, Q=16):
     L = len(data)

@@ -55,3 +55,28 @@ def test_gpu_symbol_order_recode_matches_model():
         sa, lcp = orc.gpu_order_sa_lcp(s)
         SA, RANK, _ = gm.suffix_array(s, rnd.choice([None, 32, 64]))
         assert list(sa) == SA and list(lcp) == gm.lcp_array(s, SA, RANK)
+
+
+def test_model_hybrid_rounds_and_representative_ranks():
+    """Model of the hybrid doubling rounds (csrc/big_groups.cuh) and of ranks-as-representatives: tandem-heavy texts
+    with tiny tile / outlier capacities so that the split, the pivot partition, the S/B routing, the renaming rule
+    and the redo path all run; the suffix array must be the oracle's."""
+    rnd = random.Random(12)
+    seen = dict(hybrid_rounds=0, fallbacks=0, stream_groups=0, kept=0, renamed=0)
+    for it in range(120):
+        parts = []
+        for _p in range(rnd.randint(1, 4)):
+            unit = bytes(rnd.choice(b"ACGT") for _u in range(rnd.randint(1, 5)))
+            parts.append(unit * rnd.randint(3, 60))
+            parts.append(bytes(rnd.choice(b"ACGT") for _u in range(rnd.randint(0, 12))))
+        s = b"".join(parts)
+        if it % 4 == 0:
+            s = wl.prepare_w_rc_single(s)
+        gcap, ocap = rnd.choice([(4, 6), (8, 16), (8, 3), (16, 64), (3, 1)])
+        SA, RANK, _, st = gm.suffix_array_hybrid(s, gcap, ocap, rnd.choice([None, 32, 64]), rnd)
+        sa, _ = orc.gpu_order_sa_lcp(s)
+        assert SA == list(sa), (it, gcap, ocap, s)
+        assert all(RANK[SA[k]] == k for k in range(len(SA)))
+        for k in seen:
+            seen[k] += st[k]
+    assert all(v > 0 for v in seen.values()), seen
