@@ -393,6 +393,10 @@ def run_ours(args):
             "sample": "the full 5 Mbp text, once (CPU oracle: SA-IS + Kasai + per-factor LCP-interval walk)",
             "seconds": dt, "host_cores_available": cores,
             "triples_identical_to_gpu": bool(len(f) == z and np.array_equal(f, got)),
+            "reference_published": {"value": 0.037, "unit": UNIT,
+                                    "note": "~27 s per Mbp for factorize_fasta_multiple_dna_w_rc (RC mode), "
+                                            "benchmarks/README.md:293-294 of the reference: published, hardware "
+                                            "unknown, not reproduced (the SDSL build is not available offline)"},
             "parallel_mode": {"value": n / dtp / 1e6, "unit": UNIT, "cores": used, "seconds": dtp,
                               "serial_index_seconds": idx_s, "threaded_walk_seconds": walk_s,
                               "triples_identical_to_gpu": bool(len(fp) == z and np.array_equal(fp, got)),

@@ -768,7 +768,14 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, con
             LR[i] = select_factor<RC, false>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
             HARD[i] = 0;
         } else {
-            LR[i] = (u64)dR;             // park the RC candidate depth for k_lpnf_hard
+            // Park the RC candidate depth for k_lpnf_hard, and a depth that is KNOWN to satisfy the forward predicate:
+            // the last ancestor A that failed has minF(A) + depth(A) > i, and every D < depth(A) has interval(D)
+            // containing A, so minF(interval(D)) <= minF(A); at D0 = i - minF(A) the predicate minF + D <= i holds.
+            // Inside a tandem array (minF = first position of the phase, constant along the climb) D0 IS the answer,
+            // so the depth search of k_lpnf_hard starts two probes away from it even without a carried bound
+            // (distributed runs: neighbouring positions live on other GPUs).
+            const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
+            LR[i] = ((u64)lb0 << 32) | (u64)dR;
             HARD[i] = 1;
             hard = 1;
         }
@@ -843,7 +850,9 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict
         NodeState leaf;
         leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
         const u32 Dtop = max(__ldg(LCP + r), __ldg(LCP + r + 1)) + 1;   // deeper than the leaf's parent nothing matches
-        const u32 lb = prevF > 0 ? prevF - 1 : 0;                // Kasai-style lower bound (known to hold)
+        const u64 parked = LR[i];                                // {depth known to hold, RC candidate depth} from k_lpnf_rank
+        u32 lb = prevF > 0 ? prevF - 1 : 0;                      // Kasai-style lower bound (known to hold)
+        lb = max(lb, (u32)(parked >> 32));
         NodeState U = leaf, L = leaf;
         u32 Ds;
         if (lb >= 1 && lb + 1 < Dtop) {
@@ -884,7 +893,7 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict
                 }
             }
         }
-        const u32 dR = (u32)LR[i];                               // parked by k_lpnf_rank
+        const u32 dR = (u32)parked;
         const u64 lr = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
         t8.sync();                                               // every lane has read the parked value
         if (q == 0) LR[i] = lr;

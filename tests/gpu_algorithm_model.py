@@ -594,7 +594,9 @@ def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16, real=None):
             v_min = cur[2]
             gen = (i - v_min, v_min) if v_min != i else None
         else:
-            HARD[i] = (cur, d_node if d_node is not None else d + 1, rinfo)
+            # depth known to satisfy the forward predicate: D0 = i - minF(last failing ancestor) (lpnf.cuh, k_lpnf_rank)
+            lb0 = i - cur[2] if (cur[2] != NONE_MIN and cur[2] < i) else 0
+            HARD[i] = (cur, d_node if d_node is not None else d + 1, rinfo, lb0)
             continue
         LR[i] = _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo)
 
@@ -605,9 +607,11 @@ def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16, real=None):
             if HARD[i] is None:
                 prevF = 0
                 continue
-            cur, Dtop, rinfo = HARD[i]
+            cur, Dtop, rinfo, lb0 = HARD[i]
             # (the CUDA kernel re-derives `cur` as interval(Dtop-ish) from the leaf; same state)
             lb = prevF - 1 if prevF > 0 else 0
+            lb = max(lb, lb0)
+            assert lb0 == 0 or pred_f(_extend(T, cur, lb0), lb0)      # the parked bound holds
             U = L = None
             if lb >= 1 and lb + 1 < Dtop:
                 st = _extend(T, cur, lb + 1)
