@@ -713,7 +713,7 @@ k_forward_ranks(const u32* __restrict__ SA, WalkParams p, u32* __restrict__ cta_
 
 // ---- kernel 1: rank order ---------------------------------------------------------------------
 template <bool RC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)   // 32 registers: 8 CTAs per SM (the kernel is latency-bound; 40 registers cost 14 %)
 k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, const u32* __restrict__ list,
             const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
             unsigned long long* __restrict__ counters) {
