@@ -1,6 +1,7 @@
 """Genomics entry points (reference: /root/reference/src/noLZSS/genomics/__init__.py:8-34): the RC-aware
-bindings re-exported, the FASTA readers and the sequence helpers.  Plotting, batch drivers and the
-significance analysis are outside the hot path."""
+bindings re-exported, the FASTA readers, the sequence helpers and the factor-length significance analysis that
+consumes the binary factor files.  Plotting and the batch / LSF drivers are outside
+the hot path."""
 from .._noLZSS import (  # noqa: F401
     count_factors_dna_w_rc,
     count_factors_file_dna_w_rc,
@@ -26,3 +27,10 @@ from .sequences import (  # noqa: F401
     is_protein_sequence,
 )
 from .shuffle_control import factorize_with_shuffled_control, shuffle_fasta_sequences  # noqa: F401,E402
+from .significance import (  # noqa: F401,E402
+    calculate_factor_length_threshold,
+    clopper_pearson_upper,
+    extract_factor_lengths,
+    infer_length_significance,
+    plot_significance_analysis,
+)
