@@ -1,0 +1,32 @@
+"""configs[4] tail end at reduced size: multi-record FASTA -> shuffled control -> two noLZSSv2 factor files (RC mode,
+footer V7) -> calculate_factor_length_threshold.  python scripts/c5_tail_demo.py [total_bases] [records]"""
+import os, sys, tempfile, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from nolzss_b200 import genomics, utils, workloads as wl
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+x = wl.planted_dna(n, 5, scale=max(1.0, n / 5e6)).tobytes()
+d = tempfile.mkdtemp()
+fa = os.path.join(d, "genome.fasta")
+with open(fa, "wb") as f:
+    for r in range(k):
+        s = x[r * n // k:(r + 1) * n // k]
+        f.write(b">chr%d\n" % (r + 1))
+        for i in range(0, len(s), 80):
+            f.write(s[i:i + 80] + b"\n")
+t0 = time.perf_counter()
+real_bin, shuf_bin, n_real, n_shuf = genomics.factorize_with_shuffled_control(fa, os.path.join(d, "out"), seed=6)
+t1 = time.perf_counter()
+# one shuffled genome of the same size bounds the tail at ~3/N_shuf (Clopper-Pearson), i.e. ~3 expected false
+# positives among N_real factors: tau = 10 is attainable, the default tau = 1 needs a larger control
+res = genomics.calculate_factor_length_threshold(real_bin, shuf_bin, tau_expected_fp=10.0)
+t2 = time.perf_counter()
+meta = utils.read_binary_file_metadata(real_bin)
+assert n_real == res["N_real"] and n_shuf == res["N_shuf"] and meta["num_sequences"] == k
+assert n_shuf > n_real                                   # the shuffled control has no long repeats
+assert res["L_star"] is not None
+significant = int(np.sum(genomics.extract_factor_lengths(real_bin) >= res["L_star"]))
+print(f"c5 tail ok: {k} records, {n} bases: {n_real} real / {n_shuf} shuffled factors in {t1-t0:.2f} s; "
+      f"L* = {res['L_star']} ({significant} real factors at or above it) in {t2-t1:.3f} s")
