@@ -9,45 +9,53 @@ from typing import Union
 from .. import _noLZSS as _ext
 from ..utils import validate_input
 
-_DNA = re.compile(r"^[ACGT]+$")
-_PROTEIN = re.compile(r"^[ACDEFGHIKLMNPQRSTVWY]+$")
+# sequences.py:12-59 of the reference: case-insensitive; the protein alphabet is the 20 standard amino acids plus the
+# extension codes B, J, O, U, X, Z; `$` also matches before a trailing newline (re.match semantics kept).
+_DNA = re.compile(r"^[ATGC]+$", re.IGNORECASE)
+_PROTEIN = re.compile(r"^[ACDEFGHIKLMNPQRSTVWYBJOUXZ]+$", re.IGNORECASE)
+_AMINO_ONLY = frozenset("EFHIKLMNPQRSVWY")        # amino-acid codes that are not nucleotides (:95)
+_AMINO = frozenset("ACDEFGHIKLMNPQRSTVWY")        # (:103; the detector uses the 20 standard codes only)
+_NUCLEOTIDES = frozenset("ACGT")
 
 
-def _to_str(data: Union[str, bytes]) -> str:
+def _ascii_str(data):
+    """bytes -> ASCII str (None if not ASCII); other types unchanged."""
     if isinstance(data, bytes):
         try:
             return data.decode("ascii")
         except UnicodeDecodeError:
-            return ""
+            return None
     return data
 
 
 def is_dna_sequence(data: Union[str, bytes]) -> bool:
-    return bool(_DNA.match(_to_str(data).upper()))
+    text = _ascii_str(data)
+    return isinstance(text, str) and bool(_DNA.match(text))
 
 
 def is_protein_sequence(data: Union[str, bytes]) -> bool:
-    return bool(_PROTEIN.match(_to_str(data).upper()))
+    text = _ascii_str(data)
+    return isinstance(text, str) and bool(_PROTEIN.match(text))
 
 
 def detect_sequence_type(data: Union[str, bytes]) -> str:
-    if isinstance(data, bytes):
-        try:
-            text = data.decode("ascii")
-        except UnicodeDecodeError:
-            return "binary"
-    else:
-        text = data
-    if not text:
-        return "text"
+    """'dna', 'protein', 'text' or 'binary' (reference: sequences.py:62-117): non-ASCII bytes and non-strings are
+    binary; anything with a non-alphabetic character, and the empty string, is text; then amino-acid-specific
+    letters decide between protein and DNA."""
+    text = _ascii_str(data)
+    if not isinstance(text, str):
+        return "binary"
     up = text.upper()
-    if _DNA.match(up):
-        return "dna"
-    if _PROTEIN.match(up):
-        return "protein"
-    if all(32 <= ord(c) <= 126 or c in "\t\n\r" for c in text):
+    if not up or not all(c.isalpha() for c in up):
         return "text"
-    return "binary"
+    letters = set(up)
+    has_amino_specific = bool(letters & _AMINO_ONLY)
+    all_amino = letters <= _AMINO
+    if has_amino_specific and all_amino:
+        return "protein"
+    if letters <= _NUCLEOTIDES and not has_amino_specific:
+        return "dna"
+    return "protein" if all_amino else "text"
 
 
 def _as_str(x):

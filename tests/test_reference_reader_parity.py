@@ -80,3 +80,180 @@ def test_input_helpers_match_reference():
         except Exception as e:  # noqa: BLE001
             e_us = type(e).__name__
         assert e_ref == e_us, (bad, e_ref, e_us)
+
+
+def _ref_genomics():
+    """The reference's pure-Python genomics modules (sequences.py, fasta.py) under a throw-away package name; their
+    package-relative imports are satisfied by the reference's utils.py and a stub for core.factorize / the compiled
+    extension (neither is needed by the functions compared here)."""
+    import sys
+    import types
+
+    base = "/root/reference/src/noLZSS"
+    pkg = types.ModuleType("_refpkg"); pkg.__path__ = [base]
+    gen = types.ModuleType("_refpkg.genomics"); gen.__path__ = [base + "/genomics"]
+    core = types.ModuleType("_refpkg.core")
+    core.factorize = lambda data: (_ for _ in ()).throw(RuntimeError("stub"))
+    sys.modules.update({"_refpkg": pkg, "_refpkg.genomics": gen, "_refpkg.core": core})
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    load("_refpkg.utils", base + "/utils.py")
+    seq = load("_refpkg.genomics.sequences", base + "/genomics/sequences.py")
+    fa = load("_refpkg.genomics.fasta", base + "/genomics/fasta.py")
+    return seq, fa
+
+
+def test_sequence_helpers_and_fasta_readers_match_reference(tmp_path):
+    from nolzss_b200.genomics import fasta as our_fa
+    from nolzss_b200.genomics import sequences as our_seq
+
+    ref_seq, ref_fa = _ref_genomics()
+    samples = ["ACGT", "acgtn", "ACGU", "MKVLAAGIV", "hello world", "", "ACGT\n", b"ACGT", b"\xff\xfe", b"MKV", "12345", "ACGTRYKM",
+               "A" * 50 + "X", b"acgt"]
+    for s in samples:
+        assert ref_seq.is_dna_sequence(s) == our_seq.is_dna_sequence(s), s
+        assert ref_seq.is_protein_sequence(s) == our_seq.is_protein_sequence(s), s
+        assert ref_seq.detect_sequence_type(s) == our_seq.detect_sequence_type(s), s
+    contents = [
+        ">a desc\nACGT\nAC GT\n\n>b\nMKVLA\n>c|x y\n\nacgtNN\n",
+        "no header line\nACGT\n>late\nGG\n",
+        ">only_header\n",
+        "",
+        ">dup\nAC\n>dup\nGT\n",
+        ">x\r\nACGT\r\n>y\r\nTT\r\n",
+    ]
+    for c in contents:
+        try:
+            want = ("ok", ref_fa._parse_fasta_content(c))
+        except Exception as e:  # noqa: BLE001
+            want = ("err", type(e).__name__)
+        try:
+            got = ("ok", our_fa._parse_fasta_content(c))
+        except Exception as e:  # noqa: BLE001
+            got = ("err", type(e).__name__)
+        assert want == got, c
+    prot = tmp_path / "p.fasta"
+    prot.write_text(">p1 first\nMKVLAAGIVGLLLAQW\nPEFF\n>p2\nmkvw\n")
+    assert ref_fa.read_protein_fasta(prot) == our_fa.read_protein_fasta(prot)
+    assert ref_fa.read_fasta_auto(prot) == our_fa.read_fasta_auto(prot)
+    bad = tmp_path / "bad.fasta"
+    bad.write_text(">p1\nMKV1LA\n")
+    for fn in ("read_protein_fasta",):
+        with pytest.raises(Exception) as e1:
+            getattr(ref_fa, fn)(bad)
+        with pytest.raises(Exception) as e2:
+            getattr(our_fa, fn)(bad)
+        assert type(e1.value).__name__ == type(e2.value).__name__
+    for fn in ("read_protein_fasta", "read_nucleotide_fasta", "read_fasta_auto"):
+        with pytest.raises(FileNotFoundError):
+            getattr(ref_fa, fn)(tmp_path / "missing.fasta")
+        with pytest.raises(FileNotFoundError):
+            getattr(our_fa, fn)(tmp_path / "missing.fasta")
+
+
+class _FakeExt:
+    """Recording stand-in for the compiled extension: every function records its call and returns a canned value."""
+
+    def __init__(self, tmp):
+        self.calls = []
+        self.tmp = tmp
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+
+        def fn(*args, **kwargs):
+            self.calls.append((name, tuple(a if not isinstance(a, str) else a.replace(str(self.tmp), "<tmp>") for a in args),
+                               tuple(sorted(kwargs.items()))))
+            if name.endswith("_to_file") or name.startswith("count") or name.startswith("write"):
+                # the *_to_file functions are expected to leave a factor file behind (parallel_factorize reads it back)
+                for a in args:
+                    if isinstance(a, str) and a.endswith(".bin"):
+                        tr = np.array([[0, 1, 0], [1, 2, 0]], dtype=np.uint64)
+                        _write(a, tr, b"", 0, 0, 3)
+                return 2
+            return [(0, 1, 0), (1, 2, 0)]
+
+        return fn
+
+
+def _load_reference_module(name, fake):
+    """A reference module (core.py / parallel.py) imported under a throw-away package whose _noLZSS is `fake`."""
+    import sys
+    import types
+
+    base = "/root/reference/src/noLZSS"
+    pkgname = f"_refpkg_{name}"
+    pkg = types.ModuleType(pkgname); pkg.__path__ = [base]
+    ext = types.ModuleType(pkgname + "._noLZSS")
+    ext.__getattr__ = lambda attr: getattr(fake, attr)                       # PEP 562: `from ._noLZSS import x`
+    sys.modules[pkgname] = pkg
+    sys.modules[pkgname + "._noLZSS"] = ext
+    for sub in ("utils", name):
+        spec = importlib.util.spec_from_file_location(f"{pkgname}.{sub}", f"{base}/{sub}.py")
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkgname}.{sub}"] = m
+        spec.loader.exec_module(m)
+    return sys.modules[f"{pkgname}.{name}"]
+
+
+def _outcome(fn, *args, **kwargs):
+    try:
+        return ("ok", fn(*args, **kwargs))
+    except Exception as e:  # noqa: BLE001
+        return ("err", type(e).__name__, str(e))
+
+
+def test_python_wrappers_drive_the_extension_like_the_reference(tmp_path, monkeypatch):
+    """core.py and parallel.py of the reference against this repo's, both on top of the same recording fake
+    extension: same results, same exceptions (type and message), same calls into the extension (names, argument
+    order and conversions) -- what a drop-in replacement of `_noLZSS` relies on."""
+    import nolzss_b200.core as our_core
+    import nolzss_b200.parallel as our_par
+
+    existing = tmp_path / "in.txt"
+    existing.write_bytes(b"abracadabra")
+    out = tmp_path / "sub" / "o.bin"
+    cases = {
+        "core": [
+            ("factorize", ("abracadabra",), {}), ("factorize", (b"abc",), {"validate": False}), ("factorize", ("",), {}),
+            ("factorize", (5,), {}), ("factorize", ("a\x00b",), {}), ("factorize_file", (existing,), {}),
+            ("factorize_file", (str(existing), 7), {}), ("factorize_file", (tmp_path / "nope",), {}),
+            ("count_factors", ("abc",), {}), ("count_factors", (b"",), {}), ("count_factors_file", (existing,), {}),
+            ("count_factors_file", (tmp_path / "nope",), {}), ("write_factors_binary_file", ("abc", out), {}),
+            ("write_factors_binary_file", ("", out), {}), ("factorize_with_info", ("abracadabra",), {}),
+            ("factorize_w_reference", ("ACGT", "ACGA"), {}), ("factorize_w_reference", (b"ACGT", "ACGA"), {"validate": False}),
+            ("factorize_w_reference", ("", "ACGA"), {}), ("factorize_w_reference_file", ("ACGT", b"ACGA", out), {}),
+        ],
+        "parallel": [
+            ("parallel_factorize_to_file", ("abc", out), {}), ("parallel_factorize_to_file", (b"abc", str(out), 4, 1), {"validate": False}),
+            ("parallel_factorize_to_file", ("", out), {}), ("parallel_factorize_file_to_file", (existing, out), {}),
+            ("parallel_factorize_file_to_file", (tmp_path / "nope", out, 2), {}), ("parallel_factorize", ("abracadabra",), {}),
+            ("parallel_factorize", ("abracadabra", 3, 2), {}), ("parallel_factorize", ("",), {}),
+            ("parallel_factorize_dna_w_rc_to_file", ("ACGT", out, 8), {}), ("parallel_factorize_dna_w_rc_to_file", ("", out), {}),
+            ("parallel_factorize_file_dna_w_rc_to_file", (existing, str(out)), {}),
+            ("parallel_factorize_file_dna_w_rc_to_file", (tmp_path / "nope", out), {}),
+        ],
+    }
+    for modname, ours in (("core", our_core), ("parallel", our_par)):
+        fake_ref, fake_us = _FakeExt(tmp_path), _FakeExt(tmp_path)
+        ref_mod = _load_reference_module(modname, fake_ref)
+        monkeypatch.setattr(ours, "_ext", fake_us)
+        for fname, args, kwargs in cases[modname]:
+            want = _outcome(getattr(ref_mod, fname), *args, **kwargs)
+            got = _outcome(getattr(ours, fname), *args, **kwargs)
+            strip = lambda o: tuple(str(x).replace(str(tmp_path), "<tmp>") if isinstance(x, str) else x for x in o)   # noqa: E731
+            assert strip(want) == strip(got), (modname, fname, args, kwargs)
+
+        def norm(calls):        # temp-file names of parallel_factorize differ between the two runs
+            return [(n, tuple("<tempfile>" if isinstance(a, str) and a.endswith(".bin") and "<tmp>" not in a else a for a in args), kw)
+                    for n, args, kw in calls]
+
+        assert len(fake_ref.calls) >= 7, (modname, fake_ref.calls)
+        assert norm(fake_ref.calls) == norm(fake_us.calls), modname
