@@ -77,20 +77,35 @@ def read_protein_fasta(filepath: Union[str, Path]) -> List[Tuple[str, str]]:
 
 
 def read_fasta_auto(filepath: Union[str, Path]):
+    """Nucleotide FASTA -> [(id, factors)], protein FASTA -> [(id, sequence)], decided on the first record
+    (reference: fasta.py:177-228)."""
     seqs = _read(filepath)
-    first = next(iter(seqs.values()))
-    kind = detect_sequence_type(first)
+    if not seqs:
+        raise FASTAError("No sequences found in FASTA file")
+    kind = detect_sequence_type(next(iter(seqs.values())))
     if kind == "dna":
         return read_nucleotide_fasta(filepath)
     if kind == "protein":
         return read_protein_fasta(filepath)
-    raise FASTAError(f"Cannot determine sequence type or unsupported type: {kind}")
+    raise FASTAError(f"Cannot determine sequence type. Detected: {kind}. "
+                     f"Expected DNA (A,C,T,G) or protein (amino acids) sequences.")
 
 
-def write_factors_dna_w_reference_fasta_files_to_binary(reference_fasta_path, target_fasta_path, output_path) -> int:
-    for p in (reference_fasta_path, target_fasta_path):
-        if not Path(p).exists():
-            raise FileNotFoundError(f"FASTA file not found: {p}")
-    Path(output_path).parent.mkdir(parents=True, exist_ok=True)
-    return _ext.write_factors_dna_w_reference_fasta_files_to_binary(str(reference_fasta_path), str(target_fasta_path),
-                                                                    str(output_path))
+def write_factors_dna_w_reference_fasta_files_to_binary(reference_fasta_path: Union[str, Path],
+                                                        target_fasta_path: Union[str, Path],
+                                                        output_path: Union[str, Path],
+                                                        sanitize_mode: str = "remove_ambiguous") -> int:
+    """Reference + target FASTA files -> one binary factor file of the target (reference: fasta.py:231-292; path
+    checks, output directory creation and the sanitize_mode check happen here, the work in the extension)."""
+    reference_path = Path(reference_fasta_path)
+    target_path = Path(target_fasta_path)
+    if not reference_path.exists():
+        raise FileNotFoundError(f"Reference FASTA file not found: {reference_path}")
+    if not target_path.exists():
+        raise FileNotFoundError(f"Target FASTA file not found: {target_path}")
+    output_path = Path(output_path)
+    output_path.parent.mkdir(parents=True, exist_ok=True)
+    if sanitize_mode not in {"remove_ambiguous", "strict"}:
+        raise ValueError("sanitize_mode must be 'remove_ambiguous' or 'strict'")
+    return _ext.write_factors_dna_w_reference_fasta_files_to_binary(str(reference_path), str(target_path), str(output_path),
+                                                                    sanitize_mode)

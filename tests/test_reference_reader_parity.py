@@ -257,3 +257,63 @@ def test_python_wrappers_drive_the_extension_like_the_reference(tmp_path, monkey
 
         assert len(fake_ref.calls) >= 7, (modname, fake_ref.calls)
         assert norm(fake_ref.calls) == norm(fake_us.calls), modname
+
+
+def test_genomics_wrappers_drive_the_extension_like_the_reference(tmp_path, monkeypatch):
+    """genomics/fasta.py and genomics/sequences.py of the reference against this repo's on the recording fake
+    extension: FASTA readers that factorize, the auto-detecting reader, the reference+target wrappers."""
+    import sys
+    import types
+
+    import nolzss_b200.core as our_core
+    import nolzss_b200.genomics.fasta as our_fa
+    import nolzss_b200.genomics.sequences as our_seq
+
+    fake_ref, fake_us = _FakeExt(tmp_path), _FakeExt(tmp_path)
+    base = "/root/reference/src/noLZSS"
+    pkgname = "_refpkg_gen"
+    pkg = types.ModuleType(pkgname); pkg.__path__ = [base]
+    gen = types.ModuleType(pkgname + ".genomics"); gen.__path__ = [base + "/genomics"]
+    ext = types.ModuleType(pkgname + "._noLZSS")
+    ext.__getattr__ = lambda attr: getattr(fake_ref, attr)
+    sys.modules.update({pkgname: pkg, pkgname + ".genomics": gen, pkgname + "._noLZSS": ext})
+    mods = {}
+    for sub, path in (("utils", "utils.py"), ("core", "core.py"), ("genomics.sequences", "genomics/sequences.py"),
+                      ("genomics.fasta", "genomics/fasta.py")):
+        spec = importlib.util.spec_from_file_location(f"{pkgname}.{sub}", f"{base}/{path}")
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkgname}.{sub}"] = m
+        spec.loader.exec_module(m)
+        mods[sub] = m
+    for mod in (our_core, our_fa, our_seq):
+        monkeypatch.setattr(mod, "_ext", fake_us)
+
+    dna = tmp_path / "dna.fasta"
+    dna.write_text(">s1 d\nACGTAC\nGT\n>s2\nacgt\n")
+    mixed = tmp_path / "mixed.fasta"
+    mixed.write_text(">s1\nACGTNNAC\n")
+    prot = tmp_path / "prot.fasta"
+    prot.write_text(">p\nMKVLW\n")
+    text = tmp_path / "text.fasta"
+    text.write_text(">t\nhello world 123\n")
+    out = tmp_path / "o" / "x.bin"
+    calls = [
+        ("genomics.fasta", "read_nucleotide_fasta", (dna,), {}), ("genomics.fasta", "read_nucleotide_fasta", (mixed,), {}),
+        ("genomics.fasta", "read_nucleotide_fasta", (prot,), {}), ("genomics.fasta", "read_fasta_auto", (dna,), {}),
+        ("genomics.fasta", "read_fasta_auto", (prot,), {}), ("genomics.fasta", "read_fasta_auto", (text,), {}),
+        ("genomics.fasta", "read_fasta_auto", (mixed,), {}),
+        ("genomics.fasta", "write_factors_dna_w_reference_fasta_files_to_binary", (dna, dna, out), {}),
+        ("genomics.fasta", "write_factors_dna_w_reference_fasta_files_to_binary", (tmp_path / "nope.fa", dna, out), {}),
+        ("genomics.sequences", "factorize_dna_w_reference_seq", ("ACGT", "ACGA"), {}),
+        ("genomics.sequences", "factorize_dna_w_reference_seq", (b"ACGT", b"ACGA"), {"validate": False}),
+        ("genomics.sequences", "factorize_dna_w_reference_seq", ("", "ACGA"), {}),
+        ("genomics.sequences", "factorize_dna_w_reference_seq_file", ("ACGT", "ACGA", out), {}),
+        ("genomics.sequences", "factorize_dna_w_reference_seq_file", ("ACGT", "ACGA", str(out)), {"validate": False}),
+    ]
+    ours = {"genomics.fasta": our_fa, "genomics.sequences": our_seq}
+    strip = lambda o: tuple(str(x).replace(str(tmp_path), "<tmp>") if isinstance(x, str) else x for x in o)   # noqa: E731
+    for sub, fname, args, kwargs in calls:
+        want = _outcome(getattr(mods[sub], fname), *args, **kwargs)
+        got = _outcome(getattr(ours[sub], fname), *args, **kwargs)
+        assert strip(want) == strip(got), (sub, fname, args, kwargs)
+    assert len(fake_ref.calls) >= 6 and fake_ref.calls == fake_us.calls
