@@ -317,3 +317,40 @@ def test_genomics_wrappers_drive_the_extension_like_the_reference(tmp_path, monk
         got = _outcome(getattr(ours[sub], fname), *args, **kwargs)
         assert strip(want) == strip(got), (sub, fname, args, kwargs)
     assert len(fake_ref.calls) >= 6 and fake_ref.calls == fake_us.calls
+
+
+def test_public_names_of_the_reference_python_layer_exist_here():
+    """Every public function / class the reference defines in core.py, utils.py, parallel.py, genomics/fasta.py,
+    genomics/sequences.py and genomics/significance.py exists under the same name in the mirrored module, with the
+    same parameter names (plotting is the documented exception)."""
+    import ast
+    import inspect
+
+    import nolzss_b200
+    from nolzss_b200 import core, genomics, parallel
+    from nolzss_b200 import utils as our_utils
+    from nolzss_b200.genomics import fasta, sequences, significance
+
+    base = "/root/reference/src/noLZSS"
+    pairs = [("core.py", core, nolzss_b200), ("utils.py", our_utils, nolzss_b200), ("parallel.py", parallel, None),
+             ("genomics/fasta.py", fasta, genomics), ("genomics/sequences.py", sequences, genomics),
+             ("genomics/significance.py", significance, genomics)]
+    skip = {"plot_factor_lengths"}                       # utils.py:360-: matplotlib plot, outside the hot path
+    checked = 0
+    for rel, mod, pkg in pairs:
+        tree = ast.parse(open(f"{base}/{rel}").read())
+        for node in tree.body:
+            if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and not node.name.startswith("_") and node.name not in skip:
+                assert hasattr(mod, node.name), (rel, node.name)
+                if pkg is not None:
+                    assert hasattr(pkg, node.name), (rel, node.name, "not re-exported")
+                if isinstance(node, ast.FunctionDef):
+                    want = [a.arg for a in node.args.posonlyargs + node.args.args + node.args.kwonlyargs]
+                    got = list(inspect.signature(getattr(mod, node.name)).parameters)
+                    assert want == got, (rel, node.name, want, got)
+                    defaults_ref = [ast.literal_eval(d) for d in node.args.defaults]
+                    sig = inspect.signature(getattr(mod, node.name))
+                    defaults_us = [p.default for p in sig.parameters.values() if p.default is not inspect.Parameter.empty]
+                    assert defaults_ref == defaults_us, (rel, node.name, defaults_ref, defaults_us)
+                checked += 1
+    assert checked >= 30
