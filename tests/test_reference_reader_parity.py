@@ -354,3 +354,35 @@ def test_public_names_of_the_reference_python_layer_exist_here():
                     assert defaults_ref == defaults_us, (rel, node.name, defaults_ref, defaults_us)
                 checked += 1
     assert checked >= 30
+
+
+def test_all_binding_signatures_match_bindings_cpp():
+    """src/cpp/bindings.cpp is the drop-in boundary (SURVEY.md section 8b): every m.def(name, ..., py::arg(...) [= default])
+    is parsed from the reference's source and compared with the ctypes shim's Python signature."""
+    import inspect
+    import re
+
+    from nolzss_b200 import _noLZSS as ext
+
+    src = open("/root/reference/src/cpp/bindings.cpp").read()
+    starts = [m.start() for m in re.finditer(r'\bm\.def\("', src)]
+    assert len(starts) == 42
+    for a, b in zip(starts, starts[1:] + [len(src)]):
+        block = src[a:b]
+        name = re.match(r'm\.def\("(\w+)"', block).group(1)
+        doc_at = block.find('R"doc(')
+        head = block if doc_at < 0 else block[:doc_at]
+        args = re.findall(r'py::arg\("(\w+)"\)\s*(?:=\s*([^,\n]+?))?\s*(?:,|\))', head)
+        want_names = [n for n, _ in args]
+        want_defaults = []
+        for _, d in args:
+            d = d.strip()
+            if not d:
+                continue
+            if d.startswith("std::string("):
+                d = d[len("std::string("):-1]
+            want_defaults.append(d.strip('"') if d.startswith('"') else int(d))
+        sig = inspect.signature(getattr(ext, name))
+        assert list(sig.parameters) == want_names, (name, want_names, list(sig.parameters))
+        got_defaults = [p.default for p in sig.parameters.values() if p.default is not inspect.Parameter.empty]
+        assert got_defaults == want_defaults, (name, want_defaults, got_defaults)
