@@ -34,7 +34,6 @@ sys.path.insert(0, ROOT)
 METRIC = "Mbases/s factorized end-to-end (SA+LCP+factors)"
 UNIT = "Mbases/s"
 N_BASES = 5_000_000
-REF_SAMPLE = 1_000_000
 WORKLOAD = ("configs[1]: 5 Mbp synthetic DNA with planted repeats (20 interspersed families, 40 tandem "
             "arrays), reverse-complement mode (factorize_dna_w_rc), one text per GPU")
 
@@ -77,10 +76,12 @@ def run_reference(args):
     import oracle_py as orc
     from nolzss_b200 import workloads as wl
 
-    # bounded sample: the first REF_SAMPLE bases of the same text per step (about 1.5 s of CPU work), through the
-    # reference's own parallel mode (serial index build + chunked chain walk on every host core, convergence merge:
-    # src/cpp/parallel_factorizer.cpp:849-984), which is what `parallel_factorize_dna_w_rc_to_file` would run
-    t = _text_for_rank(0)[:REF_SAMPLE]
+    # every step factorizes the FULL 5 Mbp text of configs[1] -- the same config as our arm (about 1.3 s of CPU work
+    # per step) -- through the reference's own parallel mode (serial index build + chunked chain walk on every host
+    # core, convergence merge: src/cpp/parallel_factorizer.cpp:849-984), which is what
+    # `parallel_factorize_dna_w_rc_to_file` would run.  The arm is this repo's CPU port of the reference algorithm
+    # (cpu_baseline.kind = "port"): the reference's SDSL build is not available offline.
+    t = _text_for_rank(0)
     S = wl.prepare_w_rc_single(t)
     cores = os.cpu_count() or 1
     times = []
@@ -104,11 +105,13 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_bases": N_BASES, "sample_bases_per_step": len(t), "factors": z},
+        "config": {"workload": WORKLOAD, "n_bases_per_gpu": N_BASES, "sample_bases_per_step": len(t), "factors": z,
+                   "same_config_as_ours": len(t) == N_BASES},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": f"first {len(t)} bases of the 5 Mbp text per step (SA-IS + Kasai serially, then the "
-                                   f"per-factor LCP-interval walk on {used} threads with the reference's convergence "
-                                   "merge = its parallel mode; the reference's SDSL path cannot be built offline)",
+                         "sample": f"the full {len(t)}-base text of configs[1] per step (oracle port: SA-IS + Kasai "
+                                   f"serially, then the per-factor LCP-interval walk on {used} threads with the "
+                                   "reference's convergence merge = its parallel mode; the reference's SDSL path "
+                                   "cannot be built offline)",
                          "serial_index_fraction": index_s / max(index_s + walk_s, 1e-12),
                          "host_cores_available": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -285,7 +285,13 @@ struct Problem {
     bool rc;
     // batch mode (records are independent; see k_prepare_batch)
     u32 nrec = 0;
-    const u32 *h_inoff = nullptr, *h_fstart = nullptr, *h_flen = nullptr;
+    const u32 *h_inoff = nullptr, *h_fstart = nullptr, *h_flen = nullptr;   // h_inoff: offsets into the PACKED staging copy
+    const u64* h_srcoff = nullptr;      // offset of every record in the caller's buffer (error messages)
+    // the caller's buffer may be sparse (records picked from a larger buffer): only the contiguous runs that hold
+    // records are copied, back to back, into the staging area
+    const u64 *h_run_src = nullptr, *h_run_len = nullptr;
+    u32 nruns = 0;
+    u64 packed_bytes = 0;
 };
 
 static int bits_for(u32 maxval) {
@@ -822,7 +828,15 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
     u32 prep_launches = 2;
     if (pb.nrec) {
         u8* tmp = staging;
-        NLZ_CK(cudaMemcpyAsync(tmp, src, pb.n_in, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+        if (pb.packed_bytes > 8ull * n1) { set_error("batch staging overflow (%llu bytes)", (unsigned long long)pb.packed_bytes); return ERR_RUNTIME; }
+        {
+            u64 dst = 0;
+            for (u32 r = 0; r < pb.nruns; ++r) {
+                NLZ_CK(cudaMemcpyAsync(tmp + dst, static_cast<const u8*>(src) + pb.h_run_src[r], pb.h_run_len[r],
+                                       src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+                dst += pb.h_run_len[r];
+            }
+        }
         NLZ_CK(cudaMemcpyAsync(w.INOFF, pb.h_inoff, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
         NLZ_CK(cudaMemcpyAsync(w.FSTART, pb.h_fstart, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
         NLZ_CK(cudaMemcpyAsync(w.FLEN, pb.h_flen, (size_t)pb.nrec * 4, cudaMemcpyHostToDevice, st));
@@ -877,7 +891,7 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         u32 bad = c->h_pinned[8], b = 0;
         while (b + 1 < pb.nrec && pb.h_fstart[b + 1] <= bad) ++b;
         set_error("Invalid nucleotide '%c' found in sequence %u",
-                  (char)static_cast<const u8*>(src)[(u64)pb.h_inoff[b] + (bad - pb.h_fstart[b])], b);
+                  (char)static_cast<const u8*>(src)[pb.h_srcoff[b] + (bad - pb.h_fstart[b])], b);
         return ERR_RUNTIME;
     }
     if (pb.nrec) {
@@ -1625,6 +1639,8 @@ static int debug_sort(nlz_ctx* c, KeyT* keys, uint32_t* vals, uint64_t m, int lo
 
 // =================================================================== C ABI
 extern "C" {
+static int ctx_init_impl(nlz_ctx* c);
+static int ctx_init(nlz_ctx* c) { return ctx_init_impl(c); }
 
 const char* nlz_last_error(void) { return nlz::g_err.c_str(); }
 const char* nlz_version(void) { return "1.2.0+b200.r1"; }
@@ -1646,7 +1662,16 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     nlz_ctx* c = new nlz_ctx();
     c->device = device;
     memset(&c->stats, 0, sizeof(c->stats));
+    memset(c->ev, 0, sizeof(c->ev));
+    memset(c->ring_ev, 0, sizeof(c->ring_ev));
     c->prof.reset();
+    const int rc = ctx_init(c);
+    if (rc != OK) { nlz_ctx_destroy(c); return rc; }      // tolerant of partially initialised fields
+    *out = c;
+    return OK;
+}
+
+static int ctx_init_impl(nlz_ctx* c) {
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));   // words [0, 512): readbacks; [512, 1024): pipelined round counts
     NLZ_CK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
@@ -1667,7 +1692,6 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
     }
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 48; ++i) NLZ_CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
-    *out = c;
     return OK;
 }
 
@@ -1678,9 +1702,10 @@ void nlz_ctx_destroy(nlz_ctx* c) {
     if (c->arena.base) cudaFree(c->arena.base);
     if (c->d_out) cudaFree(c->d_out);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 48; ++i) cudaEventDestroy(c->ring_ev[i]);
+    for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 48; ++i) if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     c->prof.destroy();
+    cudaGetLastError();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1765,20 +1790,26 @@ int nlz_factorize_batch(nlz_ctx* c, int with_rc, const uint8_t* concat, const ui
     *total = 0;
     if (out_triples) *out_triples = nullptr;
     std::vector<u32> rec, inoff, fstart, flen;     // non-empty records only (empty ones yield no factors)
-    u64 fwd = 0, hi = 0;
+    std::vector<u64> srcoff, run_src, run_len;     // the caller's offsets; contiguous runs of the caller's buffer
+    u64 fwd = 0, packed = 0;
     for (u64 b = 0; b < k; ++b) {
         per_record_counts[b] = 0;
         if (lens[b] == 0) continue;
-        if (offsets[b] + lens[b] > 0xFFFFFFF0ull || fwd + lens[b] + 1 > 0x7FFFFFF0ull) {
+        if (lens[b] > 0x7FFFFFF0ull || fwd + lens[b] + 1 > 0x7FFFFFF0ull || offsets[b] + lens[b] < offsets[b]) {
             set_error("batch of %llu records exceeds the 32-bit index path; split it", (unsigned long long)k);
             return ERR_INVALID;
         }
         rec.push_back((u32)b);
-        inoff.push_back((u32)offsets[b]);
+        srcoff.push_back(offsets[b]);
+        // arbitrary (sparse, unordered, overlapping) offsets are allowed: a record that starts where the previous one
+        // ended extends the current run, anything else opens a new run; records are packed back to back on the device
+        if (!run_src.empty() && run_src.back() + run_len.back() == offsets[b]) run_len.back() += lens[b];
+        else { run_src.push_back(offsets[b]); run_len.push_back(lens[b]); }
+        inoff.push_back((u32)packed);
+        packed += lens[b];
         fstart.push_back((u32)fwd);
         flen.push_back((u32)lens[b]);
         fwd += lens[b] + 1;
-        if (offsets[b] + lens[b] > hi) hi = offsets[b] + lens[b];
     }
     reset_stats(c);
     if (rec.empty()) return OK;
@@ -1786,7 +1817,7 @@ int nlz_factorize_batch(nlz_ctx* c, int with_rc, const uint8_t* concat, const ui
     Problem pb;
     pb.mode = with_rc ? NLZ_MODE_RC_PREPARED : NLZ_MODE_GENERAL;
     pb.rc = with_rc != 0;
-    pb.n_in = hi;
+    pb.n_in = packed;
     pb.N = (u32)(fwd - 1);
     pb.nfac = pb.N;                    // every position but the last forward sentinel (factorizer_core.hpp:195, :241)
     pb.L = with_rc ? 2 * fwd : fwd;
@@ -1795,6 +1826,8 @@ int nlz_factorize_batch(nlz_ctx* c, int with_rc, const uint8_t* concat, const ui
     pb.n1 = (u32)(pb.L + 1);
     pb.nrec = (u32)rec.size();
     pb.h_inoff = inoff.data(); pb.h_fstart = fstart.data(); pb.h_flen = flen.data();
+    pb.h_srcoff = srcoff.data(); pb.h_run_src = run_src.data(); pb.h_run_len = run_len.data();
+    pb.nruns = (u32)run_src.size(); pb.packed_bytes = packed;
     NLZ_TRY(ensure_workspace(c, pb.n1, pb.nrec));
     cudaStream_t st = c->own_stream;
     u64 z = 0;

@@ -42,15 +42,19 @@ class LocalGroup:
         lib = L.load()
         self.world = len(devices)
         self.ctxs, self.dists = [], []
-        for g, dev in enumerate(devices):
-            c = _vp()
-            L.check(lib.nlz_ctx_create(int(dev), ctypes.byref(c)))
-            self.ctxs.append(c)
-            d = _vp()
-            L.check(lib.nlz_dist_create(c, g, self.world, max_text_bytes, mode, ctypes.byref(d)))
-            self.dists.append(d)
-        arr = (_vp * self.world)(*[d.value for d in self.dists])
-        L.check(lib.nlz_dist_attach_local(arr, self.world))
+        try:
+            for g, dev in enumerate(devices):
+                c = _vp()
+                L.check(lib.nlz_ctx_create(int(dev), ctypes.byref(c)))
+                self.ctxs.append(c)
+                d = _vp()
+                L.check(lib.nlz_dist_create(c, g, self.world, max_text_bytes, mode, ctypes.byref(d)))
+                self.dists.append(d)
+            arr = (_vp * self.world)(*[d.value for d in self.dists])
+            L.check(lib.nlz_dist_attach_local(arr, self.world))
+        except Exception:
+            self.close()          # a later rank failed (e.g. out of memory): release what the earlier ranks hold
+            raise
 
     def factorize(self, mode: int, data):
         """Runs the collective call on one thread per rank; returns (triples of rank 0, [stats per rank])."""

@@ -153,3 +153,37 @@ def read_factors_binary_file_with_metadata(filepath: Union[str, Path]) -> Dict[s
                        (ref >> np.uint64(63)).astype(bool).tolist())) if nf else []
     return {"factors": factors, "sentinel_factor_indices": sent, "sequence_names": names, "num_sequences": nseq,
             "num_sentinels": nsent, "total_length": total}
+
+
+def plot_factor_lengths(factors_or_file, save_path=None, show_plot: bool = True) -> None:
+    """Cumulative factor length against factor index (reference: utils.py:360-430).  Plotting is outside the hot
+    path: the input handling and error types of the reference are kept so that callers and the
+    reference's tests/test_utils.py behave the same; the figure itself needs matplotlib (a warning without it)."""
+    import warnings
+
+    if isinstance(factors_or_file, (str, Path)):
+        lengths = read_factors_array(factors_or_file)[:, 1].astype(np.int64)
+    elif isinstance(factors_or_file, list):
+        lengths = np.array([f[1] for f in factors_or_file], dtype=np.int64)
+    else:
+        raise TypeError("factors_or_file must be a list of tuples or a path to a binary factors file")
+    if lengths.size == 0:
+        raise ValueError("No factors to plot")
+    try:
+        import matplotlib
+        if not show_plot:
+            matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        warnings.warn("matplotlib is required for plotting. Install with: pip install matplotlib", UserWarning)
+        return
+    fig, ax = plt.subplots(figsize=(10, 6))
+    ax.scatter(np.cumsum(lengths), np.arange(1, lengths.size + 1), s=4, alpha=0.7)
+    ax.set_xlabel("Cumulative factor length")
+    ax.set_ylabel("Factor index")
+    ax.set_title("Factor length accumulation")
+    if save_path is not None:
+        fig.savefig(str(save_path), dpi=150, bbox_inches="tight")
+    if show_plot:
+        plt.show()
+    plt.close(fig)

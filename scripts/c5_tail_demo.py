@@ -26,7 +26,11 @@ t2 = time.perf_counter()
 meta = utils.read_binary_file_metadata(real_bin)
 assert n_real == res["N_real"] and n_shuf == res["N_shuf"] and meta["num_sequences"] == k
 assert n_shuf > n_real                                   # the shuffled control has no long repeats
-assert res["L_star"] is not None
+# Round 1's run of this script asserted `L_star <= 40` with the default tau_expected_fp = 1 and fired: with ONE shuffled
+# control of the same size the Clopper-Pearson upper bound of the tail is ~3/N_shuf whatever L is, so the expected
+# false positives N_real * p_upper never drop below ~3 and no L satisfies tau = 1 (L_star is None).  At tau = 10 the
+# threshold exists and is small (the oracle simulation of this workload gives 18): the bound is enforced again.
+assert res["L_star"] is not None and res["L_star"] <= 40, res
 significant = int(np.sum(genomics.extract_factor_lengths(real_bin) >= res["L_star"]))
 print(f"c5 tail ok: {k} records, {n} bases: {n_real} real / {n_shuf} shuffled factors in {t1-t0:.2f} s; "
       f"L* = {res['L_star']} ({significant} real factors at or above it) in {t2-t1:.3f} s")

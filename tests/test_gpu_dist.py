@@ -1,6 +1,6 @@
-"""One text across several ranks (csrc/dist.cuh).  The ranks of these tests share cuda:0 -- every exchange
-step (rank replicas, Phi / LCP delivery, edge staircases, virtual ranks, LR push, barriers) runs exactly as it
-does across GPUs, only the peer pointers are local; the multi-GPU launch is covered by bench.py --gpus N."""
+"""One text across several ranks (csrc/dist.cuh).  The ranks are dealt round-robin to the visible GPUs: on a
+multi-GPU box every exchange step (Phi / LCP delivery, rank requests, edge staircases, virtual ranks, barriers) runs
+over real peer memory; on a one-GPU box the ranks share cuda:0 and only the peer pointers are local."""
 import random
 
 import numpy as np
@@ -12,6 +12,13 @@ from nolzss_b200 import dist as nd
 from nolzss_b200 import workloads as wl
 
 pytestmark = pytest.mark.gpu
+
+
+def _devs(world):
+    import torch
+
+    n = max(torch.cuda.device_count(), 1)
+    return [g % n for g in range(world)]
 
 
 def _expected(mode, s):
@@ -36,7 +43,7 @@ def _cases():
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4])
 def test_dist_small_cases_vs_oracle(world):
-    grp = nd.LocalGroup([0] * world, 200_000, L.MODE_DNA_RC)
+    grp = nd.LocalGroup(_devs(world), 200_000, L.MODE_DNA_RC)
     try:
         for s in _cases():
             for mode in (L.MODE_DNA_RC, L.MODE_GENERAL):
@@ -53,7 +60,7 @@ def test_dist_general_bytes_and_prepared():
     prose = b" ".join(words[i] for i in rng.integers(0, len(words), 8000))
     from treewalk_model import prepare_multiple_dna_sequences_w_rc
     S, _, _ = prepare_multiple_dna_sequences_w_rc([wl.uniform_dna(3000, 1).tobytes(), wl.planted_dna(5000, 2, scale=0.02).tobytes(), b"ACGTACGTAC"])
-    grp = nd.LocalGroup([0, 0, 0], 100_000, L.MODE_GENERAL)
+    grp = nd.LocalGroup(_devs(3), 100_000, L.MODE_GENERAL)
     try:
         for s in (text, prose):
             got, _ = grp.factorize(L.MODE_GENERAL, s)
@@ -68,7 +75,7 @@ def test_dist_matches_single_gpu_5mbp_rc():
     """configs[1] text on 4 ranks: identical triples to the single-GPU pipeline (itself oracle-checked)."""
     s = wl.c2_text()
     single = L.factorize_array(L.MODE_DNA_RC, s)
-    grp = nd.LocalGroup([0, 0, 0, 0], len(s), L.MODE_DNA_RC)
+    grp = nd.LocalGroup(_devs(4), len(s), L.MODE_DNA_RC)
     try:
         got, stats = grp.factorize(L.MODE_DNA_RC, s)
     finally:
@@ -83,7 +90,7 @@ def test_dist_hybrid_rounds_big_tie_groups():
     from test_gpu_parity import _hybrid_cases
     cases = _hybrid_cases()
     for world in (2, 3):
-        grp = nd.LocalGroup([0] * world, 400_000, L.MODE_DNA_RC)
+        grp = nd.LocalGroup(_devs(world), 400_000, L.MODE_DNA_RC)
         try:
             for flags in ((64 << 8), (64 << 8) | 8):
                 for c in grp.ctxs:
@@ -98,7 +105,7 @@ def test_dist_hybrid_rounds_big_tie_groups():
 
 
 def test_dist_invalid_nucleotide_is_reported_by_every_rank():
-    grp = nd.LocalGroup([0, 0, 0], 10_000, L.MODE_DNA_RC)
+    grp = nd.LocalGroup(_devs(3), 10_000, L.MODE_DNA_RC)
     try:
         s = wl.uniform_dna(5000, 3).tobytes()
         bad = s[:4100] + b"N" + s[4101:]

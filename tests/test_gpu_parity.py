@@ -319,3 +319,39 @@ def test_batch_config3_sample():
         assert counts[j] == len(e)
         assert np.array_equal(got[at:at + len(e)], e), j
         at += len(e)
+
+
+def test_batch_sparse_unordered_offsets():
+    """nlz_factorize_batch with records picked from a much larger buffer, in arbitrary order, with gaps and one
+    overlap (the staging copy used to span [0, max offset + len) and overran the workspace)."""
+    import ctypes
+
+    lib = L.load()
+    rng = np.random.default_rng(77)
+    big = wl.uniform_dna(3_000_000, 9)
+    big[100_000:100_040] = np.frombuffer(b"N" * 40, dtype=np.uint8)     # garbage between the records is never read
+    offs = np.array([2_900_000, 5, 1_500_000, 1_500_300, 700_000, 5, 2_999_900], dtype=np.uint64)
+    lens = np.array([400, 300, 300, 123, 0, 50, 100], dtype=np.uint64)
+    for with_rc in (1, 0):
+        counts = np.zeros(len(offs), dtype=np.uint64)
+        out, total = L._u64p(), L._u64(0)
+        L.check(lib.nlz_factorize_batch(L.context(None), with_rc, big.ctypes.data, offs.ctypes.data, lens.ctypes.data,
+                                        len(offs), ctypes.byref(out), counts.ctypes.data, ctypes.byref(total)))
+        got = np.ctypeslib.as_array(out, shape=(total.value * 3,)).copy().reshape(-1, 3)
+        lib.nlz_free(out)
+        at = 0
+        for j in range(len(offs)):
+            s = big[int(offs[j]):int(offs[j] + lens[j])].tobytes()
+            e = (orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(s)) if with_rc else orc.factorize(s)) if s else np.zeros((0, 3), dtype=np.uint64)
+            assert counts[j] == len(e), (with_rc, j)
+            assert np.array_equal(got[at:at + len(e)], e), (with_rc, j)
+            at += len(e)
+        assert at == total.value
+    # an invalid nucleotide inside a picked record is reported with the record's index among the non-empty ones
+    offs2 = np.array([2_900_000, 99_990], dtype=np.uint64)
+    lens2 = np.array([100, 30], dtype=np.uint64)
+    counts = np.zeros(2, dtype=np.uint64)
+    out, total = L._u64p(), L._u64(0)
+    rc = lib.nlz_factorize_batch(L.context(None), 1, big.ctypes.data, offs2.ctypes.data, lens2.ctypes.data, 2,
+                                 ctypes.byref(out), counts.ctypes.data, ctypes.byref(total))
+    assert rc == L.NLZ_ERR_RUNTIME and b"Invalid nucleotide 'N' found in sequence 1" in lib.nlz_last_error()
