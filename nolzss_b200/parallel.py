@@ -5,12 +5,15 @@ from __future__ import annotations
 import os
 import tempfile
 from pathlib import Path
-from typing import List, Tuple, Union
+from collections import namedtuple
+from typing import List, Union
 
 from . import _noLZSS as _ext
 from .utils import read_factors_binary_file, validate_input
 
-Factor = Tuple[int, int, int]
+# the reference reads the temporary file back into namedtuples with .start / .length / .ref (parallel.py:147-153),
+# which its own tests/test_parallel.py:58 relies on
+Factor = namedtuple("Factor", ["start", "length", "ref"])
 
 
 def parallel_factorize_to_file(text, output_path, num_threads: int = 0, start_pos: int = 0, validate: bool = True) -> int:
@@ -33,7 +36,7 @@ def parallel_factorize(text, num_threads: int = 0, start_pos: int = 0, validate:
     os.close(fd)
     try:
         _ext.parallel_factorize_to_file(text, tmp, num_threads, start_pos)
-        return read_factors_binary_file(tmp)
+        return [Factor(*f) for f in read_factors_binary_file(tmp)]
     finally:
         if os.path.exists(tmp):
             os.unlink(tmp)

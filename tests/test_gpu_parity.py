@@ -355,3 +355,18 @@ def test_batch_sparse_unordered_offsets():
     rc = lib.nlz_factorize_batch(L.context(None), 1, big.ctypes.data, offs2.ctypes.data, lens2.ctypes.data, 2,
                                  ctypes.byref(out), counts.ctypes.data, ctypes.byref(total))
     assert rc == L.NLZ_ERR_RUNTIME and b"Invalid nucleotide 'N' found in sequence 1" in lib.nlz_last_error()
+
+
+def test_c4_250mbp_rc_text_matches_oracle_hash():
+    """configs[3] at full size on one GPU: the 250 Mbp RC text (26 M deep-nesting positions, hybrid doubling rounds)
+    against the sha256 of the oracle's triples (tests/golden/c4_250mbp_rc.json, scripts/c4_oracle_hash.py)."""
+    import hashlib
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c4_250mbp_rc.json")))
+    t = wl.planted_dna(gold["n_bases"], 4, scale=50.0).tobytes()
+    got = L.factorize_array(L.MODE_DNA_RC, t)
+    assert len(got) == gold["factors"]
+    assert int(got[:, 1].sum()) == gold["sum_lengths"]
+    assert hashlib.sha256(got.astype("<u8").tobytes()).hexdigest() == gold["sha256_triples_le_u64"]
