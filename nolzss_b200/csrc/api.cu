@@ -20,7 +20,6 @@
 #include "../../include/nolzss_b200.h"
 #include "chain.cuh"
 #include "common.cuh"
-#include "dist.cuh"
 #include "lcp.cuh"
 #include "lpnf.cuh"
 #include "prof.cuh"
@@ -58,6 +57,7 @@ struct Workspace {
     u32 n1 = 0;
     u8* X = nullptr;
     u32 *SA = nullptr, *RANK = nullptr, *LCP = nullptr;
+    u32* R0 = nullptr;       // RC mode, stage 3: rc-class leaf values (lpnf.cuh: k_leaf_values); F0 overwrites SA in place
     u64* KEY[2] = {nullptr, nullptr};
     u32* VAL[2] = {nullptr, nullptr};
     u32* SLOT[2] = {nullptr, nullptr};
@@ -102,7 +102,7 @@ static size_t workspace_bytes_for(u64 n1, u64 nrec) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
     t += al(n1 + 192);               // X
-    t += al((n1 + 72) * 4) * 3;      // SA, RANK, LCP (+ one padded line for whole-line reads)
+    t += al((n1 + 72) * 4) * 4;      // SA, RANK, LCP, R0 (+ one padded line for whole-line reads)
     t += al((n1 + 72) * 16);         // NODE
     t += al(n1 * 8) * 2;             // KEY
     t += al(n1 * 4) * 4;             // VAL, SLOT
@@ -149,6 +149,7 @@ static int ensure_workspace(nlz_ctx* c, u64 n1, u64 nrec = 0) {
     w.SA = a.take<u32>(n1 + 72);
     w.RANK = a.take<u32>(n1 + 72);
     w.LCP = a.take<u32>(n1 + 72);
+    w.R0 = a.take<u32>(n1 + 72);
     w.NODE = a.take<uint4>(n1 + 72);
     for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(n1);
     for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(n1);
@@ -327,42 +328,24 @@ static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout
     return OK;
 }
 
-// ---- distributed runs: per-call state (nullptr on the single-GPU path) ---------------------------
-struct DistRt {
-    nlz_dist* d = nullptr;
-    int G = 1, me = 0;
-    int pbits = 0;                       // leading key bits the bucket histogram is taken over
-    u32 split[MAX_PEERS + 1] = {};       // bucket ranges
-    u32 base[MAX_PEERS + 1] = {};        // rank ranges: GPU g owns global ranks [base[g], base[g+1])
-    u32 m_loc = 0;                       // suffixes this GPU owns
-    u32 chunk = 0;                       // text positions per GPU (Kasai slices)
-};
-static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all);
-
-static RankDst rank_dst(nlz_ctx* c, DistRt* dr);
-static int dist_push_updates(DistRt* dr, cudaStream_t st, u32 cnt);
-static int dist_apply_updates(DistRt* dr, cudaStream_t st, const u32* cnts);
+static RankDst local_rank_dst(nlz_ctx* c) {   // one GPU: refined ranks go straight into RANK; no records
+    RankDst r;
+    r.rank = c->ws.RANK; r.upd = nullptr; r.upd_count = c->ws.CTR + 4; r.base = 0;
+    return r;
+}
 
 template <typename KeyT>
 static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay,
-                                    cudaStream_t st, DistRt* dr, u32 cnt, int* cur_out, u32* m_out, u32* maxg_out) {
+                                    cudaStream_t st, u32 cnt, int* cur_out, u32* m_out, u32* maxg_out) {
     Workspace& w = c->ws;
     Profiler& P = c->prof;
     const u32 n1 = pb.n1;
     const u64 kb = sizeof(KeyT);
     KeyT* k[2] = {reinterpret_cast<KeyT*>(w.KEY[0]), reinterpret_cast<KeyT*>(w.KEY[1])};
     u32* v[2] = {w.VAL[0], w.VAL[1]};
-    if (!dr) {
-        KL(P, KC_KEYS, (u64)n1 * (1 + kb + 4), st,
-           (k_build_keys<KeyT><<<ceil_div_u32(n1, KB_TP), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pb.nrec ? w.REC : nullptr,
-                                                                       k[0], v[0])));
-    } else {
-        // ordered compaction of the suffixes of this GPU's bucket range (per-CTA offsets in DCNT, scanned in dist_partition)
-        KL(P, KC_KEYS, (u64)n1 + (u64)cnt * (kb + 4), st,
-           (k_keys_partition<KeyT, 2><<<ceil_div_u32(n1, KB_TP), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, dr->pbits,
-                                                                              dr->split[dr->me], dr->split[dr->me + 1],
-                                                                              w.DCNT, k[0], v[0])));
-    }
+    KL(P, KC_KEYS, (u64)n1 * (1 + kb + 4), st,
+       (k_build_keys<KeyT><<<ceil_div_u32(n1, KB_TP), 256, 0, st>>>(w.X, pb.L, n1, tab, lay, pb.nrec ? w.REC : nullptr,
+                                                                   k[0], v[0])));
     NLZ_CK(cudaEventRecord(c->ev[EV_KEYS], st));
     *cur_out = 1; *m_out = 0; *maxg_out = 0;
     if (cnt == 0) { NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st)); return OK; }
@@ -384,14 +367,10 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
     k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
     k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, cnt, dist_mask, w.PMAX,
-                                                              w.PSUM, w.SA, rank_dst(c, dr), w.KEY[res ^ 1],
+                                                              w.PSUM, w.SA, local_rank_dst(c), w.KEY[res ^ 1],
                                                               w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
     P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8), st, 3);
     *cur_out = res ^ 1;
-    if (dr) {                                           // every rank is new: cnt records; the counts travel with the next barrier
-        k_set_u32<<<1, 1, 0, st>>>(w.CTR + 4, cnt);
-        return dist_push_updates(dr, st, cnt);
-    }
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     c->stats.host_syncs += 1;
@@ -400,10 +379,10 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     return OK;
 }
 
-// ---- S1: suffix array of the `cnt` suffixes this GPU sorts (all n1 on one GPU).  Results: w.SA (local
-// rank order), RANK (= ISA; every replica in a distributed run).
-static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay, cudaStream_t st,
-                    DistRt* dr, u32 cnt) {
+// ---- S1: suffix array of all n1 suffixes on one GPU (the distributed loop is stage_sa_dist in dist2_host.cuh).
+// Results: w.SA (rank order), RANK (= ISA).
+static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const KeyLayout& lay, cudaStream_t st) {
+    const u32 cnt = pb.n1;
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
     Profiler& P = c->prof;
@@ -411,26 +390,22 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     S.key_bits = lay.key_bits; S.sym_bits = lay.b; S.key_syms = lay.W;
     int cur = 0;
     u32 m = 0, maxg = 0;
-    if (dr) NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
-    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, dr, cnt, &cur, &m, &maxg));
-    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, dr, cnt, &cur, &m, &maxg));
-    const RankDst rdst = rank_dst(c, dr);
+    if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, cnt, &cur, &m, &maxg));
+    else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, cnt, &cur, &m, &maxg));
+    const RankDst rdst = local_rank_dst(c);
     const int nb = bits_for(n1 - 1);
     DigitPlan plan;
     plan_add_range(plan, 0, nb);
     plan_add_range(plan, 32, 32 + nb);
     u64 h = (u64)lay.W;
     int sc = 0;
-    u32 gm = m;                                          // largest active count over all GPUs
-    std::vector<u32> all((size_t)MAX_PEERS * 8);
-    u32 sent[MAX_PEERS];                                 // records every GPU pushed in the step before the barrier
-    if (dr) for (int g = 0; g < dr->G; ++g) sent[g] = dr->base[g + 1] - dr->base[g];
+    u32 gm = m;
     static const bool no_pipeline = getenv("NLZ_TRACE") != nullptr || getenv("NLZ_NO_PIPELINE") != nullptr;
     // largest tie group the shared-memory tile sort takes (test hook: debug flags >> 8 lower it so that small texts
     // reach the hybrid rounds)
     u32 gcap = (u32)TSORT_SLOTS / 2;
     if ((c->debug_flags >> 8) >= 64 && (u32)(c->debug_flags >> 8) < gcap) gcap = (u32)(c->debug_flags >> 8);
-    if (!dr && !no_pipeline && m > 0 && maxg <= gcap) {
+    if (!no_pipeline && m > 0 && maxg <= gcap) {
         // Every remaining round is a fused one (groups only shrink).  The host runs one round AHEAD of the device:
         // round r is launched with grids sized from the counts of round r-1 and reads its true list length from
         // RING[r] on the device, so the per-round count readback no longer leaves the GPU idle.
@@ -448,7 +423,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
             KL(P, KC_GATHER, (u64)bm * 24, st,
                (k_gather_rank<<<ceil_div_u32(bm, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], bm, RING + 2 * r, w.RANK, h, n1, nullptr)));
             KL(P, KC_TILE_SORT, (u64)bm * (12 + 4 + 8 + 16), st,
-               (k_tile_sort<<<ceil_div_u32(bm, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+               (k_tile_sort<32><<<ceil_div_u32(bm, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
                    w.KEY[cur], w.VAL[cur], w.SLOT[sc], bm, RING + 2 * r, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
                    w.SLOT[sc ^ 1], RING + 2 * (r + 1), RING + 2 * (r + 1) + 1, c->debug_flags)));
             NLZ_CK(cudaMemcpyAsync(hring + 2 * (r + 1), RING + 2 * (r + 1), 8, cudaMemcpyDeviceToHost, st));
@@ -489,7 +464,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
         P.begin(st);
         k_regroup_reduce<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], mm, 0ull, w.PMAX, w.PSUM);
         k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
-        k_regroup_apply<u64, false><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], mm, 0ull,
+        k_regroup_apply<u64, false, 32><<<tiles, RG_THREADS, 0, st>>>(w.KEY[rb], w.VAL[rb], w.SLOT[sc], mm, 0ull,
                                                                 w.PMAX, w.PSUM, w.SA, rdst, w.KEY[rb ^ 1],
                                                                 w.VAL[rb ^ 1], w.SLOT[sc ^ 1], w.CTR + 3);
         P.end(KC_REGROUP, (u64)mm * (16 + 4 + 4 + 8 + 16), st, 3);
@@ -497,17 +472,6 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
         return OK;
     };
     for (;;) {
-        if (dr) {
-            // every GPU has pushed the ranks it refined; learn every GPU's (m, maxg), then apply their records
-            NLZ_TRY(dist_barrier(dr, st, w.CTR, 8, all.data()));        // CTR: [0] m' (S), [3] largest group, [4] records pushed, [6] m' (B)
-            for (int g = 0; g < dr->G; ++g) sent[g] = all[(size_t)g * 8 + 4];
-            NLZ_TRY(dist_apply_updates(dr, st, sent));
-            const u32* mine = &all[(size_t)dr->me * 8];
-            if (hy.on) { hy.mS = mine[0]; hy.maxgS = mine[3]; hy.mB = mine[6]; m = hy.mS + hy.mB; }
-            else { m = mine[0]; maxg = mine[3]; }
-            gm = 0;
-            for (int g = 0; g < dr->G; ++g) gm = std::max(gm, all[(size_t)g * 8] + all[(size_t)g * 8 + 6]);
-        }
         if (gm == 0) break;
         S.doubling_rounds += 1;
         S.active_sum += m;
@@ -517,9 +481,9 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
             // split the list once: small groups to the left, big groups to the right end of the other buffers
             const u32 tiles = ceil_div_u32(m, RG_TILE);
             P.begin(st);
-            k_split_count<<<tiles, RG_THREADS, 0, st>>>(w.KEY[cur], w.SLOT[sc], m, gcap, w.PSUM);
+            k_split_count<32><<<tiles, RG_THREADS, 0, st>>>(w.KEY[cur], w.SLOT[sc], m, gcap, w.PSUM);
             k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.PSUM, tiles, w.CTR + 6);
-            k_split_apply<<<tiles, RG_THREADS, 0, st>>>(w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, gcap, w.PSUM, w.CTR + 6, END,
+            k_split_apply<32><<<tiles, RG_THREADS, 0, st>>>(w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, gcap, w.PSUM, w.CTR + 6, END,
                                                         w.KEY[cur ^ 1], w.VAL[cur ^ 1], w.SLOT[sc ^ 1]);
             P.end(KC_REGROUP, (u64)m * 40, st, 3);
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
@@ -539,13 +503,12 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                        (k_gather_rank<<<ceil_div_u32(mS, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], mS, nullptr, w.RANK, h, n1, nullptr)));
             if (mB) KL(P, KC_GATHER, (u64)mB * 24, st,
                        (k_gather_rank<<<ceil_div_u32(mB, 256), 256, 0, st>>>(w.KEY[cur] + b0, w.VAL[cur] + b0, mB, nullptr, w.RANK, h, n1, nullptr)));
-            if (dr) { NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 4, st)); NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr)); }
             if (mS) {
                 u32 cap = 32;
                 while (cap < hy.maxgS) cap <<= 1;
                 const u32 tile = TSORT_SLOTS - cap;
                 KL(P, KC_TILE_SORT, (u64)mS * 40, st,
-                   (k_tile_sort<<<ceil_div_u32(mS, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                   (k_tile_sort<32><<<ceil_div_u32(mS, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
                        w.KEY[cur], w.VAL[cur], w.SLOT[sc], mS, nullptr, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
                        w.SLOT[sc ^ 1], w.CTR, w.CTR + 3, c->debug_flags)));
             }
@@ -555,7 +518,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                 so.end = END; so.mS = w.CTR; so.maxgS = w.CTR + 3; so.mB = w.CTR + 6; so.fallback = w.CTR + 7;
                 const int dbg = (c->debug_flags & 8) && S.doubling_rounds >= 3 ? 8 : 0;   // test hook: fail the third round
                 KL(P, KC_STREAM, (u64)mB * 44, st,
-                   (k_group_stream<<<ceil_div_u32(mB, gcap), GS_THREADS, GS_SMEM, st>>>(
+                   (k_group_stream<32><<<ceil_div_u32(mB, gcap), GS_THREADS, GS_SMEM, st>>>(
                        w.KEY[cur], w.VAL[cur], w.SLOT[sc], b0, mB, gcap, w.SA, rdst, so, dbg)));
             }
             S.tile_sort_rounds += 1;
@@ -590,13 +553,13 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                 hy.on = false; hy.off = ++hy.fallbacks >= 2;            // one more try from a fresh split after this round
                 if (trace) fprintf(stderr, "[nlz] round %u: outliers exceed the stream kernel, back to radix rounds\n", S.doubling_rounds);
                 NLZ_TRY(radix_round(mS + mB, &rb, nullptr));
-                if (!dr) {
+                {
                     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
                     NLZ_CK(cudaStreamSynchronize(st));
                     S.host_syncs += 1;
                     m = c->h_pinned[0]; maxg = c->h_pinned[3]; gm = m;
                 }
-            } else if (!dr) {
+            } else {
                 hy.mS = c->h_pinned[0]; hy.maxgS = c->h_pinned[3]; hy.mB = c->h_pinned[6];
                 if (trace) {
                     float tms = 0.f;
@@ -606,7 +569,6 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                 }
                 m = hy.mS + hy.mB; gm = m;
             }
-            if (dr) NLZ_TRY(dist_push_updates(dr, st, mS + mB));
         } else {
             const bool fused = maxg <= gcap;
             if (m > 0)
@@ -614,14 +576,13 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                    (k_gather_rank<<<ceil_div_u32(m, 256), 256, 0, st>>>(w.KEY[cur], w.VAL[cur], m, nullptr, w.RANK, h, n1,
                                                                          fused ? w.CTR : nullptr)));
             else NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
-            if (dr) { NLZ_CK(cudaMemsetAsync(w.CTR + 4, 0, 4, st)); NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr)); }   // every GPU has applied its inbox: it may be overwritten
             if (m > 0 && fused) {
                 // every tie group fits in shared memory: segmented sort + regroup in one pass
                 u32 cap = 32;
                 while (cap < maxg) cap <<= 1;
                 const u32 tile = TSORT_SLOTS - cap;
                 KL(P, KC_TILE_SORT, (u64)m * (12 + 4 + 8 + 16), st,
-                   (k_tile_sort<<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
+                   (k_tile_sort<32><<<ceil_div_u32(m, tile), TSORT_THREADS, TSORT_SMEM, st>>>(
                        w.KEY[cur], w.VAL[cur], w.SLOT[sc], m, nullptr, tile, cap, w.SA, rdst, w.KEY[cur ^ 1], w.VAL[cur ^ 1],
                        w.SLOT[sc ^ 1], w.CTR, w.CTR + 3, c->debug_flags)));
                 rb = cur;                       // next round's lists were written to the cur^1 buffers
@@ -630,8 +591,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
             } else if (m > 0) {
                 NLZ_TRY(radix_round(m, &rb, tev1));
             }
-            if (dr) NLZ_TRY(dist_push_updates(dr, st, m));
-            if (!dr) {
+            {
                 NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
                 NLZ_CK(cudaStreamSynchronize(st));
                 S.host_syncs += 1;
@@ -655,17 +615,18 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     return OK;
 }
 
-// ---- S3: per-position factor rule over the rank-ordered arrays (SA, LCP) of `cnt` ranks; in a
-// distributed run these hold virtual ranks around the real ones [wp.real_lo, wp.real_hi).
-static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32* SA, const u32* LCP, WalkParams wp,
-                      const u32* RANK, u64* LR, u8* HARDF) {
+// ---- S3: per-position factor rule over the rank-ordered arrays (leaf values F0 / R0, LCP) of wp.n1 ranks; in a
+// distributed run these hold virtual ranks around the real ones [wp.real_lo, wp.real_hi) and the results are indexed
+// by work item (`bylist`, see k_lpnf_rank) instead of by text position.
+static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const u32* R0, const u32* LCP, WalkParams wp,
+                      const u32* RANK, u64* LR, u8* FLAGS, bool bylist) {
     Workspace& w = c->ws;
     Profiler& P = c->prof;
     const u32 n1 = wp.n1;
     Trees T;
     memset(&T, 0, sizeof(T));
     T.lcp[0] = LCP; T.cntL[0] = n1 + 1;
-    T.f[0] = SA; T.r[0] = SA; T.cntS[0] = n1;
+    T.f[0] = F0; T.r[0] = R0; T.cntS[0] = n1;
     int lev = 0;
     P.begin(st);
     while (T.cntL[lev] > 32 && lev + 1 < TREE_MAX_LEVELS) {
@@ -673,10 +634,10 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
         u32 nodes = cl > cs ? cl : cs;
         u32 grid = ceil_div_u32((u64)nodes * 32, 256);
         if (lev == 0) {
-            if (pb.rc) k_tree_level1<true><<<grid, 256, 0, st>>>(LCP, T.cntL[0], SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
-            else k_tree_level1<false><<<grid, 256, 0, st>>>(LCP, T.cntL[0], SA, T.cntS[0], wp, w.tl[1], cl, w.tf[1], w.tr[1], cs);
+            if (rc) k_tree_level1<true><<<grid, 256, 0, st>>>(LCP, T.cntL[0], F0, R0, T.cntS[0], w.tl[1], cl, w.tf[1], w.tr[1], cs);
+            else k_tree_level1<false><<<grid, 256, 0, st>>>(LCP, T.cntL[0], F0, R0, T.cntS[0], w.tl[1], cl, w.tf[1], w.tr[1], cs);
         } else {
-            if (pb.rc) k_tree_level_up<true><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
+            if (rc) k_tree_level_up<true><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
             else k_tree_level_up<false><<<grid, 256, 0, st>>>(T.lcp[lev], T.cntL[lev], T.f[lev], T.r[lev], T.cntS[lev], w.tl[lev + 1], cl, w.tf[lev + 1], w.tr[lev + 1], cs);
         }
         ++lev;
@@ -688,11 +649,11 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
     c->trees = T;
     if (!LR) return OK;                                  // trees only (edge staircases of a distributed run)
     KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
-       (pb.rc ? k_node_tables<true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
-              : k_node_tables<false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
+       (rc ? k_node_tables<true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
+           : k_node_tables<false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
     RNear rn;
     memset(&rn, 0, sizeof(rn));
-    if (pb.rc) {
+    if (rc) {
         // nearest rc(T) rank on either side of every rank + LCP minimum on the way (two segmented scans)
         u32* PR = reinterpret_cast<u32*>(w.KEY[1]);
         u32* ML = PR + n1;
@@ -700,40 +661,53 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
         u32* MR = w.VAL[1];
         const u32 tiles = ceil_div_u32(n1, RN_TILE);
         P.begin(st);
-        k_rnear_reduce<0><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM);
+        k_rnear_reduce<0><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM);
         k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
-        k_rnear_apply<0><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM, PR, ML);
-        k_rnear_reduce<1><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM);
+        k_rnear_apply<0><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM, PR, ML);
+        k_rnear_reduce<1><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM);
         k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
-        k_rnear_apply<1><<<tiles, RN_THREADS, 0, st>>>(SA, LCP, wp, w.PMAX, w.PSUM, NR, MR);
+        k_rnear_apply<1><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM, NR, MR);
         P.end(KC_RNEAR, (u64)n1 * (4 * 8 + 4 * 4), st, 6);
         rn.PR = PR; rn.ML = ML; rn.NR = NR; rn.MR = MR;
     }
     unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);   // [0] probes, [1] hard
     NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 16, st));
-    // algorithmic bytes: SA[r] for every rank; per factorized position the two LCP neighbours, the
-    // LR store and the hard flag; plus (added after the run, from the probe counter) 16 B per probe
+    // algorithmic bytes: the leaf value of every rank; per factorized position the two LCP neighbours, the
+    // LR store and the flag byte; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
     static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
-    if (pb.rc) {
+    const u32 nreal = wp.real_hi - wp.real_lo;
+    u32 nwork;                                           // work items of both kernels when the results are indexed by item
+    u32* list = nullptr;
+    if (rc) {
         // compact the ranks that hold a forward suffix (about half): no idle lanes in the walk
-        u32* list = w.SLOT[1];
+        list = w.SLOT[1];
         const u32 tiles = ceil_div_u32(n1, FR_TILE);
-        k_forward_ranks<1><<<tiles, 256, 0, st>>>(SA, wp, w.PMAX, nullptr);
+        k_forward_ranks<1><<<tiles, 256, 0, st>>>(F0, wp, w.PMAX, nullptr);
         k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.PMAX, tiles, w.CTR + 5);
-        k_forward_ranks<2><<<tiles, 256, 0, st>>>(SA, wp, w.PMAX, list);
-        const u32 bound = wp.real_hi - wp.real_lo < pb.nfac ? wp.real_hi - wp.real_lo : pb.nfac;
-        k_lpnf_rank<true><<<ceil_div_u32(bound, 256), 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, HARDF, visit_ctr);
+        k_forward_ranks<2><<<tiles, 256, 0, st>>>(F0, wp, w.PMAX, list);
+        nwork = nreal < wp.nfac ? nreal : wp.nfac;
+        const u32 grid = ceil_div_u32(nwork ? nwork : 1, 256);
+        if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+        else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
     } else {
-        k_lpnf_rank<false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, HARDF, visit_ctr);
+        nwork = nreal;
+        if (bylist) k_lpnf_rank<false, true><<<ceil_div_u32(nreal ? nreal : 1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+        else k_lpnf_rank<false, false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
     }
-    P.end(KC_WALK, (u64)n1 * (pb.rc ? 12 : 4) + (u64)(wp.real_hi - wp.real_lo) * 17, st, pb.rc ? 4 : 1);
+    P.end(KC_WALK, (u64)n1 * (rc ? 12 : 4) + (u64)nreal * 17, st, rc ? 4 : 1);
     {
-        const u32 grid = ceil_div_u32((u64)ceil_div_u32(pb.nfac, WALK_Q) * 8, 256);   // one 8-lane tile per run
+        const u64 items = bylist ? (u64)nwork : (u64)wp.nfac;
+        const u32 grid = ceil_div_u32((u64)ceil_div_u32(items ? items : 1, WALK_Q) * 8, 256);   // one 8-lane tile per run
         P.begin(st);
-        if (pb.rc) k_lpnf_hard<true><<<grid, 256, 0, st>>>(T, wp, RANK, LR, HARDF, visit_ctr);
-        else k_lpnf_hard<false><<<grid, 256, 0, st>>>(T, wp, RANK, LR, HARDF, visit_ctr);
-        P.end(KC_WALK_HARD, (u64)pb.nfac, st);
+        if (bylist) {
+            if (rc) k_lpnf_hard<true, true><<<grid, 256, 0, st>>>(T, wp, nullptr, list, w.CTR + 5, nwork, LR, FLAGS, visit_ctr);
+            else k_lpnf_hard<false, true><<<grid, 256, 0, st>>>(T, wp, nullptr, nullptr, nullptr, nwork, LR, FLAGS, visit_ctr);
+        } else {
+            if (rc) k_lpnf_hard<true, false><<<grid, 256, 0, st>>>(T, wp, RANK, nullptr, nullptr, 0, LR, FLAGS, visit_ctr);
+            else k_lpnf_hard<false, false><<<grid, 256, 0, st>>>(T, wp, RANK, nullptr, nullptr, 0, LR, FLAGS, visit_ctr);
+        }
+        P.end(KC_WALK_HARD, items, st);
     }
     NLZ_CK(cudaMemcpyAsync(c->h_pinned + 4, visit_ctr, 16, cudaMemcpyDeviceToHost, st));
     return OK;
@@ -742,7 +716,7 @@ static int stage_lpnf(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u32*
 // ---- S4: chain extraction over LR[0, nfac) and emission of the triples.  Scratch: EXIT, J2, alist
 // (u32 x nfac), REACH (u8 x nfac), MASK (u32 x (33 x chunks)).
 struct ChainScratch { u32 *EXIT, *J2, *alist; u8* REACH; u32* MASK; };
-static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64* LR, const ChainScratch& cs,
+static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64* LR, const u8* FLAGS, const ChainScratch& cs,
                        u64* d_out, u64 capacity, bool count_only, u64* out_count) {
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
@@ -758,17 +732,16 @@ static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64
     u32* acount = w.CTR + 1;
     P.begin(st);
     NLZ_CK(cudaMemsetAsync(REACH, 0, nfac, st));
-    k_chain_init<<<1, 1, 0, st>>>(alist, acount, REACH, (u32)pb.start_pos);
-    k_chain_exit<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, EXIT, alist, acount);
+    ChainDom dom;
+    memset(&dom, 0, sizeof(dom));
+    dom.t0 = 0; dom.t1 = nfac; dom.nfac = nfac; dom.chunk = nfac; dom.G = 1;
+    dom.J[0] = EXIT; dom.J2[0] = J2; dom.REACH[0] = REACH;
+    k_chain_init<<<1, 1, 0, st>>>(alist, acount, REACH, (u32)pb.start_pos, 0u, nfac);
+    k_chain_exit<<<nchunks, CH_THREADS, 0, st>>>(LR, 0u, nfac, nfac, EXIT, alist, acount);
     int rounds = bits_for(nchunks) + 1;
     {
-        u32* Ja = EXIT;
-        u32* Jb = J2;
         u32 grid = nchunks < (u32)kNumSM * 2 ? (nchunks ? nchunks : 1) : kNumSM * 2;
-        for (int r = 0; r < rounds; ++r) {
-            k_chain_double<<<grid, 256, 0, st>>>(alist, acount, Ja, Jb, REACH, nfac);
-            u32* t = Ja; Ja = Jb; Jb = t;
-        }
+        for (int r = 0; r < rounds; ++r) k_chain_double<<<grid, 256, 0, st>>>(alist, acount, dom, r & 1);
     }
     k_chain_mark<<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, REACH, MASK, CNT);
     k_scan_u32_single_cta<<<1, 1024, 0, st>>>(CNT, nchunks, w.CTR + 2);
@@ -802,11 +775,11 @@ static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64
         }
         P.begin(st);
         if (pb.nrec) {
-            if (pb.rc) k_chain_emit<true, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
-            else k_chain_emit<false, true><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, w.SENTIDX);
+            if (pb.rc) k_chain_emit<true, true><<<nchunks, CH_THREADS, 0, st>>>(LR, FLAGS, 0u, MASK, CNT, dst, capacity, bv, w.SENTIDX);
+            else k_chain_emit<false, true><<<nchunks, CH_THREADS, 0, st>>>(LR, FLAGS, 0u, MASK, CNT, dst, capacity, bv, w.SENTIDX);
         } else {
-            if (pb.rc) k_chain_emit<true, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
-            else k_chain_emit<false, false><<<nchunks, CH_THREADS, 0, st>>>(LR, nfac, MASK, CNT, dst, capacity, bv, nullptr);
+            if (pb.rc) k_chain_emit<true, false><<<nchunks, CH_THREADS, 0, st>>>(LR, FLAGS, 0u, MASK, CNT, dst, capacity, bv, nullptr);
+            else k_chain_emit<false, false><<<nchunks, CH_THREADS, 0, st>>>(LR, FLAGS, 0u, MASK, CNT, dst, capacity, bv, nullptr);
         }
         P.end(KC_CHAIN, (u64)nfac / 8 + z * 32, st);
     }
@@ -814,12 +787,8 @@ static int stage_chain(nlz_ctx* c, const Problem& pb, cudaStream_t st, const u64
 }
 
 // ---- S0: text into X (validated / reverse-complemented on the device), byte histogram, key layout
-struct DistRt;
-static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all);
-static int dist_prepare_sliced(DistRt* dr, nlz_ctx* c, const Problem& pb, const void* src, cudaStream_t st);
-
 static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool src_on_host, cudaStream_t st,
-                         u8* staging, ClassTable& tab, KeyLayout& lay, DistRt* dr = nullptr) {
+                         u8* staging, ClassTable& tab, KeyLayout& lay) {
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
     Profiler& P = c->prof;
@@ -843,9 +812,6 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, 0xFFFFFFFFu);
         k_prepare_batch<<<ceil_div_u32((u64)pb.N + 1, 256), 256, 0, st>>>(tmp, w.INOFF, w.FSTART, w.FLEN, pb.nrec, pb.N,
                                                                         pb.rc, w.X, w.REC, w.CTR + 8);
-        prep_launches += 2;
-    } else if (pb.mode == NLZ_MODE_DNA_RC && dr) {
-        NLZ_TRY(dist_prepare_sliced(dr, c, pb, src, st));
         prep_launches += 2;
     } else if (pb.mode == NLZ_MODE_DNA_RC) {
         const u8* dT = static_cast<const u8*>(src);
@@ -938,7 +904,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     ClassTable tab;
     KeyLayout lay;
     NLZ_TRY(stage_prepare(c, pb, src, src_on_host, st, reinterpret_cast<u8*>(w.KEY[1]), tab, lay));
-    NLZ_TRY(stage_sa(c, pb, tab, lay, st, nullptr, n1));
+    NLZ_TRY(stage_sa(c, pb, tab, lay, st));
     NLZ_TRY(check_dna_deferred(c, pb, src, src_on_host));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
@@ -964,8 +930,13 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     wp.n1 = n1; wp.nfac = pb.nfac; wp.N = pb.N; wp.twoN = 2 * pb.N;
     wp.real_lo = 0; wp.real_hi = n1; wp.rank_add = 0;
     u64* LR = w.KEY[0];
-    u8* HARDF = reinterpret_cast<u8*>(w.SLOT[0]);
-    NLZ_TRY(stage_lpnf(c, pb, st, w.SA, w.LCP, wp, w.RANK, LR, HARDF));
+    u8* HARDF = reinterpret_cast<u8*>(w.SLOT[0]);       // flag plane: hard / reverse-complement bits, read again by the emit pass
+    // leaf values: general mode reads the suffix array as it is; RC mode splits it into forward starts (in place over
+    // SA, which no later stage reads) and rc values
+    if (pb.rc)
+        KL(P, KC_TREE, (u64)n1 * 12, st,
+           (k_leaf_values<true, u32><<<ceil_div_u32(n1, 256), 256, 0, st>>>(w.SA, n1, wp, w.SA, w.R0)));
+    NLZ_TRY(stage_lpnf(c, pb.rc, st, w.SA, w.R0, w.LCP, wp, w.RANK, LR, HARDF, false));
     NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
     if (stop_after_lpnf) {
         NLZ_CK(cudaGetLastError());
@@ -974,541 +945,14 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
 
     // ---- S4: chain
     ChainScratch cs;
-    cs.EXIT = w.VAL[0]; cs.J2 = w.VAL[1]; cs.alist = w.SLOT[0];
+    cs.EXIT = w.VAL[0]; cs.J2 = w.VAL[1];
+    cs.alist = reinterpret_cast<u32*>(w.NODE);          // the node table is dead after stage 3 (SLOT[0] holds the flag plane)
     cs.REACH = reinterpret_cast<u8*>(w.SLOT[1]);
     cs.MASK = reinterpret_cast<u32*>(w.KEY[1]);
-    NLZ_TRY(stage_chain(c, pb, st, LR, cs, d_out, capacity, count_only, out_count));
+    NLZ_TRY(stage_chain(c, pb, st, LR, HARDF, cs, d_out, capacity, count_only, out_count));
     account_walk(c);
     NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
     NLZ_CK(cudaGetLastError());
-    return OK;
-}
-
-// =================================================================== one text across G GPUs (dist.cuh)
-struct HostBarrier {          // in-process groups only (several ranks of one process, e.g. sharing a GPU in tests)
-    std::mutex mu;
-    std::condition_variable cv;
-    int world = 0, waiting = 0;
-    unsigned gen = 0;
-    bool broken = false;      // a rank gave up waiting (a peer failed earlier): the group is unusable
-    bool arrive() {
-        std::unique_lock<std::mutex> lk(mu);
-        if (broken) return false;
-        const unsigned g = gen;
-        if (++waiting == world) { waiting = 0; ++gen; cv.notify_all(); return true; }
-        if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g || broken; }) || broken) {
-            broken = true;
-            cv.notify_all();
-            return false;
-        }
-        return true;
-    }
-};
-
-}  // namespace nlz
-
-struct nlz_dist {
-    nlz_ctx* ctx = nullptr;
-    int rank = 0, world = 1;
-    u64 max_n1 = 0;
-    u8* seg = nullptr;                 // shared segment: DistCtl | RANK replica | local LCP | Phi slice | LR (rank 0)
-    size_t seg_bytes = 0, off_x = 0, off_rank = 0, off_lcp = 0, off_phi = 0, off_upd = 0, off_lr = 0, off_pos = 0;
-    u8* peer[MAX_PEERS] = {};
-    bool ipc_opened[MAX_PEERS] = {};
-    bool attached = false;
-    u32 epoch = 0;
-    int xparity = 0;
-    HostBarrier* hb = nullptr;
-    bool owns_hb = false;
-    u32* h_pin = nullptr;              // pinned: exchange readback
-    // persistent device buffers sized by max_n1
-    u32 *DCNT = nullptr, *HISTP = nullptr, *SMALL = nullptr;   // SMALL: CTR[64] | BYTEHIST[256] | SPLIT[16] | BASE[16] | PAYLOAD[512]
-    Arena arena;                       // per-call private workspace
-};
-
-namespace nlz {
-
-static RankDst rank_dst(nlz_ctx* c, DistRt* dr) {
-    RankDst r;
-    r.rank = c->ws.RANK; r.upd = nullptr; r.upd_count = c->ws.CTR + 4; r.base = 0;
-    if (dr) {
-        r.base = dr->base[dr->me];
-        if (dr->G > 1) r.upd = reinterpret_cast<u64*>(dr->d->seg + dr->d->off_upd) + r.base;
-    }
-    return r;
-}
-
-// The (suffix, rank) records this GPU produced in the step (CTR[4] of them, at most `bound`) -> every other GPU's
-// inbox (bulk stores over NVLink; each source owns the inbox slice [base[src], base[src+1])).
-static int dist_push_updates(DistRt* dr, cudaStream_t st, u32 bound) {
-    nlz_dist* d = dr->d;
-    if (!bound || dr->G == 1) return OK;
-    UpdDst ud;
-    memset(&ud, 0, sizeof(ud));
-    for (int g = 0; g < dr->G; ++g) ud.p[g] = reinterpret_cast<u64*>(d->peer[g] + d->off_upd) + dr->base[dr->me];
-    ud.n = dr->G; ud.me = dr->me;
-    u32 grid = ceil_div_u32(bound, 256 * 4);
-    if (grid > (u32)kNumSM * 8) grid = kNumSM * 8;
-    KL(d->ctx->prof, KC_BARRIER, (u64)bound * 8 * (dr->G - 1), st,
-       (k_dist_push_ranks<<<grid, 256, 0, st>>>(ud.p[dr->me], d->ctx->ws.CTR + 4, ud)));
-    return OK;
-}
-// after the barrier: apply what the other GPUs sent (cnts[g] records from GPU g)
-static int dist_apply_updates(DistRt* dr, cudaStream_t st, const u32* cnts) {
-    nlz_dist* d = dr->d;
-    Profiler& P = d->ctx->prof;
-    for (int g = 0; g < dr->G; ++g) {
-        if (g == dr->me || !cnts[g]) continue;
-        d->ctx->stats.rank_records_applied += cnts[g];
-        const u64* inbox = reinterpret_cast<const u64*>(d->seg + d->off_upd) + dr->base[g];
-        KL(P, KC_REGROUP, (u64)cnts[g] * 12, st,
-           (k_dist_apply_ranks<<<ceil_div_u32(cnts[g], 256), 256, 0, st>>>(inbox, cnts[g], d->ctx->ws.RANK)));
-    }
-    return OK;
-}
-
-// Stream-ordered barrier over all ranks; optionally every rank contributes `nwords` words (device
-// buffer d_src) and receives everybody's words in h_all[g * nwords ..] (host sync).
-static int dist_barrier(DistRt* dr, cudaStream_t st, const u32* d_src, u32 nwords, u32* h_all) {
-    nlz_dist* d = dr->d;
-    DistPeers peers;
-    memset(&peers, 0, sizeof(peers));
-    for (int g = 0; g < dr->G; ++g) peers.ctl[g] = reinterpret_cast<DistCtl*>(d->peer[g]);
-    peers.n = dr->G; peers.me = dr->me;
-    d->epoch += 1;
-    if (nwords) d->xparity ^= 1;
-    static const u32 timeout_s = getenv("NLZ_BARRIER_TIMEOUT_S") ? (u32)atoi(getenv("NLZ_BARRIER_TIMEOUT_S")) : 60u;
-    static const bool trace = getenv("NLZ_TRACE_DIST") != nullptr;
-    if (trace) fprintf(stderr, "[nlz dist] rank %d barrier %u (%u payload words)\n", dr->me, d->epoch, nwords);
-    if (d->hb) {
-        // In-process groups (ranks that may share ONE device): the ranks first meet on the host, so that no barrier
-        // kernel spins on the device while another rank still has work to launch.  A kernel launched for the first
-        // time is loaded lazily by the CUDA runtime, and that load waits for running kernels -- behind a spinning
-        // barrier it would wait for ever (and the barrier for it).  One process per GPU needs no such care.
-        NLZ_CK(cudaStreamSynchronize(st));
-        if (!d->hb->arrive()) {
-            set_error("distributed barrier %u: a rank of the in-process group failed or never arrived (rank %d waited)", d->epoch, dr->me);
-            return ERR_RUNTIME;
-        }
-    }
-    KL(d->ctx->prof, KC_BARRIER, (u64)nwords * 4 * dr->G, st,
-       (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords, timeout_s)));
-    // In-process groups may share ONE device (tests): a copy or memset queued behind a spinning barrier kernel
-    // blocks its hardware copy queue for the other ranks' copies, which then never reach their barrier.  There the
-    // host waits for the barrier before it enqueues anything else; one process per GPU needs no such care.
-    if (d->hb) NLZ_CK(cudaStreamSynchronize(st));
-    if (!h_all) return OK;
-    DistCtl* mine = reinterpret_cast<DistCtl*>(d->seg);
-    for (int g = 0; g < dr->G; ++g)
-        NLZ_CK(cudaMemcpyAsync(d->h_pin + (size_t)g * nwords, &mine->xch[d->xparity][g][0], (size_t)nwords * 4,
-                               cudaMemcpyDeviceToHost, st));
-    NLZ_CK(cudaMemcpyAsync(d->h_pin + (size_t)MAX_PEERS * DIST_XCH_WORDS, &mine->error, 4, cudaMemcpyDeviceToHost, st));
-    NLZ_CK(cudaStreamSynchronize(st));
-    d->ctx->stats.host_syncs += 1;
-    if (d->h_pin[(size_t)MAX_PEERS * DIST_XCH_WORDS] != 0) {
-        set_error("distributed barrier %u timed out on rank %d (a peer failed or never arrived)", d->epoch, dr->me);
-        return ERR_RUNTIME;
-    }
-    memcpy(h_all, d->h_pin, (size_t)dr->G * nwords * 4);
-    if (trace) {
-        fprintf(stderr, "[nlz dist] rank %d passed %u:", dr->me, d->epoch);
-        for (u32 i = 0; i < (u32)dr->G * nwords && i < 32; ++i) fprintf(stderr, " %u", h_all[i]);
-        fprintf(stderr, "\n");
-    }
-    return OK;
-}
-
-// DNA_RC text of a distributed run: slice upload + peer stores into every replica of X, then a barrier that also
-// agrees on the first invalid nucleotide (every GPU must take the same exit).
-static int dist_prepare_sliced(DistRt* dr, nlz_ctx* c, const Problem& pb, const void* src, cudaStream_t st) {
-    nlz_dist* d = dr->d;
-    Workspace& w = c->ws;
-    const u32 n = (u32)pb.n_in;
-    const u32 per = (u32)(((u64)ceil_div_u32(n, dr->G) + 255) / 256 * 256);
-    const u32 lo = (u32)std::min<u64>((u64)dr->me * per, n), hi = (u32)std::min<u64>((u64)(dr->me + 1) * per, n);
-    XDst xd;
-    memset(&xd, 0, sizeof(xd));
-    for (int g = 0; g < dr->G; ++g) xd.p[g] = d->peer[g] + d->off_x;
-    xd.n = dr->G;
-    k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, 0xFFFFFFFFu);
-    if (hi > lo) {
-        NLZ_CK(cudaMemcpyAsync(w.X + lo, static_cast<const u8*>(src) + lo, hi - lo, cudaMemcpyHostToDevice, st));
-        u32 grid = ceil_div_u32(hi - lo, 256);
-        if (grid > (u32)kNumSM * 16) grid = kNumSM * 16;
-        k_prepare_dna_rc_slice<<<grid, 256, 0, st>>>(w.X, n, lo, hi, xd, dr->me == 0, w.CTR + 8);
-    } else if (dr->me == 0) {
-        k_prepare_dna_rc_slice<<<1, 256, 0, st>>>(w.X, n, 0, 0, xd, true, w.CTR + 8);
-    }
-    std::vector<u32> all(MAX_PEERS);
-    NLZ_TRY(dist_barrier(dr, st, w.CTR + 8, 1, all.data()));
-    u32 bad = 0xFFFFFFFFu;
-    for (int g = 0; g < dr->G; ++g) bad = std::min(bad, all[g]);
-    c->h_pinned[8] = bad;                               // read by check_dna_deferred on every GPU
-    k_set_u32<<<1, 1, 0, st>>>(w.CTR + 8, bad);
-    return OK;
-}
-
-static size_t dist_private_bytes(u64 cap, u64 nfac, bool rank0) {
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    size_t t = 0;
-    t += al((cap + 72) * 4) + al((cap + 72) * 16);   // SA, NODE
-    t += al(cap * 8) * 2 + al(cap * 4) * 4;
-    t += al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);
-    size_t tiles = (cap + RG_TILE - 1) / RG_TILE + 1;
-    t += al(tiles * 4) * 2;
-    u64 cnt = cap + 1;
-    for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; t += al((cnt + 72) * 4) * 3; }
-    t += al(nfac * 8) + al(nfac + 64);    // LRloc, HARD
-    if (rank0) t += al(nfac * 4) * 3 + al(nfac + 64) + al(((nfac + CH_CHUNK - 1) / CH_CHUNK + 1) * 33 * 4);
-    return t + 4096;
-}
-
-// Buckets this GPU's pairs by destination, ships every bucket with one bulk copy into the destination's inbox
-// slice [base[me], ...) and scatters what arrived from everybody into `dst` (see k_dist_bucket_pairs).
-// Collective: 2 barriers.  `staging` holds ps.count pairs; `all` receives the count matrix.
-template <int SRC>
-static int dist_exchange_pairs(DistRt* dr, cudaStream_t st, const PairSrc& ps, u64* staging, u32* dst, std::vector<u32>& all) {
-    nlz_dist* d = dr->d;
-    Profiler& P = d->ctx->prof;
-    const int G = dr->G, me = dr->me;
-    u32* cnts = d->SMALL + 352;          // payload area: counts[G]
-    u32* cursor = d->SMALL + 352 + 16;
-    NLZ_CK(cudaMemsetAsync(cnts, 0, 32 * 4, st));
-    if (ps.count) {
-        const u32 grid = ceil_div_u32(ps.count, 256);
-        P.begin(st);
-        k_dist_bucket_pairs<SRC, 0><<<grid, 256, 0, st>>>(ps, cnts, nullptr);
-        k_dist_bucket_starts<<<1, 32, 0, st>>>(cnts, cursor, G);
-        k_dist_bucket_pairs<SRC, 1><<<grid, 256, 0, st>>>(ps, cursor, staging);
-        P.end(KC_LCP, (u64)ps.count * 24, st, 3);
-    }
-    NLZ_TRY(dist_barrier(dr, st, cnts, (u32)G, all.data()));          // all[g * G + dst] = pairs g sends to dst
-    // receiver d lays the buckets out in sender order: the bucket of sender g starts at sum_{g' < g} cnt(g' -> d)
-    auto inbox_off = [&](int g, int dst_gpu) { u64 o = 0; for (int q = 0; q < g; ++q) o += all[(size_t)q * G + dst_gpu]; return o; };
-    u64 start = 0;
-    for (int g = 0; g < G; ++g) {
-        const u32 cnt = all[(size_t)me * G + g];
-        if (g != me && cnt) {
-            u64* theirs = reinterpret_cast<u64*>(d->peer[g] + d->off_upd) + inbox_off(me, g);
-            NLZ_CK(cudaMemcpyAsync(theirs, staging + start, (size_t)cnt * 8, cudaMemcpyDefault, st));
-            P.bytes[KC_BARRIER] += (u64)cnt * 8;
-        }
-        start += cnt;
-    }
-    NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
-    start = 0;
-    for (int g = 0; g < G; ++g) {
-        const u32 mine = all[(size_t)me * G + g];
-        const u32 cnt = all[(size_t)g * G + me];
-        if (cnt) {
-            const u64* src = g == me ? staging + start : reinterpret_cast<const u64*>(d->seg + d->off_upd) + inbox_off(g, me);
-            KL(P, KC_LCP, (u64)cnt * 12, st, (k_dist_apply_pairs<<<ceil_div_u32(cnt, 256), 256, 0, st>>>(src, cnt, dst)));
-        }
-        start += mine;
-    }
-    return OK;
-}
-
-struct VirtBlock { u32 cnt = 0, F = NONE_MIN, R = 0; };
-
-// Factorizes one text with all ranks of the group (every rank passes the same text).  Rank 0 receives
-// the factors; every rank learns the count.
-static int run_dist(nlz_dist* d, const Problem& pb, const u8* text, u64** out_alloc, u64* out_count) {
-    nlz_ctx* c = d->ctx;
-    Workspace& w = c->ws;
-    Profiler& P = c->prof;
-    cudaStream_t st = c->own_stream;
-    const u32 n1 = pb.n1;
-    const int G = d->world, me = d->rank;
-    DistRt rt;
-    rt.d = d; rt.G = G; rt.me = me;
-    DistRt* dr = &rt;
-    w = Workspace();
-    w.n1 = n1;
-    w.X = d->seg + d->off_x;
-    w.DCNT = d->DCNT;
-    w.CTR = d->SMALL; w.BYTEHIST = d->SMALL + 64;
-    u32* d_split = d->SMALL + 320;
-    u32* d_base = d->SMALL + 336;
-    u32* d_pay = d->SMALL + 352;
-    w.RANK = reinterpret_cast<u32*>(d->seg + d->off_rank);
-    u32* LCPbuf = reinterpret_cast<u32*>(d->seg + d->off_lcp);     // [DIST_VIRT virtual | real | virtual | guard]
-    u32* PHI = reinterpret_cast<u32*>(d->seg + d->off_phi);
-    NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
-
-    // ---- S0 (replicated) + bucket histogram -> rank ranges
-    ClassTable tab;
-    KeyLayout lay;
-    NLZ_TRY(stage_prepare(c, pb, text, true, st, w.X, tab, lay, G > 1 ? dr : nullptr));
-    int pbits = lay.W * lay.b;
-    if (pbits > 24) pbits = 24;
-    { int lim = bits_for(n1) + 2; if (pbits > lim) pbits = lim; }
-    pbits -= pbits % lay.b;
-    if (pbits < lay.b) pbits = lay.b;
-    const int K = pbits / lay.b;                                     // crossing nodes are shallower than K symbols
-    rt.pbits = pbits;
-    const u32 nb = 1u << pbits;
-    const u32 nctas = ceil_div_u32(n1, KB_TP);
-    KeyLayout lay_top = lay;                                         // the bucket of a suffix only needs its first K symbols
-    lay_top.W = K;
-    P.begin(st);
-    NLZ_CK(cudaMemsetAsync(d->HISTP, 0, (size_t)nb * 4, st));
-    if (lay.key_bits == 32) k_keys_partition<u32, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, 0, 0, d->HISTP, nullptr, nullptr);
-    else k_keys_partition<u64, 0><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, 0, 0, d->HISTP, nullptr, nullptr);
-    {
-        const u32 nt = ceil_div_u32(nb, SCAN_TILE);
-        u32* tsum = d->HISTP + (size_t)(1u << 24) + 16;             // tile sums live behind the histogram
-        if (nt > 1) {
-            k_scan_tiles<false><<<nt, 1024, 0, st>>>(d->HISTP, nb, tsum);
-            k_scan_u32_single_cta<<<1, 1024, 0, st>>>(tsum, nt, nullptr);
-            k_scan_tiles<true><<<nt, 1024, 0, st>>>(d->HISTP, nb, tsum);
-        } else {
-            k_scan_u32_single_cta<<<1, 1024, 0, st>>>(d->HISTP, nb, nullptr);
-        }
-    }
-    k_dist_splitters<<<1, 32, 0, st>>>(d->HISTP, nb, n1, G, d_split, d_base);
-    P.end(KC_KEYS, (u64)n1 + (u64)nb * 8, st, 3);
-    NLZ_CK(cudaMemcpyAsync(d->h_pin, d_split, 32 * 4, cudaMemcpyDeviceToHost, st));   // SPLIT[16] | BASE[16]
-    NLZ_CK(cudaStreamSynchronize(st));
-    for (int g = 0; g <= G; ++g) { rt.split[g] = d->h_pin[g]; rt.base[g] = d->h_pin[16 + g]; }
-    rt.m_loc = rt.base[me + 1] - rt.base[me];
-    rt.chunk = (u32)(((u64)ceil_div_u32(n1, G) + 1023) / 1024 * 1024);
-    const u32 m_loc = rt.m_loc;
-    P.begin(st);
-    if (lay.key_bits == 32) k_keys_partition<u32, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
-    else k_keys_partition<u64, 1><<<nctas, 256, 0, st>>>(w.X, pb.L, n1, tab, lay_top, pbits, rt.split[me], rt.split[me + 1], w.DCNT, nullptr, nullptr);
-    k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.DCNT, nctas, nullptr);
-    P.end(KC_KEYS, (u64)n1, st, 2);
-
-    // ---- private workspace for this GPU's share (allocated before the first barrier: cudaFree synchronises the device)
-    // (sort buffers double as staging of the pair exchanges: at least one position slice)
-    const u64 cap = (u64)std::max(m_loc, rt.chunk) + 2 * DIST_VIRT + 8;
-    {
-        const size_t need = dist_private_bytes(cap, pb.nfac, me == 0);
-        if (need > d->arena.cap) {
-            NLZ_CK(cudaStreamSynchronize(st));
-            if (d->arena.base) { NLZ_CK(cudaFree(d->arena.base)); d->arena.base = nullptr; d->arena.cap = 0; }
-            const size_t want = need + need / 8;
-            cudaError_t e = cudaMalloc(&d->arena.base, want);
-            if (e != cudaSuccess) { set_error("cudaMalloc of %zu workspace bytes failed: %s", want, cudaGetErrorString(e)); return ERR_CUDA; }
-            d->arena.cap = want;
-        }
-        if (d->hb && !d->hb->arrive()) { set_error("a rank of the in-process group failed before the workspace rendezvous"); return ERR_RUNTIME; }
-        Arena& a = d->arena;
-        a.off = 0;
-        u32* SAbuf = a.take<u32>(cap + 72);
-        w.SA = SAbuf + DIST_VIRT;
-        w.NODE = a.take<uint4>(cap + 72);
-        for (int i = 0; i < 2; ++i) w.KEY[i] = a.take<u64>(cap);
-        for (int i = 0; i < 2; ++i) w.VAL[i] = a.take<u32>(cap);
-        for (int i = 0; i < 2; ++i) w.SLOT[i] = a.take<u32>(cap);
-        w.HIST = a.take<u32>((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS);
-        size_t tiles = (cap + RG_TILE - 1) / RG_TILE + 1;
-        w.PMAX = a.take<u32>(tiles);
-        w.PSUM = a.take<u32>(tiles);
-        u64 cnt = cap + 1;
-        for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) {
-            cnt = (cnt + 31) / 32;
-            w.tl[lev] = a.take<u32>(cnt + 72);
-            w.tf[lev] = a.take<u32>(cnt + 72);
-            w.tr[lev] = a.take<u32>(cnt + 72);
-        }
-        c->stats.workspace_bytes = d->arena.cap + d->seg_bytes;
-    }
-    u32* SAbuf = w.SA - DIST_VIRT;
-    u64* LRloc = d->arena.take<u64>(pb.nfac);
-    u8* HARDF = d->arena.take<u8>(pb.nfac + 64);
-    ChainScratch cs;
-    memset(&cs, 0, sizeof(cs));
-    if (me == 0) {
-        cs.EXIT = d->arena.take<u32>(pb.nfac); cs.J2 = d->arena.take<u32>(pb.nfac); cs.alist = d->arena.take<u32>(pb.nfac);
-        cs.REACH = d->arena.take<u8>(pb.nfac + 64);
-        cs.MASK = d->arena.take<u32>((size_t)(ceil_div_u32(pb.nfac, CH_CHUNK) + 1) * 33);
-    }
-    w.LCP = LCPbuf + DIST_VIRT;
-
-    // ---- S1: rank-range-local suffix sorting; refined ranks go to every replica
-    NLZ_TRY(stage_sa(c, pb, tab, lay, st, dr, m_loc));
-    NLZ_TRY(check_dna_deferred(c, pb, text, true));
-    NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
-
-    // ---- S2: Phi to the position owners, Kasai per position slice, LCP back to the rank owners
-    std::vector<u32> all((size_t)MAX_PEERS * DIST_XCH_WORDS);
-    if (m_loc) NLZ_CK(cudaMemcpyAsync(d_pay, w.SA + (m_loc - 1), 4, cudaMemcpyDeviceToDevice, st));
-    else k_set_u32<<<1, 1, 0, st>>>(d_pay, NONE_MIN);
-    NLZ_TRY(dist_barrier(dr, st, d_pay, 1, all.data()));
-    {
-        u32 left_sa = NONE_MIN;
-        for (int g = me - 1; g >= 0; --g)
-            if (rt.base[g + 1] > rt.base[g]) { left_sa = all[g]; break; }
-        const u32 pos0 = (u32)std::min<u64>((u64)me * rt.chunk, n1);
-        const u32 pos1 = (u32)std::min<u64>((u64)(me + 1) * rt.chunk, n1);
-        const u32 npos = pos1 - pos0;
-        PairSrc ps;
-        memset(&ps, 0, sizeof(ps));
-        ps.SA = w.SA; ps.left_sa = left_sa; ps.chunk = rt.chunk;
-        ps.RANK = w.RANK; ps.PLCP = PHI; ps.pos0 = pos0;
-        for (int g = 0; g <= G; ++g) ps.base[g] = rt.base[g];
-        ps.G = G;
-        // Phi: rank owners -> position owners
-        ps.count = m_loc;
-        NLZ_TRY((dist_exchange_pairs<0>(dr, st, ps, w.KEY[0], PHI, all)));
-        LcpDist ld;
-        ld.PHI = PHI; ld.pos0 = pos0; ld.pos1 = pos1;
-        BatchView bv;
-        memset(&bv, 0, sizeof(bv));
-        if (npos)
-            KL(P, KC_LCP, (u64)npos * 28, st,
-               (k_lcp_kasai<false, true><<<ceil_div_u32(ceil_div_u32(npos, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, nullptr, w.RANK, nullptr, bv, ld)));
-        // LCP: position owners -> rank owners (PLCP sits in the Phi slice, text order)
-        ps.count = npos;
-        NLZ_TRY((dist_exchange_pairs<1>(dr, st, ps, w.KEY[0], w.LCP, all)));
-    }
-    NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
-
-    // ---- S3a: boundary exchange.  Edge staircases of the local range (trees over the real ranks, guards at both ends)
-    WalkParams wp;
-    wp.n1 = m_loc; wp.nfac = pb.nfac; wp.N = pb.N; wp.twoN = 2 * pb.N;
-    wp.real_lo = 0; wp.real_hi = m_loc; wp.rank_add = 0;
-    NLZ_CK(cudaMemsetAsync(d_pay, 0, DIST_XCH_WORDS * 4, st));
-    if (m_loc) {
-        NLZ_CK(cudaMemcpyAsync(d_pay, w.LCP, 4, cudaMemcpyDeviceToDevice, st));          // c0 = lcp(previous GPU's last, my first)
-        NLZ_CK(cudaMemsetAsync(w.LCP, 0, 4, st));
-        NLZ_CK(cudaMemsetAsync(w.LCP + m_loc, 0, 4, st));
-        k_set_u32<<<1, 1, 0, st>>>(d_pay + 1, m_loc);
-        NLZ_TRY(stage_lpnf(c, pb, st, w.SA, w.LCP, wp, nullptr, nullptr, nullptr));
-        if (pb.rc) k_dist_edges<true><<<1, 64, 0, st>>>(c->trees, wp, m_loc, K, d_pay + 4);
-        else k_dist_edges<false><<<1, 64, 0, st>>>(c->trees, wp, m_loc, K, d_pay + 4);
-    }
-    const u32 pay_words = 4 + 8 * (u32)K;
-    NLZ_TRY(dist_barrier(dr, st, d_pay, pay_words, all.data()));
-    u32 n_ext = 0;
-    if (m_loc) {
-        auto C0 = [&](int g) { return all[(size_t)g * pay_words + 0]; };
-        auto M = [&](int g) { return all[(size_t)g * pay_words + 1]; };
-        auto E = [&](int g, int side, int v) { return &all[(size_t)g * pay_words + 4 + (size_t)(side * K + v - 1) * 4]; };
-        auto minint = [&](int g) { u32 r = 0; for (int v = 1; v <= K; ++v) if (E(g, 0, v)[3]) r = (u32)v; return r; };
-        auto prev_ne = [&](int g) { for (--g; g >= 0; --g) if (M(g)) return g; return -1; };
-        auto next_ne = [&](int g) { for (++g; g < G; ++g) if (M(g)) return g; return -1; };
-        auto merge = [&](std::vector<VirtBlock>& blk, int g, int side, u32 cur) {
-            for (int v = 1; v <= K; ++v) {
-                const u32* e = E(g, side, v);
-                if (!e[0]) continue;
-                const u32 eff = (u32)v < cur ? (u32)v : cur;
-                VirtBlock& b = blk[eff];
-                b.cnt += e[0];
-                if (e[1] < b.F) b.F = e[1];
-                if (e[2] > b.R) b.R = e[2];
-            }
-        };
-        std::vector<VirtBlock> left(K + 1), right(K + 1);
-        const u32 c0 = C0(me);
-        {
-            u32 cur = c0 < (u32)K ? c0 : (u32)K;
-            for (int g = prev_ne(me); g >= 0 && cur > 0; g = prev_ne(g)) {
-                merge(left, g, 0, cur);
-                cur = std::min(cur, std::min(minint(g), C0(g)));
-            }
-        }
-        {
-            int g = next_ne(me);
-            u32 cur = g >= 0 ? std::min<u32>(C0(g), (u32)K) : 0u;
-            while (g >= 0 && cur > 0) {
-                merge(right, g, 1, cur);
-                cur = std::min(cur, minint(g));
-                g = next_ne(g);
-                if (g >= 0) cur = std::min(cur, C0(g));
-            }
-        }
-        // virtual ranks: per block one representative per class (min forward start / max rc start), or a null leaf
-        u32* hv = d->h_pin;                                  // [SA left 64 | LCP left 64 | SA right 64 | LCP right 64 + guard]
-        u32 *sl = hv, *ll = hv + 64, *sr = hv + 128, *lr = hv + 192;
-        for (int i = 0; i < 64; ++i) { sl[i] = NONE_MIN; ll[i] = 0; sr[i] = NONE_MIN; lr[i] = 0; }
-        lr[64] = 0;
-        auto reps_of = [&](const VirtBlock& b, u32 reps[2]) {
-            int k = 0;
-            if (b.F != NONE_MIN) reps[k++] = b.F;
-            if (b.R != 0) reps[k++] = b.R;
-            if (!k) reps[k++] = NONE_MIN;
-            return k;
-        };
-        u32 vl = 0;
-        for (int eff = 1; eff <= K; ++eff) if (left[eff].cnt) { u32 r2[2]; vl += (u32)reps_of(left[eff], r2); }
-        {
-            u32 idx = DIST_VIRT - vl, prev_eff = 0;
-            for (int eff = 1; eff <= K; ++eff) {
-                if (!left[eff].cnt) continue;
-                u32 r2[2];
-                const int k = reps_of(left[eff], r2);
-                for (int j = 0; j < k; ++j) { sl[idx] = r2[j]; ll[idx] = j == 0 ? prev_eff : (u32)eff; ++idx; }
-                prev_eff = (u32)eff;
-            }
-        }
-        u32 vr = 0;
-        for (int eff = K; eff >= 1; --eff) {
-            if (!right[eff].cnt) continue;
-            u32 r2[2];
-            const int k = reps_of(right[eff], r2);
-            for (int j = 0; j < k; ++j) { sr[vr] = r2[j]; lr[vr] = (u32)eff; ++vr; }
-        }
-        lr[vr] = 0;                                          // right guard
-        NLZ_CK(cudaMemcpyAsync(SAbuf, sl, 64 * 4, cudaMemcpyHostToDevice, st));
-        NLZ_CK(cudaMemcpyAsync(LCPbuf, ll, 64 * 4, cudaMemcpyHostToDevice, st));
-        NLZ_CK(cudaMemcpyAsync(w.SA + m_loc, sr, 64 * 4, cudaMemcpyHostToDevice, st));
-        NLZ_CK(cudaMemcpyAsync(w.LCP + m_loc, lr, 65 * 4, cudaMemcpyHostToDevice, st));
-        NLZ_CK(cudaMemcpyAsync(w.LCP, &all[(size_t)me * pay_words], 4, cudaMemcpyHostToDevice, st));   // restore c0
-        n_ext = DIST_VIRT + m_loc + vr;
-
-        // ---- S3b: factor rule in rank space over [virtual | real | virtual]
-        wp.n1 = n_ext;
-        wp.real_lo = DIST_VIRT; wp.real_hi = DIST_VIRT + m_loc;
-        wp.rank_add = (u32)DIST_VIRT - rt.base[me];
-        NLZ_CK(cudaMemsetAsync(HARDF, 0, pb.nfac, st));
-        NLZ_TRY(stage_lpnf(c, pb, st, SAbuf, LCPbuf, wp, w.RANK, LRloc, HARDF));
-        // results to GPU 0: (SA, LR[SA]) of the local ranks in rank order, bulk-copied into its inboxes
-        u64* lval = reinterpret_cast<u64*>(d->seg + d->off_upd) + rt.base[me];
-        KL(P, KC_WALK, (u64)m_loc * 20, st, (k_dist_pack_lr<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(w.SA, m_loc, pb.nfac, LRloc, lval)));
-        if (me != 0) {
-            NLZ_CK(cudaMemcpyAsync(reinterpret_cast<u64*>(d->peer[0] + d->off_upd) + rt.base[me], lval, (size_t)m_loc * 8, cudaMemcpyDefault, st));
-            NLZ_CK(cudaMemcpyAsync(reinterpret_cast<u32*>(d->peer[0] + d->off_pos) + rt.base[me], w.SA, (size_t)m_loc * 4, cudaMemcpyDefault, st));
-        }
-    }
-    NLZ_TRY(dist_barrier(dr, st, nullptr, 0, nullptr));
-    if (me == 0) {
-        u64* LR0 = reinterpret_cast<u64*>(d->seg + d->off_lr);
-        const u64* lval = reinterpret_cast<const u64*>(d->seg + d->off_upd);
-        u32* pos = reinterpret_cast<u32*>(d->seg + d->off_pos);
-        if (m_loc) NLZ_CK(cudaMemcpyAsync(pos, w.SA, (size_t)m_loc * 4, cudaMemcpyDeviceToDevice, st));   // base[0] = 0
-        KL(P, KC_WALK, (u64)n1 * 20, st, (k_dist_apply_lr<<<ceil_div_u32(n1, 256), 256, 0, st>>>(pos, lval, n1, pb.nfac, LR0)));
-    }
-    NLZ_CK(cudaEventRecord(c->ev[EV_LPNF], st));
-
-    // ---- S4: chain on rank 0; the count travels with the closing barrier
-    u64 z = 0;
-    NLZ_CK(cudaMemsetAsync(d_pay, 0, 8, st));
-    // in-process groups may share a device: rank 0's output (re)allocation synchronises that device, so no
-    // other rank may sit in a spinning barrier kernel meanwhile -> host rendezvous around the chain stage
-    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); if (!d->hb->arrive()) { set_error("a rank of the in-process group failed before the chain stage"); return ERR_RUNTIME; } }
-    if (me == 0) {
-        const u64* LR0 = reinterpret_cast<const u64*>(d->seg + d->off_lr);
-        NLZ_TRY(stage_chain(c, pb, st, LR0, cs, nullptr, 0, out_alloc == nullptr, &z));
-        k_set_u32<<<1, 1, 0, st>>>(d_pay, (u32)z);
-    }
-    if (d->hb) { NLZ_CK(cudaStreamSynchronize(st)); if (!d->hb->arrive()) { set_error("rank 0 of the in-process group failed in the chain stage"); return ERR_RUNTIME; } }
-    NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
-    NLZ_TRY(dist_barrier(dr, st, d_pay, 2, all.data()));
-    if (m_loc) account_walk(c);
-    z = all[0];
-    c->stats.n_factors = z;
-    if (me == 0 && out_alloc && z) {
-        u64* dst = static_cast<u64*>(malloc((size_t)z * 24));
-        if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)z); return ERR_RUNTIME; }
-        *out_alloc = dst;
-        NLZ_CK(cudaMemcpyAsync(dst, c->d_out, (size_t)z * 24, cudaMemcpyDeviceToHost, st));
-    }
-    NLZ_CK(cudaStreamSynchronize(st));
-    NLZ_CK(cudaGetLastError());
-    *out_count = z;
     return OK;
 }
 
@@ -1637,6 +1081,9 @@ static int debug_sort(nlz_ctx* c, KeyT* keys, uint32_t* vals, uint64_t m, int lo
     return OK;
 }
 
+// =================================================================== one text across G GPUs
+#include "dist2_host.cuh"
+
 // =================================================================== C ABI
 extern "C" {
 static int ctx_init_impl(nlz_ctx* c);
@@ -1674,8 +1121,10 @@ int nlz_ctx_create(int device, nlz_ctx** out) {
 static int ctx_init_impl(nlz_ctx* c) {
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));   // words [0, 512): readbacks; [512, 1024): pipelined round counts
-    NLZ_CK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
-    NLZ_CK(cudaFuncSetAttribute(k_group_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_tile_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_tile_sort<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
     {
         // First launches of these kernels now, while nothing else runs: the CUDA runtime loads a kernel lazily at
         // its first launch, and that load waits for running kernels.  Inside a distributed doubling round a peer
@@ -1685,9 +1134,12 @@ static int ctx_init_impl(nlz_ctx* c) {
         memset(&so, 0, sizeof(so));
         RankDst rd;
         memset(&rd, 0, sizeof(rd));
-        k_group_stream<<<1, GS_THREADS, GS_SMEM, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
-        k_split_count<<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, 0, 64, nullptr);
-        k_split_apply<<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 64, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
+        k_group_stream<32><<<1, GS_THREADS, GS_SMEM, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_split_count<32><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, 0, 64, nullptr);
+        k_split_apply<32><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 64, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
+        k_group_stream<33><<<1, GS_THREADS, GS_SMEM, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_split_count<33><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, 0, 64, nullptr);
+        k_split_apply<33><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 64, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
         NLZ_CK(cudaStreamSynchronize(c->own_stream));
     }
     for (int i = 0; i < EV_COUNT; ++i) NLZ_CK(cudaEventCreate(&c->ev[i]));
@@ -1853,137 +1305,7 @@ int nlz_factorize_batch(nlz_ctx* c, int with_rc, const uint8_t* concat, const ui
     return OK;
 }
 
-// ---- one text across G GPUs ------------------------------------------------------------------
-static size_t dist_al(size_t b) { return (b + 255) & ~(size_t)255; }
-
-int nlz_dist_create(nlz_ctx* c, int rank, int world, uint64_t max_text_bytes, int max_mode, nlz_dist** out) {
-    if (!c || !out) { set_error("null argument"); return ERR_INVALID; }
-    *out = nullptr;
-    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) { set_error("bad rank %d / world %d (at most %d ranks)", rank, world, MAX_PEERS); return ERR_INVALID; }
-    const u64 max_n1 = (max_mode == NLZ_MODE_DNA_RC ? 2 * max_text_bytes + 2 : max_text_bytes) + 1;
-    if (max_n1 >= 0xFFFFFFF0ull) { set_error("text of %llu symbols exceeds the 32-bit index path of this build", (unsigned long long)max_n1); return ERR_RUNTIME; }
-    std::lock_guard<std::mutex> lock(c->mu);
-    NLZ_CK(cudaSetDevice(c->device));
-    nlz_dist* d = new nlz_dist();
-    d->ctx = c; d->rank = rank; d->world = world; d->max_n1 = max_n1;
-    d->off_x = dist_al(sizeof(DistCtl));
-    d->off_rank = d->off_x + dist_al(max_n1 + 512);
-    d->off_lcp = d->off_rank + dist_al((max_n1 + 72) * 4);
-    d->off_phi = d->off_lcp + dist_al((max_n1 + 2 * DIST_VIRT + 200) * 4);
-    d->off_upd = d->off_phi + dist_al((max_n1 / world + 4096) * 4);
-    d->off_lr = d->off_upd + dist_al((max_n1 + 64) * 8);
-    d->off_pos = d->off_lr + dist_al((max_n1 + 64) * 8);
-    d->seg_bytes = rank == 0 ? d->off_pos + dist_al((max_n1 + 64) * 4) : d->off_lr;
-    cudaError_t e = cudaMalloc(&d->seg, d->seg_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&d->DCNT, (max_n1 / KB_TP + 8) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d->HISTP, ((size_t)(1u << 24) + 8192) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d->SMALL, 1024 * 4);
-    if (e == cudaSuccess) e = cudaMallocHost(&d->h_pin, ((size_t)MAX_PEERS * DIST_XCH_WORDS + 64) * 4);
-    if (e == cudaSuccess) e = cudaMemset(d->seg, 0, d->off_x);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) {
-        set_error("allocating the distributed workspace (%zu bytes shared) failed: %s", d->seg_bytes, cudaGetErrorString(e));
-        cudaGetLastError();
-        nlz_dist_destroy(d);
-        return ERR_CUDA;
-    }
-    d->peer[rank] = d->seg;
-    *out = d;
-    return OK;
-}
-
-void nlz_dist_destroy(nlz_dist* d) {
-    if (!d) return;
-    cudaSetDevice(d->ctx->device);
-    cudaDeviceSynchronize();
-    for (int g = 0; g < MAX_PEERS; ++g) if (d->ipc_opened[g]) cudaIpcCloseMemHandle(d->peer[g]);
-    if (d->seg) cudaFree(d->seg);
-    if (d->DCNT) cudaFree(d->DCNT);
-    if (d->HISTP) cudaFree(d->HISTP);
-    if (d->SMALL) cudaFree(d->SMALL);
-    if (d->arena.base) cudaFree(d->arena.base);
-    if (d->h_pin) cudaFreeHost(d->h_pin);
-    if (d->owns_hb) delete d->hb;
-    cudaGetLastError();
-    delete d;
-}
-
-int nlz_dist_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
-
-int nlz_dist_export(nlz_dist* d, uint8_t* handle_out) {
-    if (!d || !handle_out) { set_error("null argument"); return ERR_INVALID; }
-    NLZ_CK(cudaSetDevice(d->ctx->device));
-    cudaIpcMemHandle_t h;
-    NLZ_CK(cudaIpcGetMemHandle(&h, d->seg));
-    memcpy(handle_out, &h, sizeof(h));
-    return OK;
-}
-
-int nlz_dist_attach(nlz_dist* d, const uint8_t* all_handles) {
-    if (!d || !all_handles) { set_error("null argument"); return ERR_INVALID; }
-    NLZ_CK(cudaSetDevice(d->ctx->device));
-    for (int g = 0; g < d->world; ++g) {
-        if (g == d->rank) continue;
-        cudaIpcMemHandle_t h;
-        memcpy(&h, all_handles + (size_t)g * sizeof(h), sizeof(h));
-        void* p = nullptr;
-        NLZ_CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        d->peer[g] = static_cast<u8*>(p);
-        d->ipc_opened[g] = true;
-    }
-    d->attached = true;
-    return OK;
-}
-
-int nlz_dist_attach_local(nlz_dist* const* ranks, int world) {
-    if (!ranks || world < 1 || world > MAX_PEERS) { set_error("bad local group"); return ERR_INVALID; }
-    HostBarrier* hb = new HostBarrier();
-    hb->world = world;
-    for (int a = 0; a < world; ++a) {
-        nlz_dist* d = ranks[a];
-        if (!d || d->rank != a || d->world != world) { set_error("local group: rank %d is missing or misnumbered", a); delete hb; return ERR_INVALID; }
-        NLZ_CK(cudaSetDevice(d->ctx->device));
-        for (int g = 0; g < world; ++g) {
-            d->peer[g] = ranks[g]->seg;
-            const int dev = ranks[g]->ctx->device;
-            if (dev != d->ctx->device) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
-                    set_error("cannot enable peer access %d -> %d: %s", d->ctx->device, dev, cudaGetErrorString(e));
-                    delete hb;
-                    return ERR_CUDA;
-                }
-                cudaGetLastError();
-            }
-        }
-        d->hb = hb;
-        d->owns_hb = a == 0;
-        d->attached = true;
-    }
-    return OK;
-}
-
-int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples, uint64_t* out_count) {
-    if (!d || !out_count) { set_error("null argument"); return ERR_INVALID; }
-    if (n && !text) { set_error("null text"); return ERR_INVALID; }
-    if (!d->attached && d->world > 1) { set_error("distributed group is not attached"); return ERR_INVALID; }
-    nlz_ctx* c = d->ctx;
-    std::lock_guard<std::mutex> lock(c->mu);
-    NLZ_CK(cudaSetDevice(c->device));
-    *out_count = 0;
-    if (out_triples) *out_triples = nullptr;
-    Problem pb;
-    bool empty = false;
-    NLZ_TRY(make_problem(mode, n, 0, pb, &empty));
-    reset_stats(c);
-    if (empty) return OK;
-    if (pb.n1 > d->max_n1) { set_error("text of %llu suffixes exceeds the group's capacity of %llu", (unsigned long long)pb.n1, (unsigned long long)d->max_n1); return ERR_INVALID; }
-    u64 z = 0;
-    NLZ_TRY(run_dist(d, pb, text, d->rank == 0 ? out_triples : nullptr, &z));
-    finish_stats(c, pb);
-    *out_count = z;
-    return OK;
-}
+// ---- one text across G GPUs: nlz_dist_* live in dist2_host.cuh ---------------------------------
 
 int nlz_factorize(nlz_ctx* c, const uint8_t* t, uint64_t n, uint64_t sp, uint64_t** o, uint64_t* cnt) {
     return nlz_factorize_mode(c, NLZ_MODE_GENERAL, t, n, sp, o, cnt);
@@ -2051,12 +1373,13 @@ int nlz_debug_per_position(nlz_ctx* c, int mode, const uint8_t* text, uint64_t n
     *nfac_out = pb.nfac;
     if (capacity < pb.nfac) { set_error("capacity too small"); return ERR_RUNTIME; }
     std::vector<u64> lr(pb.nfac);
+    std::vector<u8> fl(pb.nfac);
     NLZ_CK(cudaMemcpy(lr.data(), c->ws.KEY[0], (size_t)pb.nfac * 8, cudaMemcpyDeviceToHost));
+    NLZ_CK(cudaMemcpy(fl.data(), c->ws.SLOT[0], (size_t)pb.nfac, cudaMemcpyDeviceToHost));
     for (u32 i = 0; i < pb.nfac; ++i) {
         u32 ref32 = (u32)(lr[i] >> 32);
         if (len_out) len_out[i] = (u32)lr[i];
-        if (ref_out)
-            ref_out[i] = pb.rc ? ((u64)(ref32 & ~LR_RC_FLAG) | ((ref32 & LR_RC_FLAG) ? NLZ_RC_MASK : 0ull)) : (u64)ref32;
+        if (ref_out) ref_out[i] = (u64)ref32 | ((pb.rc && (fl[i] & FLAG_RC)) ? NLZ_RC_MASK : 0ull);
     }
     return OK;
 }

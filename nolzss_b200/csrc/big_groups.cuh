@@ -24,6 +24,7 @@
 #pragma once
 #include "common.cuh"
 #include "sa.cuh"
+#include "tile_sort.cuh"
 
 namespace nlz {
 
@@ -36,18 +37,23 @@ constexpr size_t GS_OFF_MISC = GS_OFF_SIZE + (size_t)GS_OUT_CAP * 2;   // u32[12
 constexpr size_t GS_SMEM = GS_OFF_MISC + 512 + 2 * 64 * 4;        // + big sub-group list: u32 head[64], u32 base[64]
 constexpr u32 GS_MAX_BIGSUB = 64;                                 // outlier sub-groups larger than gcap per group (more: fallback)
 
-__device__ __forceinline__ u32 gs_grp(u64 k) { return (u32)(k >> 32); }
+template <int GS> __device__ __forceinline__ u32 gs_grp(u64 k) { return KeyHalves<GS>::grp(k); }
+// sorted outliers in shared memory: rank << OKV_SHIFT | suffix.  GS = 33 (distributed path): ranks of up to 34 bits,
+// suffixes are local handles below 2^30.
+template <int GS> struct OkvLayout { static constexpr int SHIFT = GS == 32 ? 32 : 30; };
 
 // ---- split of a unified list into S and B (once, when the hybrid rounds start) -------------------------------
 // member j belongs to a group of more than gcap members iff the list position gcap behind its group's head still
 // holds the same group.
+template <int GS>
 __device__ __forceinline__ bool bg_is_big(const u64* __restrict__ key, const u32* __restrict__ slot, u32 m, u32 j, u32 gcap) {
-    const u32 g = gs_grp(key[j]);
+    const u32 g = gs_grp<GS>(key[j]);
     const u32 hj = j - (slot[j] - g);
     const u32 p = hj + gcap;
-    return p < m && gs_grp(key[p]) == g;
+    return p < m && gs_grp<GS>(key[p]) == g;
 }
 
+template <int GS>
 __global__ void __launch_bounds__(RG_THREADS)
 k_split_count(const u64* __restrict__ key, const u32* __restrict__ slot, u32 m, u32 gcap, u32* __restrict__ psum) {
     __shared__ u32 ws[33];
@@ -56,7 +62,7 @@ k_split_count(const u64* __restrict__ key, const u32* __restrict__ slot, u32 m, 
 #pragma unroll
     for (int t = 0; t < RG_ITEMS; ++t) {
         const u64 e = tile_start + (u64)t * RG_THREADS + threadIdx.x;
-        if (e < m && bg_is_big(key, slot, m, (u32)e, gcap)) ++c;
+        if (e < m && bg_is_big<GS>(key, slot, m, (u32)e, gcap)) ++c;
     }
     u32 total;
     cta_excl_scan(c, ws, total);
@@ -64,6 +70,7 @@ k_split_count(const u64* __restrict__ key, const u32* __restrict__ slot, u32 m, 
 }
 
 // stable partition: small-group members to [0, mS), big-group members to [end - mB, end); mB = *mB_dev
+template <int GS>
 __global__ void __launch_bounds__(RG_THREADS)
 k_split_apply(const u64* __restrict__ key, const u32* __restrict__ val, const u32* __restrict__ slot, u32 m, u32 gcap,
               const u32* __restrict__ psum, const u32* __restrict__ mB_dev, u32 end,
@@ -77,7 +84,7 @@ k_split_apply(const u64* __restrict__ key, const u32* __restrict__ val, const u3
 #pragma unroll
     for (int q = 0; q < RG_ITEMS; ++q) {
         const u32 e = i0 + q;
-        big[q] = e < m && bg_is_big(key, slot, m, e, gcap);
+        big[q] = e < m && bg_is_big<GS>(key, slot, m, e, gcap);
         c += big[q] ? 1u : 0u;
     }
     u32 total;
@@ -106,6 +113,7 @@ struct StreamOut {
     u32* fallback;                                  // set when a group cannot be handled here
 };
 
+template <int GS>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in,
                u32 b0, u32 mB, u32 gcap, u32* __restrict__ SA, RankDst RANK, StreamOut out, int dbg) {
@@ -114,6 +122,11 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     unsigned short* ohead = reinterpret_cast<unsigned short*>(gs_smem + GS_OFF_HEAD);
     unsigned short* osize = reinterpret_cast<unsigned short*>(gs_smem + GS_OFF_SIZE);
     u32* misc = reinterpret_cast<u32*>(gs_smem + GS_OFF_MISC);
+    using KH = KeyHalves<GS>;
+    using RT = typename KH::RT;
+    constexpr int OS = OkvLayout<GS>::SHIFT;
+    constexpr u64 OMASK = (1ull << OS) - 1;
+    __shared__ unsigned long long s_piv;
     u32& s_head = misc[0];
     u32& s_probe = misc[1];
     u32& s_endpos = misc[2];
@@ -138,16 +151,16 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     if (tid == 0) { s_head = 0xFFFFFFFFu; s_probe = 0xFFFFFFFFu; s_endpos = 0xFFFFFFFFu; s_nout = 0; s_nlt = 0; s_eq = 0; s_nbig = 0; }
     __syncthreads();
     for (u32 j = c0 + tid; j < c1; j += GS_THREADS)
-        if (j == b0 || gs_grp(key_in[j - 1]) != gs_grp(key_in[j])) s_head = j;    // at most one head per chunk
+        if (j == b0 || gs_grp<GS>(key_in[j - 1]) != gs_grp<GS>(key_in[j])) s_head = j;    // at most one head per chunk
     __syncthreads();
     const u32 head = s_head;
     if (head == 0xFFFFFFFFu) return;
-    const u32 g = gs_grp(key_in[head]);        // the group's rank: a slot inside the group's slot range (see below)
+    const u32 g = gs_grp<GS>(key_in[head]);        // the group's rank: a slot inside the group's slot range (see below)
     const u32 gbase = slot_in[head];            // first slot of the group
     // group end: first probe position (head + t * gcap) outside the group, then the exact end inside that stride
     for (u32 tb = 0;; tb += GS_THREADS) {
         const u64 p = (u64)head + (u64)(tb + tid + 1) * gcap;
-        const bool outside = p >= bend || gs_grp(key_in[p]) != g;
+        const bool outside = p >= bend || gs_grp<GS>(key_in[p]) != g;
         if (outside) atomicMin(&s_probe, tb + tid + 1);
         __syncthreads();
         if (s_probe != 0xFFFFFFFFu) break;
@@ -158,7 +171,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
         const u64 lo = (u64)head + (u64)(t - 1) * gcap + 1;
         for (u32 o = tid; o < gcap; o += GS_THREADS) {
             const u64 p = lo + o;
-            if (p >= bend || gs_grp(key_in[p]) != g) atomicMin(&s_endpos, (u32)(p < bend ? p : bend));
+            if (p >= bend || gs_grp<GS>(key_in[p]) != g) atomicMin(&s_endpos, (u32)(p < bend ? p : bend));
         }
         __syncthreads();
     }
@@ -168,22 +181,22 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     // group are in no particular order after a streamed round, and a pivot that is itself an outlier turns the whole
     // group into outliers -- more than fit in shared memory.)
     if (tid < 32) {
-        const u32 k2 = (u32)key_in[head + (u32)(((u64)M * lane) >> 5)];
+        const RT k2 = KH::rank(key_in[head + (u32)(((u64)M * lane) >> 5)]);
         const u32 votes = __popc(__match_any_sync(0xffffffffu, k2));
         const u32 best = __reduce_max_sync(0xffffffffu, votes);
         const u32 who = __ffs(__ballot_sync(0xffffffffu, votes == best)) - 1;
-        const u32 pv = __shfl_sync(0xffffffffu, k2, who);
-        if (lane == 0) s_probe = pv;
+        const RT pv = __shfl_sync(0xffffffffu, k2, who);
+        if (lane == 0) s_piv = (unsigned long long)pv;
     }
     __syncthreads();
-    const u32 piv = s_probe;
+    const RT piv = (RT)s_piv;
     // ---- pass A: outliers to shared memory, members below the pivot counted
     for (u32 jb = head; jb < gend; jb += GS_THREADS) {
         const u32 j = jb + tid;
         bool outl = false, less = false;
-        u32 k2 = 0;
+        RT k2 = 0;
         if (j < gend) {
-            k2 = (u32)key_in[j];
+            k2 = KH::rank(key_in[j]);
             outl = k2 != piv;
             less = k2 < piv;
         }
@@ -195,7 +208,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
             base = __shfl_sync(0xffffffffu, base, 0);
             if (outl) {
                 const u32 q = base + __popc(om & lanemask_lt());
-                if (q < GS_OUT_CAP) okv[q] = ((u64)k2 << 32) | (u64)val_in[j];
+                if (q < GS_OUT_CAP) okv[q] = ((u64)k2 << OS) | (u64)val_in[j];
             }
         }
     }
@@ -235,7 +248,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
         for (u32 i = 0; i < PER; ++i) {
             const u32 q = q0 + i;
             if (q < nout) {
-                const bool hd = q == 0 || q == nlt || (u32)(okv[q] >> 32) != (u32)(okv[q - 1] >> 32);
+                const bool hd = q == 0 || q == nlt || (okv[q] >> OS) != (okv[q - 1] >> OS);
                 if (hd) run = q + 1;
             }
             loc[i] = run;
@@ -265,7 +278,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
         for (u32 i = 0; i < PER; ++i) {
             const u32 q = q0 + i;
             if (q < nout) {
-                const bool last = q + 1 == nout || q + 1 == nlt || (u32)(okv[q + 1] >> 32) != (u32)(okv[q] >> 32);
+                const bool last = q + 1 == nout || q + 1 == nlt || (okv[q + 1] >> OS) != (okv[q] >> OS);
                 if (last) {
                     const u32 hq = ohead[q], sz = q - hq + 1;
                     osize[hq] = (unsigned short)sz;
@@ -345,14 +358,14 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
             const u32 q = q0 + i;
             if (q >= nout) break;
             const u64 kv = okv[q];
-            const u32 s = (u32)kv;
+            const u32 s = (u32)(kv & OMASK);
             const u32 hq = ohead[q], sz = osize[hq];
             const u32 pos = q < nlt ? q : neq + q;                  // position inside the group
             const u32 hpos = hq < nlt ? hq : neq + hq;
             const u32 slot = gbase + pos, newrank = gbase + hpos;
             SA[slot - RANK.base] = s;
             if (newrank != g) {
-                RANK.rank[s] = newrank;
+                if (RANK.rank) RANK.rank[s] = newrank;
                 // record index: rank among the changed outliers (sorted order minus the sub-group that kept the rank)
                 if (RANK.upd) RANK.upd[baseU + (q - ((qu != 0xFFFFFFFFu && q >= qu + usz) ? usz : 0u))] = ((u64)newrank << 32) | (u64)s;
             }
@@ -364,7 +377,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
                     while (big_head[k] != hq) ++k;
                     dst = big_base[k] + (q - hq);
                 }
-                out.key_next[dst] = (u64)newrank << 32;
+                out.key_next[dst] = (u64)newrank << GS;
                 out.val_next[dst] = s;
                 out.slot_next[dst] = slot;
             }
@@ -378,7 +391,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
         for (u32 jb = head; jb < gend; jb += GS_THREADS) {
             const u32 j = jb + tid;
             bool eq = false;
-            if (j < gend) eq = (u32)key_in[j] == piv;
+            if (j < gend) eq = KH::rank(key_in[j]) == piv;
             const u32 em = __ballot_sync(0xffffffffu, eq);
             if (!em) continue;
             u32 base = 0;
@@ -390,13 +403,13 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
                 const u32 slot = slot0 + e;
                 SA[slot - RANK.base] = s;
                 if (changed) {
-                    RANK.rank[s] = newrank;
+                    if (RANK.rank) RANK.rank[s] = newrank;
                     // records: [changed outliers | pivot block]
                     if (RANK.upd) RANK.upd[baseU + (nout - usz) + e] = ((u64)newrank << 32) | (u64)s;
                 }
                 if (eq_act) {
                     const u32 dst = baseEq + e;
-                    out.key_next[dst] = (u64)newrank << 32;
+                    out.key_next[dst] = (u64)newrank << GS;
                     out.val_next[dst] = s;
                     out.slot_next[dst] = slot;
                 }

@@ -56,19 +56,23 @@ __device__ __forceinline__ u32 warp_extend_match(const u64* __restrict__ xw, u64
 //    LCP_LOCAL_WORDS words hands the comparison to its warp.
 // BATCH: suffixes of different records share nothing, and a match stops at the sentinel that ends
 // either segment (batch sentinels all carry the same byte, so the raw compare alone would run on).
-// DIST (one text across GPUs, dist.cuh): this GPU owns the text positions [pos0, pos1).  PHI[i - pos0] =
-// SA[RANK[i] - 1] arrives from the owners of the ranks; the result overwrites it in place (PLCP, text order)
-// and is sent to the owners of the ranks afterwards (bucketed pair exchange).
-struct LcpDist {
-    u32* PHI;
-    u32 pos0, pos1;
-    __device__ __forceinline__ void store(u64 i, u32 l) const { PHI[i - pos0] = l; }
+// DIST (one text across GPUs, dist2.cuh): this GPU owns the text positions [pos0, pos1) and the slice of RANK that
+// belongs to them (global ranks, PT = u64: up to 33 bits).  PHI[i - pos0] = SA[RANK[i] - 1] (an S-position, PT) arrives
+// from the owners of the ranks; the result goes to PLCP (text order) and is sent to the owners of the ranks
+// afterwards (bucketed exchange).
+template <typename PT>
+struct LcpDistT {
+    const PT* PHI;
+    u32* PLCP;
+    u64 pos0, pos1;
+    __device__ __forceinline__ void store(u64 i, u32 l) const { PLCP[i - pos0] = l; }
 };
+using LcpDist = LcpDistT<u32>;
 
-template <bool BATCH, bool DIST>
+template <bool BATCH, bool DIST, typename PT = u32>
 __global__ void __launch_bounds__(256)
-k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
-            const u32* __restrict__ RANK, u32* __restrict__ LCP, BatchView bv, LcpDist ld) {
+k_lcp_kasai(const u8* __restrict__ x, u64 L, u64 n1, const u32* __restrict__ SA,
+            const PT* __restrict__ RANK, u32* __restrict__ LCP, BatchView bv, LcpDistT<PT> ld) {
     const u64* xw = reinterpret_cast<const u64*>(x);
     const u32 lane = threadIdx.x & 31;
     const u64 c = (u64)blockIdx.x * 256 + threadIdx.x;
@@ -80,17 +84,19 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
 #pragma unroll 1
     for (int k = 0; k < LCP_Q; ++k) {
         const u64 i = i0 + k;
-        u32 r = 0, j = 0, maxl = 0;
+        PT r = 0, j = 0;
+        u32 maxl = 0;
         bool need = false;
         if (i < n1) {
-            r = RANK[i];
+            r = RANK[DIST ? i - ld.pos0 : i];
             if (r == 0) { if (DIST) ld.store(i, 0); else LCP[0] = 0; l = 0; }
             else {
-                j = DIST ? ld.PHI[i - ld.pos0] : SA[r - 1];
-                maxl = (u32)(L - (i > j ? i : (u64)j));
+                j = DIST ? ld.PHI[i - ld.pos0] : (PT)SA[r - 1];
+                const u64 room = L - (i > (u64)j ? i : (u64)j);
+                maxl = room > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)room;     // a match ends at a unique sentinel: < 2^32 anyway
                 if (BATCH) {
                     if (bv.REC[i] != bv.REC[j]) maxl = 0;
-                    else maxl = min(maxl, min(batch_cap(bv, (u32)i), batch_cap(bv, j)));
+                    else maxl = min(maxl, min(batch_cap(bv, (u32)i), batch_cap(bv, (u32)j)));
                 }
                 if (l > maxl) l = maxl;
                 need = true;
@@ -101,7 +107,7 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
 #pragma unroll 1
             for (int src = 0; src < 32; ++src) {
                 const u64 a = __shfl_sync(0xffffffffu, i, src);
-                const u64 b = (u64)__shfl_sync(0xffffffffu, j, src);
+                const u64 b = __shfl_sync(0xffffffffu, (u64)j, src);
                 const u32 ml = __shfl_sync(0xffffffffu, maxl, src);
                 const bool nd = __shfl_sync(0xffffffffu, need ? 1u : 0u, src) != 0;
                 u32 res = 0;
@@ -140,7 +146,7 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u32 n1, const u32* __restrict__ SA,
             while (pending) {
                 const int src = __ffs(pending) - 1;
                 const u64 a = __shfl_sync(0xffffffffu, i, src);
-                const u64 b = (u64)__shfl_sync(0xffffffffu, j, src);
+                const u64 b = __shfl_sync(0xffffffffu, (u64)j, src);
                 const u32 l0 = __shfl_sync(0xffffffffu, l, src);
                 const u32 ml = __shfl_sync(0xffffffffu, maxl, src);
                 const u32 res = warp_extend_match(xw, a, b, l0, ml, lane);

@@ -52,8 +52,8 @@ struct Trees {
     int nlev;                          // number of levels including level 0
     const u32* lcp[TREE_MAX_LEVELS];   // lcp[0] = LCP (n1+1 entries), lcp[t] = block minima
     u32 cntL[TREE_MAX_LEVELS];
-    const u32* f[TREE_MAX_LEVELS];     // f[0] = SA; f[t] = block min of F-class values
-    const u32* r[TREE_MAX_LEVELS];     // r[t] = block max of R-class values (RC mode only)
+    const u32* f[TREE_MAX_LEVELS];     // f[0] = F0 (leaf values, see k_leaf_values); f[t] = block min of F-class values
+    const u32* r[TREE_MAX_LEVELS];     // r[0] = R0; r[t] = block max of R-class values (RC mode only)
     u32 cntS[TREE_MAX_LEVELS];
 };
 
@@ -68,19 +68,35 @@ struct WalkParams {
     u32 real_lo, real_hi, rank_add;
 };
 
-template <bool RC> __device__ __forceinline__ u32 f_value(u32 s, const WalkParams& p) {
-    return RC ? (s < p.N ? s : NONE_MIN) : s;
+// Leaf values.  Every rank k carries two 32-bit values derived from its suffix start s = SA[k] (an S-position, up
+// to 33 bits on the wide distributed path -- which is why stage 3 never reads SA itself):
+//   F0[k]  forward class: the T-coordinate s          (general mode: every s; RC mode: s < N), else NONE_MIN
+//   R0[k]  rc class (RC mode, N < s <= 2N):  s - N in [1, N]  -- larger = smaller T-end e = 2N - s = N - R0;  0 = none
+// T-coordinates stay below 2^32 for any text this build takes (nfac <= 0xFFFFFFF0), so the node tables, the summary
+// trees and the per-position results are 32-bit on every path.
+template <bool RC> __device__ __forceinline__ u32 f_value(u64 s, const WalkParams& p) {
+    return RC ? (s < (u64)p.N ? (u32)s : NONE_MIN) : (u32)s;
 }
-__device__ __forceinline__ u32 r_value(u32 s, const WalkParams& p) {
-    return (s > p.N && s <= p.twoN) ? s : 0u;   // 0 = none (valid values are >= N+1 >= 1)
+__device__ __forceinline__ u32 r_value(u64 s, const WalkParams& p) {
+    return (s > (u64)p.N && s <= 2ull * p.N) ? (u32)(s - p.N) : 0u;
+}
+// SAT = u32 (one GPU) or u64 (distributed, S-positions).  F0 may alias SA when SAT is u32 (in-place conversion).
+template <bool RC, typename SAT>
+__global__ void __launch_bounds__(256)
+k_leaf_values(const SAT* SA, u32 cnt, WalkParams p, u32* F0, u32* __restrict__ R0) {
+    const u32 k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= cnt) return;
+    const u64 s = (u64)SA[k];
+    F0[k] = f_value<RC>(s, p);
+    if (RC) R0[k] = r_value(s, p);
 }
 
 // ---- tree construction ----------------------------------------------------------------------
 // level-1 nodes from level 0: LCP minima and, from SA, F minima / R maxima.
 template <bool RC>
 __global__ void __launch_bounds__(256)
-k_tree_level1(const u32* __restrict__ LCP, u32 cntL0, const u32* __restrict__ SA, u32 cntS0,
-              WalkParams p, u32* __restrict__ lcp1, u32 cntL1, u32* __restrict__ f1,
+k_tree_level1(const u32* __restrict__ LCP, u32 cntL0, const u32* __restrict__ F0, const u32* __restrict__ R0, u32 cntS0,
+              u32* __restrict__ lcp1, u32 cntL1, u32* __restrict__ f1,
               u32* __restrict__ r1, u32 cntS1) {
     // one warp per node: coalesced 128-byte line, shuffle reduction
     const u32 node = (blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -95,9 +111,8 @@ k_tree_level1(const u32* __restrict__ LCP, u32 cntL0, const u32* __restrict__ SA
     if (node < cntS1) {
         u32 fv = NONE_MIN, rv = 0;
         if (e < cntS0) {
-            u32 s = SA[e];
-            fv = f_value<RC>(s, p);
-            if (RC) rv = r_value(s, p);
+            fv = F0[e];
+            if (RC) rv = R0[e];
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
@@ -262,7 +277,7 @@ __device__ __forceinline__ u32 find_next_less(const Trees& T, u32 pos, u32 d) {
 }
 
 __device__ __forceinline__ u32 r_node(const Trees& T, const WalkParams& p, int lev, i64 j) {
-    return lev == 0 ? r_value(T.f[0][j], p) : T.r[lev][j];
+    return T.r[lev][j];
 }
 // largest k <= q with r_value(SA[k]) > thr, or -1 (scalar; fallback of the RC neighbour hop)
 __device__ __forceinline__ i64 find_prev_r_greater(const Trees& T, const WalkParams& p, i64 q, u32 thr) {
@@ -329,16 +344,7 @@ __device__ __forceinline__ void agg_line(const Trees& T, const WalkParams& p, in
         const uint4 xf = __ldg(reinterpret_cast<const uint4*>(T.f[lev] + gstart) + q);
         const u32 fv4[4] = {xf.x, xf.y, xf.z, xf.w};
         u32 fv = NONE_MIN, rv = 0;
-        if (lev == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const u32 k = 4 * q + j;
-                if (k >= lob && k <= hib) {
-                    fv = min(fv, f_value<RC>(fv4[j], p));
-                    if (WANT_R) rv = max(rv, r_value(fv4[j], p));
-                }
-            }
-        } else {
+        {
             uint4 xr = make_uint4(0, 0, 0, 0);
             if (WANT_R) xr = __ldg(reinterpret_cast<const uint4*>(T.r[lev] + gstart) + q);
             const u32 rv4[4] = {xr.x, xr.y, xr.z, xr.w};
@@ -355,14 +361,7 @@ __device__ __forceinline__ void agg_line(const Trees& T, const WalkParams& p, in
         if (WANT_R) rmax = max(rmax, cg::reduce(t, rv, cg::greater<u32>()));
         return;
     }
-    if (lev == 0) {
-        const u32* sa = T.f[0] + gstart;
-        for (u32 k = lob; k <= hib; ++k) {
-            const u32 s = sa[k];
-            fmin = min(fmin, f_value<RC>(s, p));
-            if (WANT_R) rmax = max(rmax, r_value(s, p));
-        }
-    } else {
+    {
         const u32* fa = T.f[lev] + gstart;
         const u32* ra = T.r[lev] + gstart;
         for (u32 k = lob; k <= hib; ++k) {
@@ -423,21 +422,20 @@ __device__ __forceinline__ RnState rn_combine(RnState a, RnState b) {   // a the
     else { o.idx = a.idx; o.mn = min(a.mn, b.mn); }
     return o;
 }
-__device__ __forceinline__ bool is_r_class(u32 s, const WalkParams& p) { return s > p.N && s <= p.twoN; }
 
 // element e of the scan in direction DIR (0: left-to-right over k, 1: right-to-left)
 template <int DIR>
-__device__ __forceinline__ RnState rn_element(const u32* __restrict__ SA, const u32* __restrict__ LCP, u32 k,
+__device__ __forceinline__ RnState rn_element(const u32* __restrict__ R0, const u32* __restrict__ LCP, u32 k,
                                               const WalkParams& p) {
     RnState e;
-    if (is_r_class(SA[k], p)) { e.idx = k; e.mn = NONE_MIN; }
+    if (R0[k] != 0) { e.idx = k; e.mn = NONE_MIN; }
     else { e.idx = NONE_MIN; e.mn = DIR == 0 ? LCP[k] : LCP[k + 1]; }
     return e;
 }
 
 template <int DIR>
 __global__ void __launch_bounds__(RN_THREADS)
-k_rnear_reduce(const u32* __restrict__ SA, const u32* __restrict__ LCP, WalkParams p, u32* __restrict__ tile_idx,
+k_rnear_reduce(const u32* __restrict__ R0, const u32* __restrict__ LCP, WalkParams p, u32* __restrict__ tile_idx,
                u32* __restrict__ tile_mn) {
     __shared__ RnState wagg[RN_THREADS / 32];
     const u32 n1 = p.n1;
@@ -448,7 +446,7 @@ k_rnear_reduce(const u32* __restrict__ SA, const u32* __restrict__ LCP, WalkPara
         const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;     // scan position
         if (o < n1) {
             const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
-            acc = rn_combine(acc, rn_element<DIR>(SA, LCP, k, p));
+            acc = rn_combine(acc, rn_element<DIR>(R0, LCP, k, p));
         }
     }
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -505,7 +503,7 @@ k_rnear_scan_tiles(u32* __restrict__ tile_idx, u32* __restrict__ tile_mn, u32 nt
 
 template <int DIR>
 __global__ void __launch_bounds__(RN_THREADS)
-k_rnear_apply(const u32* __restrict__ SA, const u32* __restrict__ LCP, WalkParams p, const u32* __restrict__ tile_idx,
+k_rnear_apply(const u32* __restrict__ R0, const u32* __restrict__ LCP, WalkParams p, const u32* __restrict__ tile_idx,
               const u32* __restrict__ tile_mn, u32* __restrict__ out_idx, u32* __restrict__ out_mn) {
     __shared__ RnState wagg[RN_THREADS / 32];
     const u32 n1 = p.n1;
@@ -518,7 +516,7 @@ k_rnear_apply(const u32* __restrict__ SA, const u32* __restrict__ LCP, WalkParam
         el[q].idx = NONE_MIN; el[q].mn = NONE_MIN;
         if (o < n1) {
             const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
-            el[q] = rn_element<DIR>(SA, LCP, k, p);
+            el[q] = rn_element<DIR>(R0, LCP, k, p);
             acc = rn_combine(acc, el[q]);
         }
     }
@@ -561,7 +559,7 @@ struct RNear {
 constexpr int RHOP_MAX = 24;
 template <int DIR>
 __device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p, const RNear& rn, u32 r, u32 thr) {
-    const u32* SA = T.f[0];
+    const u32* R0 = T.r[0];
     const u32* LCP = T.lcp[0];
     u32 k = r;            // current rank (start: the F-class leaf itself)
     u32 run = NONE_MIN;   // min LCP between k and r
@@ -586,7 +584,7 @@ __device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p
             k = tgt;
         }
         if (run == 0) return 0;                       // left the last non-root ancestor
-        if (SA[k] > thr) return run;                  // rc rank (<= 2N by construction) that qualifies
+        if (R0[k] > thr) return run;                  // rc rank whose T-end N - R0 lies before i
     }
     // rare: many non-qualifying rc suffixes in a row -> summary-tree search from k
     if (DIR == 0) {
@@ -600,8 +598,10 @@ __device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p
 }
 
 // ---- the factor rule ------------------------------------------------------------------------
-// LR[i] = (ref | rc_flag<<31) << 32 | len        for every factorized position i
-constexpr u32 LR_RC_FLAG = 0x80000000u;
+// LR[i] = ref << 32 | len for every factorized position i; FLAGS[i] (one byte): bit 0 = "hard" (left to k_lpnf_hard),
+// bit 1 = the factor is a reverse-complement one.  (ref and len both need 32 bits at genome scale -- refs of a 3.1 Gbp
+// text exceed 2^31 -- so the RC flag cannot ride in either.)
+constexpr u8 FLAG_HARD = 1, FLAG_RC = 2;
 constexpr int WALK_MAX_NODES = 512;    // default: ancestors climbed in rank order before a position is "hard" (250 Mbp text: 2048 -> 512 saves 15 ms of failed climbs; the 5 Mbp text never exceeds 500)
 constexpr int WALK_Q = 32;             // consecutive text positions per 8-lane tile in k_lpnf_hard (the carried bound
                                        // links them: the first one pays a full bisection, the others 2-3 probes)
@@ -636,8 +636,9 @@ __device__ __forceinline__ bool pred_f(const NodeState& s, u32 D, u32 i) {
 // node, :290-299) is a range max over interval(dR) and is only evaluated when the RC candidate wins.
 template <bool RC, bool VEC>
 __device__ __forceinline__ u64 select_factor(const Trees& T, const WalkParams& p, u32 r, u32 i, bool have_f,
-                                             u32 fwd_len, u32 jF, u32 gen_len, u32 gen_ref, u32 dR) {
+                                             u32 fwd_len, u32 jF, u32 gen_len, u32 gen_ref, u32 dR, bool& is_rc) {
     u32 len, ref;
+    is_rc = false;
     if (!RC) {
         if (gen_len >= 1) { len = gen_len; ref = gen_ref; }
         else { len = 1; ref = i; }
@@ -653,9 +654,10 @@ __device__ __forceinline__ u64 select_factor(const Trees& T, const WalkParams& p
             NodeState leaf;
             leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
             const u32 mR = extend_to<RC, true, VEC>(T, p, leaf, dR).R;
-            const u32 e = p.twoN - mR;                           // smallest RC end in T coordinates
+            const u32 e = p.N - mR;                              // smallest RC end in T coordinates (R0 = s - N, e = 2N - s)
             len = rc_len;
-            ref = (e - rc_len + 1) | LR_RC_FLAG;                 // :362-364 (start-anchored + RC flag)
+            ref = e - rc_len + 1;                                // :362-364 (start-anchored; the RC flag travels in the flag plane)
+            is_rc = true;
         }
     }
     return ((u64)ref << 32) | (u64)len;
@@ -690,14 +692,14 @@ k_node_tables(Trees T, WalkParams p, uint4* __restrict__ NODE) {
 constexpr int FR_TILE = 2048;
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_forward_ranks(const u32* __restrict__ SA, WalkParams p, u32* __restrict__ cta_off, u32* __restrict__ list) {
+k_forward_ranks(const u32* __restrict__ F0, WalkParams p, u32* __restrict__ cta_off, u32* __restrict__ list) {
     __shared__ u32 wcnt[8];
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 run = MODE == 2 ? cta_off[blockIdx.x] : 0u;
 #pragma unroll 1
     for (int t = 0; t < FR_TILE / 256; ++t) {
         const u32 r = blockIdx.x * FR_TILE + t * 256 + threadIdx.x;
-        const bool keep = r >= p.real_lo && r < p.real_hi && SA[r] < p.nfac;
+        const bool keep = r >= p.real_lo && r < p.real_hi && F0[r] < p.nfac;
         const u32 bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) wcnt[w] = __popc(bal);
         __syncthreads();
@@ -712,19 +714,24 @@ k_forward_ranks(const u32* __restrict__ SA, WalkParams p, u32* __restrict__ cta_
 }
 
 // ---- kernel 1: rank order ---------------------------------------------------------------------
-template <bool RC>
+// BYLIST (distributed runs): results are indexed by the thread's work index t (the position in the compacted list of
+// forward ranks, or r - real_lo without a list) instead of by the text position -- the text positions of a rank range
+// are scattered over the whole text, and the results travel to their position owners as (position, value) records.
+template <bool RC, bool BYLIST>
 __global__ void __launch_bounds__(256, 8)   // 32 registers: 8 CTAs per SM (the kernel is latency-bound; 40 registers cost 14 %)
 k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, const u32* __restrict__ list,
             const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
             unsigned long long* __restrict__ counters) {
-    u32 r = blockIdx.x * 256 + threadIdx.x;
-    if (list) r = r < *nlist ? list[r] : 0xFFFFFFFFu;       // compacted forward ranks (RC mode)
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    u32 r = list ? 0xFFFFFFFFu : t + (BYLIST ? p.real_lo : 0u);
+    if (list && t < *nlist) r = list[t];                    // compacted forward ranks (RC mode)
     u32 visited = 0, hard = 0;
     const u32* LCP = T.lcp[0];
-    const u32* SA = T.f[0];
+    const u32* F0 = T.f[0];
     u32 i = 0xFFFFFFFFu;
-    if (r >= p.real_lo && r < p.real_hi) i = SA[r];         // r = 0xFFFFFFFF: no work
+    if (r >= p.real_lo && r < p.real_hi) i = F0[r];         // r = 0xFFFFFFFF: no work
     if (i < p.nfac) {
+        const u32 o = BYLIST ? t : i;                       // where this position's results go
         bool have_f = false, at_root = false;
         u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
         u32 childF = i;                  // F-min of the last node that failed (starts at the leaf)
@@ -749,7 +756,7 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, con
         }
         u32 dR = 0;
         if (RC) {
-            const u32 thr = p.twoN - i;
+            const u32 thr = p.N - i;                        // an rc suffix qualifies when its T-end N - R0 is < i
             dR = max(rc_side_depth<0>(T, p, rn, r, thr), rc_side_depth<1>(T, p, rn, r, thr));
             visited += 2;
         }
@@ -765,8 +772,9 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, con
                 gen_len = (v_min != i) ? i - v_min : 0;                 // :96-107 with u = root, or literal
                 gen_ref = v_min;
             }
-            LR[i] = select_factor<RC, false>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
-            HARD[i] = 0;
+            bool is_rc;
+            LR[o] = select_factor<RC, false>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR, is_rc);
+            HARD[o] = is_rc ? FLAG_RC : 0;
         } else {
             // Park the RC candidate depth for k_lpnf_hard, and a depth that is KNOWN to satisfy the forward predicate:
             // the last ancestor A that failed has minF(A) + depth(A) > i, and every D < depth(A) has interval(D)
@@ -775,8 +783,8 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, con
             // so the depth search of k_lpnf_hard starts two probes away from it even without a carried bound
             // (distributed runs: neighbouring positions live on other GPUs).
             const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
-            LR[i] = ((u64)lb0 << 32) | (u64)dR;
-            HARD[i] = 1;
+            LR[o] = ((u64)lb0 << 32) | (u64)dR;
+            HARD[o] = FLAG_HARD;
             hard = 1;
         }
     }
@@ -820,20 +828,25 @@ __device__ __forceinline__ u32 depth_search(const Trees& T, const WalkParams& p,
     return loD;
 }
 
-template <bool RC>
+// BYLIST (distributed runs): the work items are the entries of k_lpnf_rank's list (rank order; `nwork` of them, or
+// *nlist), the leaf is list[t] and no RANK lookup is needed; consecutive items are unrelated text positions, so there is
+// no carried bound -- the search starts from the depth k_lpnf_rank parked.
+template <bool RC, bool BYLIST>
 __global__ void __launch_bounds__(256)
-k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict__ LR,
-            const u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
+k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, const u32* __restrict__ list, const u32* __restrict__ nlist,
+            u32 nwork, u64* __restrict__ LR, u8* __restrict__ HARD, unsigned long long* __restrict__ counters) {
     const Tile8 t8 = tile8();
     const u64 tile_id = ((u64)blockIdx.x * 256 + threadIdx.x) >> 3;
     const u64 i0 = tile_id * WALK_Q;
-    if (i0 >= p.nfac) return;                                   // tile-uniform
+    if (BYLIST && nlist) nwork = *nlist;
+    const u64 bound = BYLIST ? (u64)nwork : (u64)p.nfac;
+    if (i0 >= bound) return;                                    // tile-uniform
     const u32 q = t8.thread_rank();
-    u32 todo = 0;                                               // bit k: position i0 + k is hard
+    u32 todo = 0;                                               // bit k: item i0 + k is hard
 #pragma unroll
     for (int j = 0; j < WALK_Q / 8; ++j) {
         const u64 ii = i0 + (u64)(j * 8) + q;
-        todo |= t8.ballot(ii < p.nfac && HARD[ii] != 0) << (8 * j);
+        todo |= t8.ballot(ii < bound && (HARD[ii] & FLAG_HARD) != 0) << (8 * j);
     }
     if (!todo) return;
     const u32* LCP = T.lcp[0];
@@ -843,14 +856,15 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict
     while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        if (k != prev_k + 1) prevF = 0;                          // the carry only links consecutive positions
+        if (BYLIST || k != prev_k + 1) prevF = 0;                // the carry only links consecutive positions
         prev_k = k;
-        const u32 i = (u32)(i0 + k);
-        const u32 r = __ldg(RANK + i) + p.rank_add;
+        const u32 o = (u32)(i0 + k);                             // where the item's results live
+        const u32 r = BYLIST ? (list ? __ldg(list + o) : o + p.real_lo) : __ldg(RANK + o) + p.rank_add;
+        const u32 i = BYLIST ? __ldg(T.f[0] + r) : o;
         NodeState leaf;
         leaf.lo = r; leaf.hi = r; leaf.F = i; leaf.R = 0;
         const u32 Dtop = max(__ldg(LCP + r), __ldg(LCP + r + 1)) + 1;   // deeper than the leaf's parent nothing matches
-        const u64 parked = LR[i];                                // {depth known to hold, RC candidate depth} from k_lpnf_rank
+        const u64 parked = LR[o];                                // {depth known to hold, RC candidate depth} from k_lpnf_rank
         u32 lb = prevF > 0 ? prevF - 1 : 0;                      // Kasai-style lower bound (known to hold)
         lb = max(lb, (u32)(parked >> 32));
         NodeState U = leaf, L = leaf;
@@ -894,9 +908,10 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, u64* __restrict
             }
         }
         const u32 dR = (u32)parked;
-        const u64 lr = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR);
+        bool is_rc;
+        const u64 lr = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR, is_rc);
         t8.sync();                                               // every lane has read the parked value
-        if (q == 0) LR[i] = lr;
+        if (q == 0) { LR[o] = lr; HARD[o] = is_rc ? FLAG_RC : 0; }
     }
     if (q == 0 && visited) atomicAdd(counters, (unsigned long long)visited);
 }

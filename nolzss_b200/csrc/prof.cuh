@@ -25,12 +25,13 @@ enum KClass : int {
     KC_CHAIN,         // chain extraction (exit, doubling, mark, scan, emit)
     KC_BARRIER,       // distributed runs: flag barrier in peer memory (time = waiting for the slowest GPU)
     KC_STREAM,        // doubling: tie groups beyond the tile, one CTA streaming each (pivot partition + outlier sort)
+    KC_XCHG,          // distributed runs: bucketing by destination, bulk copies over NVLink, local apply
     KC_COUNT
 };
 
 static const char* const kClassNames[KC_COUNT] = {
     "prepare", "build_keys", "radix_hist", "radix_scan", "radix_scatter", "gather_rank",
-    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain", "dist_barrier", "group_stream"};
+    "tile_sort", "regroup", "lcp_kasai", "summary_trees", "node_tables", "rc_neighbours", "lpnf_rank", "lpnf_hard", "chain", "dist_barrier", "group_stream", "dist_exchange"};
 
 struct Profiler {
     bool timing = false;

@@ -304,8 +304,9 @@ k_regroup_scan_partials(u32* __restrict__ pmax, u32* __restrict__ psum, u32 ntil
     if (threadIdx.x == 0) *m_out = tot;
 }
 
-// phase C: ranks, SA write-back and compaction of the still-active elements.
-template <typename KeyT, bool INITIAL>
+// phase C: ranks, SA write-back and compaction of the still-active elements.  GS: the doubling keys are
+// group << GS | rank (tile_sort.cuh); 33 on the distributed path, where RANK.rank is null (records only).
+template <typename KeyT, bool INITIAL, int GS = 32>
 __global__ void __launch_bounds__(RG_THREADS)
 k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ slots,
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
@@ -372,9 +373,9 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
             u32 s = vals[e];
             u32 slot = INITIAL ? e + RANK.base : slots[e];
             // the old rank of a member is its group's head slot = the high half of its doubling key
-            const bool changed = INITIAL || newrank != (u32)((u64)keys[e] >> 32);
+            const bool changed = INITIAL || newrank != (u32)((u64)keys[e] >> GS);
             if (changed) {
-                RANK.rank[s] = newrank;
+                if (RANK.rank) RANK.rank[s] = newrank;
                 if (RANK.upd) {
                     if (INITIAL) RANK.upd[e] = ((u64)newrank << 32) | (u64)s;      // every rank is new: dense list
                     else { upd_rec[nupd] = ((u64)newrank << 32) | (u64)s; ++nupd; }
@@ -383,7 +384,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
             SA[slot - RANK.base] = s;
             if (act[q]) {
                 u32 pos = cs + ps[q];
-                key_next[pos] = (u64)newrank << 32;
+                key_next[pos] = (u64)newrank << GS;
                 val_next[pos] = s;
                 slot_next[pos] = slot;
                 if (sh_head[idx + 1] != 0) gmax = max(gmax, e - hj + 1);   // last element of its group

@@ -22,11 +22,24 @@
 // detects the new sub-groups, writes the refined ranks (RANK = ISA in the end) and the suffix array
 // slots, and appends the members that are still tied to the next round's list (one atomic range
 // reservation per tile; the order of groups in that list is irrelevant).
+//
+// Key layout: key = group << GS | rank.  GS = 32 on one GPU (global slots and ranks below 2^32).  The distributed
+// path (dist2.cuh) instantiates GS = 33: groups are named by LOCAL slots (a rank range holds fewer than 2^30
+// suffixes) while the second half is a GLOBAL rank of up to 33 bits (6.2 * 10^9 suffixes for a 3.1 Gbp text in RC
+// mode); there the pivot and the compacted outliers are kept as tile indices and compared through the full keys.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "sa.cuh"
 
 namespace nlz {
+
+template <int GS> struct KeyHalves {
+    using RT = typename std::conditional<GS == 32, u32, u64>::type;     // rank type
+    static __device__ __forceinline__ u32 grp(u64 k) { return (u32)(k >> GS); }
+    static __device__ __forceinline__ RT rank(u64 k) { return GS == 32 ? (RT)k : (RT)(k & ((1ull << GS) - 1)); }
+};
 
 constexpr int TSORT_THREADS = 1024;
 constexpr int TSORT_SLOTS = 4096;
@@ -85,6 +98,7 @@ __device__ __forceinline__ void tsort_scan_flags(const u8* __restrict__ flag, un
     __syncthreads();
 }
 
+template <int GS>
 __global__ void __launch_bounds__(TSORT_THREADS, 2)
 k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in, u32 m,
             const u32* __restrict__ m_dev /* overrides m when the host runs ahead (pipelined rounds) */,
@@ -111,6 +125,9 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     unsigned short* biglist = reinterpret_cast<unsigned short*>(misc + 64);   // starts of the groups with many outliers
     unsigned short* spos = reinterpret_cast<unsigned short*>(tsort_smem + TSORT_OFF_POS);
 
+    using KH = KeyHalves<GS>;
+    using RT = typename KH::RT;
+    constexpr bool WIDE = GS != 32;
     const u32 tid = threadIdx.x, lane = tid & 31;
     if (m_dev) m = *m_dev;
     const u32 a = blockIdx.x * tile;
@@ -129,8 +146,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         u32 fo = 0xFFFFFFFFu, fe = 0xFFFFFFFFu;
         if (o < nload) {
             const u32 j = a + o;
-            const u32 g = (u32)(key_in[j] >> 32);
-            const bool head = (j == 0) || ((u32)(key_in[j - 1] >> 32) != g);
+            const u32 g = KH::grp(key_in[j]);
+            const bool head = (j == 0) || (KH::grp(key_in[j - 1]) != g);
             if (head) {
                 if (j < b) fo = j;
                 else fe = j;
@@ -157,7 +174,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     }
     __syncthreads();
     for (u32 o = tid; o < TSORT_SLOTS; o += TSORT_THREADS)
-        flag[o] = (o < cnt && (o == 0 || (u32)(skey[o] >> 32) != (u32)(skey[o - 1] >> 32))) ? 1 : 0;
+        flag[o] = (o < cnt && (o == 0 || KH::grp(skey[o]) != KH::grp(skey[o - 1]))) ? 1 : 0;
     __syncthreads();
     tsort_scan_flags<true>(flag, sgs, wscratch);                  // sgs[o] = start of o's group
     // group ends (high half of gle), by group
@@ -170,8 +187,10 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
     for (u32 o = tid; o < cnt; o += TSORT_THREADS) {
         if (flag[o]) {
             const u32 e = gle[o >> 1] >> 16;
-            const u32 ka = (u32)skey[o], kb = (u32)skey[(o + e) >> 1], kc = (u32)skey[e - 1];
-            gpiv[o >> 1] = (ka == kb || ka == kc) ? ka : kb;
+            const RT ka = KH::rank(skey[o]), kb = KH::rank(skey[(o + e) >> 1]), kc = KH::rank(skey[e - 1]);
+            // 32-bit ranks: the pivot rank itself; wide ranks: the tile index of a member that carries it
+            if (WIDE) gpiv[o >> 1] = (ka == kb || ka == kc) ? o : ((o + e) >> 1);
+            else gpiv[o >> 1] = (u32)((ka == kb || ka == kc) ? ka : kb);
         }
     }
     __syncthreads();
@@ -183,7 +202,8 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         bool less = false, eq = false;
         if (valid) {
             gs = sgs[o];
-            const u32 k2 = (u32)skey[o], pv = gpiv[gs >> 1];
+            const RT k2 = KH::rank(skey[o]);
+            const RT pv = WIDE ? KH::rank(skey[gpiv[gs >> 1]]) : (RT)gpiv[gs >> 1];
             less = k2 < pv;
             eq = k2 == pv;
             if (dbg & 2) eq = false;
@@ -207,7 +227,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         const u32 o = ob + tid;
         u32 cost = 0;
         if (o < cnt) {
-            if (!flag[o]) outk[o - (u32)seq[o]] = (u32)skey[o];
+            if (!flag[o]) outk[o - (u32)seq[o]] = WIDE ? o : (u32)skey[o];   // wide ranks: the member's tile index
             if (o == 0 || sgs[o] != sgs[o - 1]) {
                 const u32 e = gle[o >> 1] >> 16, size = e - o;
                 const u32 eqc = (u32)seq[e - 1] + flag[e - 1] - (u32)seq[o];
@@ -237,12 +257,13 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
                     const u32 xe = e - ((u32)seq[e - 1] + flag[e - 1]);
                     if (xe - xb <= TSORT_BIG_OUTLIERS) {
                         const u32 me = o - (u32)seq[o];
-                        const u32 k32 = (u32)skey[o];
+                        const RT k32 = KH::rank(skey[o]);
                         u32 smaller = 0;
-                        for (u32 x = xb; x < me; ++x) smaller += outk[x] <= k32 ? 1u : 0u;       // earlier members win ties
-                        for (u32 x = me + 1; x < xe; ++x) smaller += outk[x] < k32 ? 1u : 0u;
+                        for (u32 x = xb; x < me; ++x) smaller += (WIDE ? KH::rank(skey[outk[x]]) : (RT)outk[x]) <= k32 ? 1u : 0u;       // earlier members win ties
+                        for (u32 x = me + 1; x < xe; ++x) smaller += (WIDE ? KH::rank(skey[outk[x]]) : (RT)outk[x]) < k32 ? 1u : 0u;
                         const u32 eqc = (e - gs) - (xe - xb);
-                        spos[o] = (unsigned short)(gs + smaller + (k32 > gpiv[gs >> 1] ? eqc : 0u));
+                        const RT pv = WIDE ? KH::rank(skey[gpiv[gs >> 1]]) : (RT)gpiv[gs >> 1];
+                        spos[o] = (unsigned short)(gs + smaller + (k32 > pv ? eqc : 0u));
                     }
                 }
             }
@@ -255,14 +276,14 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
             const u32 xb = gs - (u32)seq[gs];
             const u32 xe = e - ((u32)seq[e - 1] + flag[e - 1]);
             const u32 eqc = (e - gs) - (xe - xb);
-            const u32 piv = gpiv[gs >> 1];
+            const RT piv = WIDE ? KH::rank(skey[gpiv[gs >> 1]]) : (RT)gpiv[gs >> 1];
             for (u32 o = gs + warp; o < e; o += TSORT_THREADS / 32) {
                 if (flag[o]) continue;                                              // warp-uniform
                 const u32 me = o - (u32)seq[o];
-                const u32 k32 = (u32)skey[o];
+                const RT k32 = KH::rank(skey[o]);
                 u32 smaller = 0;
                 for (u32 x = xb + lane; x < xe; x += 32) {
-                    const u32 kx = outk[x];
+                    const RT kx = WIDE ? KH::rank(skey[outk[x]]) : (RT)outk[x];
                     smaller += (kx < k32 || (kx == k32 && x < me)) ? 1u : 0u;
                 }
                 smaller = __reduce_add_sync(0xffffffffu, smaller);
@@ -289,7 +310,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         // fallback: bitonic network over the padded tile.  The groups of the list are in no particular
         // order of their head slots, so the network sorts by (position of the group in the tile, rank):
         // groups stay where they are, members are ordered inside them.
-        for (u32 o = tid; o < cnt; o += TSORT_THREADS) skey[o] = ((u64)sgs[o] << 32) | (u64)(u32)skey[o];
+        for (u32 o = tid; o < cnt; o += TSORT_THREADS) skey[o] = ((u64)sgs[o] << GS) | (u64)KH::rank(skey[o]);
         __syncthreads();
         u32 ns = 32;
         while (ns < cnt) ns <<= 1;
@@ -348,7 +369,7 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
         if (o < cnt) {
             const u32 s = sval[o];
             const u32 slot = sslot[o];
-            const u32 gid0 = (u32)(skey[o] >> 32);
+            const u32 gid0 = KH::grp(skey[o]);
             // New rank of the member's sub-group: any slot inside the sub-group's slot range is a valid name (the
             // ranges of different groups are disjoint; a singleton's range is its slot).  The sub-group that still
             // holds the slot the old group was named by KEEPS that name -- a tandem-array group that sheds a few
@@ -363,16 +384,16 @@ k_tile_sort(const u64* __restrict__ key_in, const u32* __restrict__ val_in, cons
             // old rank = the high key half.  The bitonic path keyed the members by their group's tile position and has
             // lost it; it cannot assume the head slot either (a group that comes from k_group_stream may be named by
             // any slot of its range), so there every rank is stored.
-            const u32 gid = (u32)(skey[o] >> 32);
+            const u32 gid = KH::grp(skey[o]);
             const u32 oldrank = used_bitonic ? 0xFFFFFFFFu : gid;
             if (newrank != oldrank) {
-                RANK.rank[s] = newrank;
+                if (RANK.rank) RANK.rank[s] = newrank;
                 if (RANK.upd) { upd_rec[nupd] = ((u64)newrank << 32) | (u64)s; ++nupd; }
             }
             SA[slot - RANK.base] = s;
             if (act[o]) {
                 const u32 pos = base + seq[o];
-                key_next[pos] = (u64)newrank << 32;
+                key_next[pos] = (u64)newrank << GS;
                 val_next[pos] = s;
                 slot_next[pos] = slot;
             }
