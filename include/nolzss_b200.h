@@ -77,7 +77,9 @@ int nlz_kernel_class_count(void);
 /* test hook: forces the fallback paths of the shared-memory group sort (1 bitonic network, 2 no pivot fast path,
  * 4 counting only); 8 makes the group-stream kernel of the hybrid doubling rounds give up from the third round
  * on (the round is redone through the radix path); flags >> 8, when in [64, 2048), lowers the largest tie group
- * the tile sort takes, so that small texts run the hybrid rounds; 0 = normal operation */
+ * the tile sort takes, so that small texts run the hybrid rounds; 0x1000000 (distributed path) adds 2^32 + 12345 to every
+ * global rank, so that small texts carry 33-bit ranks through the doubling keys, the sort kernels and the exchanges --
+ * the widths a 3.1 Gbp text needs; 0 = normal operation */
 int nlz_set_debug_flags(nlz_ctx* ctx, int flags);
 int nlz_get_kernel_stats(nlz_ctx* ctx, int cls, const char** name, double* ms, uint64_t* bytes,
                          uint32_t* launches);

@@ -404,7 +404,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     // largest tie group the shared-memory tile sort takes (test hook: debug flags >> 8 lower it so that small texts
     // reach the hybrid rounds)
     u32 gcap = (u32)TSORT_SLOTS / 2;
-    if ((c->debug_flags >> 8) >= 64 && (u32)(c->debug_flags >> 8) < gcap) gcap = (u32)(c->debug_flags >> 8);
+    if (((c->debug_flags >> 8) & 0xFFFF) >= 64 && (u32)((c->debug_flags >> 8) & 0xFFFF) < gcap) gcap = (u32)((c->debug_flags >> 8) & 0xFFFF);
     if (!no_pipeline && m > 0 && maxg <= gcap) {
         // Every remaining round is a fused one (groups only shrink).  The host runs one round AHEAD of the device:
         // round r is launched with grids sized from the counts of round r-1 and reads its true list length from

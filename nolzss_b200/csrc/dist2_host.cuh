@@ -68,6 +68,8 @@ struct D2 {
     u32 split[MAX_PEERS + 1];
     u64 base[MAX_PEERS + 1];
     u32 m_loc;
+    u64 rank_bias;                     // test hook (debug flag 0x1000000): added to every global rank, so that small texts
+                                       // carry 33-bit ranks through the keys, the sort kernels and the exchanges
     HandleMap hm;
     u32 *CTR, *PAY, *CURSOR;           // device scratch (PAY[0..8) doubles as the per-destination counts)
     u64* inbox;                        // my inbox (device pointer into the shared segment)
@@ -224,7 +226,7 @@ static int d2_publish_ranks(D2& r, const D2Sa& a, u32 bound, const u32* count_de
     Workspace& w = r.c->ws;
     cudaStream_t st = r.st;
     UpdItem it;
-    it.upd = a.UPD; it.hm = r.hm; it.rbase = r.base[r.me];
+    it.upd = a.UPD; it.hm = r.hm; it.rbase = r.base[r.me] + r.rank_bias;
     NLZ_TRY((d2_bucket<UpdItem, false>(r, it, bound, count_dev, a.ST, nullptr, 24)));
     k_set_u32<<<1, 1, 0, st>>>(r.PAY + MAX_PEERS, my_active);
     XInfo x;
@@ -310,7 +312,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
     m = c->h_pinned[0]; maxg = c->h_pinned[3];
     u32 nupd_bound = cnt;
 
-    const int nbr = bits_for((u32)std::min<u64>(pb.n1 - 1, 0xFFFFFFFFull)) + (pb.n1 > 0x100000000ull ? 1 : 0);   // bits of a global rank
+    const int nbr = r.rank_bias ? 33 : bits_for((u32)std::min<u64>(pb.n1 - 1, 0xFFFFFFFFull)) + (pb.n1 > 0x100000000ull ? 1 : 0);   // bits of a global rank
     const int nbg = bits_for(cnt ? cnt - 1 : 0);                                                                  // bits of a local group name
     DigitPlan plan;
     plan_add_range(plan, 0, nbr > GS ? GS : nbr);
@@ -318,7 +320,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
     u64 h = (u64)lay.W;
     int sc = 0;
     u32 gcap = (u32)TSORT_SLOTS / 2;
-    if ((c->debug_flags >> 8) >= 64 && (u32)(c->debug_flags >> 8) < gcap) gcap = (u32)(c->debug_flags >> 8);
+    if (((c->debug_flags >> 8) & 0xFFFF) >= 64 && (u32)((c->debug_flags >> 8) & 0xFFFF) < gcap) gcap = (u32)((c->debug_flags >> 8) & 0xFFFF);
     struct { bool on = false, off = false; u32 mS = 0, mB = 0, maxgS = 0; int fallbacks = 0; } hy;
     static const bool no_hybrid = getenv("NLZ_NO_HYBRID") != nullptr;
     hy.off = no_hybrid;
@@ -467,6 +469,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     const int G = d->world, me = d->rank;
     D2 r;
     r.d = d; r.c = c; r.st = st; r.G = G; r.me = me;
+    r.rank_bias = (c->debug_flags & 0x1000000) ? 0x100003039ull : 0ull;
     w = Workspace();
     w.X = d->seg + d->off_x;
     w.CTR = d->SMALL;
@@ -738,7 +741,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));
         if (x.in_total) KL(P, KC_LCP, (u64)x.in_total * 16, st, (k_d2_apply_phi<<<ceil_div_u32(x.in_total, 256), 256, 0, st>>>(r.inbox, x.in_total, PHI)));
         LcpDistT<u64> ld;
-        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = r.pos0; ld.pos1 = r.pos1;
+        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = r.pos0; ld.pos1 = r.pos1; ld.rank0 = r.rank_bias;
         BatchView bv;
         memset(&bv, 0, sizeof(bv));
         if (ch)
@@ -746,8 +749,8 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
                (k_lcp_kasai<false, true, u64><<<ceil_div_u32(ceil_div_u32(ch, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, nullptr, RANKL, nullptr, bv, ld)));
         LcpItem li;
         li.RANKL = RANKL; li.PLCP = PLCP; li.rb.G = G;
-        for (int g = 0; g <= G; ++g) li.rb.base[g] = r.base[g];
-        for (int g = G + 1; g <= MAX_PEERS; ++g) li.rb.base[g] = r.base[G];
+        for (int g = 0; g <= G; ++g) li.rb.base[g] = r.base[g] + r.rank_bias;
+        for (int g = G + 1; g <= MAX_PEERS; ++g) li.rb.base[g] = r.base[G] + r.rank_bias;
         NLZ_TRY((d2_bucket<LcpItem, false>(r, li, ch, nullptr, ST, nullptr, 20)));
         NLZ_TRY(d2_counts(r, 0, 8, x));
         NLZ_TRY(d2_push(r, x, ST, 8, 0));

@@ -65,6 +65,7 @@ struct LcpDistT {
     const PT* PHI;
     u32* PLCP;
     u64 pos0, pos1;
+    PT rank0;      // value of global rank 0 (0, or the test hook's rank bias)
     __device__ __forceinline__ void store(u64 i, u32 l) const { PLCP[i - pos0] = l; }
 };
 using LcpDist = LcpDistT<u32>;
@@ -89,7 +90,7 @@ k_lcp_kasai(const u8* __restrict__ x, u64 L, u64 n1, const u32* __restrict__ SA,
         bool need = false;
         if (i < n1) {
             r = RANK[DIST ? i - ld.pos0 : i];
-            if (r == 0) { if (DIST) ld.store(i, 0); else LCP[0] = 0; l = 0; }
+            if (DIST ? r == ld.rank0 : r == 0) { if (DIST) ld.store(i, 0); else LCP[0] = 0; l = 0; }
             else {
                 j = DIST ? ld.PHI[i - ld.pos0] : (PT)SA[r - 1];
                 const u64 room = L - (i > (u64)j ? i : (u64)j);

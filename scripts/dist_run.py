@@ -48,6 +48,13 @@ for r in range(world):
     dist.barrier()
     if r == rank: print(f"rank {rank} kernel classes (ms, launches): {ks}", flush=True)
 L.check(L.load().nlz_set_profiling(grp.ctx, 0))
+gold_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "c4_250mbp_rc.json")
+if rank == 0 and n == 250_000_000 and mode == L.MODE_DNA_RC and os.path.exists(gold_path):
+    import hashlib, json
+    gold = json.load(open(gold_path))
+    hsh = hashlib.sha256(got.astype("<u8").tobytes()).hexdigest()
+    print(f"[dist_run] oracle sha256 of the 250 Mbp RC text: {'MATCH' if hsh == gold['sha256_triples_le_u64'] and len(got) == gold['factors'] else 'MISMATCH'} ({len(got)} factors)", flush=True)
+    assert hsh == gold["sha256_triples_le_u64"]
 if check and rank == 0:
     t0 = time.perf_counter()
     single = L.factorize_array(mode, text, device=local)

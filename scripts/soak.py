@@ -8,7 +8,9 @@ from nolzss_b200 import _lib as L, dist as nd, workloads as wl
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-grp = nd.LocalGroup([0, 0, 0], 2_000_000, L.MODE_DNA_RC)
+import torch
+_nd = max(torch.cuda.device_count(), 1)
+grp = nd.LocalGroup([g % _nd for g in range(3)], 2_000_000, L.MODE_DNA_RC)
 t_end = time.time() + budget
 n_cases = 0
 def gen():

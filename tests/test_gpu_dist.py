@@ -115,3 +115,24 @@ def test_dist_invalid_nucleotide_is_reported_by_every_rank():
         assert np.array_equal(got, _expected(L.MODE_DNA_RC, s))
     finally:
         grp.close()
+
+
+def test_dist_33_bit_ranks_on_small_texts():
+    """Debug flag 0x1000000: every global rank carries an offset of 2^32 + 12345, so the doubling keys (group << 33 |
+    rank), the tile sort / group stream / radix rounds and every exchanged record run with ranks beyond 32 bits -- the
+    widths of configs[4] (6.2 * 10^9 suffixes) -- on texts the oracle can check."""
+    from test_gpu_parity import _hybrid_cases
+    cases = _cases()[:30] + _hybrid_cases()[:4] + [wl.planted_dna(300_000, 21, scale=0.3).tobytes()]
+    for world in (1, 3):
+        grp = nd.LocalGroup(_devs(world), 400_000, L.MODE_DNA_RC)
+        try:
+            for flags in (0x1000000, 0x1000000 | (64 << 8), 0x1000000 | (64 << 8) | 8, 0x1000000 | 1):
+                for c in grp.ctxs:
+                    L.check(L.load().nlz_set_debug_flags(c, flags))
+                for s in cases:
+                    modes = (L.MODE_GENERAL, L.MODE_DNA_RC) if set(s) <= set(b"ACGT") else (L.MODE_GENERAL,)
+                    for mode in modes:
+                        got, _ = grp.factorize(mode, s)
+                        assert np.array_equal(got, _expected(mode, s)), (world, hex(flags), mode, len(s))
+        finally:
+            grp.close()
