@@ -108,11 +108,14 @@ int nlz_factorize_batch(nlz_ctx* ctx, int with_rc, const uint8_t* concat, const 
                         uint64_t k, uint64_t** out_triples, uint64_t* per_record_counts, uint64_t* total);
 
 /* ---- ONE text across the GPUs of a box (replaces the single serial index build of the reference's parallel mode,
- * src/cpp/parallel_factorizer.cpp:78-84; see csrc/dist.cuh).  One nlz_dist per rank (GPU).  Every rank calls
- * nlz_dist_factorize with the same text; rank 0 receives the factors, every rank the count.  The ranks exchange
- * data through peer memory: either all ranks live in one process (nlz_dist_attach_local) or one process per GPU
- * exchanges the CUDA IPC handles of the shared segments (nlz_dist_export / nlz_dist_attach; e.g. all-gathered
- * with torch.distributed).  max_text_bytes / max_mode size the shared segment (mode as in nlz_factorize_mode). */
+ * src/cpp/parallel_factorizer.cpp:78-84, and its 64-bit index vectors, src/cpp/factorizer_core.hpp:195-232; see
+ * csrc/dist2.cuh).  One nlz_dist per rank (GPU).  Every rank calls nlz_dist_factorize with the same text; rank 0
+ * receives the factors, every rank the count.  Texts of up to 2^32 - 16 bases are taken (6.2 * 10^9 indexed suffixes for
+ * a 3.1 Gbp genome in DNA_RC mode: global ranks and S-positions are 33-bit on this path); a GPU can own at most 2^30
+ * suffixes, so such a text needs 8 GPUs.  The ranks exchange data through peer memory: either all ranks live in one
+ * process (nlz_dist_attach_local) or one process per GPU exchanges the CUDA IPC handles of the shared segments
+ * (nlz_dist_export / nlz_dist_attach; e.g. all-gathered with torch.distributed).  max_text_bytes / max_mode size the
+ * shared segment (mode as in nlz_factorize_mode). */
 typedef struct nlz_dist nlz_dist;
 int nlz_dist_create(nlz_ctx* ctx, int rank, int world, uint64_t max_text_bytes, int max_mode, nlz_dist** out);
 void nlz_dist_destroy(nlz_dist* d);
@@ -122,6 +125,11 @@ int nlz_dist_attach(nlz_dist* d, const uint8_t* all_handles /* world x nlz_dist_
 int nlz_dist_attach_local(nlz_dist* const* ranks, int world);
 int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples,
                        uint64_t* out_count);
+/* as above; `text` may be a host pointer (pageable or pinned) or a DEVICE pointer (every rank holds the text in its own
+ * HBM), and rank 0 receives the factors in a caller-provided (ideally pinned) buffer of `capacity` factors
+ * (out_triples == NULL: count only) */
+int nlz_dist_factorize_into(nlz_dist* d, int mode, const void* text, uint64_t n, uint64_t* out_triples,
+                            uint64_t capacity, uint64_t* out_count);
 
 /* ---- named entry points: one per reference function on the path ------------------------- */
 /* noLZSS::factorize(std::string_view, start_pos)                 src/cpp/factorizer.cpp:378-384 */

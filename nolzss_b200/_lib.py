@@ -67,6 +67,7 @@ SIGNATURES = {
     "nlz_dist_attach": (ctypes.c_int, [_vp, _vp]),
     "nlz_dist_attach_local": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
     "nlz_dist_factorize": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _u64pp, _u64p]),
+    "nlz_dist_factorize_into": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _u64, _vp, _u64, _u64p]),
     "nlz_factorize": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64pp, _u64p]),
     "nlz_count_factors": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64p]),
     "nlz_factorize_dna_w_rc": (ctypes.c_int, [_vp, _vp, _u64, _u64pp, _u64p]),

@@ -461,7 +461,9 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
 
 // Factorizes one text with all ranks of the group (every rank passes the same text).  Rank 0 receives the factors;
 // every rank learns the count.
-static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out_alloc, u64* out_count) {
+// `text` may be a host pointer (pageable or pinned) or a device pointer (unified addressing); `out_into` (rank 0) is a
+// caller-provided, ideally pinned, buffer of `capacity` factors that replaces the malloc'ed result.
+static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out_alloc, u64* out_into, u64 capacity, u64* out_count) {
     nlz_ctx* c = d->ctx;
     Workspace& w = c->ws;
     Profiler& P = c->prof;
@@ -508,7 +510,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         xp.n = G;
         k_d2_set_u64<<<1, 1, 0, st>>>(reinterpret_cast<u64*>(d_bad), ~0ull);
         if (hi > lo) {
-            NLZ_CK(cudaMemcpyAsync(w.X + lo, text + lo, hi - lo, cudaMemcpyHostToDevice, st));
+            NLZ_CK(cudaMemcpyAsync(w.X + lo, text + lo, hi - lo, cudaMemcpyDefault, st));
             u32 grid = ceil_div_u32(hi - lo, 256);
             if (grid > (u32)kNumSM * 16) grid = kNumSM * 16;
             k_d2_prepare_dna_rc_slice<<<grid, 256, 0, st>>>(w.X, n, lo, hi, xp, me == 0, d_bad);
@@ -525,7 +527,9 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
             bad = std::min(bad, b);
         }
         if (bad != ~0ull) {
-            set_error("Invalid nucleotide '%c' found in sequence 0", (char)text[bad]);   // factorizer.cpp:91-92
+            u8 chb = 0;
+            NLZ_CK(cudaMemcpy(&chb, text + bad, 1, cudaMemcpyDefault));
+            set_error("Invalid nucleotide '%c' found in sequence 0", (char)chb);   // factorizer.cpp:91-92
             return ERR_RUNTIME;
         }
         u32 hist[256];
@@ -533,7 +537,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         hist['A'] = hist['C'] = hist['G'] = hist['T'] = 2;
         choose_layout(hist, 0xFFFFFFFFu, tab, lay);                         // forces 64-bit keys
     } else {
-        NLZ_CK(cudaMemcpyAsync(w.X, text, pb.n_in, cudaMemcpyHostToDevice, st));
+        NLZ_CK(cudaMemcpyAsync(w.X, text, pb.n_in, cudaMemcpyDefault, st));
         k_zero_pad<<<1, 128, 0, st>>>(w.X, pb.L);
         u32* BYTEHIST = d->SMALL + 64 + 512 + 128;
         NLZ_CK(cudaMemsetAsync(BYTEHIST, 0, 256 * 4, st));
@@ -932,7 +936,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     (void)want;
     // every rank emits the factors of its slice into its own inbox (free by now); rank 0 gathers them
     // (count-only calls skip the emission: rank 0 decides, the others learn it through the barrier payload)
-    k_set_u32<<<1, 1, 0, st>>>(r.PAY, (me == 0 && out_alloc) ? 1u : 0u);
+    k_set_u32<<<1, 1, 0, st>>>(r.PAY, (me == 0 && (out_alloc || out_into)) ? 1u : 0u);
     NLZ_TRY(d2_barrier(r, r.PAY, 1, true));
     const bool emit = r.all[0] != 0;
     if (emit) {
@@ -948,9 +952,16 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));
         if (me == 0 && z) {
-            u64* dst = static_cast<u64*>(malloc((size_t)z * 24));
-            if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)z); return ERR_RUNTIME; }
-            *out_alloc = dst;
+            u64* dst = out_into;
+            if (!dst) {
+                dst = static_cast<u64*>(malloc((size_t)z * 24));
+                if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)z); return ERR_RUNTIME; }
+                *out_alloc = dst;
+            } else if (z > capacity) {
+                set_error("output capacity %llu factors is too small for %llu factors", (unsigned long long)capacity, (unsigned long long)z);
+                *out_count = z;
+                return ERR_RUNTIME;      // the other ranks run into the closing barrier's timeout: size the buffer from a count-only call
+            }
             u64 at = 0;
             for (int g = 0; g < G; ++g) {
                 if (zg[g]) NLZ_CK(cudaMemcpyAsync(dst + 3 * at, d->peer[g] + d->off_inbox, (size_t)zg[g] * 24, cudaMemcpyDefault, st));
@@ -1109,7 +1120,8 @@ int nlz_dist_attach_local(nlz_dist* const* ranks, int world) {
     return OK;
 }
 
-int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples, uint64_t* out_count) {
+static int dist_factorize_impl(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples, uint64_t* out_into,
+                               uint64_t capacity, uint64_t* out_count) {
     if (!d || !out_count) { set_error("null argument"); return ERR_INVALID; }
     if (n && !text) { set_error("null text"); return ERR_INVALID; }
     if (!d->attached && d->world > 1) { set_error("distributed group is not attached"); return ERR_INVALID; }
@@ -1125,13 +1137,21 @@ int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, u
     if (empty) return OK;
     if (pb.n1 > d->max_n1 || pb.nfac > d->max_nfac) { set_error("text of %llu suffixes exceeds the group's capacity of %llu", (unsigned long long)pb.n1, (unsigned long long)d->max_n1); return ERR_INVALID; }
     u64 z = 0;
-    NLZ_TRY(run_dist2(d, pb, text, d->rank == 0 ? out_triples : nullptr, &z));
+    NLZ_TRY(run_dist2(d, pb, text, d->rank == 0 ? out_triples : nullptr, d->rank == 0 ? out_into : nullptr, capacity, &z));
     Problem pstat{};
     pstat.n_in = pb.n_in; pstat.n1 = (u32)std::min<u64>(pb.n1, 0xFFFFFFFFull); pstat.nfac = pb.nfac;
     finish_stats(c, pstat);
     c->stats.n_suffixes = pb.n1;
     *out_count = z;
     return OK;
+}
+
+int nlz_dist_factorize(nlz_dist* d, int mode, const uint8_t* text, uint64_t n, uint64_t** out_triples, uint64_t* out_count) {
+    return dist_factorize_impl(d, mode, text, n, out_triples, nullptr, 0, out_count);
+}
+int nlz_dist_factorize_into(nlz_dist* d, int mode, const void* text, uint64_t n, uint64_t* out_triples, uint64_t capacity,
+                            uint64_t* out_count) {
+    return dist_factorize_impl(d, mode, static_cast<const uint8_t*>(text), n, nullptr, out_triples, capacity, out_count);
 }
 
 }  // extern "C"
