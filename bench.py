@@ -594,8 +594,10 @@ def configs2_leg(world, rank, local, dist, barrier, rmax, steps=3):
     for it in range(steps + 1):
         barrier()
         t0 = time.perf_counter()
-        counts, trip = sharding.factorize_batch_distributed(recs, True, want_factors=(it == 0), group=group, device=local)
+        counts, tr = sharding.factorize_batch_distributed(recs, True, want_factors=(it == 0), group=group, device=local)
         dt = time.perf_counter() - t0
+        if it == 0:
+            trip = tr                                         # the triples are gathered once (parity), the timed steps count
         st = L.stats(local)
         if it:
             times.append(rmax(dt * 1e3))

@@ -908,17 +908,24 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     NLZ_TRY(check_dna_deferred(c, pb, src, src_on_host));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
-    // ---- S2: LCP
+    // ---- S2: LCP (lcp.cuh): Phi gather, Kasai in text order, scatter to rank order.  PHI / PLCP live in the sort
+    // buffers, which are free between the doubling and stage 3.
     BatchView bv;
     bv.REC = w.REC; bv.fstart = w.FSTART; bv.flen = w.FLEN; bv.k = pb.nrec; bv.N = pb.rc ? pb.N : 0xFFFFFFFFu;
-    LcpDist nold;
-    memset(&nold, 0, sizeof(nold));
-    if (pb.nrec)
-        KL(P, KC_LCP, (u64)n1 * 36, st,
-           (k_lcp_kasai<true, false><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv, nold)));
-    else
-        KL(P, KC_LCP, (u64)n1 * 28, st,
-           (k_lcp_kasai<false, false><<<ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, w.SA, w.RANK, w.LCP, bv, nold)));
+    {
+        u32* PHI = reinterpret_cast<u32*>(w.KEY[0]);
+        u32* PLCP = reinterpret_cast<u32*>(w.KEY[1]);
+        LcpSlice<u32> ld;
+        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = 0; ld.pos1 = n1;
+        const u32 g1 = ceil_div_u32(n1, 256);
+        const u32 gk = ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256);
+        P.begin(st);
+        k_phi_gather<<<g1, 256, 0, st>>>(w.SA, w.RANK, n1, PHI);
+        if (pb.nrec) k_lcp_kasai<true, u32><<<gk, 256, 0, st>>>(w.X, pb.L, bv, ld);
+        else k_lcp_kasai<false, u32><<<gk, 256, 0, st>>>(w.X, pb.L, bv, ld);
+        k_lcp_scatter<<<g1, 256, 0, st>>>(PLCP, w.RANK, n1, w.LCP);
+        P.end(KC_LCP, (u64)n1 * (pb.nrec ? 40 : 32), st, 3);
+    }
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
     if (stop_after_index) {
         NLZ_CK(cudaGetLastError());

@@ -40,7 +40,7 @@
 namespace nlz {
 
 constexpr u64 D2_MASK34 = (1ull << 34) - 1;
-constexpr u64 D2_NO_PHI = D2_MASK34;            // Phi of global rank 0 (never read: Kasai tests the rank first)
+constexpr u64 D2_NO_PHI = D2_MASK34;            // Phi of global rank 0 (= PhiNone<u64>::value in lcp.cuh: Kasai stores 0 for it)
 constexpr u32 D2_MAX_LOCAL = 0x3FFFFF00u;       // suffixes / positions one GPU can own (30-bit local indices)
 
 // suffix handle -> S-position.  Handles are arrival indices at the rank owner: the pairs of sender g occupy
@@ -451,5 +451,30 @@ k_d2_prepare_dna_rc_slice(const u8* T, u64 n, u64 lo, u64 hi, XPeers X, bool wri
 }
 
 __global__ void k_d2_set_u64(u64* p, u64 v) { *p = v; }
+
+// One launch moves every bucket of an 8-byte-item exchange: element e of the staging list belongs to the bucket g with
+// off[g] <= e < off[g+1] and goes to dst[g][e - off[g]] (push: coalesced peer stores) or comes from there (pull).
+constexpr u32 D2_KERNEL_PUSH_MAX = 8u << 20;       // items (64 MB); larger exchanges use the copy engines
+struct PushGeom { u64* dst[MAX_PEERS]; u32 off[MAX_PEERS + 1]; int G; };
+__device__ __forceinline__ int pg_bucket(const PushGeom& pg, u32 e) {
+    int g = 0;
+#pragma unroll
+    for (int q = 1; q < MAX_PEERS; ++q) g += (q < pg.G && e >= pg.off[q]) ? 1 : 0;
+    return g;
+}
+__global__ void __launch_bounds__(256)
+k_d2_push(const u64* __restrict__ staging, u32 total, PushGeom pg) {
+    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const int g = pg_bucket(pg, e);
+        pg.dst[g][e - pg.off[g]] = staging[e];
+    }
+}
+__global__ void __launch_bounds__(256)
+k_d2_pull(u64* __restrict__ staging, u32 total, PushGeom pg) {
+    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const int g = pg_bucket(pg, e);
+        staging[e] = pg.dst[g][e - pg.off[g]];
+    }
+}
 
 }  // namespace nlz

@@ -132,30 +132,39 @@ static int d2_barrier(D2& r, const u32* d_src, u32 nwords, bool want_host) {
 
 // ---- bucketed bulk exchange ------------------------------------------------------------------------------------------
 // 1. bucket the items by destination into the staging list(s); per-destination counts end up in r.PAY[0..8)
+// (`slot`: several exchanges may share one counts barrier; exchange s keeps its counts in r.PAY[8s .. 8s+8))
 template <typename F, bool TWO>
-static int d2_bucket(D2& r, const F& f, u32 bound, const u32* count_dev, u64* stA, u64* stB, u64 alg_bytes_per_item) {
+static int d2_bucket(D2& r, const F& f, u32 bound, const u32* count_dev, u64* stA, u64* stB, u64 alg_bytes_per_item, int slot = 0) {
     cudaStream_t st = r.st;
-    NLZ_CK(cudaMemsetAsync(r.PAY, 0, MAX_PEERS * 4, st));
+    u32* cnts = r.PAY + MAX_PEERS * slot;
+    u32* cursor = r.CURSOR + MAX_PEERS * slot;
+    NLZ_CK(cudaMemsetAsync(cnts, 0, MAX_PEERS * 4, st));
     if (!bound) return OK;
     const u32 grid = ceil_div_u32(bound, 256);
     Profiler& P = r.c->prof;
     P.begin(st);
-    k_d2_bucket<F, 0, TWO><<<grid, 256, 0, st>>>(f, bound, count_dev, r.PAY, nullptr, nullptr);
-    k_d2_bucket_starts<<<1, 32, 0, st>>>(r.PAY, r.CURSOR, r.G);
-    k_d2_bucket<F, 1, TWO><<<grid, 256, 0, st>>>(f, bound, count_dev, r.CURSOR, stA, stB);
+    k_d2_bucket<F, 0, TWO><<<grid, 256, 0, st>>>(f, bound, count_dev, cnts, nullptr, nullptr);
+    k_d2_bucket_starts<<<1, 32, 0, st>>>(cnts, cursor, r.G);
+    k_d2_bucket<F, 1, TWO><<<grid, 256, 0, st>>>(f, bound, count_dev, cursor, stA, stB);
     P.end(KC_XCHG, (u64)bound * alg_bytes_per_item, st, 3);
     return OK;
 }
 // 2. counts barrier: payload = [counts[8] | nextra extra words from PAY[8..]]; fills the exchange geometry and
 //    checks every rank's inbox capacity (the same verdict on every rank)
+static int d2_geometry(D2& r, u32 nw, int slot, size_t item_bytes, XInfo& x, bool two_regions);
 static int d2_counts(D2& r, u32 nextra, size_t item_bytes, XInfo& x, bool two_regions = false) {
     const u32 nw = MAX_PEERS + nextra;
     NLZ_TRY(d2_barrier(r, r.PAY, nw, true));
+    return d2_geometry(r, nw, 0, item_bytes, x, two_regions);
+}
+// geometry of exchange `slot` from the gathered payloads (nw words per rank)
+static int d2_geometry(D2& r, u32 nw, int slot, size_t item_bytes, XInfo& x, bool two_regions) {
     const int G = r.G, me = r.me;
+    const size_t so = (size_t)MAX_PEERS * slot;
     memset(&x, 0, sizeof(x));
     for (int dst = 0; dst < G; ++dst) {
         u64 tot = 0;
-        for (int g = 0; g < G; ++g) tot += r.all[(size_t)g * nw + dst];
+        for (int g = 0; g < G; ++g) tot += r.all[(size_t)g * nw + so + dst];
         if (tot * item_bytes > r.d->inbox_items * 16ull || tot > 0xFFFFFFF0ull || (two_regions && tot > r.d->inbox_items)) {
             set_error("distributed exchange: rank %d would receive %llu items of %zu bytes, its inbox holds %llu bytes "
                       "(the partition of this text is too unbalanced for %d GPUs)", dst, (unsigned long long)tot, item_bytes,
@@ -165,27 +174,45 @@ static int d2_counts(D2& r, u32 nextra, size_t item_bytes, XInfo& x, bool two_re
     }
     u32 run = 0;
     for (int g = 0; g < G; ++g) {
-        x.out_cnt[g] = r.all[(size_t)me * nw + g];
+        x.out_cnt[g] = r.all[(size_t)me * nw + so + g];
         x.out_off[g] = run;
         run += x.out_cnt[g];
     }
     x.out_total = run;
     run = 0;
     for (int g = 0; g < G; ++g) {
-        x.in_cnt[g] = r.all[(size_t)g * nw + me];
+        x.in_cnt[g] = r.all[(size_t)g * nw + so + me];
         x.in_off[g] = run;
         run += x.in_cnt[g];
     }
     x.in_total = run;
     for (int g = 0; g < G; ++g) {            // where MY bucket starts in g's inbox: after the buckets of the ranks before me
         u32 o = 0;
-        for (int q = 0; q < me; ++q) o += r.all[(size_t)q * nw + g];
+        for (int q = 0; q < me; ++q) o += r.all[(size_t)q * nw + so + g];
         x.their_off[g] = o;
     }
     return OK;
 }
 // 3. one bulk copy per destination into its inbox (at `inbox_byte_off` + the bucket's offset), then a barrier
 static int d2_push(D2& r, const XInfo& x, const void* staging, size_t item_bytes, size_t inbox_byte_off) {
+    static const bool no_kernel_push = getenv("NLZ_NO_KERNEL_PUSH") != nullptr;
+    if (item_bytes == 8 && r.G > 1 && x.out_total && x.out_total <= D2_KERNEL_PUSH_MAX && !no_kernel_push) {
+        // one launch instead of G copies: coalesced 8-byte peer stores (the copies of a late doubling round are a few
+        // kilobytes each -- their launch and DMA set-up latency, not their size, is what the round pays for)
+        PushGeom pg;
+        memset(&pg, 0, sizeof(pg));
+        for (int g = 0; g < r.G; ++g) {
+            pg.dst[g] = reinterpret_cast<u64*>(r.d->peer[g] + r.d->off_inbox + inbox_byte_off) + x.their_off[g];
+            pg.off[g] = x.out_off[g];
+        }
+        for (int g = r.G; g <= MAX_PEERS; ++g) pg.off[g] = x.out_total;
+        pg.G = r.G;
+        u32 grid = ceil_div_u32(x.out_total, 256 * 4);
+        if (grid > (u32)kNumSM * 4) grid = kNumSM * 4;
+        k_d2_push<<<grid, 256, 0, r.st>>>(static_cast<const u64*>(staging), x.out_total, pg);
+        r.c->prof.bytes[KC_XCHG] += (u64)x.out_total * 8;
+        return OK;
+    }
     for (int g = 0; g < r.G; ++g) {
         if (!x.out_cnt[g]) continue;
         u8* dst = r.d->peer[g] + r.d->off_inbox + inbox_byte_off + (size_t)x.their_off[g] * item_bytes;
@@ -196,10 +223,26 @@ static int d2_push(D2& r, const XInfo& x, const void* staging, size_t item_bytes
     return OK;
 }
 // responses: one bulk copy per peer FROM its inbox (my bucket there, answered in place) into `dst` (staging order)
-static int d2_pull(D2& r, const XInfo& x, void* dst, size_t item_bytes) {
+static int d2_pull(D2& r, const XInfo& x, void* dst, size_t item_bytes, size_t inbox_byte_off = 0) {
+    static const bool no_kernel_push = getenv("NLZ_NO_KERNEL_PUSH") != nullptr;
+    if (item_bytes == 8 && r.G > 1 && x.out_total && x.out_total <= D2_KERNEL_PUSH_MAX && !no_kernel_push) {
+        PushGeom pg;
+        memset(&pg, 0, sizeof(pg));
+        for (int g = 0; g < r.G; ++g) {
+            pg.dst[g] = reinterpret_cast<u64*>(r.d->peer[g] + r.d->off_inbox + inbox_byte_off) + x.their_off[g];
+            pg.off[g] = x.out_off[g];
+        }
+        for (int g = r.G; g <= MAX_PEERS; ++g) pg.off[g] = x.out_total;
+        pg.G = r.G;
+        u32 grid = ceil_div_u32(x.out_total, 256 * 4);
+        if (grid > (u32)kNumSM * 4) grid = kNumSM * 4;
+        k_d2_pull<<<grid, 256, 0, r.st>>>(static_cast<u64*>(dst), x.out_total, pg);
+        r.c->prof.bytes[KC_XCHG] += (u64)x.out_total * 8;
+        return OK;
+    }
     for (int g = 0; g < r.G; ++g) {
         if (!x.out_cnt[g]) continue;
-        const u8* src = r.d->peer[g] + r.d->off_inbox + (size_t)x.their_off[g] * item_bytes;
+        const u8* src = r.d->peer[g] + r.d->off_inbox + inbox_byte_off + (size_t)x.their_off[g] * item_bytes;
         u8* to = static_cast<u8*>(dst) + (size_t)x.out_off[g] * item_bytes;
         NLZ_CK(cudaMemcpyAsync(to, src, (size_t)x.out_cnt[g] * item_bytes, cudaMemcpyDefault, r.st));
         r.c->prof.bytes[KC_XCHG] += (u64)x.out_cnt[g] * item_bytes;
@@ -217,53 +260,56 @@ static size_t d2_al(size_t b) { return (b + 255) & ~(size_t)255; }
 struct D2Sa {
     u64* UPD;          // records of changed ranks (cnt entries)
     u64* ST;           // exchange staging (cnt entries)
+    u64* REQ;          // request staging (cnt entries)
     u64* RESP;         // pulled responses (cnt entries)
     u64* RANKL;        // my slice of RANK
 };
 
-static int d2_publish_ranks(D2& r, const D2Sa& a, u32 bound, const u32* count_dev, u32 my_active, u32* gm_out) {
-    // bucket by position owner, exchange, apply; the counts barrier also carries every GPU's active count
+// One exchange step of a doubling round: (1) the ranks refined in the previous step travel to their position owners and
+// (2) the rank requests of THIS round (RANK[pos(val[j]) + h] for the S list [0, mS) and the B list [b0, b0 + mB) of the
+// `cur` buffers) travel to the same owners -- both under ONE counts barrier (which also carries every GPU's active
+// count: *gm_out = the largest) and ONE data barrier; the owners apply the records, then answer the requests in place;
+// after a third barrier the answers are pulled back and complete the keys: key[j] |= RANK[..].
+// With no active suffix anywhere (*gm_out == 0) only the records are delivered.
+static int d2_round_exchange(D2& r, const D2Sa& a, u32 nupd_bound, const u32* nupd_dev, int cur, u32 mS, u32 b0, u32 mB, u64 h,
+                             u32* gm_out) {
     Workspace& w = r.c->ws;
     cudaStream_t st = r.st;
-    UpdItem it;
-    it.upd = a.UPD; it.hm = r.hm; it.rbase = r.base[r.me] + r.rank_bias;
-    NLZ_TRY((d2_bucket<UpdItem, false>(r, it, bound, count_dev, a.ST, nullptr, 24)));
-    k_set_u32<<<1, 1, 0, st>>>(r.PAY + MAX_PEERS, my_active);
-    XInfo x;
-    NLZ_TRY(d2_counts(r, 1, 8, x));
+    Profiler& P = r.c->prof;
+    UpdItem ui;
+    ui.upd = a.UPD; ui.hm = r.hm; ui.rbase = r.base[r.me] + r.rank_bias;
+    NLZ_TRY((d2_bucket<UpdItem, false>(r, ui, nupd_bound, nupd_dev, a.ST, nullptr, 24, 0)));
+    ReqItem qi;
+    qi.val = w.VAL[cur]; qi.hm = r.hm; qi.h = h; qi.mS = mS; qi.b0 = b0;
+    NLZ_TRY((d2_bucket<ReqItem, false>(r, qi, mS + mB, nullptr, a.REQ, nullptr, 20, 1)));
+    k_set_u32<<<1, 1, 0, st>>>(r.PAY + 2 * MAX_PEERS, mS + mB);
+    const u32 nw = 2 * MAX_PEERS + 1;
+    NLZ_TRY(d2_barrier(r, r.PAY, nw, true));
+    XInfo xu, xq;
+    NLZ_TRY(d2_geometry(r, nw, 0, 8, xu, true));
+    NLZ_TRY(d2_geometry(r, nw, 1, 8, xq, true));
     u32 gm = 0;
-    for (int g = 0; g < r.G; ++g) gm = std::max(gm, r.all[(size_t)g * (MAX_PEERS + 1) + MAX_PEERS]);
+    for (int g = 0; g < r.G; ++g) gm = std::max(gm, r.all[(size_t)g * nw + 2 * MAX_PEERS]);
     *gm_out = gm;
-    NLZ_TRY(d2_push(r, x, a.ST, 8, 0));
-    NLZ_TRY(d2_barrier(r, nullptr, 0, false));
-    if (x.in_total) {
-        r.c->stats.rank_records_applied += x.in_total;
-        KL(r.c->prof, KC_XCHG, (u64)x.in_total * 16, st,
-           (k_d2_apply_ranks<<<ceil_div_u32(x.in_total, 256), 256, 0, st>>>(r.inbox, x.in_total, a.RANKL)));
+    const size_t off_b = (size_t)r.d->inbox_items * 8;              // second inbox region: the requests
+    u64* inboxB = reinterpret_cast<u64*>(r.d->seg + r.d->off_inbox + off_b);
+    NLZ_TRY(d2_push(r, xu, a.ST, 8, 0));
+    if (gm) NLZ_TRY(d2_push(r, xq, a.REQ, 8, off_b));
+    NLZ_TRY(d2_barrier(r, nullptr, 0, false));                     // records and requests have arrived everywhere
+    if (xu.in_total) {
+        r.c->stats.rank_records_applied += xu.in_total;
+        KL(P, KC_XCHG, (u64)xu.in_total * 16, st,
+           (k_d2_apply_ranks<<<ceil_div_u32(xu.in_total, 256), 256, 0, st>>>(r.inbox, xu.in_total, a.RANKL)));
     }
-    (void)w;
-    return OK;
-}
-
-// key[j] |= RANK[pos(val[j]) + h] for the S list [0, mS) and the B list [b0, b0 + mB) of the `cur` buffers
-static int d2_gather_ranks(D2& r, const D2Sa& a, int cur, u32 mS, u32 b0, u32 mB, u64 h) {
-    Workspace& w = r.c->ws;
-    cudaStream_t st = r.st;
-    ReqItem it;
-    it.val = w.VAL[cur]; it.hm = r.hm; it.h = h; it.mS = mS; it.b0 = b0;
-    NLZ_TRY((d2_bucket<ReqItem, false>(r, it, mS + mB, nullptr, a.ST, nullptr, 20)));
-    XInfo x;
-    NLZ_TRY(d2_counts(r, 0, 8, x));
-    NLZ_TRY(d2_push(r, x, a.ST, 8, 0));
-    NLZ_TRY(d2_barrier(r, nullptr, 0, false));                 // requests have arrived everywhere
-    if (x.in_total)
-        KL(r.c->prof, KC_GATHER, (u64)x.in_total * 24, st,
-           (k_d2_serve<<<ceil_div_u32(x.in_total, 256), 256, 0, st>>>(r.inbox, x.in_total, a.RANKL, (u64)r.ch)));
-    NLZ_TRY(d2_barrier(r, nullptr, 0, false));                 // every inbox holds the answers
-    NLZ_TRY(d2_pull(r, x, a.RESP, 8));
-    if (x.out_total)
-        KL(r.c->prof, KC_GATHER, (u64)x.out_total * 32, st,
-           (k_d2_apply_resp<<<ceil_div_u32(x.out_total, 256), 256, 0, st>>>(a.ST, a.RESP, x.out_total, w.KEY[cur])));
+    if (!gm) return OK;
+    if (xq.in_total)
+        KL(P, KC_GATHER, (u64)xq.in_total * 24, st,
+           (k_d2_serve<<<ceil_div_u32(xq.in_total, 256), 256, 0, st>>>(inboxB, xq.in_total, a.RANKL, (u64)r.ch)));
+    NLZ_TRY(d2_barrier(r, nullptr, 0, false));                     // every inbox holds the answers
+    NLZ_TRY(d2_pull(r, xq, a.RESP, 8, off_b));
+    if (xq.out_total)
+        KL(P, KC_GATHER, (u64)xq.out_total * 32, st,
+           (k_d2_apply_resp<<<ceil_div_u32(xq.out_total, 256), 256, 0, st>>>(a.REQ, a.RESP, xq.out_total, w.KEY[cur])));
     // the next exchange writes into the inboxes only after its own counts barrier, which every rank reaches after its
     // pulls have completed (stream order): no extra barrier needed here
     return OK;
@@ -343,12 +389,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         return OK;
     };
     for (;;) {
-        // deliver the ranks refined in the previous step; learn the largest active count over all GPUs
-        u32 gm = 0;
-        NLZ_TRY(d2_publish_ranks(r, a, nupd_bound, w.CTR + 4, hy.on ? hy.mS + hy.mB : m, &gm));
-        if (gm == 0) break;
-        S.doubling_rounds += 1;
-        S.active_sum += hy.on ? hy.mS + hy.mB : m;
+        // the one-time split into the S / B lists is local: do it before the exchange, which addresses list entries
         if (!hy.on && !hy.off && m > 0 && maxg > gcap) {
             const u32 tiles = ceil_div_u32(m, RG_TILE);
             P.begin(st);
@@ -365,10 +406,19 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
             cur ^= 1; sc ^= 1;
             if (trace) fprintf(stderr, "[nlz] rank %d: hybrid rounds from here: S=%u B=%u (groups > %u)\n", r.me, hy.mS, hy.mB, gcap);
         }
+        // deliver the ranks refined in the previous step, fetch RANK[s+h] for this round's lists; learn the largest
+        // active count over all GPUs
+        u32 gm = 0;
+        {
+            const u32 mS = hy.on ? hy.mS : m, mB = hy.on ? hy.mB : 0u;
+            NLZ_TRY(d2_round_exchange(r, a, nupd_bound, w.CTR + 4, cur, mS, END - mB, mB, h, &gm));
+        }
+        if (gm == 0) break;
+        S.doubling_rounds += 1;
+        S.active_sum += hy.on ? hy.mS + hy.mB : m;
         int rb = cur;
         if (hy.on) {
             const u32 mS = hy.mS, mB = hy.mB, b0 = END - mB;
-            NLZ_TRY(d2_gather_ranks(r, a, cur, mS, b0, mB, h));
             NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));                  // [0] next S length, [3] its largest group, [4] records, [6] next B length, [7] fallback flag
             if (mS) {
                 u32 cap = 32;
@@ -427,7 +477,6 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
             nupd_bound = mS + mB;
         } else {
             const bool fused = maxg <= gcap;
-            NLZ_TRY(d2_gather_ranks(r, a, cur, m, 0, 0, h));
             NLZ_CK(cudaMemsetAsync(w.CTR, 0, 32, st));
             if (m > 0 && fused) {
                 u32 cap = 32;
@@ -722,7 +771,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     // ---- S1: local sort + doubling rounds (ranks travel as records, RANK[s+h] by request / response)
     if (ch) NLZ_CK(cudaMemsetAsync(RANKL, 0, ((size_t)ch + 8) * 8, st));
     D2Sa sa;
-    sa.UPD = UPD; sa.ST = ST; sa.RESP = RESP; sa.RANKL = RANKL;
+    sa.UPD = UPD; sa.ST = ST; sa.REQ = STB; sa.RESP = RESP; sa.RANKL = RANKL;
     NLZ_TRY(d2_stage_sa(r, pb, lay, sa, m_loc));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
@@ -744,13 +793,13 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         NLZ_TRY(d2_push(r, x, ST, 8, 0));
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));
         if (x.in_total) KL(P, KC_LCP, (u64)x.in_total * 16, st, (k_d2_apply_phi<<<ceil_div_u32(x.in_total, 256), 256, 0, st>>>(r.inbox, x.in_total, PHI)));
-        LcpDistT<u64> ld;
-        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = r.pos0; ld.pos1 = r.pos1; ld.rank0 = r.rank_bias;
+        LcpSlice<u64> ld;
+        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = r.pos0; ld.pos1 = r.pos1;
         BatchView bv;
         memset(&bv, 0, sizeof(bv));
         if (ch)
-            KL(P, KC_LCP, (u64)ch * 36, st,
-               (k_lcp_kasai<false, true, u64><<<ceil_div_u32(ceil_div_u32(ch, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, n1, nullptr, RANKL, nullptr, bv, ld)));
+            KL(P, KC_LCP, (u64)ch * 28, st,
+               (k_lcp_kasai<false, u64><<<ceil_div_u32(ceil_div_u32(ch, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, bv, ld)));
         LcpItem li;
         li.RANKL = RANKL; li.PLCP = PLCP; li.rb.G = G;
         for (int g = 0; g <= G; ++g) li.rb.base[g] = r.base[g] + r.rank_bias;

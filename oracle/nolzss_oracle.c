@@ -26,7 +26,17 @@
 #include <string.h>
 #include <time.h>
 
+/* Index width.  The reference is 64-bit end to end (sdsl::int_vector<64>, factorizer_core.hpp:211-213).  The default
+ * build uses 32-bit indices (texts below 2^31 suffixes: everything the CPU tests and the bench legs run); -DNLZO_IDX64
+ * (libnlz_oracle64.so) widens every index to 64 bits -- same code, checked against the 32-bit build by
+ * tests/test_oracle.py -- for texts beyond that (host memory permitting: 24 bytes per suffix). */
+#ifdef NLZO_IDX64
+typedef int64_t idx_t;
+#define NLZO_IDX_LIMIT (1ULL << 62)
+#else
 typedef int32_t idx_t;
+#define NLZO_IDX_LIMIT (1ULL << 31)
+#endif
 #define RC_MASK (1ULL << 63)
 
 /* ------------------------------------------------------------------ SA-IS (Nong, Zhang, Chan) */
@@ -109,10 +119,12 @@ static int sais(const idx_t *s, idx_t *SA, idx_t n, idx_t K) {
     return 0;
 }
 
+#ifndef NLZO_IDX64
 int nlzo_suffix_array_i32(const int32_t *s, int32_t n, int32_t K, int32_t *sa) {
     if (n <= 0) return 0;
     return sais(s, sa, n, K);
 }
+#endif
 
 /* ------------------------------------------------------------------ index over bytes·$ */
 typedef struct {
@@ -125,7 +137,7 @@ static void index_free(index_t *ix) { free(ix->sa); free(ix->isa); free(ix->lcp)
 
 static int index_build(const uint8_t *x, uint64_t n, index_t *ix) {
     memset(ix, 0, sizeof(*ix));
-    if (n + 1 >= (1ULL << 31)) return -2;
+    if (n + 1 >= NLZO_IDX_LIMIT) return -2;
     idx_t n1 = (idx_t)n + 1;
     idx_t *s = (idx_t *)malloc(sizeof(idx_t) * (size_t)n1);
     ix->sa = (idx_t *)malloc(sizeof(idx_t) * (size_t)n1);
@@ -152,6 +164,7 @@ static int index_build(const uint8_t *x, uint64_t n, index_t *ix) {
     return 0;
 }
 
+#ifndef NLZO_IDX64
 int nlzo_sa_lcp_bytes(const uint8_t *text, uint64_t n, int32_t *sa, int32_t *lcp) {
     index_t ix;
     int rc = index_build(text, n, &ix);
@@ -161,6 +174,7 @@ int nlzo_sa_lcp_bytes(const uint8_t *text, uint64_t n, int32_t *sa, int32_t *lcp
     index_free(&ix);
     return 0;
 }
+#endif
 
 /* factorizer_helpers.hpp:20-24 : LCA string depth == number of equal leading symbols of the two
  * suffixes of x·$ ($ unique).  `cap` lets callers stop once the answer cannot matter. */

@@ -92,3 +92,42 @@ def test_parallel_mode_equals_serial():
             assert np.array_equal(got, want), (seed, threads)
     got, used = orc.parallel_factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(b"ACGTACGTTTGCA"), 8)
     assert used == 1 and np.array_equal(got, orc.factorize_multiple_dna_w_rc(wl.prepare_w_rc_single(b"ACGTACGTTTGCA")))
+
+
+def test_oracle_64bit_index_build_matches_32bit():
+    """-DNLZO_IDX64 (libnlz_oracle64.so): every index widened to 64 bits -- the reference's own width
+    (factorizer_core.hpp:211-213) -- gives the same triples as the default 32-bit build."""
+    import ctypes
+    import os
+    import subprocess
+
+    import numpy as np
+
+    from nolzss_b200 import workloads as wl
+
+    here = os.path.dirname(os.path.abspath(orc.__file__))
+    subprocess.check_call(["make", "-C", here, "libnlz_oracle64.so"], stdout=subprocess.DEVNULL)
+    L64 = ctypes.CDLL(os.path.join(here, "libnlz_oracle64.so"))
+    pp = ctypes.POINTER(ctypes.POINTER(ctypes.c_uint64))
+    for name in ("nlzo_factorize", "nlzo_factorize_multiple_dna_w_rc"):
+        f = getattr(L64, name)
+        f.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, pp, ctypes.POINTER(ctypes.c_uint64)]
+        f.restype = ctypes.c_int
+    L64.nlzo_free.argtypes = [ctypes.c_void_p]
+
+    def run64(fn, data, sp=0):
+        out = ctypes.POINTER(ctypes.c_uint64)()
+        cnt = ctypes.c_uint64(0)
+        assert fn(data, len(data), sp, ctypes.byref(out), ctypes.byref(cnt)) == 0
+        arr = np.ctypeslib.as_array(out, shape=(cnt.value * 3,)).copy().reshape(-1, 3) if cnt.value else np.zeros((0, 3), np.uint64)
+        if cnt.value:
+            L64.nlzo_free(out)
+        return arr
+
+    texts = [b"abracadabra", b"A" * 500, wl.planted_dna(40_000, 3, scale=0.05).tobytes(), wl.uniform_dna(20_000, 9).tobytes()]
+    for t in texts:
+        assert np.array_equal(run64(L64.nlzo_factorize, t), orc.factorize(t))
+        if set(t) <= set(b"ACGT"):
+            S = wl.prepare_w_rc_single(t)
+            assert np.array_equal(run64(L64.nlzo_factorize_multiple_dna_w_rc, S), orc.factorize_multiple_dna_w_rc(S))
+            assert np.array_equal(run64(L64.nlzo_factorize_multiple_dna_w_rc, S, 100), orc.factorize_multiple_dna_w_rc(S, 100))
