@@ -60,6 +60,9 @@ typedef struct nlz_stats {
     float ms_total, ms_prepare, ms_keys, ms_sort0, ms_doubling, ms_lcp, ms_lpnf, ms_chain;
     /* distributed runs: (suffix, rank) records this GPU received from the others and applied to its replica */
     uint64_t rank_records_applied;
+    /* suffixes still tied after the initial key sort (members of tie groups): an upper bound of the positions whose LCP
+     * the Kasai kernel computes from the text -- every other LCP value follows from a pair of sort keys */
+    uint64_t lcp_marked;
 } nlz_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

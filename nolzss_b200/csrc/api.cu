@@ -58,6 +58,7 @@ struct Workspace {
     u8* X = nullptr;
     u32 *SA = nullptr, *RANK = nullptr, *LCP = nullptr;
     u32* R0 = nullptr;       // RC mode, stage 3: rc-class leaf values (lpnf.cuh: k_leaf_values); F0 overwrites SA in place
+    u8* NEED = nullptr;      // by text position: the LCP of this suffix is left to the Kasai kernel (lcp.cuh)
     u64* KEY[2] = {nullptr, nullptr};
     u32* VAL[2] = {nullptr, nullptr};
     u32* SLOT[2] = {nullptr, nullptr};
@@ -101,7 +102,7 @@ namespace nlz {
 static size_t workspace_bytes_for(u64 n1, u64 nrec) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t t = 0;
-    t += al(n1 + 192);               // X
+    t += al(n1 + 192) + al(n1 + 64); // X, NEED
     t += al((n1 + 72) * 4) * 4;      // SA, RANK, LCP, R0 (+ one padded line for whole-line reads)
     t += al((n1 + 72) * 16);         // NODE
     t += al(n1 * 8) * 2;             // KEY
@@ -146,6 +147,7 @@ static int ensure_workspace(nlz_ctx* c, u64 n1, u64 nrec = 0) {
     a.off = 0;
     w.n1 = (u32)n1;
     w.X = a.take<u8>(n1 + 192);
+    w.NEED = a.take<u8>(n1 + 64);
     w.SA = a.take<u32>(n1 + 72);
     w.RANK = a.take<u32>(n1 + 72);
     w.LCP = a.take<u32>(n1 + 72);
@@ -328,6 +330,27 @@ static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout
     return OK;
 }
 
+// k_group_stream in two sizes (big_groups.cuh): SMALL outlier buffer for every chunk (two CTAs per SM), then persistent
+// CTAs with the BIG buffer over the groups that overflowed.  The overflow list lives in the radix-sort histogram table.
+template <int GS>
+static void launch_group_stream(nlz_ctx* c, cudaStream_t st, const u64* key, const u32* val, const u32* slot, u32 b0, u32 mB,
+                                u32 gcap, u32* SA, const RankDst& rdst, StreamOut so, int dbg) {
+    Workspace& w = c->ws;
+    const u32 chunks = ceil_div_u32(mB, gcap);
+    static const bool one_size = getenv("NLZ_GS_ONE_SIZE") != nullptr;
+    so.ovf_out = nullptr; so.ovf_cnt_out = nullptr; so.ovf_in = nullptr; so.ovf_cnt_in = nullptr;
+    if (chunks <= (u32)RS_BINS * RS_MAX_CTAS && !one_size && !(dbg & 8)) {
+        u32* ovf_cnt = w.CTR + 32;
+        cudaMemsetAsync(ovf_cnt, 0, 4, st);
+        so.ovf_out = w.HIST; so.ovf_cnt_out = ovf_cnt;
+        k_group_stream<GS, GS_CAP_SMALL><<<chunks, GS_THREADS, gs_smem(GS_CAP_SMALL), st>>>(key, val, slot, b0, mB, gcap, SA, rdst, so, dbg);
+        so.ovf_out = nullptr; so.ovf_cnt_out = nullptr; so.ovf_in = w.HIST; so.ovf_cnt_in = ovf_cnt;
+        k_group_stream<GS, GS_CAP_BIG><<<chunks < (u32)kNumSM ? chunks : (u32)kNumSM, GS_THREADS, gs_smem(GS_CAP_BIG), st>>>(key, val, slot, b0, mB, gcap, SA, rdst, so, dbg);
+    } else {
+        k_group_stream<GS, GS_CAP_BIG><<<chunks, GS_THREADS, gs_smem(GS_CAP_BIG), st>>>(key, val, slot, b0, mB, gcap, SA, rdst, so, dbg);
+    }
+}
+
 static RankDst local_rank_dst(nlz_ctx* c) {   // one GPU: refined ranks go straight into RANK; no records
     RankDst r;
     r.rank = c->ws.RANK; r.upd = nullptr; r.upd_count = c->ws.CTR + 4; r.base = 0;
@@ -362,14 +385,19 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
     const KeyT dist_mask = ((KeyT)1 << lay.D) - 1;
     const u32 tiles = ceil_div_u32(cnt, RG_TILE);
-    // compaction target must not alias the sorted buffers: use the other KEY/VAL pair
+    // compaction target must not alias the sorted buffers: use the other KEY/VAL pair.  The first regroup also seeds
+    // the LCP array from adjacent key pairs and marks the suffixes whose LCP needs the text (lcp.cuh).
+    LcpSeed seed;
+    seed.LCP = w.LCP; seed.NEED = w.NEED; seed.lay = lay; seed.first_pending = false;
+    NLZ_CK(cudaMemsetAsync(w.NEED, 0, (size_t)n1 + 64, st));
+    NLZ_CK(cudaMemsetAsync(w.LCP + n1, 0, 4, st));              // right guard used by the interval walks
     P.begin(st);
     k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
     k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
     k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, cnt, dist_mask, w.PMAX,
                                                               w.PSUM, w.SA, local_rank_dst(c), w.KEY[res ^ 1],
-                                                              w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
-    P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8), st, 3);
+                                                              w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3, seed);
+    P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8 + 4), st, 3);
     *cur_out = res ^ 1;
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
@@ -393,6 +421,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
     if (lay.key_bits == 32) NLZ_TRY(initial_sort_and_regroup<u32>(c, pb, tab, lay, st, cnt, &cur, &m, &maxg));
     else NLZ_TRY(initial_sort_and_regroup<u64>(c, pb, tab, lay, st, cnt, &cur, &m, &maxg));
     const RankDst rdst = local_rank_dst(c);
+    S.lcp_marked = m;
     const int nb = bits_for(n1 - 1);
     DigitPlan plan;
     plan_add_range(plan, 0, nb);
@@ -518,8 +547,7 @@ static int stage_sa(nlz_ctx* c, const Problem& pb, const ClassTable& tab, const 
                 so.end = END; so.mS = w.CTR; so.maxgS = w.CTR + 3; so.mB = w.CTR + 6; so.fallback = w.CTR + 7;
                 const int dbg = (c->debug_flags & 8) && S.doubling_rounds >= 3 ? 8 : 0;   // test hook: fail the third round
                 KL(P, KC_STREAM, (u64)mB * 44, st,
-                   (k_group_stream<32><<<ceil_div_u32(mB, gcap), GS_THREADS, GS_SMEM, st>>>(
-                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], b0, mB, gcap, w.SA, rdst, so, dbg)));
+                   (launch_group_stream<32>(c, st, w.KEY[cur], w.VAL[cur], w.SLOT[sc], b0, mB, gcap, w.SA, rdst, so, dbg)));
             }
             S.tile_sort_rounds += 1;
             if (trace) cudaEventRecord(tev1, st);
@@ -908,23 +936,19 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     NLZ_TRY(check_dna_deferred(c, pb, src, src_on_host));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
-    // ---- S2: LCP (lcp.cuh): Phi gather, Kasai in text order, scatter to rank order.  PHI / PLCP live in the sort
-    // buffers, which are free between the doubling and stage 3.
+    // ---- S2: LCP (lcp.cuh): the first regroup has written every LCP value that follows from a key pair; the Kasai pass
+    // resolves the marked positions (members of tie groups behind their head)
     BatchView bv;
     bv.REC = w.REC; bv.fstart = w.FSTART; bv.flen = w.FLEN; bv.k = pb.nrec; bv.N = pb.rc ? pb.N : 0xFFFFFFFFu;
     {
-        u32* PHI = reinterpret_cast<u32*>(w.KEY[0]);
-        u32* PLCP = reinterpret_cast<u32*>(w.KEY[1]);
         LcpSlice<u32> ld;
-        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = 0; ld.pos1 = n1;
-        const u32 g1 = ceil_div_u32(n1, 256);
-        const u32 gk = ceil_div_u32(ceil_div_u32(n1, LCP_Q), 256);
-        P.begin(st);
-        k_phi_gather<<<g1, 256, 0, st>>>(w.SA, w.RANK, n1, PHI);
-        if (pb.nrec) k_lcp_kasai<true, u32><<<gk, 256, 0, st>>>(w.X, pb.L, bv, ld);
-        else k_lcp_kasai<false, u32><<<gk, 256, 0, st>>>(w.X, pb.L, bv, ld);
-        k_lcp_scatter<<<g1, 256, 0, st>>>(PLCP, w.RANK, n1, w.LCP);
-        P.end(KC_LCP, (u64)n1 * (pb.nrec ? 40 : 32), st, 3);
+        memset(&ld, 0, sizeof(ld));
+        ld.NEED = w.NEED; ld.SA = w.SA; ld.RANK = w.RANK; ld.LCP = w.LCP; ld.pos0 = 0; ld.pos1 = n1;
+        ld.blocks_per_warp = lcp_blocks_per_warp(n1);
+        const u32 gk = ceil_div_u32(ceil_div_u32(n1, (u64)LCP_Q * ld.blocks_per_warp), 256);
+        // algorithmic bytes: the marks of every position + 28 bytes per marked position (added from the active count)
+        if (pb.nrec) KL(P, KC_LCP, (u64)n1 + (u64)c->stats.lcp_marked * 36, st, (k_lcp_kasai<true, false, u32><<<gk, 256, 0, st>>>(w.X, pb.L, bv, ld)));
+        else KL(P, KC_LCP, (u64)n1 + (u64)c->stats.lcp_marked * 28, st, (k_lcp_kasai<false, false, u32><<<gk, 256, 0, st>>>(w.X, pb.L, bv, ld)));
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));
     if (stop_after_index) {
@@ -1129,9 +1153,11 @@ static int ctx_init_impl(nlz_ctx* c) {
     NLZ_CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     NLZ_CK(cudaMallocHost(&c->h_pinned, 4096));   // words [0, 512): readbacks; [512, 1024): pipelined round counts
     NLZ_CK(cudaFuncSetAttribute(k_tile_sort<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
-    NLZ_CK(cudaFuncSetAttribute(k_group_stream<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream<32, GS_CAP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs_smem(GS_CAP_BIG)));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream<32, GS_CAP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs_smem(GS_CAP_SMALL)));
     NLZ_CK(cudaFuncSetAttribute(k_tile_sort<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSORT_SMEM));
-    NLZ_CK(cudaFuncSetAttribute(k_group_stream<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream<33, GS_CAP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs_smem(GS_CAP_BIG)));
+    NLZ_CK(cudaFuncSetAttribute(k_group_stream<33, GS_CAP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs_smem(GS_CAP_SMALL)));
     {
         // First launches of these kernels now, while nothing else runs: the CUDA runtime loads a kernel lazily at
         // its first launch, and that load waits for running kernels.  Inside a distributed doubling round a peer
@@ -1141,10 +1167,12 @@ static int ctx_init_impl(nlz_ctx* c) {
         memset(&so, 0, sizeof(so));
         RankDst rd;
         memset(&rd, 0, sizeof(rd));
-        k_group_stream<32><<<1, GS_THREADS, GS_SMEM, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_group_stream<32, GS_CAP_BIG><<<1, GS_THREADS, gs_smem(GS_CAP_BIG), c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_group_stream<32, GS_CAP_SMALL><<<1, GS_THREADS, gs_smem(GS_CAP_SMALL), c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
         k_split_count<32><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, 0, 64, nullptr);
         k_split_apply<32><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 64, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
-        k_group_stream<33><<<1, GS_THREADS, GS_SMEM, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_group_stream<33, GS_CAP_BIG><<<1, GS_THREADS, gs_smem(GS_CAP_BIG), c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
+        k_group_stream<33, GS_CAP_SMALL><<<1, GS_THREADS, gs_smem(GS_CAP_SMALL), c->own_stream>>>(nullptr, nullptr, nullptr, 0, 0, 64, nullptr, rd, so, 0);
         k_split_count<33><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, 0, 64, nullptr);
         k_split_apply<33><<<1, RG_THREADS, 0, c->own_stream>>>(nullptr, nullptr, nullptr, 0, 64, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
         NLZ_CK(cudaStreamSynchronize(c->own_stream));

@@ -29,12 +29,19 @@
 namespace nlz {
 
 constexpr int GS_THREADS = 1024;
-constexpr u32 GS_OUT_CAP = 16384;                                 // outliers a CTA can sort in shared memory
-constexpr size_t GS_OFF_KV = 0;                                   // u64[CAP]  (key2 << 32 | suffix), sorted
-constexpr size_t GS_OFF_HEAD = GS_OFF_KV + (size_t)GS_OUT_CAP * 8;     // u16[CAP] head index of the outlier's sub-group
-constexpr size_t GS_OFF_SIZE = GS_OFF_HEAD + (size_t)GS_OUT_CAP * 2;   // u16[CAP] sub-group size, stored at its head (0 = 65536 never occurs: CAP < 65536)
-constexpr size_t GS_OFF_MISC = GS_OFF_SIZE + (size_t)GS_OUT_CAP * 2;   // u32[128]
-constexpr size_t GS_SMEM = GS_OFF_MISC + 512 + 2 * 64 * 4;        // + big sub-group list: u32 head[64], u32 base[64]
+// Two sizes of the outlier buffer.  A tandem-array group sheds only a few members per round, so nearly every group fits
+// the SMALL buffer (48 KB: two 1024-thread CTAs per SM -- with the one 193 KB buffer of round 1 the kernel ran one CTA
+// per SM at 48 % active warps); a group whose outliers do not fit is appended to an overflow list and redone by a
+// second, persistent launch with the BIG buffer.
+constexpr u32 GS_CAP_SMALL = 4096;
+constexpr u32 GS_CAP_BIG = 16384;                                 // outliers a CTA can sort in shared memory
+// shared memory layout for a buffer of CAP outliers: u64[CAP] (key2 << shift | suffix), sorted | u16[CAP] head index of
+// the outlier's sub-group | u16[CAP] sub-group size, stored at its head (CAP < 65536) | u32[128] misc | big sub-group
+// list: u32 head[64], u32 base[64]
+__host__ __device__ constexpr size_t gs_off_head(u32 cap) { return (size_t)cap * 8; }
+__host__ __device__ constexpr size_t gs_off_size(u32 cap) { return gs_off_head(cap) + (size_t)cap * 2; }
+__host__ __device__ constexpr size_t gs_off_misc(u32 cap) { return gs_off_size(cap) + (size_t)cap * 2; }
+__host__ __device__ constexpr size_t gs_smem(u32 cap) { return gs_off_misc(cap) + 512 + 2 * 64 * 4; }
 constexpr u32 GS_MAX_BIGSUB = 64;                                 // outlier sub-groups larger than gcap per group (more: fallback)
 
 template <int GS> __device__ __forceinline__ u32 gs_grp(u64 k) { return KeyHalves<GS>::grp(k); }
@@ -111,17 +118,21 @@ struct StreamOut {
     u32* maxgS;                                     // largest group appended to S
     u32* mB;                                        // next B length
     u32* fallback;                                  // set when a group cannot be handled here
+    // two-size launch: the SMALL pass appends the chunks whose group overflowed its buffer (ovf_out / ovf_cnt_out);
+    // the BIG pass (persistent CTAs) works through that list (ovf_in / ovf_cnt_in).  All null: one pass over all chunks.
+    u32* ovf_out; u32* ovf_cnt_out;
+    const u32* ovf_in; const u32* ovf_cnt_in;
 };
 
-template <int GS>
-__global__ void __launch_bounds__(GS_THREADS, 1)
-k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in,
-               u32 b0, u32 mB, u32 gcap, u32* __restrict__ SA, RankDst RANK, StreamOut out, int dbg) {
-    extern __shared__ __align__(16) unsigned char gs_smem[];
-    u64* okv = reinterpret_cast<u64*>(gs_smem + GS_OFF_KV);
-    unsigned short* ohead = reinterpret_cast<unsigned short*>(gs_smem + GS_OFF_HEAD);
-    unsigned short* osize = reinterpret_cast<unsigned short*>(gs_smem + GS_OFF_SIZE);
-    u32* misc = reinterpret_cast<u32*>(gs_smem + GS_OFF_MISC);
+template <int GS, u32 CAP>
+__device__ __forceinline__ void gs_process_chunk(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in,
+                                                 u32 b0, u32 mB, u32 gcap, u32* __restrict__ SA, const RankDst& RANK, const StreamOut& out, int dbg,
+                                                 u32 chunk_idx, unsigned char* gs_smem_base) {
+    constexpr u32 GS_OUT_CAP = CAP;
+    u64* okv = reinterpret_cast<u64*>(gs_smem_base);
+    unsigned short* ohead = reinterpret_cast<unsigned short*>(gs_smem_base + gs_off_head(CAP));
+    unsigned short* osize = reinterpret_cast<unsigned short*>(gs_smem_base + gs_off_size(CAP));
+    u32* misc = reinterpret_cast<u32*>(gs_smem_base + gs_off_misc(CAP));
     using KH = KeyHalves<GS>;
     using RT = typename KH::RT;
     constexpr int OS = OkvLayout<GS>::SHIFT;
@@ -144,7 +155,7 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
 
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 bend = b0 + mB;
-    const u32 c0 = b0 + blockIdx.x * gcap;
+    const u32 c0 = b0 + chunk_idx * gcap;
     if (c0 >= bend) return;
     u32 c1 = c0 + gcap;
     if (c1 > bend) c1 = bend;
@@ -215,7 +226,11 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
     __syncthreads();
     const u32 nout = s_nout, nlt = s_nlt, neq = M - nout;
     if (nout > GS_OUT_CAP || (dbg & 8)) {
-        if (tid == 0) atomicExch(out.fallback, 1u);
+        // does not fit: nothing has been written yet.  SMALL pass: leave the group to the BIG pass; otherwise: fallback
+        if (tid == 0) {
+            if (out.ovf_out && !(dbg & 8) && nout <= GS_CAP_BIG) out.ovf_out[atomicAdd(out.ovf_cnt_out, 1u)] = chunk_idx;
+            else atomicExch(out.fallback, 1u);
+        }
         return;
     }
     // ---- sort the outliers by (key2, suffix)
@@ -416,6 +431,24 @@ k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, c
             }
         }
     }
+}
+
+// One CTA per chunk of gcap list positions (a chunk holds at most one group head), or -- BIG pass of the two-size
+// launch -- persistent CTAs over the overflow list.
+template <int GS, u32 CAP>
+__global__ void __launch_bounds__(GS_THREADS, CAP <= GS_CAP_SMALL ? 2 : 1)
+k_group_stream(const u64* __restrict__ key_in, const u32* __restrict__ val_in, const u32* __restrict__ slot_in,
+               u32 b0, u32 mB, u32 gcap, u32* __restrict__ SA, RankDst RANK, StreamOut out, int dbg) {
+    extern __shared__ __align__(16) unsigned char gs_shared[];
+    if (out.ovf_in) {
+        const u32 n = *out.ovf_cnt_in;
+        for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
+            gs_process_chunk<GS, CAP>(key_in, val_in, slot_in, b0, mB, gcap, SA, RANK, out, dbg, out.ovf_in[q], gs_shared);
+            __syncthreads();
+        }
+        return;
+    }
+    gs_process_chunk<GS, CAP>(key_in, val_in, slot_in, b0, mB, gcap, SA, RANK, out, dbg, blockIdx.x, gs_shared);
 }
 
 }  // namespace nlz

@@ -40,6 +40,7 @@
 namespace nlz {
 
 constexpr u64 D2_MASK34 = (1ull << 34) - 1;
+constexpr u64 D2_MASK33 = (1ull << 33) - 1;      // a global rank (n' < 2^33)
 constexpr u64 D2_NO_PHI = D2_MASK34;            // Phi of global rank 0 (= PhiNone<u64>::value in lcp.cuh: Kasai stores 0 for it)
 constexpr u32 D2_MAX_LOCAL = 0x3FFFFF00u;       // suffixes / positions one GPU can own (30-bit local indices)
 
@@ -296,7 +297,9 @@ __global__ void k_d2_bucket_starts(const u32* __restrict__ counts, u32* __restri
     if (threadIdx.x == 0) { u32 run = 0; for (int g = 0; g < MAX_PEERS; ++g) { cursor[g] = run; run += g < G ? counts[g] : 0u; } }
 }
 
-// refined ranks: records (local rank << 32 | handle) of this round -> (position offset at its owner << 34 | global rank)
+// refined ranks: records (local rank << 32 | handle) of this round -> (position offset at its owner << 34 |
+// "LCP is pending" mark << 33 | global rank).  The mark (first regroup only, UPD_NEED_BIT) tells the position owner
+// that this suffix's LCP has to be computed from the text (lcp.cuh).
 struct UpdItem {
     const u64* upd;
     HandleMap hm;
@@ -306,16 +309,17 @@ struct UpdItem {
         const u64 p = hm.pos((u32)u);
         const u64 d = p / hm.chunk;
         dest = (u32)d;
-        a = ((p - d * hm.chunk) << 34) | (rbase + (u64)(u32)(u >> 32));
+        a = ((p - d * hm.chunk) << 34) | ((u >> 63) << 33) | (rbase + (u64)((u32)(u >> 32) & 0x7FFFFFFFu));
         return true;
     }
 };
 __global__ void __launch_bounds__(256)
-k_d2_apply_ranks(const u64* __restrict__ inbox, u32 cnt, u64* __restrict__ RANKL) {
+k_d2_apply_ranks(const u64* __restrict__ inbox, u32 cnt, u64* __restrict__ RANKL, u8* __restrict__ NEED) {
     const u32 e = blockIdx.x * 256 + threadIdx.x;
     if (e >= cnt) return;
     const u64 u = inbox[e];
-    RANKL[u >> 34] = u & D2_MASK34;
+    RANKL[u >> 34] = u & D2_MASK33;
+    if ((u >> 33) & 1ull) NEED[u >> 34] = 1;
 }
 
 // rank requests of a doubling round: active list entry j (S list [0, mS), B list [b0, b0 + mB)) asks the owner of
@@ -361,9 +365,11 @@ k_d2_sa_positions(const u32* __restrict__ SAh, u32 cnt, HandleMap hm, u64* __res
 // Phi: rank owner -> position owner.  item = local rank r:  (offset of SA[r] at its owner << 34 | SA[r-1])
 struct PhiItem {
     const u64* SA64;
+    const u32* LCP;         // local rank order: only the ranks whose LCP is still pending send their Phi
     u64 left_sa;            // SA of the global rank just before this GPU's range (D2_NO_PHI for global rank 0)
     u64 chunk;
     __device__ __forceinline__ bool item(u32 t, u32& dest, u64& a, u64& b) const {
+        if (LCP[t] != LCP_PENDING) return false;
         const u64 s = SA64[t];
         const u64 prev = t ? SA64[t - 1] : left_sa;
         const u64 d = s / chunk;
@@ -383,8 +389,10 @@ k_d2_apply_phi(const u64* __restrict__ inbox, u32 cnt, u64* __restrict__ PHI) {
 struct LcpItem {
     const u64* RANKL;
     const u32* PLCP;
+    const u8* NEED;         // only the marked positions were resolved
     RankBases rb;
     __device__ __forceinline__ bool item(u32 t, u32& dest, u64& a, u64& b) const {
+        if (!NEED[t]) return false;
         const u64 r = RANKL[t];
         const int g = rb.owner(r);
         dest = (u32)g;

@@ -263,6 +263,7 @@ struct D2Sa {
     u64* REQ;          // request staging (cnt entries)
     u64* RESP;         // pulled responses (cnt entries)
     u64* RANKL;        // my slice of RANK
+    u8* NEED;          // marks of my positions: LCP pending (lcp.cuh)
 };
 
 // One exchange step of a doubling round: (1) the ranks refined in the previous step travel to their position owners and
@@ -299,7 +300,7 @@ static int d2_round_exchange(D2& r, const D2Sa& a, u32 nupd_bound, const u32* nu
     if (xu.in_total) {
         r.c->stats.rank_records_applied += xu.in_total;
         KL(P, KC_XCHG, (u64)xu.in_total * 16, st,
-           (k_d2_apply_ranks<<<ceil_div_u32(xu.in_total, 256), 256, 0, st>>>(r.inbox, xu.in_total, a.RANKL)));
+           (k_d2_apply_ranks<<<ceil_div_u32(xu.in_total, 256), 256, 0, st>>>(r.inbox, xu.in_total, a.RANKL, a.NEED)));
     }
     if (!gm) return OK;
     if (xq.in_total)
@@ -344,8 +345,10 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         P.begin(st);
         k_regroup_reduce<u64, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
         k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
+        LcpSeed seed;                                        // LCP values that follow from adjacent key pairs; the rest is marked
+        seed.LCP = w.LCP; seed.NEED = nullptr; seed.lay = lay; seed.first_pending = r.base[r.me] > 0;
         k_regroup_apply<u64, true, GS><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, cnt, dist_mask, w.PMAX, w.PSUM,
-                                                                     w.SA, rdst, w.KEY[res ^ 1], w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3);
+                                                                     w.SA, rdst, w.KEY[res ^ 1], w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3, seed);
         P.end(KC_REGROUP, (u64)cnt * (2 * 8 + 4 + 8), st, 3);
         cur = res ^ 1;
         k_set_u32<<<1, 1, 0, st>>>(w.CTR + 4, cnt);           // every rank is new: cnt dense records
@@ -356,6 +359,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
     NLZ_CK(cudaStreamSynchronize(st));
     S.host_syncs += 1;
     m = c->h_pinned[0]; maxg = c->h_pinned[3];
+    S.lcp_marked = m;
     u32 nupd_bound = cnt;
 
     const int nbr = r.rank_bias ? 33 : bits_for((u32)std::min<u64>(pb.n1 - 1, 0xFFFFFFFFull)) + (pb.n1 > 0x100000000ull ? 1 : 0);   // bits of a global rank
@@ -435,8 +439,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
                 so.end = END; so.mS = w.CTR; so.maxgS = w.CTR + 3; so.mB = w.CTR + 6; so.fallback = w.CTR + 7;
                 const int dbg = (c->debug_flags & 8) && S.doubling_rounds >= 3 ? 8 : 0;
                 KL(P, KC_STREAM, (u64)mB * 44, st,
-                   (k_group_stream<GS><<<ceil_div_u32(mB, gcap), GS_THREADS, GS_SMEM, st>>>(
-                       w.KEY[cur], w.VAL[cur], w.SLOT[sc], b0, mB, gcap, w.SA, rdst, so, dbg)));
+                   (launch_group_stream<GS>(c, st, w.KEY[cur], w.VAL[cur], w.SLOT[sc], b0, mB, gcap, w.SA, rdst, so, dbg)));
             }
             S.tile_sort_rounds += 1;
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
@@ -667,6 +670,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     // ---- private workspace
     const u64 cap = (u64)std::max(m_loc, ch) + 2 * DIST_VIRT + 72;
     u64 *UPD, *ST, *RESP, *RANKL, *SA64, *PHI, *STB;
+    u8* NEED;
     u32 *OFFIN, *PLCP, *F0buf, *R0buf, *LCPbuf, *DCNT;
     u64* LRT; u8* FLT; u32 *alist, *MASK;
     u64* LRl; u8* FLl;
@@ -680,7 +684,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         need += d2_al(tiles_of(cap) * 4) * 2;                            // PMAX, PSUM
         { u64 cnt = cap + 1; for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; need += d2_al((cnt + 72) * 4) * 3; } }
         need += d2_al(cap * 8) * 4;                                      // UPD (later SA64), ST, STB, RESP
-        need += d2_al(((size_t)ch + 8) * 8);                             // RANKL
+        need += d2_al(((size_t)ch + 8) * 8) + d2_al((size_t)ch + 128);   // RANKL, NEED
         need += d2_al(cap * 4);                                          // OFFIN
         need += d2_al((cap + 72) * 4) * 3;                               // F0, R0, LCP (with virtual ranks)
         need += d2_al(ndc * 4 + SCAN_TILE * 4 + (ndc / SCAN_TILE + 8) * 4);   // DCNT + tile sums
@@ -711,6 +715,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         { u64 cnt = cap + 1; for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; w.tl[lev] = a.take<u32>(cnt + 72); w.tf[lev] = a.take<u32>(cnt + 72); w.tr[lev] = a.take<u32>(cnt + 72); } }
         UPD = a.take<u64>(cap); ST = a.take<u64>(cap); STB = a.take<u64>(cap); RESP = a.take<u64>(cap);
         RANKL = a.take<u64>((size_t)ch + 8);
+        NEED = a.take<u8>((size_t)ch + 128);
         OFFIN = a.take<u32>(cap);
         F0buf = a.take<u32>(cap + 72); R0buf = a.take<u32>(cap + 72); LCPbuf = a.take<u32>(cap + 72);
         DCNT = a.take<u32>(ndc + SCAN_TILE + ndc / SCAN_TILE + 8);
@@ -770,8 +775,10 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
 
     // ---- S1: local sort + doubling rounds (ranks travel as records, RANK[s+h] by request / response)
     if (ch) NLZ_CK(cudaMemsetAsync(RANKL, 0, ((size_t)ch + 8) * 8, st));
+    NLZ_CK(cudaMemsetAsync(NEED, 0, (size_t)ch + 128, st));
+    w.LCP = LCPbuf + DIST_VIRT;                                   // seeded by the first regroup
     D2Sa sa;
-    sa.UPD = UPD; sa.ST = ST; sa.REQ = STB; sa.RESP = RESP; sa.RANKL = RANKL;
+    sa.UPD = UPD; sa.ST = ST; sa.REQ = STB; sa.RESP = RESP; sa.RANKL = RANKL; sa.NEED = NEED;
     NLZ_TRY(d2_stage_sa(r, pb, lay, sa, m_loc));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 
@@ -786,7 +793,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         for (int g = me - 1; g >= 0; --g)
             if (r.base[g + 1] > r.base[g]) { left_sa = (u64)r.all[(size_t)g * 2] | ((u64)r.all[(size_t)g * 2 + 1] << 32); break; }
         PhiItem pi;
-        pi.SA64 = SA64; pi.left_sa = left_sa; pi.chunk = r.chunk;
+        pi.SA64 = SA64; pi.LCP = w.LCP; pi.left_sa = left_sa; pi.chunk = r.chunk;
         NLZ_TRY((d2_bucket<PhiItem, false>(r, pi, m_loc, nullptr, ST, nullptr, 24)));
         XInfo x;
         NLZ_TRY(d2_counts(r, 0, 8, x));
@@ -794,21 +801,22 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));
         if (x.in_total) KL(P, KC_LCP, (u64)x.in_total * 16, st, (k_d2_apply_phi<<<ceil_div_u32(x.in_total, 256), 256, 0, st>>>(r.inbox, x.in_total, PHI)));
         LcpSlice<u64> ld;
-        ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = r.pos0; ld.pos1 = r.pos1;
+        memset(&ld, 0, sizeof(ld));
+        ld.NEED = NEED; ld.PHI = PHI; ld.PLCP = PLCP; ld.pos0 = r.pos0; ld.pos1 = r.pos1;
+        ld.blocks_per_warp = lcp_blocks_per_warp(ch);
         BatchView bv;
         memset(&bv, 0, sizeof(bv));
         if (ch)
             KL(P, KC_LCP, (u64)ch * 28, st,
-               (k_lcp_kasai<false, u64><<<ceil_div_u32(ceil_div_u32(ch, LCP_Q), 256), 256, 0, st>>>(w.X, pb.L, bv, ld)));
+               (k_lcp_kasai<false, true, u64><<<ceil_div_u32(ceil_div_u32(ch, (u64)LCP_Q * ld.blocks_per_warp), 256), 256, 0, st>>>(w.X, pb.L, bv, ld)));
         LcpItem li;
-        li.RANKL = RANKL; li.PLCP = PLCP; li.rb.G = G;
+        li.RANKL = RANKL; li.PLCP = PLCP; li.NEED = NEED; li.rb.G = G;
         for (int g = 0; g <= G; ++g) li.rb.base[g] = r.base[g] + r.rank_bias;
         for (int g = G + 1; g <= MAX_PEERS; ++g) li.rb.base[g] = r.base[G] + r.rank_bias;
         NLZ_TRY((d2_bucket<LcpItem, false>(r, li, ch, nullptr, ST, nullptr, 20)));
         NLZ_TRY(d2_counts(r, 0, 8, x));
         NLZ_TRY(d2_push(r, x, ST, 8, 0));
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));
-        w.LCP = LCPbuf + DIST_VIRT;
         if (x.in_total) KL(P, KC_LCP, (u64)x.in_total * 12, st, (k_d2_apply_lcp<<<ceil_div_u32(x.in_total, 256), 256, 0, st>>>(r.inbox, x.in_total, w.LCP)));
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_LCP], st));

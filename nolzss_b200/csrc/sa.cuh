@@ -304,6 +304,36 @@ k_regroup_scan_partials(u32* __restrict__ pmax, u32* __restrict__ psum, u32 ntil
     if (threadIdx.x == 0) *m_out = tot;
 }
 
+// LCP of two adjacent suffixes of the initially sorted list, from their packed-prefix keys alone: the number of
+// leading symbols the keys share, cut at the first sentinel of either window (sentinels are unique symbols; batch
+// sentinels end their record).  Exact whenever the keys differ or a window holds a sentinel; W (the window) otherwise --
+// those pairs (members of a tie group behind its head) are the only ones the Kasai kernel has to look at.
+template <typename KeyT>
+__device__ __forceinline__ u32 key_pair_lcp(KeyT a, KeyT b, const KeyLayout& lay) {
+    const KeyT dmask = ((KeyT)1 << lay.D) - 1;
+    const KeyT x = a ^ b;
+    u32 common = (u32)lay.W;
+    if (x) {
+        const int p = sizeof(KeyT) == 8 ? __clzll((long long)x) : __clz((int)x);     // identical leading bits
+        if (p < lay.R) return 0;                                                      // different records (batch mode)
+        const u32 cs = (u32)(p - lay.R) / (u32)lay.b;
+        if (cs < common) common = cs;
+    }
+    const KeyT da = a & dmask, db = b & dmask;
+    if (da != dmask && (u32)da < common) common = (u32)da;
+    if (db != dmask && (u32)db < common) common = (u32)db;
+    return common;
+}
+constexpr u32 LCP_PENDING = 0xFFFFFFFFu;      // LCP entry left to the Kasai kernel
+// INITIAL regroup only: where the key-derived LCP values and the "Kasai has to compute this one" marks go
+struct LcpSeed {
+    u32* LCP;            // rank order (local slots); nullptr: no seeding
+    u8* NEED;            // by text position (one GPU); nullptr on the distributed path (the mark travels in the record)
+    KeyLayout lay;
+    bool first_pending;  // element 0 follows a suffix of ANOTHER GPU: its LCP cannot come from a key pair
+};
+constexpr u64 UPD_NEED_BIT = 1ull << 63;      // INITIAL records: the suffix is a member of a tie group (its LCP is pending)
+
 // phase C: ranks, SA write-back and compaction of the still-active elements.  GS: the doubling keys are
 // group << GS | rank (tile_sort.cuh); 33 on the distributed path, where RANK.rank is null (records only).
 template <typename KeyT, bool INITIAL, int GS = 32>
@@ -311,7 +341,8 @@ __global__ void __launch_bounds__(RG_THREADS)
 k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ slots,
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
                 u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
-                u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out) {
+                u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out,
+                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{0, 0, 0, 0, 0}, false}) {
     __shared__ u8 sh_head[RG_TILE + 8];
     __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
     const u64 tile_start = (u64)blockIdx.x * RG_TILE;
@@ -374,10 +405,20 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
             u32 slot = INITIAL ? e + RANK.base : slots[e];
             // the old rank of a member is its group's head slot = the high half of its doubling key
             const bool changed = INITIAL || newrank != (u32)((u64)keys[e] >> GS);
+            bool lcp_pending = false;
+            if (INITIAL && seed.LCP) {
+                // A singleton's LCP with its predecessor follows from the two keys.  The members of a tie group share their
+                // whole window (LCP >= W) and the doubling rounds still permute them inside the group's slot range -- which
+                // suffix ends up in which slot is not known yet -- so EVERY member is left to the Kasai kernel (for the one
+                // that lands in the head slot it recomputes what the key pair says).
+                lcp_pending = act[q] || (e == 0 && seed.first_pending);
+                seed.LCP[slot - RANK.base] = lcp_pending ? LCP_PENDING : (e == 0 ? 0u : key_pair_lcp<KeyT>(keys[e - 1], keys[e], seed.lay));
+                if (lcp_pending && seed.NEED) seed.NEED[s] = 1;
+            }
             if (changed) {
                 if (RANK.rank) RANK.rank[s] = newrank;
                 if (RANK.upd) {
-                    if (INITIAL) RANK.upd[e] = ((u64)newrank << 32) | (u64)s;      // every rank is new: dense list
+                    if (INITIAL) RANK.upd[e] = ((u64)newrank << 32) | (u64)s | (lcp_pending ? UPD_NEED_BIT : 0ull);      // every rank is new: dense list
                     else { upd_rec[nupd] = ((u64)newrank << 32) | (u64)s; ++nupd; }
                 }
             }
