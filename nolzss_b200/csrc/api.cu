@@ -303,7 +303,24 @@ static int bits_for(u32 maxval) {
     return nb;
 }
 
-static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout& lay) {
+// Symbols per 64-bit key: enough that a random text keeps its expected fraction of colliding windows below ~1.5 %
+// (sigma^W >= 64 n'), rounded up to fill the 8-bit radix passes that many symbols need anyway, at most 29.  Fewer symbols
+// = fewer passes of the initial sort; suffixes that tie on the window go through prefix doubling either way (they are
+// the repeats), which then starts from h = W.
+static int layout_symbols(int sigma, int b, int R, int D, u64 n1) {
+    const int wmax = std::min(29, (64 - R - D) / b);
+    double space = 1.0;
+    int wmin = 0;
+    while (wmin < wmax && space < 64.0 * (double)n1) { space *= (double)(sigma > 1 ? sigma : 2); ++wmin; }
+    if (wmin < 1) wmin = 1;
+    const int passes = (R + wmin * b + D + 7) / 8;
+    int W = (passes * 8 - R - D) / b;
+    if (W > wmax) W = wmax;
+    if (W < wmin) W = wmin;
+    return W;
+}
+
+static int choose_layout(const u32 hist[256], u64 n1, ClassTable& tab, KeyLayout& lay) {
     int sigma = 0;
     for (int c = 0; c < 256; ++c) {
         if (hist[c] >= 2) tab.cls[c] = (u8)sigma++;
@@ -323,9 +340,8 @@ static int choose_layout(const u32 hist[256], u32 n1, ClassTable& tab, KeyLayout
     if (use32) {
         lay.key_bits = 32; lay.b = b; lay.W = w32; lay.D = 4; lay.R = 0;
     } else {
-        int w64 = 59 / b;
-        if (w64 > 29) w64 = 29;
-        lay.key_bits = 64; lay.b = b; lay.W = w64; lay.D = 5; lay.R = 0;
+        lay.key_bits = 64; lay.b = b; lay.D = 5; lay.R = 0;
+        lay.W = layout_symbols(sigma, b, 0, 5, n1);
     }
     return OK;
 }
@@ -373,17 +389,11 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     *cur_out = 1; *m_out = 0; *maxg_out = 0;
     if (cnt == 0) { NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st)); return OK; }
     DigitPlan plan;
-    const int used_lo = lay.key_bits - lay.R - lay.W * lay.b;   // lowest symbol bit
-    if (used_lo - lay.D >= 6) {                         // wide unused gap: skip it
-        plan_add_range(plan, 0, lay.D);                 // sentinel-offset field
-        plan_add_range(plan, used_lo, lay.key_bits);    // symbols
-    } else {
-        plan_add_range(plan, 0, lay.key_bits);
-    }
+    plan_add_range(plan, lay.dshift(), lay.key_bits);   // sentinel-offset field, symbols (, record id): one bit range
     int res = 0;
     NLZ_TRY(radix_sort_pairs<KeyT>(k, v, cnt, plan, w.HIST, st, &res, P));
     NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
-    const KeyT dist_mask = ((KeyT)1 << lay.D) - 1;
+    const KeyT dist_mask = (((KeyT)1 << lay.D) - 1) << lay.dshift();
     const u32 tiles = ceil_div_u32(cnt, RG_TILE);
     // compaction target must not alias the sorted buffers: use the other KEY/VAL pair.  The first regroup also seeds
     // the LCP array from adjacent key pairs and marks the suffixes whose LCP needs the text (lcp.cuh).
@@ -893,8 +903,10 @@ static int stage_prepare(nlz_ctx* c, const Problem& pb, const void* src, bool sr
         for (int ch = 0; ch < 256; ++ch) tab.cls[ch] = (u8)SENT_CLASS;
         tab.cls['A'] = 0; tab.cls['C'] = 1; tab.cls['G'] = 2; tab.cls['T'] = 3;
         lay.key_bits = 64; lay.b = 2; lay.D = 5; lay.R = bits_for(pb.nrec);
-        lay.W = (59 - lay.R) / 2;
-        if (lay.W > 29) lay.W = 29;
+        // windows only collide inside a record: size the window for the longest record
+        u32 longest = 1;
+        for (u32 q = 0; q < pb.nrec; ++q) longest = std::max(longest, pb.h_flen[q]);
+        lay.W = layout_symbols(4, 2, lay.R, 5, (u64)longest * (pb.rc ? 2 : 1) + 2);
     } else {
         choose_layout(c->h_pinned + 16, n1, tab, lay);
     }

@@ -38,6 +38,7 @@ struct DistCtl {
     u32 error;                                         // set by a barrier that timed out
     u32 pad[7];
     u32 xch[2][MAX_PEERS][DIST_XCH_WORDS];             // exchange slots, double-buffered by exchange parity
+    u32 packed[MAX_PEERS * DIST_XCH_WORDS + 8];        // after a payload barrier: [g * nwords + w] of every rank, then the time-out flag
 };
 
 struct DistPeers {
@@ -77,6 +78,13 @@ k_dist_barrier(DistPeers peers, u32 epoch, int parity, const u32* __restrict__ s
         }
     }
     __threadfence_system();
+    if (nwords) {                                       // pack everybody's words for ONE host readback
+        __syncthreads();
+        DistCtl* my = peers.ctl[me];
+        for (u32 i = threadIdx.x; i < nwords * (u32)G; i += blockDim.x)
+            my->packed[i] = *(volatile u32*)&my->xch[parity][i / nwords][i % nwords];
+        if (threadIdx.x == 0) my->packed[nwords * (u32)G] = *(volatile u32*)&my->error;
+    }
 }
 
 // splitters from the scanned prefix histogram: rank g owns buckets [split[g], split[g+1]) = global

@@ -110,14 +110,13 @@ static int d2_barrier(D2& r, const u32* d_src, u32 nwords, bool want_host) {
        (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords, timeout_s)));
     if (d->hb) NLZ_CK(cudaStreamSynchronize(st));
     if (!want_host) return OK;
+    // one readback for everybody's words (the barrier kernel packs them, together with the time-out flag, into a
+    // contiguous block of this rank's control area) -- a copy per rank costs more than the barrier itself
     DistCtl* mine = reinterpret_cast<DistCtl*>(d->seg);
-    for (int g = 0; g < r.G; ++g)
-        NLZ_CK(cudaMemcpyAsync(d->h_pin + (size_t)g * nwords, &mine->xch[d->xparity][g][0], (size_t)nwords * 4,
-                               cudaMemcpyDeviceToHost, st));
-    NLZ_CK(cudaMemcpyAsync(d->h_pin + (size_t)MAX_PEERS * DIST_XCH_WORDS, &mine->error, 4, cudaMemcpyDeviceToHost, st));
+    NLZ_CK(cudaMemcpyAsync(d->h_pin, &mine->packed[0], ((size_t)r.G * nwords + 1) * 4, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
     r.c->stats.host_syncs += 1;
-    if (d->h_pin[(size_t)MAX_PEERS * DIST_XCH_WORDS] != 0) {
+    if (d->h_pin[(size_t)r.G * nwords] != 0) {
         set_error("distributed barrier %u timed out on rank %d (a peer failed or never arrived)", d->epoch, r.me);
         return ERR_RUNTIME;
     }
@@ -334,13 +333,11 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         u64* k[2] = {w.KEY[0], w.KEY[1]};
         u32* v[2] = {w.VAL[0], w.VAL[1]};
         DigitPlan plan;
-        const int used_lo = lay.key_bits - lay.R - lay.W * lay.b;
-        if (used_lo - lay.D >= 6) { plan_add_range(plan, 0, lay.D); plan_add_range(plan, used_lo, lay.key_bits); }
-        else plan_add_range(plan, 0, lay.key_bits);
+        plan_add_range(plan, lay.dshift(), lay.key_bits);
         int res = 0;
         NLZ_TRY(radix_sort_pairs<u64>(k, v, cnt, plan, w.HIST, st, &res, P));
         NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
-        const u64 dist_mask = (1ull << lay.D) - 1;
+        const u64 dist_mask = ((1ull << lay.D) - 1) << lay.dshift();
         const u32 tiles = ceil_div_u32(cnt, RG_TILE);
         P.begin(st);
         k_regroup_reduce<u64, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
@@ -587,7 +584,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         u32 hist[256];
         for (int ch = 0; ch < 256; ++ch) hist[ch] = 0;
         hist['A'] = hist['C'] = hist['G'] = hist['T'] = 2;
-        choose_layout(hist, 0xFFFFFFFFu, tab, lay);                         // forces 64-bit keys
+        choose_layout(hist, std::max<u64>(pb.n1, 0x100000000ull), tab, lay);   // forces 64-bit keys
     } else {
         NLZ_CK(cudaMemcpyAsync(w.X, text, pb.n_in, cudaMemcpyDefault, st));
         k_zero_pad<<<1, 128, 0, st>>>(w.X, pb.L);
@@ -599,7 +596,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         P.end(KC_PREPARE, pb.n_in + 2 * pb.L, st, 2);
         NLZ_CK(cudaMemcpyAsync(c->h_pinned + 16, BYTEHIST, 256 * 4, cudaMemcpyDeviceToHost, st));
         NLZ_CK(cudaStreamSynchronize(st));
-        choose_layout(c->h_pinned + 16, 0xFFFFFFFFu, tab, lay);             // forces 64-bit keys
+        choose_layout(c->h_pinned + 16, std::max<u64>(pb.n1, 0x100000000ull), tab, lay);   // forces 64-bit keys
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));                          // (keeps the barrier sequence of both branches aligned)
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_PREP], st));

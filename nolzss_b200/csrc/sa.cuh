@@ -33,6 +33,10 @@ struct KeyLayout {
     int W;          // symbols per key
     int D;          // bits of the sentinel-offset field
     int R;          // bits of the record-id prefix (batch mode: suffixes are grouped by record first)
+    // Bit layout, MSB first: [R record id][W*b symbols][D sentinel offset][unused zeros].  The offset field sits directly
+    // below the symbols, so the initial sort covers ONE bit range [dshift(), key_bits) -- and W is chosen as small as
+    // the text allows (layout_symbols in api.cu): a 250 Mbp text sorts 47 bits in 6 passes instead of 64 in 8.
+    __host__ __device__ int dshift() const { return key_bits - R - W * b - D; }
 };
 
 // Batch mode (many independent records in one text): record id of every text position and the
@@ -132,6 +136,7 @@ __device__ __forceinline__ KeyT kb_key(const u8* cls, const u8* tile, int o, u64
     const int kb = lay.key_bits, b = lay.b, W = lay.W;
     KeyT key = 0;
     KeyT dist = ((KeyT)1 << lay.D) - 1;
+    const int dsh = lay.dshift();
     int sh = kb - lay.R - b;
     if (lay.R) key = (KeyT)REC[p] << (kb - lay.R);
     for (int t = 0; t < W; ++t, sh -= b) {
@@ -139,7 +144,7 @@ __device__ __forceinline__ KeyT kb_key(const u8* cls, const u8* tile, int o, u64
         if (c == SENT_CLASS) { dist = (KeyT)t; break; }
         key |= (KeyT)c << sh;
     }
-    return key | dist;
+    return key | (dist << dsh);
 }
 
 template <typename KeyT>
@@ -311,6 +316,7 @@ k_regroup_scan_partials(u32* __restrict__ pmax, u32* __restrict__ psum, u32 ntil
 template <typename KeyT>
 __device__ __forceinline__ u32 key_pair_lcp(KeyT a, KeyT b, const KeyLayout& lay) {
     const KeyT dmask = ((KeyT)1 << lay.D) - 1;
+    const int dsh = lay.dshift();
     const KeyT x = a ^ b;
     u32 common = (u32)lay.W;
     if (x) {
@@ -319,7 +325,7 @@ __device__ __forceinline__ u32 key_pair_lcp(KeyT a, KeyT b, const KeyLayout& lay
         const u32 cs = (u32)(p - lay.R) / (u32)lay.b;
         if (cs < common) common = cs;
     }
-    const KeyT da = a & dmask, db = b & dmask;
+    const KeyT da = (a >> dsh) & dmask, db = (b >> dsh) & dmask;
     if (da != dmask && (u32)da < common) common = (u32)da;
     if (db != dmask && (u32)db < common) common = (u32)db;
     return common;
@@ -342,7 +348,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
                 u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
                 u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out,
-                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{0, 0, 0, 0, 0}, false}) {
+                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{64, 1, 1, 1, 0}, false}) {
     __shared__ u8 sh_head[RG_TILE + 8];
     __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
     const u64 tile_start = (u64)blockIdx.x * RG_TILE;
