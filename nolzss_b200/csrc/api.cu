@@ -398,16 +398,34 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     // compaction target must not alias the sorted buffers: use the other KEY/VAL pair.  The first regroup also seeds
     // the LCP array from adjacent key pairs and marks the suffixes whose LCP needs the text (lcp.cuh).
     LcpSeed seed;
-    seed.LCP = w.LCP; seed.NEED = w.NEED; seed.lay = lay; seed.first_pending = false;
+    seed.LCP = w.LCP; seed.NEED = w.NEED; seed.lay = lay; seed.first_pending = false; seed.RANKOUT = nullptr;
+    RankDst rdst0 = local_rank_dst(c);
+    // RANK beyond the L2 cache: partitioned scatter of the inverse suffix array (see LcpSeed::RANKOUT); the node table
+    // (dead until stage 3) lends the three n'-word buffers
+    static const bool no_part = getenv("NLZ_NO_PARTITIONED_ISA") != nullptr;
+    const bool part_isa = cnt > (48u << 20) && !no_part;
+    u32* NR = reinterpret_cast<u32*>(w.NODE);
+    if (part_isa) { seed.RANKOUT = NR; rdst0.rank = nullptr; }
     NLZ_CK(cudaMemsetAsync(w.NEED, 0, (size_t)n1 + 64, st));
     NLZ_CK(cudaMemsetAsync(w.LCP + n1, 0, 4, st));              // right guard used by the interval walks
     P.begin(st);
     k_regroup_reduce<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
     k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
     k_regroup_apply<KeyT, true><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, cnt, dist_mask, w.PMAX,
-                                                              w.PSUM, w.SA, local_rank_dst(c), w.KEY[res ^ 1],
+                                                              w.PSUM, w.SA, rdst0, w.KEY[res ^ 1],
                                                               w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3, seed);
     P.end(KC_REGROUP, (u64)cnt * (2 * kb + 4 + 8 + 4), st, 3);
+    if (part_isa) {
+        u32* pk[2] = {w.SA, NR + (size_t)cnt};                 // one pass: the input pair (SA, new ranks) is only read
+        u32* pv[2] = {NR, NR + 2 * (size_t)cnt};
+        DigitPlan pp;
+        const int nbp = bits_for(n1 - 1);
+        plan_add_range(pp, nbp > 8 ? nbp - 8 : 0, nbp);
+        int pres = 0;
+        NLZ_TRY(radix_sort_pairs<u32>(pk, pv, cnt, pp, w.HIST, st, &pres, P));
+        u32 grid = ceil_div_u32(cnt, 256 * 8);
+        KL(P, KC_REGROUP, (u64)cnt * 12, st, (k_scatter_pairs<<<grid, 256, 0, st>>>(pk[pres], pv[pres], cnt, w.RANK)));
+    }
     *cur_out = res ^ 1;
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));
     NLZ_CK(cudaStreamSynchronize(st));
@@ -710,6 +728,8 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
     }
     unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);   // [0] probes, [1] hard
     NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 16, st));
+    // flag plane: zero = ordinary forward / literal factor; k_lpnf_rank stores only the hard and the RC marks
+    NLZ_CK(cudaMemsetAsync(FLAGS, 0, bylist ? (size_t)(wp.real_hi - wp.real_lo) : (size_t)wp.nfac, st));
     // algorithmic bytes: the leaf value of every rank; per factorized position the two LCP neighbours, the
     // LR store and the flag byte; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);

@@ -774,7 +774,7 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, con
             }
             bool is_rc;
             LR[o] = select_factor<RC, false>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR, is_rc);
-            HARD[o] = is_rc ? FLAG_RC : 0;
+            if (is_rc) HARD[o] = FLAG_RC;           // the plane is zeroed beforehand: most positions need no (scattered) store
         } else {
             // Park the RC candidate depth for k_lpnf_hard, and a depth that is KNOWN to satisfy the forward predicate:
             // the last ancestor A that failed has minF(A) + depth(A) > i, and every D < depth(A) has interval(D)

@@ -337,7 +337,16 @@ struct LcpSeed {
     u8* NEED;            // by text position (one GPU); nullptr on the distributed path (the mark travels in the record)
     KeyLayout lay;
     bool first_pending;  // element 0 follows a suffix of ANOTHER GPU: its LCP cannot come from a key pair
+    // Large texts, one GPU: the inverse suffix array RANK[s] = rank is a scatter of n' 4-byte stores over gigabytes --
+    // bound by the GPU's random-access rate.  Instead the new ranks are written in rank order here (coalesced), the
+    // (suffix, rank) pairs are partitioned by the top 8 bits of the suffix position (one radix pass), and a last
+    // kernel scatters them window by window (8 MB of RANK at a time: L2-resident).  nullptr: direct scatter.
+    u32* RANKOUT;
 };
+__global__ void __launch_bounds__(256)
+k_scatter_pairs(const u32* __restrict__ pos, const u32* __restrict__ val, u32 m, u32* __restrict__ dst) {
+    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < m; e += gridDim.x * 256) dst[pos[e]] = val[e];
+}
 constexpr u64 UPD_NEED_BIT = 1ull << 63;      // INITIAL records: the suffix is a member of a tie group (its LCP is pending)
 
 // phase C: ranks, SA write-back and compaction of the still-active elements.  GS: the doubling keys are
@@ -348,7 +357,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
                 u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
                 u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out,
-                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{64, 1, 1, 1, 0}, false}) {
+                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{64, 1, 1, 1, 0}, false, nullptr}) {
     __shared__ u8 sh_head[RG_TILE + 8];
     __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
     const u64 tile_start = (u64)blockIdx.x * RG_TILE;
@@ -421,6 +430,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
                 seed.LCP[slot - RANK.base] = lcp_pending ? LCP_PENDING : (e == 0 ? 0u : key_pair_lcp<KeyT>(keys[e - 1], keys[e], seed.lay));
                 if (lcp_pending && seed.NEED) seed.NEED[s] = 1;
             }
+            if (INITIAL && seed.RANKOUT) seed.RANKOUT[e] = newrank;
             if (changed) {
                 if (RANK.rank) RANK.rank[s] = newrank;
                 if (RANK.upd) {
