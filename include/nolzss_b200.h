@@ -63,6 +63,8 @@ typedef struct nlz_stats {
     /* suffixes still tied after the initial key sort (members of tie groups): an upper bound of the positions whose LCP
      * the Kasai kernel computes from the text -- every other LCP value follows from a pair of sort keys */
     uint64_t lcp_marked;
+    /* distributed runs: suffixes of this GPU's rank range (the partition's balance: max over ranks / mean) */
+    uint64_t n_local_suffixes;
 } nlz_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -33,7 +33,7 @@ class Stats(ctypes.Structure):
         ("ms_total", ctypes.c_float), ("ms_prepare", ctypes.c_float), ("ms_keys", ctypes.c_float),
         ("ms_sort0", ctypes.c_float), ("ms_doubling", ctypes.c_float), ("ms_lcp", ctypes.c_float),
         ("ms_lpnf", ctypes.c_float), ("ms_chain", ctypes.c_float),
-        ("rank_records_applied", _u64), ("lcp_marked", _u64),
+        ("rank_records_applied", _u64), ("lcp_marked", _u64), ("n_local_suffixes", _u64),
     ]
 
     def as_dict(self):

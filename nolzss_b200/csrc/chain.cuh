@@ -23,6 +23,7 @@ constexpr int CH_THREADS = 256;
 constexpr int CH_CHUNK = 1024;
 constexpr int CH_PER_THREAD = CH_CHUNK / CH_THREADS;
 constexpr int CH_ROUNDS = 10;  // 2^10 = CH_CHUNK hops
+constexpr int CH_HASH_BITS = 11, CH_HASH = 1 << CH_HASH_BITS;
 
 // One text across G GPUs (dist2.cuh): the positions [0, nfac) are dealt in G slices of `chunk` positions (a multiple
 // of CH_CHUNK); GPU g holds LR / FLAGS / MASK of its slice [t0, t1) and the slice of the chain-node arrays (exit
@@ -49,11 +50,13 @@ __global__ void __launch_bounds__(CH_THREADS)
 k_chain_exit(const u64* __restrict__ LR, u32 t0, u32 t1, u32 nfac, u32* __restrict__ EXIT, u32* __restrict__ alist,
              u32* __restrict__ acount) {
     __shared__ u32 nx[2][CH_CHUNK];
+    __shared__ u32 hs[CH_HASH];            // exit values already listed by this chunk
     __shared__ u32 s_cnt, s_base;
     const u32 base = t0 + blockIdx.x * CH_CHUNK;
     u32 end = base + CH_CHUNK;
     if (end > t1) end = t1;
     if (threadIdx.x == 0) s_cnt = 0;
+    for (int i = threadIdx.x; i < CH_HASH; i += CH_THREADS) hs[i] = 0xFFFFFFFFu;
 #pragma unroll
     for (int t = 0; t < CH_PER_THREAD; ++t) {
         u32 o = t * CH_THREADS + threadIdx.x;
@@ -74,7 +77,10 @@ k_chain_exit(const u64* __restrict__ LR, u32 t0, u32 t1, u32 nfac, u32* __restri
         __syncthreads();
         cur ^= 1;
     }
-    // publish exits; collect the distinct in-range exit values (adjacent de-duplication)
+    // publish exits; collect the DISTINCT in-range exit values.  The chains of a chunk converge onto a handful of exits,
+    // but neighbouring positions sit on different chains, so equal values interleave: a small shared-memory hash set
+    // keeps each value once (round 1 de-duplicated adjacent positions only and listed ~50 nodes per chunk; every listed
+    // node costs three scattered accesses in each of the ~20 doubling rounds)
     u32 myv[CH_PER_THREAD];
     u32 myslot[CH_PER_THREAD];
 #pragma unroll
@@ -86,8 +92,17 @@ k_chain_exit(const u64* __restrict__ LR, u32 t0, u32 t1, u32 nfac, u32* __restri
         if (e < t1) {
             u32 v = nx[cur][o];
             EXIT[e - t0] = v;
-            bool fresh = (o == 0) || (nx[cur][o - 1] != v);
-            if (v < nfac && fresh) { myv[t] = v; myslot[t] = atomicAdd(&s_cnt, 1u); }
+            bool fresh = v < nfac && ((o == 0) || (nx[cur][o - 1] != v));
+            if (fresh) {
+                u32 slot = (v * 2654435761u) >> (32 - CH_HASH_BITS);
+                for (int probe = 0; probe < 8; ++probe) {
+                    const u32 old = atomicCAS(&hs[slot], 0xFFFFFFFFu, v);
+                    if (old == 0xFFFFFFFFu) break;                   // first to list v
+                    if (old == v) { fresh = false; break; }          // already listed
+                    slot = (slot + 1) & (CH_HASH - 1);               // (table full around here: list v again, harmless)
+                }
+            }
+            if (fresh) { myv[t] = v; myslot[t] = atomicAdd(&s_cnt, 1u); }
         }
     }
     __syncthreads();

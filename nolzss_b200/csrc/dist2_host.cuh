@@ -43,6 +43,7 @@ struct nlz_dist {
     HostBarrier* hb = nullptr;
     bool owns_hb = false;
     u32* h_pin = nullptr;              // pinned: exchange readback
+    u64 last_m_loc = 0;                // suffixes of this rank's range in the last call
     u32* SMALL = nullptr;              // device scratch: CTR[64] | PAY[512] | CURSOR[16] | SPLIT[16] | BASE64[2*16] | misc
     Arena arena;                       // per-call private workspace
 };
@@ -660,6 +661,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         }
     }
     r.m_loc = (u32)(r.base[me + 1] - r.base[me]);
+    d->last_m_loc = r.m_loc;
     const u32 m_loc = r.m_loc;
     const u32 ch = r.ch;
     const u32 nT = r.t1 - r.t0;                                      // T-positions of my slice
@@ -1079,7 +1081,9 @@ int nlz_dist_create(nlz_ctx* c, int rank, int world, uint64_t max_text_bytes, in
     nlz_dist* d = new nlz_dist();
     d->ctx = c; d->rank = rank; d->world = world; d->max_n1 = max_n1; d->max_nfac = max_text_bytes;
     const u64 chunk = ((max_n1 + world - 1) / world + KB_TP - 1) / KB_TP * KB_TP;
-    d->inbox_items = 2 * chunk + 65536;
+    // room for a rank range of up to 4x the mean (a text whose suffixes crowd into a few 12-symbol buckets -- long
+    // homopolymers, short-period tandem arrays -- cannot be balanced by ANY prefix partition: a tie group is one unit)
+    d->inbox_items = 4 * chunk + 65536;
     d->max_chT = ((max_text_bytes + world - 1) / world + CH_CHUNK - 1) / CH_CHUNK * CH_CHUNK + CH_CHUNK;
     d->off_x = d2_al(sizeof(DistCtl));
     d->off_hist = d->off_x + d2_al(max_n1 + 512);
@@ -1196,6 +1200,7 @@ static int dist_factorize_impl(nlz_dist* d, int mode, const uint8_t* text, uint6
     pstat.n_in = pb.n_in; pstat.n1 = (u32)std::min<u64>(pb.n1, 0xFFFFFFFFull); pstat.nfac = pb.nfac;
     finish_stats(c, pstat);
     c->stats.n_suffixes = pb.n1;
+    c->stats.n_local_suffixes = d->last_m_loc;
     *out_count = z;
     return OK;
 }

@@ -88,6 +88,38 @@ class LocalGroup:
         assert len(counts) == 1, f"ranks disagree on the factor count: {counts}"
         return results[0][0], [_ctx_stats(c) for c in self.ctxs]
 
+    def factorize_device_text(self, mode: int, data, devices):
+        """As `factorize`, through nlz_dist_factorize_into: every rank passes a DEVICE pointer to its own copy of the text
+        (already resident in its HBM) and rank 0 a caller-provided output buffer.  Returns the triples of rank 0."""
+        import torch
+
+        lib = L.load()
+        addr, n, keep = L._as_buffer(data)
+        host = np.frombuffer(keep, dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
+        texts = [torch.from_numpy(host.copy()).to(f"cuda:{dev}") for dev in devices]
+        cap = n + 16
+        out = np.zeros((cap, 3), dtype=np.uint64)
+        counts = [None] * self.world
+        errors = [None] * self.world
+
+        def work(g):
+            cnt = L._u64(0)
+            rc = lib.nlz_dist_factorize_into(self.dists[g], mode, texts[g].data_ptr() if n else None, n,
+                                             out.ctypes.data if g == 0 else None, cap if g == 0 else 0, ctypes.byref(cnt))
+            if rc != L.NLZ_OK:
+                errors[g] = lib.nlz_last_error().decode("utf-8", "replace")
+            counts[g] = cnt.value
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(self.world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if any(errors):
+            raise RuntimeError("; ".join(f"rank {g}: {e}" for g, e in enumerate(errors) if e))
+        assert len(set(counts)) == 1
+        return out[:counts[0]].copy()
+
     def close(self):
         lib = L.load()
         for d in self.dists:

@@ -4,7 +4,9 @@ Reference: `shuffle_fasta_sequences` in /root/reference/src/noLZSS/genomics/batc
 record is shuffled on its own, headers are kept, lines are 80 characters.  `method="reference"` reproduces the
 reference's output byte for byte for a given seed (same `random.seed` / `random.shuffle` calls in record order);
 `method="numpy"` permutes with numpy (vectorised: the reference needs about a microsecond per base in Python,
-i.e. the better part of an hour for a 3.1 Gbp genome) and is NOT seed-compatible with the reference.
+i.e. the better part of an hour for a 3.1 Gbp genome) and is NOT seed-compatible with the reference;
+`method="gpu"` permutes every record on the GPU (`torch.randperm` on the device the factorizer runs on, seeded
+generator; deterministic for a given seed and device type, not seed-compatible with the reference either).
 
 `factorize_with_shuffled_control` is the two-job driver: real and shuffled FASTA -> two noLZSSv2 factor files
 (the inputs of `calculate_factor_length_threshold`).
@@ -25,8 +27,8 @@ def shuffle_fasta_sequences(input_path: Union[str, Path], output_path: Union[str
                             logger: Optional[logging.Logger] = None, method: str = "reference") -> bool:
     logger = logger or logging.getLogger(__name__)
     input_path, output_path = Path(input_path), Path(output_path)
-    if method not in ("reference", "numpy"):
-        raise ValueError("method must be 'reference' or 'numpy'")
+    if method not in ("reference", "numpy", "gpu"):
+        raise ValueError("method must be 'reference', 'numpy' or 'gpu'")
     try:
         logger.info(f"Creating shuffled version of {input_path}")
         with open(input_path, "r", encoding="utf-8") as f:
@@ -39,8 +41,15 @@ def shuffle_fasta_sequences(input_path: Union[str, Path], output_path: Union[str
         if method == "reference":
             if seed is not None:
                 random.seed(seed)                              # batch_factorize.py:244-246 (module-level generator)
-        else:
+        elif method == "numpy":
             rng = np.random.default_rng(seed)
+        else:
+            import torch
+
+            if not torch.cuda.is_available():
+                raise RuntimeError("method='gpu' needs a CUDA device")
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(0 if seed is None else int(seed))
         output_path.parent.mkdir(parents=True, exist_ok=True)
         with open(output_path, "w", encoding="utf-8") as f:
             for seq_id, sequence in sequences.items():
@@ -48,9 +57,13 @@ def shuffle_fasta_sequences(input_path: Union[str, Path], output_path: Union[str
                     seq_list = list(sequence)
                     random.shuffle(seq_list)                   # :255-257
                     shuffled = "".join(seq_list)
-                else:
+                elif method == "numpy":
                     arr = np.frombuffer(sequence.encode("ascii"), dtype=np.uint8)
                     shuffled = rng.permutation(arr).tobytes().decode("ascii")
+                else:
+                    arr = torch.frombuffer(bytearray(sequence.encode("ascii")), dtype=torch.uint8).cuda()
+                    perm = torch.randperm(arr.numel(), device="cuda", generator=gen)
+                    shuffled = arr[perm].cpu().numpy().tobytes().decode("ascii")
                 f.write(f">{seq_id}\n")
                 for i in range(0, len(shuffled), 80):          # :261-263
                     f.write(shuffled[i:i + 80] + "\n")

@@ -27,7 +27,7 @@ def launches(src, dst):
         t[0] += 1
         t[1] += float(r[vi].replace(",", ""))
     total = sum(v[1] for v in tot.values())
-    mine = {k: v for k, v in tot.items() if "nlz::" in k}
+    mine = {k: v for k, v in tot.items() if "nlz::" in k or k.startswith("k_")}
     mtotal = sum(v[1] for v in mine.values())
     with open(dst, "w") as f:
         f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)\n\n")

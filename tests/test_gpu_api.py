@@ -250,3 +250,33 @@ def test_multi_record_fasta_config3_style(tmp_path):
         for i in share:
             merged[i] = ext.factorize_dna_w_rc(recs[i][1])
     assert [merged[i] for i in range(len(recs))] == per
+
+
+def test_shuffled_control_on_the_gpu_and_two_file_threshold(tmp_path):
+    """configs[4] tail: per-record permutation on the GPU (same multiset of bases per record, headers
+    kept, deterministic for a seed), then real + shuffled factor files (footer V7) -> calculate_factor_length_threshold."""
+    from collections import Counter
+
+    from nolzss_b200 import genomics
+    from nolzss_b200.genomics import shuffle_control
+
+    fa = tmp_path / "g.fasta"
+    recs = [wl.planted_dna(120_000, 50 + r, scale=0.2).tobytes() for r in range(3)]
+    with open(fa, "wb") as f:
+        for r, s in enumerate(recs):
+            f.write(b">chr%d desc\n" % r)
+            for i in range(0, len(s), 80):
+                f.write(s[i:i + 80] + b"\n")
+    a, b = tmp_path / "a.fasta", tmp_path / "b.fasta"
+    assert shuffle_control.shuffle_fasta_sequences(fa, a, seed=7, method="gpu")
+    assert shuffle_control.shuffle_fasta_sequences(fa, b, seed=7, method="gpu")
+    assert a.read_bytes() == b.read_bytes()
+    from nolzss_b200.genomics.fasta import _parse_fasta_content
+    sh = _parse_fasta_content(a.read_text())
+    assert list(sh.keys()) == ["chr0", "chr1", "chr2"]
+    for r, s in enumerate(recs):
+        assert Counter(sh[f"chr{r}"].encode()) == Counter(s) and sh[f"chr{r}"].encode() != s
+    real_bin, shuf_bin, n_real, n_shuf = shuffle_control.factorize_with_shuffled_control(fa, tmp_path / "out", seed=6, method="gpu")
+    res = genomics.calculate_factor_length_threshold(real_bin, shuf_bin, tau_expected_fp=10.0)
+    assert res["N_real"] == n_real and res["N_shuf"] == n_shuf and n_shuf > n_real
+    assert res["L_star"] is not None and res["L_star"] <= 40

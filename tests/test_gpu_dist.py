@@ -136,3 +136,39 @@ def test_dist_33_bit_ranks_on_small_texts():
                         assert np.array_equal(got, _expected(mode, s)), (world, hex(flags), mode, len(s))
         finally:
             grp.close()
+
+
+def test_dist_device_resident_text_and_caller_buffer():
+    """nlz_dist_factorize_into: the text is a device pointer on every rank, rank 0 hands in the output buffer
+    (the entry point bench.py times)."""
+    for world in (1, 3):
+        devs = _devs(world)
+        grp = nd.LocalGroup(devs, 400_000, L.MODE_DNA_RC)
+        try:
+            for s in (wl.planted_dna(200_000, 31, scale=0.2).tobytes(), b"ACGT" * 500, b"A" * 1000):
+                for mode in (L.MODE_DNA_RC, L.MODE_GENERAL):
+                    got = grp.factorize_device_text(mode, s, devs)
+                    assert np.array_equal(got, _expected(mode, s)), (world, mode, len(s))
+        finally:
+            grp.close()
+
+
+def test_dist_partition_balance_on_low_complexity_text():
+    """A text whose suffixes crowd into two 12-symbol buckets: 9 Mbp of (AT)^n (its own reverse complement) inside 10 Mbp
+    -- 90 % of all suffixes start with ATATATATATAT or TATATATATATA.  A prefix partition cannot balance such a text (a tie
+    group is one unit, and deeper splitters do not split (AT)^n either); the run must stay correct, and the imbalance
+    is reported (max / mean of the rank-range sizes)."""
+    x = wl.uniform_dna(10_000_000, 13).copy()
+    x[500_000:9_500_000] = np.frombuffer(b"AT" * 4_500_000, dtype=np.uint8)
+    s = x.tobytes()
+    single = L.factorize_array(L.MODE_DNA_RC, s)
+    grp = nd.LocalGroup(_devs(4), len(s), L.MODE_DNA_RC)
+    try:
+        got, stats = grp.factorize(L.MODE_DNA_RC, s)
+    finally:
+        grp.close()
+    assert np.array_equal(got, single)
+    sizes = [st["n_local_suffixes"] for st in stats]
+    assert sum(sizes) == 2 * len(s) + 3
+    print(f"rank-range sizes {sizes}: max/mean = {max(sizes) / (sum(sizes) / len(sizes)):.2f}")
+    assert max(sizes) / (sum(sizes) / len(sizes)) > 1.5          # the case is unbalanced by construction
