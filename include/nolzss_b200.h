@@ -75,6 +75,10 @@ const char* nlz_last_error(void);
 void nlz_free(void* p);
 int nlz_get_stats(nlz_ctx* ctx, nlz_stats* out);
 const char* nlz_version(void); /* bindings.cpp:1513-1517 (__version__) */
+/* page-locks / releases a caller-owned host range (e.g. the slice of a memory-mapped genome a rank uploads), so that
+ * the H2D copy inside an entry point runs at PCIe speed instead of through a pageable staging buffer */
+int nlz_host_register(void* p, uint64_t bytes);
+int nlz_host_unregister(void* p);
 /* per-kernel-class accounting of the last call: launches and algorithmic bytes always, device time
  * (CUDA events around every launch, on the launching stream) when profiling is switched on */
 int nlz_set_profiling(nlz_ctx* ctx, int on);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "nlz_free": (None, [_vp]),
     "nlz_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
     "nlz_version": (ctypes.c_char_p, []),
+    "nlz_host_register": (ctypes.c_int, [_vp, _u64]),
+    "nlz_host_unregister": (ctypes.c_int, [_vp]),
     "nlz_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
     "nlz_kernel_class_count": (ctypes.c_int, []),
     "nlz_set_debug_flags": (ctypes.c_int, [_vp, ctypes.c_int]),

@@ -1155,6 +1155,24 @@ static int ctx_init(nlz_ctx* c) { return ctx_init_impl(c); }
 const char* nlz_last_error(void) { return nlz::g_err.c_str(); }
 const char* nlz_version(void) { return "1.2.0+b200.r1"; }
 void nlz_free(void* p) { free(p); }
+int nlz_host_register(void* p, uint64_t bytes) {
+    if (!p || !bytes) { set_error("null range"); return ERR_INVALID; }
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {                       // a read-only mapping (np.load(..., mmap_mode="r")) needs the read-only flag
+        cudaGetLastError();
+        e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterReadOnly);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostRegister of %llu bytes failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+        return ERR_CUDA;
+    }
+    return OK;
+}
+int nlz_host_unregister(void* p) {
+    NLZ_CK(cudaHostUnregister(p));
+    return OK;
+}
 
 int nlz_ctx_create(int device, nlz_ctx** out) {
     if (!out) { set_error("null out"); return ERR_INVALID; }

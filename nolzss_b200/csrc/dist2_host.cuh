@@ -57,6 +57,22 @@ struct D2Problem {
     bool rc;
 };
 
+// Host side of a stream sync on the distributed path: busy-poll the stream.  A doubling round of a late round is a few
+// hundred microseconds of GPU work between two host decisions on EVERY rank; a blocking / yielding
+// cudaStreamSynchronize wakes up tens of microseconds late, each rank at a different moment, and the next barrier waits
+// for the latest of them.  (NLZ_DIST_BLOCKING_SYNC=1 restores cudaStreamSynchronize.)
+static inline cudaError_t d2_sync(cudaStream_t st) {
+    static const bool blocking = getenv("NLZ_DIST_BLOCKING_SYNC") != nullptr;
+    if (blocking) return cudaStreamSynchronize(st);
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady) return e;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 // per-call runtime of one rank
 struct D2 {
     nlz_dist* d;
@@ -101,7 +117,7 @@ static int d2_barrier(D2& r, const u32* d_src, u32 nwords, bool want_host) {
         // kernel spins on the device while another rank still has work to launch (a kernel launched for the first time
         // is loaded lazily, and that load waits for running kernels; copies queued behind a spinning kernel block the
         // copy queue of the other ranks).  One process per GPU needs no such care.
-        NLZ_CK(cudaStreamSynchronize(st));
+        NLZ_CK(d2_sync(st));
         if (!d->hb->arrive()) {
             set_error("distributed barrier %u: a rank of the in-process group failed or never arrived (rank %d waited)", d->epoch, r.me);
             return ERR_RUNTIME;
@@ -109,13 +125,13 @@ static int d2_barrier(D2& r, const u32* d_src, u32 nwords, bool want_host) {
     }
     KL(r.c->prof, KC_BARRIER, (u64)nwords * 4 * r.G, st,
        (k_dist_barrier<<<1, 256, 0, st>>>(peers, d->epoch, d->xparity, d_src, nwords, timeout_s)));
-    if (d->hb) NLZ_CK(cudaStreamSynchronize(st));
+    if (d->hb) NLZ_CK(d2_sync(st));
     if (!want_host) return OK;
     // one readback for everybody's words (the barrier kernel packs them, together with the time-out flag, into a
     // contiguous block of this rank's control area) -- a copy per rank costs more than the barrier itself
     DistCtl* mine = reinterpret_cast<DistCtl*>(d->seg);
     NLZ_CK(cudaMemcpyAsync(d->h_pin, &mine->packed[0], ((size_t)r.G * nwords + 1) * 4, cudaMemcpyDeviceToHost, st));
-    NLZ_CK(cudaStreamSynchronize(st));
+    NLZ_CK(d2_sync(st));
     r.c->stats.host_syncs += 1;
     if (d->h_pin[(size_t)r.G * nwords] != 0) {
         set_error("distributed barrier %u timed out on rank %d (a peer failed or never arrived)", d->epoch, r.me);
@@ -354,7 +370,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
     }
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
-    NLZ_CK(cudaStreamSynchronize(st));
+    NLZ_CK(d2_sync(st));
     S.host_syncs += 1;
     m = c->h_pinned[0]; maxg = c->h_pinned[3];
     S.lcp_marked = m;
@@ -401,7 +417,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
                                                             w.KEY[cur ^ 1], w.VAL[cur ^ 1], w.SLOT[sc ^ 1]);
             P.end(KC_REGROUP, (u64)m * 40, st, 3);
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
-            NLZ_CK(cudaStreamSynchronize(st));
+            NLZ_CK(d2_sync(st));
             S.host_syncs += 1;
             hy.on = true;
             hy.mB = c->h_pinned[6]; hy.mS = m - hy.mB; hy.maxgS = gcap;
@@ -441,7 +457,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
             }
             S.tile_sort_rounds += 1;
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
-            NLZ_CK(cudaStreamSynchronize(st));
+            NLZ_CK(d2_sync(st));
             S.host_syncs += 1;
             if (c->h_pinned[7]) {
                 // a group had more outliers than fit in shared memory: unify the lists and redo the round with the radix
@@ -468,7 +484,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
                 if (trace) fprintf(stderr, "[nlz] rank %d round %u: outliers exceed the stream kernel, back to radix rounds\n", r.me, S.doubling_rounds);
                 NLZ_TRY(radix_round(mS + mB, &rb));
                 NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
-                NLZ_CK(cudaStreamSynchronize(st));
+                NLZ_CK(d2_sync(st));
                 S.host_syncs += 1;
                 m = c->h_pinned[0]; maxg = c->h_pinned[3];
             } else {
@@ -494,7 +510,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
             }
             nupd_bound = m;
             NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 32, cudaMemcpyDeviceToHost, st));
-            NLZ_CK(cudaStreamSynchronize(st));
+            NLZ_CK(d2_sync(st));
             S.host_syncs += 1;
             if (trace) fprintf(stderr, "[nlz] rank %d round %u h=%llu m=%u maxg=%u -> m'=%u maxg'=%u records=%u\n", r.me, S.doubling_rounds,
                                (unsigned long long)h, m, maxg, c->h_pinned[0], c->h_pinned[3], c->h_pinned[4]);

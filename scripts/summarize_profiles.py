@@ -41,8 +41,16 @@ def launches(src, dst):
                 f.write(f"- `{k}`: {v[0]} launches, {v[1]/1e3:.1f} us\n")
 
 
+def _raw(src):
+    """raw-page CSV of a report: either the .ncu-rep itself or a CSV exported on the GPU box (reports of more than a few
+    dozen launches exceed what gpurun brings back)"""
+    if src.endswith(".csv"):
+        return open(src).read()
+    return subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = _raw(src)
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
@@ -60,7 +68,7 @@ def full(src, dst):
 def traffic(src, dst):
     """mean dram__bytes_read.sum + dram__bytes_write.sum per captured launch of every kernel -> JSON (bench.py's roofline.traffic)"""
     import json
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = _raw(src)
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
@@ -73,7 +81,9 @@ def traffic(src, dst):
         a[0] += 1
         a[1] += b
     with open(dst, "w") as f:
-        json.dump({k: {"launches_captured": v[0], "dram_bytes_per_launch": v[1] / v[0]} for k, v in acc.items()}, f, indent=1)
+        d = {k: {"launches_captured": v[0], "dram_bytes_per_launch": v[1] / v[0]} for k, v in acc.items()}
+        d["_captured_at"] = sys.argv[4] if len(sys.argv) > 4 else ""
+        json.dump(d, f, indent=1)
 
 
 if __name__ == "__main__":
