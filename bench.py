@@ -80,9 +80,9 @@ def _traffic(kernel_class: str):
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
         e = t.get(names.get(kernel_class, ""))
-        return (e["dram_bytes_per_launch"], e["launches_captured"], t.get("_captured_at", "")) if e else (None, 0, "")
+        return (e["dram_bytes_per_launch"], e["launches_captured"], t.get("_captured_at", ""), e.get("dram_bytes_per_alg_byte")) if e else (None, 0, "", None)
     except Exception:
-        return (None, 0, "")
+        return (None, 0, "", None)
 
 
 def _peaks():
@@ -267,12 +267,16 @@ def _roofline(ksum, peak, peak_src, exclude=("dist_barrier",)):
     dom = max(cand, key=lambda k: cand[k]["ms"])
     d = cand[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
-    traffic, nl, when = _traffic(dom)
+    traffic, nl, when, per_alg = _traffic(dom)
     total = sum(v["ms"] for v in ksum.values())
+    alg_launch = d["bytes"] / max(d["launches"], 1)
+    # the capture ran a smaller text of the same recipe: DRAM bytes per ALGORITHMIC byte carry over, absolute bytes do not
+    if per_alg:
+        traffic = per_alg * alg_launch
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src,
-            "traffic_source": (f"ncu --set full, mean of {nl} captured launches (profiles/r2_traffic.json, captured {when}; "
-                               "not re-measured in this run)") if traffic else None,
+            "traffic": traffic, "traffic_per_algorithmic_byte": per_alg, "peak_source": peak_src,
+            "traffic_source": (f"ncu --set full, {nl} captured launches (profiles/r2_traffic.json, r2_full.md; {when}): DRAM bytes per "
+                               "algorithmic byte there x this run's algorithmic bytes per launch; not re-measured in this run") if traffic else None,
             "kernel_share_of_step": d["ms"] / total if total else None,
             "alg_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
             "avg_launch_us": 1e3 * d["ms"] / max(d["launches"], 1)}
