@@ -755,7 +755,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         u32* OOUT = reinterpret_cast<u32*>(STB);
         P.begin(st);
         NLZ_CK(cudaMemsetAsync(DCNT, 0, (ndc + 8) * 4, st));
-        if (ch) k_d2_keys<1><<<nctas, 256, 0, st>>>(w.X, pb.L, r.pos0, r.pos1, tab, lay, pbits, sp, DCNT, nctas, nullptr, nullptr);
+        if (ch) k_d2_keys<1><<<nctas, 256, 0, st>>>(w.X, pb.L, r.pos0, r.pos1, tab, lay_top, pbits, sp, DCNT, nctas, nullptr, nullptr);   // the destination only needs the prefix
         {
             const u32 cntd = (u32)ndc;
             const u32 nt = ceil_div_u32(cntd, SCAN_TILE);

@@ -104,7 +104,7 @@ struct LcpSlice {
 // (milliseconds of dependent steps); carried across consecutive blocks that scan happens once per blocks_per_warp * 1024
 // positions.  Small texts keep one block per warp (parallelism first).
 static inline u32 lcp_blocks_per_warp(u64 positions) {
-    u64 b = positions / (1024ull * 24000ull);
+    u64 b = positions / (1024ull * 6000ull);       // keep >= ~6000 warps (most exit at once: unmarked blocks)
     return (u32)(b < 1 ? 1 : (b > 32 ? 32 : b));
 }
 

@@ -718,7 +718,7 @@ k_forward_ranks(const u32* __restrict__ F0, WalkParams p, u32* __restrict__ cta_
 // forward ranks, or r - real_lo without a list) instead of by the text position -- the text positions of a rank range
 // are scattered over the whole text, and the results travel to their position owners as (position, value) records.
 template <bool RC, bool BYLIST>
-__global__ void __launch_bounds__(256, 8)   // 32 registers: 8 CTAs per SM (the kernel is latency-bound; 40 registers cost 14 %)
+__global__ void __launch_bounds__(256, BYLIST ? 6 : 8)   // 32 registers: 8 CTAs per SM (the kernel is latency-bound; 40 registers cost 14 %); the by-item variant spills at 32
 k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, const u32* __restrict__ list,
             const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
             unsigned long long* __restrict__ counters) {

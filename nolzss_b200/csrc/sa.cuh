@@ -57,13 +57,14 @@ __device__ __forceinline__ u32 batch_cap(const BatchView& bv, u32 p) {
     return 2 * bv.N - fs + 1 - p;                         // rc half: its segment ends at the mirror of the sentinel before fs
 }
 
-// Where refined ranks are written.  One GPU: its RANK array.  Distributed (one rank range of the suffix
-// array per GPU, dist.cuh): the local replica of RANK, plus one (suffix, rank) record per CHANGED rank in
-// `upd` -- a contiguous list (appended with one atomic range reservation per CTA, *upd_count entries) that is
-// bulk-copied to the other GPUs over NVLink and applied to their replicas there (scattered peer stores collapse
-// beyond ~1 GB of span; bulk copies do not).  A member that stays in the first sub-group of its group keeps its
-// rank (= the group's head slot): neither a store nor a record.
-// `base` = the first global rank this GPU owns: slots and ranks are global, the local SA array starts at `base`.
+// Where refined ranks are written.  One GPU: its RANK array (`rank`).  Distributed (one rank range of the suffix
+// array per GPU, dist2.cuh): `rank` is null and every CHANGED rank leaves as a record (local rank << 32 | suffix
+// handle) in `upd` -- a contiguous list (appended with one atomic range reservation per CTA, *upd_count entries) that
+// is bucketed by position owner, bulk-copied over NVLink and applied to the owners' slices of RANK (scattered peer
+// stores collapse beyond ~1 GB of span; bulk copies do not).  A member that stays in the sub-group that keeps its
+// group's name keeps its rank: neither a store nor a record.
+// `base`: 0 on both paths today (slots and group names are local to the GPU; dist2 adds the GPU's first global rank
+// when it turns a record into an exchange item).
 struct RankDst {
     u32* rank;
     u64* upd;
@@ -162,64 +163,6 @@ k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout 
         if (p >= n1) break;
         keys[p] = kb_key<KeyT>(cls, tile, o, p, L, lay, REC);
         vals[p] = (u32)p;
-    }
-}
-
-// Distributed suffix array: every GPU scans the whole (replicated) text but keeps only the suffixes whose
-// key prefix (top `pbits` bits) falls into its bucket range [plo, phi).
-//   MODE 0: histogram of the key prefixes (atomicAdd into hist[2^pbits]);
-//   MODE 1: number of kept suffixes per CTA;
-//   MODE 2: ordered (position order = stable) compaction of the kept (key, suffix) pairs.
-template <typename KeyT, int MODE>
-__global__ void __launch_bounds__(256)
-k_keys_partition(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay, int pbits, u32 plo, u32 phi,
-                 u32* __restrict__ hist_or_counts, KeyT* __restrict__ keys, u32* __restrict__ vals) {
-    __shared__ u8 cls[256];
-    __shared__ __align__(16) u8 tile[KB_TP + KB_HALO];
-    __shared__ u32 wcnt[8];
-    __shared__ u32 s_run;
-    kb_stage(x, L, tab, cls, tile);
-    const u64 base = (u64)blockIdx.x * KB_TP;
-    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    u32 run = (MODE == 2) ? hist_or_counts[blockIdx.x] : 0u;    // MODE 2: exclusive prefix of the CTA counts
-    u32 mine = 0;
-#pragma unroll 1
-    for (int r = 0; r < KB_TP / 256; ++r) {
-        const int o = r * 256 + threadIdx.x;
-        const u64 p = base + o;
-        KeyT key = 0;
-        bool keep = false;
-        if (p < n1) {
-            key = kb_key<KeyT>(cls, tile, o, p, L, lay, nullptr);
-            const u32 pre = (u32)(key >> (lay.key_bits - pbits));
-            if (MODE == 0) atomicAdd(&hist_or_counts[pre], 1u);
-            keep = pre >= plo && pre < phi;
-        }
-        if (MODE == 1) mine += keep ? 1u : 0u;
-        if (MODE == 2) {
-            const u32 bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) wcnt[w] = __popc(bal);
-            __syncthreads();
-            u32 before = 0, tot = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const u32 c = wcnt[i]; if (i < (int)w) before += c; tot += c; }
-            if (keep) {
-                const u32 dst = run + before + __popc(bal & lanemask_lt());
-                keys[dst] = key;
-                vals[dst] = (u32)p;
-            }
-            run += tot;
-            __syncthreads();
-        }
-    }
-    if (MODE == 1) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if (threadIdx.x == 0) s_run = 0;
-        __syncthreads();
-        if (lane == 0 && mine) atomicAdd(&s_run, mine);
-        __syncthreads();
-        if (threadIdx.x == 0) hist_or_counts[blockIdx.x] = s_run;
     }
 }
 

@@ -1,4 +1,4 @@
-"""One text across the GPUs of a box (configs[3]/[4]; C side: csrc/dist.cuh, nlz_dist_* in the C ABI).
+"""One text across the GPUs of a box (configs[3]/[4]; C side: csrc/dist2.cuh + csrc/dist2_host.cuh, nlz_dist_* in the C ABI).
 
 Two ways to form a group of ranks, one rank per GPU:
 

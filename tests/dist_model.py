@@ -1,9 +1,9 @@
-"""CPU model of the boundary exchange of the distributed path (csrc/dist.cuh, run_dist in api.cu).
+"""CPU model of the boundary exchange of the distributed path (k_dist_edges in csrc/dist.cuh, the virtual-rank merge of run_dist2 in csrc/dist2_host.cuh).
 
 The suffix array is cut into G rank ranges at boundaries whose LCP is < K (what the bucket partition of the
 GPU path guarantees).  Every range publishes its two edge staircases; every range appends its neighbours'
 staircases as virtual ranks and evaluates the factor rule on [virtual | real | virtual] with the ordinary
-stage-3 model.  The merge below mirrors the host code of run_dist line by line."""
+stage-3 model.  The merge below mirrors the host code of run_dist2 line by line (the model keeps S-positions where the device keeps the equivalent leaf values F0 / R0)."""
 import gpu_algorithm_model as gm
 
 NONE_MIN = gm.NONE_MIN
@@ -58,7 +58,7 @@ def edge_staircases(SA, LCP, lo, hi, K, rc, N):
 
 
 def virtual_ranks(me, bounds, c0, edges, K):
-    """Host merge of run_dist: (left SA, left LCP, right SA, right LCP incl. guard) for range `me`."""
+    """Host merge of run_dist2: (left SA, left LCP, right SA, right LCP incl. guard) for range `me`."""
     G = len(bounds) - 1
     M = [bounds[g + 1] - bounds[g] for g in range(G)]
 

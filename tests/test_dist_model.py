@@ -1,5 +1,5 @@
 """CPU: the boundary exchange of the distributed path (edge staircases -> virtual ranks, tests/dist_model.py,
-mirroring run_dist in csrc/api.cu) against the oracle, for every cut of the suffix array into rank ranges."""
+mirroring run_dist2 in csrc/dist2_host.cuh) against the oracle, for every cut of the suffix array into rank ranges."""
 import random
 
 import dist_model as dm

@@ -1,4 +1,4 @@
-"""One text across several ranks (csrc/dist.cuh).  The ranks are dealt round-robin to the visible GPUs: on a
+"""One text across several ranks (csrc/dist2.cuh, csrc/dist2_host.cuh).  The ranks are dealt round-robin to the visible GPUs: on a
 multi-GPU box every exchange step (Phi / LCP delivery, rank requests, edge staircases, virtual ranks, barriers) runs
 over real peer memory; on a one-GPU box the ranks share cuda:0 and only the peer pointers are local."""
 import random
