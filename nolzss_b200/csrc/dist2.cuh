@@ -44,20 +44,31 @@ constexpr u64 D2_MASK33 = (1ull << 33) - 1;      // a global rank (n' < 2^33)
 constexpr u64 D2_NO_PHI = D2_MASK34;            // Phi of global rank 0 (= PhiNone<u64>::value in lcp.cuh: Kasai stores 0 for it)
 constexpr u32 D2_MAX_LOCAL = 0x3FFFFF00u;       // suffixes / positions one GPU can own (30-bit local indices)
 
-// suffix handle -> S-position.  Handles are arrival indices at the rank owner: the pairs of sender g occupy
-// [seg[g], seg[g+1]) and carry their offset inside the sender's position slice.
+// suffix handle -> S-position.  A handle is the index of the suffix in the INITIALLY SORTED list of its rank owner
+// (so the active lists, which stay in slot order, look their positions up nearly sequentially -- with arrival-order
+// handles every lookup was a scattered read, four per member and round).  The position is kept as the sender's GPU
+// number and the offset inside that sender's position slice: 5 bytes instead of a 33-bit value in 8.
 struct HandleMap {
     const u32* off;
-    u32 seg[MAX_PEERS + 1];
+    const u8* snd;
     u64 chunk;
-    int G;
-    __device__ __forceinline__ u64 pos(u32 h) const {
-        int g = 0;
-#pragma unroll
-        for (int q = 1; q < MAX_PEERS; ++q) g += (q < G && h >= seg[q]) ? 1 : 0;
-        return (u64)g * chunk + off[h];
-    }
+    __device__ __forceinline__ u64 pos(u32 h) const { return (u64)snd[h] * chunk + off[h]; }
 };
+// after the initial sort: arrival index (pairs of sender g occupy [seg[g], seg[g+1])) of the e-th sorted suffix ->
+// handle tables in sorted order
+struct ArrivalSegs { u32 seg[MAX_PEERS + 1]; int G; };
+__global__ void __launch_bounds__(256)
+k_d2_sorted_handles(const u32* __restrict__ arrival_sorted, u32 cnt, const u32* __restrict__ off_arrival, ArrivalSegs sg,
+                    u32* __restrict__ off_sorted, u8* __restrict__ snd_sorted) {
+    const u32 e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= cnt) return;
+    const u32 a = arrival_sorted[e];
+    int g = 0;
+#pragma unroll
+    for (int q = 1; q < MAX_PEERS; ++q) g += (q < sg.G && a >= sg.seg[q]) ? 1 : 0;
+    off_sorted[e] = off_arrival[a];
+    snd_sorted[e] = (u8)g;
+}
 
 struct RankBases {
     u64 base[MAX_PEERS + 1];

@@ -280,6 +280,10 @@ struct D2Sa {
     u64* RESP;         // pulled responses (cnt entries)
     u64* RANKL;        // my slice of RANK
     u8* NEED;          // marks of my positions: LCP pending (lcp.cuh)
+    const u32* OFFIN;  // arrival order: offset of every received suffix in its sender's slice
+    ArrivalSegs segs;  // arrival segments per sender
+    u32* OFFR;         // handle tables in sorted order (HandleMap)
+    u8* SNDR;
 };
 
 // One exchange step of a doubling round: (1) the ranks refined in the previous step travel to their position owners and
@@ -333,6 +337,7 @@ static int d2_round_exchange(D2& r, const D2Sa& a, u32 nupd_bound, const u32* nu
 }
 
 static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D2Sa& a, u32 cnt) {
+    r.hm.off = a.OFFR; r.hm.snd = a.SNDR; r.hm.chunk = r.chunk;
     nlz_ctx* c = r.c;
     Workspace& w = c->ws;
     nlz_stats& S = c->stats;
@@ -354,6 +359,9 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         int res = 0;
         NLZ_TRY(radix_sort_pairs<u64>(k, v, cnt, plan, w.HIST, st, &res, P));
         NLZ_CK(cudaEventRecord(c->ev[EV_SORT0], st));
+        // suffix handles = sorted indices from here on: position tables in sorted order
+        KL(P, KC_REGROUP, (u64)cnt * 13, st,
+           (k_d2_sorted_handles<<<ceil_div_u32(cnt, 256), 256, 0, st>>>(v[res], cnt, a.OFFIN, a.segs, a.OFFR, a.SNDR)));
         const u64 dist_mask = ((1ull << lay.D) - 1) << lay.dshift();
         const u32 tiles = ceil_div_u32(cnt, RG_TILE);
         P.begin(st);
@@ -361,7 +369,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
         LcpSeed seed;                                        // LCP values that follow from adjacent key pairs; the rest is marked
         seed.LCP = w.LCP; seed.NEED = nullptr; seed.lay = lay; seed.first_pending = r.base[r.me] > 0; seed.RANKOUT = nullptr;
-        k_regroup_apply<u64, true, GS><<<tiles, RG_THREADS, 0, st>>>(k[res], v[res], nullptr, cnt, dist_mask, w.PMAX, w.PSUM,
+        k_regroup_apply<u64, true, GS><<<tiles, RG_THREADS, 0, st>>>(k[res], nullptr, nullptr, cnt, dist_mask, w.PMAX, w.PSUM,
                                                                      w.SA, rdst, w.KEY[res ^ 1], w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3, seed);
         P.end(KC_REGROUP, (u64)cnt * (2 * 8 + 4 + 8), st, 3);
         cur = res ^ 1;
@@ -686,7 +694,8 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     const u64 cap = (u64)std::max(m_loc, ch) + 2 * DIST_VIRT + 72;
     u64 *UPD, *ST, *RESP, *RANKL, *SA64, *PHI, *STB;
     u8* NEED;
-    u32 *OFFIN, *PLCP, *F0buf, *R0buf, *LCPbuf, *DCNT;
+    u32 *OFFIN, *OFFR, *PLCP, *F0buf, *R0buf, *LCPbuf, *DCNT;
+    u8* SNDR;
     u64* LRT; u8* FLT; u32 *alist, *MASK;
     u64* LRl; u8* FLl;
     {
@@ -700,7 +709,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         { u64 cnt = cap + 1; for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; need += d2_al((cnt + 72) * 4) * 3; } }
         need += d2_al(cap * 8) * 4;                                      // UPD (later SA64), ST, STB, RESP
         need += d2_al(((size_t)ch + 8) * 8) + d2_al((size_t)ch + 128);   // RANKL, NEED
-        need += d2_al(cap * 4);                                          // OFFIN
+        need += d2_al(cap * 4) * 2 + d2_al(cap);                         // OFFIN, OFFR, SNDR
         need += d2_al((cap + 72) * 4) * 3;                               // F0, R0, LCP (with virtual ranks)
         need += d2_al(ndc * 4 + SCAN_TILE * 4 + (ndc / SCAN_TILE + 8) * 4);   // DCNT + tile sums
         need += d2_al(((size_t)nT + 8) * 8) + d2_al((size_t)nT + 64);    // LRT, FLT
@@ -732,6 +741,8 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         RANKL = a.take<u64>((size_t)ch + 8);
         NEED = a.take<u8>((size_t)ch + 128);
         OFFIN = a.take<u32>(cap);
+        OFFR = a.take<u32>(cap);
+        SNDR = a.take<u8>(cap);
         F0buf = a.take<u32>(cap + 72); R0buf = a.take<u32>(cap + 72); LCPbuf = a.take<u32>(cap + 72);
         DCNT = a.take<u32>(ndc + SCAN_TILE + ndc / SCAN_TILE + 8);
         LRT = a.take<u64>((size_t)nT + 8); FLT = a.take<u8>((size_t)nT + 64);
@@ -781,9 +792,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
             KL(P, KC_KEYS, (u64)m_loc * 28, st,
                (k_d2_unpack_keys<<<ceil_div_u32(m_loc, 256), 256, 0, st>>>(r.inbox, reinterpret_cast<const u32*>(d->seg + d->off_inbox + off_b),
                                                                          m_loc, w.KEY[0], w.VAL[0], OFFIN)));
-        r.hm.off = OFFIN; r.hm.chunk = r.chunk; r.hm.G = G;
-        for (int g = 0; g < G; ++g) r.hm.seg[g] = xk.in_off[g];
-        for (int g = G; g <= MAX_PEERS; ++g) r.hm.seg[g] = xk.in_total;
+        // (the handle tables r.hm are built from the arrival tables after the sort: d2_stage_sa)
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));                    // everyone has unpacked: the inboxes are free again
     }
     NLZ_CK(cudaEventRecord(c->ev[EV_KEYS], st));
@@ -794,6 +803,11 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     w.LCP = LCPbuf + DIST_VIRT;                                   // seeded by the first regroup
     D2Sa sa;
     sa.UPD = UPD; sa.ST = ST; sa.REQ = STB; sa.RESP = RESP; sa.RANKL = RANKL; sa.NEED = NEED;
+    sa.OFFIN = OFFIN; sa.OFFR = OFFR; sa.SNDR = SNDR;
+    memset(&sa.segs, 0, sizeof(sa.segs));
+    sa.segs.G = G;
+    for (int g = 0; g < G; ++g) sa.segs.seg[g] = xk.in_off[g];
+    for (int g = G; g <= MAX_PEERS; ++g) sa.segs.seg[g] = xk.in_total;
     NLZ_TRY(d2_stage_sa(r, pb, lay, sa, m_loc));
     NLZ_CK(cudaEventRecord(c->ev[EV_DOUBLING], st));
 

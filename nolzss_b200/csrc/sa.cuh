@@ -359,7 +359,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
             u32 e = (u32)(tile_start + idx);
             u32 hj = max(hm[q], cm) - 1;          // index (in this sorted list) of the group head
             u32 newrank = INITIAL ? hj + RANK.base : slots[hj];
-            u32 s = vals[e];
+            u32 s = vals ? vals[e] : e;            // (distributed path, first regroup: the sorted index IS the suffix handle)
             u32 slot = INITIAL ? e + RANK.base : slots[e];
             // the old rank of a member is its group's head slot = the high half of its doubling key
             const bool changed = INITIAL || newrank != (u32)((u64)keys[e] >> GS);
