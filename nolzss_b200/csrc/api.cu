@@ -733,7 +733,8 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
     // algorithmic bytes: the leaf value of every rank; per factorized position the two LCP neighbours, the
     // LR store and the flag byte; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
-    static const int walk_nodes = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : WALK_MAX_NODES;
+    static const int walk_env = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : 0;
+    const int walk_nodes = walk_env ? walk_env : (wp.n1 > WALK_LARGE_TEXT ? WALK_MAX_NODES_LARGE : WALK_MAX_NODES);
     const u32 nreal = wp.real_hi - wp.real_lo;
     u32 nwork;                                           // work items of both kernels when the results are indexed by item
     u32* list = nullptr;

@@ -602,7 +602,14 @@ __device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p
 // bit 1 = the factor is a reverse-complement one.  (ref and len both need 32 bits at genome scale -- refs of a 3.1 Gbp
 // text exceed 2^31 -- so the RC flag cannot ride in either.)
 constexpr u8 FLAG_HARD = 1, FLAG_RC = 2;
-constexpr int WALK_MAX_NODES = 512;    // default: ancestors climbed in rank order before a position is "hard" (250 Mbp text: 2048 -> 512 saves 15 ms of failed climbs; the 5 Mbp text never exceeds 500)
+// Ancestors climbed in rank order before a position is "hard" (left to the depth search of k_lpnf_hard).  Chromosome-scale
+// texts: nearly every position that needs more than 64 climbs needs thousands (megabase tandem arrays) -- 250 Mbp text,
+// budget 512 -> 64: lpnf_rank 38 -> 32 ms with 1.5 % more hard positions; below 24 the depth search costs more than the
+// climbs save.  Small texts: their arrays have a few hundred copies, which the climb finishes cheaper than the depth
+// search (5 Mbp text: budget 64 costs 0.9 ms of k_lpnf_hard to save 0.1 ms of climbs).
+constexpr int WALK_MAX_NODES = 512;
+constexpr int WALK_MAX_NODES_LARGE = 64;
+constexpr u32 WALK_LARGE_TEXT = 1u << 26;   // suffixes
 constexpr int WALK_Q = 32;             // consecutive text positions per 8-lane tile in k_lpnf_hard (the carried bound
                                        // links them: the first one pays a full bisection, the others 2-3 probes)
 
