@@ -94,6 +94,7 @@ struct nlz_ctx {
     nlz_stats stats;
     Profiler prof;
     Trees trees;                // summary trees of the last stage_lpnf call
+    u64 text_suffixes = 0;      // suffixes of the WHOLE text of the current call (a distributed rank sees only its range)
     int debug_flags = 0;        // test hook: 1 force the bitonic tile path, 2 disable the pivot fast path, 4 force counting
 };
 
@@ -734,7 +735,7 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
     // LR store and the flag byte; plus (added after the run, from the probe counter) 16 B per probe
     P.begin(st);
     static const int walk_env = getenv("NLZ_WALK_NODES") ? atoi(getenv("NLZ_WALK_NODES")) : 0;
-    const int walk_nodes = walk_env ? walk_env : (wp.n1 > WALK_LARGE_TEXT ? WALK_MAX_NODES_LARGE : WALK_MAX_NODES);
+    const int walk_nodes = walk_env ? walk_env : (c->text_suffixes > WALK_LARGE_TEXT ? WALK_MAX_NODES_LARGE : WALK_MAX_NODES);
     const u32 nreal = wp.real_hi - wp.real_lo;
     u32 nwork;                                           // work items of both kernels when the results are indexed by item
     u32* list = nullptr;
@@ -962,6 +963,7 @@ static int run_pipeline(nlz_ctx* c, const Problem& pb, const void* src, bool src
     Profiler& P = c->prof;
     const u32 n1 = pb.n1;
     NLZ_CK(cudaEventRecord(c->ev[EV_BEGIN], st));
+    c->text_suffixes = n1;
     ClassTable tab;
     KeyLayout lay;
     NLZ_TRY(stage_prepare(c, pb, src, src_on_host, st, reinterpret_cast<u8*>(w.KEY[1]), tab, lay));

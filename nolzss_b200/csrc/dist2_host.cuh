@@ -546,6 +546,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     D2 r;
     r.d = d; r.c = c; r.st = st; r.G = G; r.me = me;
     r.rank_bias = (c->debug_flags & 0x1000000) ? 0x100003039ull : 0ull;
+    c->text_suffixes = pb.n1;
     w = Workspace();
     w.X = d->seg + d->off_x;
     w.CTR = d->SMALL;
