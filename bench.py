@@ -648,7 +648,7 @@ def configs4_leg(world, rank, local, dist, barrier, rmax, runs=2):
         del mm
     barrier()
     gen_s = time.perf_counter() - t0
-    text = np.load(path, mmap_mode="r")
+    text = np.load(path, mmap_mode="r+")          # (writable mapping: a read-only one cannot be page-locked on this platform)
     lib = L.load()
     # page-lock the slice of the mapped text this rank uploads (DNA_RC: every rank uploads ONE slice, csrc/dist2_host.cuh):
     # a pageable upload of 388 MB costs ~370 ms of the 1.5 s run, a pinned one ~10 ms

@@ -1026,6 +1026,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     k_set_u32<<<1, 1, 0, st>>>(r.PAY, (me == 0 && (out_alloc || out_into)) ? 1u : 0u);
     NLZ_TRY(d2_barrier(r, r.PAY, 1, true));
     const bool emit = r.all[0] != 0;
+    bool too_small = false;
     if (emit) {
         if (zg[me] * 24 > d->inbox_items * 16ull) { set_error("internal: %llu factors of one slice exceed the inbox", (unsigned long long)zg[me]); return ERR_RUNTIME; }
         BatchView bv;
@@ -1045,18 +1046,22 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
                 if (!dst) { set_error("out of host memory for %llu factors", (unsigned long long)z); return ERR_RUNTIME; }
                 *out_alloc = dst;
             } else if (z > capacity) {
-                set_error("output capacity %llu factors is too small for %llu factors", (unsigned long long)capacity, (unsigned long long)z);
-                *out_count = z;
-                return ERR_RUNTIME;      // the other ranks run into the closing barrier's timeout: size the buffer from a count-only call
+                too_small = true;        // reported after the closing barrier, so that the other ranks are not left waiting
             }
             u64 at = 0;
-            for (int g = 0; g < G; ++g) {
+            for (int g = 0; g < G && !too_small; ++g) {
                 if (zg[g]) NLZ_CK(cudaMemcpyAsync(dst + 3 * at, d->peer[g] + d->off_inbox, (size_t)zg[g] * 24, cudaMemcpyDefault, st));
                 at += zg[g];
             }
             NLZ_CK(cudaStreamSynchronize(st));
         }
         NLZ_TRY(d2_barrier(r, nullptr, 0, false));          // rank 0 has read every inbox
+        if (too_small) {
+            set_error("output capacity %llu factors is too small for %llu factors", (unsigned long long)capacity, (unsigned long long)z);
+            *out_count = z;
+            NLZ_CK(cudaStreamSynchronize(st));
+            return ERR_RUNTIME;
+        }
     } else {
         NLZ_CK(cudaEventRecord(c->ev[EV_CHAIN], st));
     }

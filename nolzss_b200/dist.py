@@ -88,7 +88,7 @@ class LocalGroup:
         assert len(counts) == 1, f"ranks disagree on the factor count: {counts}"
         return results[0][0], [_ctx_stats(c) for c in self.ctxs]
 
-    def factorize_device_text(self, mode: int, data, devices):
+    def factorize_device_text(self, mode: int, data, devices, capacity=None):
         """As `factorize`, through nlz_dist_factorize_into: every rank passes a DEVICE pointer to its own copy of the text
         (already resident in its HBM) and rank 0 a caller-provided output buffer.  Returns the triples of rank 0."""
         import torch
@@ -97,8 +97,8 @@ class LocalGroup:
         addr, n, keep = L._as_buffer(data)
         host = np.frombuffer(keep, dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
         texts = [torch.from_numpy(host.copy()).to(f"cuda:{dev}") for dev in devices]
-        cap = n + 16
-        out = np.zeros((cap, 3), dtype=np.uint64)
+        cap = n + 16 if capacity is None else int(capacity)
+        out = np.zeros((max(cap, 1), 3), dtype=np.uint64)
         counts = [None] * self.world
         errors = [None] * self.world
 

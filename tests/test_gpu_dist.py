@@ -149,6 +149,12 @@ def test_dist_device_resident_text_and_caller_buffer():
                 for mode in (L.MODE_DNA_RC, L.MODE_GENERAL):
                     got = grp.factorize_device_text(mode, s, devs)
                     assert np.array_equal(got, _expected(mode, s)), (world, mode, len(s))
+            # a caller buffer that is too small is reported by rank 0 AFTER the closing barrier: no rank is left waiting,
+            # and the group stays usable
+            with pytest.raises(RuntimeError, match="output capacity 3 factors is too small"):
+                grp.factorize_device_text(L.MODE_DNA_RC, b"ACGT" * 500, devs, capacity=3)
+            got = grp.factorize_device_text(L.MODE_DNA_RC, b"ACGT" * 500, devs)
+            assert np.array_equal(got, _expected(L.MODE_DNA_RC, b"ACGT" * 500))
         finally:
             grp.close()
 
