@@ -20,7 +20,7 @@
 //                 inbox, and the receiver applies the items locally.  (Scattered fine-grained peer stores collapse on
 //                 this machine beyond ~1 GB of span; bulk copies run at link speed.)  Used for: the initial
 //                 (key, position) pairs; refined ranks -> position owners; rank REQUESTS (position s+h -> its owner)
-//                 and RESPONSES (served in place in the inbox, pulled back with one bulk copy per peer); Phi -> position
+//                 and RESPONSES (the owner answers and pushes every answer into its requester's answer region); Phi -> position
 //                 owners; PLCP -> rank owners; per-position results -> T-position owners.
 //   * widths:     inside a GPU everything is 32-bit: local slots and list indices (< 2^30 per GPU), suffix HANDLES
 //                 (the arrival index of a suffix at its rank owner; its S-position is pos0[sender] + OFF[handle]),
@@ -349,13 +349,19 @@ struct ReqItem {
         return true;
     }
 };
-// the owner answers in place: inbox[e] = RANK of the requested position
+// the owner answers the requests of its inbox ...
+// ... and pushes every answer straight into the requester's answer region (coalesced peer stores, in the requester's
+// staging order): request e of source g's bucket [in_off[g], in_off[g+1]) -> dst[g][e - in_off[g]]
+struct ServeGeom { u64* dst[MAX_PEERS]; u32 in_off[MAX_PEERS + 1]; int G; };
 __global__ void __launch_bounds__(256)
-k_d2_serve(u64* __restrict__ inbox, u32 cnt, const u64* __restrict__ RANKL, u64 nloc) {
+k_d2_serve_push(const u64* __restrict__ inbox, u32 cnt, const u64* __restrict__ RANKL, u64 nloc, ServeGeom sg) {
     const u32 e = blockIdx.x * 256 + threadIdx.x;
     if (e >= cnt) return;
     const u64 q = inbox[e] >> 32;
-    inbox[e] = q < nloc ? RANKL[q] : 0ull;
+    int g = 0;
+#pragma unroll
+    for (int s = 1; s < MAX_PEERS; ++s) g += (s < sg.G && e >= sg.in_off[s]) ? 1 : 0;
+    sg.dst[g][e - sg.in_off[g]] = q < nloc ? RANKL[q] : 0ull;
 }
 // the requester completes its keys: key[j] |= response (requests and responses share their staging order)
 __global__ void __launch_bounds__(256)
@@ -472,7 +478,7 @@ k_d2_prepare_dna_rc_slice(const u8* T, u64 n, u64 lo, u64 hi, XPeers X, bool wri
 __global__ void k_d2_set_u64(u64* p, u64 v) { *p = v; }
 
 // One launch moves every bucket of an 8-byte-item exchange: element e of the staging list belongs to the bucket g with
-// off[g] <= e < off[g+1] and goes to dst[g][e - off[g]] (push: coalesced peer stores) or comes from there (pull).
+// off[g] <= e < off[g+1] and goes to dst[g][e - off[g]] (coalesced peer stores).
 constexpr u32 D2_KERNEL_PUSH_MAX = 8u << 20;       // items (64 MB); larger exchanges use the copy engines
 struct PushGeom { u64* dst[MAX_PEERS]; u32 off[MAX_PEERS + 1]; int G; };
 __device__ __forceinline__ int pg_bucket(const PushGeom& pg, u32 e) {
@@ -486,13 +492,6 @@ k_d2_push(const u64* __restrict__ staging, u32 total, PushGeom pg) {
     for (u32 e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
         const int g = pg_bucket(pg, e);
         pg.dst[g][e - pg.off[g]] = staging[e];
-    }
-}
-__global__ void __launch_bounds__(256)
-k_d2_pull(u64* __restrict__ staging, u32 total, PushGeom pg) {
-    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
-        const int g = pg_bucket(pg, e);
-        staging[e] = pg.dst[g][e - pg.off[g]];
     }
 }
 

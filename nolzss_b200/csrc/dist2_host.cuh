@@ -238,34 +238,6 @@ static int d2_push(D2& r, const XInfo& x, const void* staging, size_t item_bytes
     }
     return OK;
 }
-// responses: one bulk copy per peer FROM its inbox (my bucket there, answered in place) into `dst` (staging order)
-static int d2_pull(D2& r, const XInfo& x, void* dst, size_t item_bytes, size_t inbox_byte_off = 0) {
-    static const bool no_kernel_push = getenv("NLZ_NO_KERNEL_PUSH") != nullptr;
-    if (item_bytes == 8 && r.G > 1 && x.out_total && x.out_total <= D2_KERNEL_PUSH_MAX && !no_kernel_push) {
-        PushGeom pg;
-        memset(&pg, 0, sizeof(pg));
-        for (int g = 0; g < r.G; ++g) {
-            pg.dst[g] = reinterpret_cast<u64*>(r.d->peer[g] + r.d->off_inbox + inbox_byte_off) + x.their_off[g];
-            pg.off[g] = x.out_off[g];
-        }
-        for (int g = r.G; g <= MAX_PEERS; ++g) pg.off[g] = x.out_total;
-        pg.G = r.G;
-        u32 grid = ceil_div_u32(x.out_total, 256 * 4);
-        if (grid > (u32)kNumSM * 4) grid = kNumSM * 4;
-        k_d2_pull<<<grid, 256, 0, r.st>>>(static_cast<u64*>(dst), x.out_total, pg);
-        r.c->prof.bytes[KC_XCHG] += (u64)x.out_total * 8;
-        return OK;
-    }
-    for (int g = 0; g < r.G; ++g) {
-        if (!x.out_cnt[g]) continue;
-        const u8* src = r.d->peer[g] + r.d->off_inbox + inbox_byte_off + (size_t)x.their_off[g] * item_bytes;
-        u8* to = static_cast<u8*>(dst) + (size_t)x.out_off[g] * item_bytes;
-        NLZ_CK(cudaMemcpyAsync(to, src, (size_t)x.out_cnt[g] * item_bytes, cudaMemcpyDefault, r.st));
-        r.c->prof.bytes[KC_XCHG] += (u64)x.out_cnt[g] * item_bytes;
-    }
-    return OK;
-}
-
 struct VirtBlock { u32 cnt = 0, F = NONE_MIN, R = 0; };
 
 static size_t d2_al(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -277,7 +249,6 @@ struct D2Sa {
     u64* UPD;          // records of changed ranks (cnt entries)
     u64* ST;           // exchange staging (cnt entries)
     u64* REQ;          // request staging (cnt entries)
-    u64* RESP;         // pulled responses (cnt entries)
     u64* RANKL;        // my slice of RANK
     u8* NEED;          // marks of my positions: LCP pending (lcp.cuh)
     const u32* OFFIN;  // arrival order: offset of every received suffix in its sender's slice
@@ -289,8 +260,9 @@ struct D2Sa {
 // One exchange step of a doubling round: (1) the ranks refined in the previous step travel to their position owners and
 // (2) the rank requests of THIS round (RANK[pos(val[j]) + h] for the S list [0, mS) and the B list [b0, b0 + mB) of the
 // `cur` buffers) travel to the same owners -- both under ONE counts barrier (which also carries every GPU's active
-// count: *gm_out = the largest) and ONE data barrier; the owners apply the records, then answer the requests in place;
-// after a third barrier the answers are pulled back and complete the keys: key[j] |= RANK[..].
+// count: *gm_out = the largest) and ONE data barrier; the owners apply the records, then answer the requests and push
+// every answer into its requester's answer region; after a third barrier (answers arrived) they complete the keys:
+// key[j] |= RANK[..].  (Three inbox regions: records | requests | answers.)
 // With no active suffix anywhere (*gm_out == 0) only the records are delivered.
 static int d2_round_exchange(D2& r, const D2Sa& a, u32 nupd_bound, const u32* nupd_dev, int cur, u32 mS, u32 b0, u32 mB, u64 h,
                              u32* gm_out) {
@@ -307,13 +279,30 @@ static int d2_round_exchange(D2& r, const D2Sa& a, u32 nupd_bound, const u32* nu
     const u32 nw = 2 * MAX_PEERS + 1;
     NLZ_TRY(d2_barrier(r, r.PAY, nw, true));
     XInfo xu, xq;
-    NLZ_TRY(d2_geometry(r, nw, 0, 8, xu, true));
-    NLZ_TRY(d2_geometry(r, nw, 1, 8, xq, true));
+    NLZ_TRY(d2_geometry(r, nw, 0, 8, xu, false));
+    NLZ_TRY(d2_geometry(r, nw, 1, 8, xq, false));
     u32 gm = 0;
     for (int g = 0; g < r.G; ++g) gm = std::max(gm, r.all[(size_t)g * nw + 2 * MAX_PEERS]);
     *gm_out = gm;
-    const size_t off_b = (size_t)r.d->inbox_items * 8;              // second inbox region: the requests
+    // three inbox regions of cap3 items: records | requests | answers
+    const u64 cap3 = (r.d->inbox_items * 16 / 24) & ~(u64)31;
+    for (int g = 0; g < r.G; ++g) {
+        u64 in_u = 0, in_q = 0, out_q = 0;
+        for (int q = 0; q < r.G; ++q) {
+            in_u += r.all[(size_t)q * nw + g];
+            in_q += r.all[(size_t)q * nw + MAX_PEERS + g];
+            out_q += r.all[(size_t)g * nw + MAX_PEERS + q];
+        }
+        if (in_u > cap3 || in_q > cap3 || out_q > cap3) {
+            set_error("distributed doubling round: rank %d would exchange %llu records / %llu requests / %llu answers, its inbox regions hold %llu "
+                      "(the partition of this text is too unbalanced for %d GPUs)", g, (unsigned long long)in_u, (unsigned long long)in_q,
+                      (unsigned long long)out_q, (unsigned long long)cap3, r.G);
+            return ERR_RUNTIME;
+        }
+    }
+    const size_t off_b = (size_t)cap3 * 8, off_c = (size_t)cap3 * 16;
     u64* inboxB = reinterpret_cast<u64*>(r.d->seg + r.d->off_inbox + off_b);
+    const u64* inboxC = reinterpret_cast<const u64*>(r.d->seg + r.d->off_inbox + off_c);
     NLZ_TRY(d2_push(r, xu, a.ST, 8, 0));
     if (gm) NLZ_TRY(d2_push(r, xq, a.REQ, 8, off_b));
     NLZ_TRY(d2_barrier(r, nullptr, 0, false));                     // records and requests have arrived everywhere
@@ -323,16 +312,29 @@ static int d2_round_exchange(D2& r, const D2Sa& a, u32 nupd_bound, const u32* nu
            (k_d2_apply_ranks<<<ceil_div_u32(xu.in_total, 256), 256, 0, st>>>(r.inbox, xu.in_total, a.RANKL, a.NEED)));
     }
     if (!gm) return OK;
-    if (xq.in_total)
+    if (xq.in_total) {
+        // answer the requests and push every answer into its requester's answer region, at the place of the request in
+        // the requester's staging list (= the start of its bucket for me + the index inside the bucket)
+        ServeGeom sg;
+        memset(&sg, 0, sizeof(sg));
+        sg.G = r.G;
+        for (int g = 0; g < r.G; ++g) {
+            u64 o = 0;                                             // where g staged its bucket for me: after its buckets for the ranks before me
+            for (int q = 0; q < r.me; ++q) o += r.all[(size_t)g * nw + MAX_PEERS + q];
+            sg.dst[g] = reinterpret_cast<u64*>(r.d->peer[g] + r.d->off_inbox + off_c) + o;
+            sg.in_off[g] = xq.in_off[g];
+        }
+        for (int g = r.G; g <= MAX_PEERS; ++g) sg.in_off[g] = xq.in_total;
         KL(P, KC_GATHER, (u64)xq.in_total * 24, st,
-           (k_d2_serve<<<ceil_div_u32(xq.in_total, 256), 256, 0, st>>>(inboxB, xq.in_total, a.RANKL, (u64)r.ch)));
-    NLZ_TRY(d2_barrier(r, nullptr, 0, false));                     // every inbox holds the answers
-    NLZ_TRY(d2_pull(r, xq, a.RESP, 8, off_b));
+           (k_d2_serve_push<<<ceil_div_u32(xq.in_total, 256), 256, 0, st>>>(inboxB, xq.in_total, a.RANKL, (u64)r.ch, sg)));
+        P.bytes[KC_XCHG] += (u64)xq.in_total * 8;
+    }
+    NLZ_TRY(d2_barrier(r, nullptr, 0, false));                     // every answer has arrived
     if (xq.out_total)
         KL(P, KC_GATHER, (u64)xq.out_total * 32, st,
-           (k_d2_apply_resp<<<ceil_div_u32(xq.out_total, 256), 256, 0, st>>>(a.REQ, a.RESP, xq.out_total, w.KEY[cur])));
-    // the next exchange writes into the inboxes only after its own counts barrier, which every rank reaches after its
-    // pulls have completed (stream order): no extra barrier needed here
+           (k_d2_apply_resp<<<ceil_div_u32(xq.out_total, 256), 256, 0, st>>>(a.REQ, inboxC, xq.out_total, w.KEY[cur])));
+    // the next exchange writes into the inbox regions only after its own counts barrier, which every rank reaches after
+    // its apply kernels have completed (stream order): no extra barrier needed here
     return OK;
 }
 
@@ -693,7 +695,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
 
     // ---- private workspace
     const u64 cap = (u64)std::max(m_loc, ch) + 2 * DIST_VIRT + 72;
-    u64 *UPD, *ST, *RESP, *RANKL, *SA64, *PHI, *STB;
+    u64 *UPD, *ST, *RANKL, *SA64, *PHI, *STB;
     u8* NEED;
     u32 *OFFIN, *OFFR, *PLCP, *F0buf, *R0buf, *LCPbuf, *DCNT;
     u8* SNDR;
@@ -708,7 +710,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         need += d2_al(((size_t)RS_BINS * RS_MAX_CTAS + RS_BINS) * 4);    // HIST
         need += d2_al(tiles_of(cap) * 4) * 2;                            // PMAX, PSUM
         { u64 cnt = cap + 1; for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; need += d2_al((cnt + 72) * 4) * 3; } }
-        need += d2_al(cap * 8) * 4;                                      // UPD (later SA64), ST, STB, RESP
+        need += d2_al(cap * 8) * 3;                                      // UPD (later SA64), ST, STB
         need += d2_al(((size_t)ch + 8) * 8) + d2_al((size_t)ch + 128);   // RANKL, NEED
         need += d2_al(cap * 4) * 2 + d2_al(cap);                         // OFFIN, OFFR, SNDR
         need += d2_al((cap + 72) * 4) * 3;                               // F0, R0, LCP (with virtual ranks)
@@ -738,7 +740,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
         w.PMAX = a.take<u32>(tiles_of(cap));
         w.PSUM = a.take<u32>(tiles_of(cap));
         { u64 cnt = cap + 1; for (int lev = 1; lev < TREE_MAX_LEVELS; ++lev) { cnt = (cnt + 31) / 32; w.tl[lev] = a.take<u32>(cnt + 72); w.tf[lev] = a.take<u32>(cnt + 72); w.tr[lev] = a.take<u32>(cnt + 72); } }
-        UPD = a.take<u64>(cap); ST = a.take<u64>(cap); STB = a.take<u64>(cap); RESP = a.take<u64>(cap);
+        UPD = a.take<u64>(cap); ST = a.take<u64>(cap); STB = a.take<u64>(cap);
         RANKL = a.take<u64>((size_t)ch + 8);
         NEED = a.take<u8>((size_t)ch + 128);
         OFFIN = a.take<u32>(cap);
@@ -803,7 +805,7 @@ static int run_dist2(nlz_dist* d, const D2Problem& pb, const u8* text, u64** out
     NLZ_CK(cudaMemsetAsync(NEED, 0, (size_t)ch + 128, st));
     w.LCP = LCPbuf + DIST_VIRT;                                   // seeded by the first regroup
     D2Sa sa;
-    sa.UPD = UPD; sa.ST = ST; sa.REQ = STB; sa.RESP = RESP; sa.RANKL = RANKL; sa.NEED = NEED;
+    sa.UPD = UPD; sa.ST = ST; sa.REQ = STB; sa.RANKL = RANKL; sa.NEED = NEED;
     sa.OFFIN = OFFIN; sa.OFFR = OFFR; sa.SNDR = SNDR;
     memset(&sa.segs, 0, sizeof(sa.segs));
     sa.segs.G = G;
