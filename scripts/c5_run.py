@@ -34,9 +34,20 @@ if rank == 0:
     del mm
     print(f"[c5] text of {n} bases generated in {time.perf_counter() - t0:.1f} s", flush=True)
 dist.barrier()
-text = np.load(path + ".npy", mmap_mode="r")
-grp = nd.ProcessGroup(n, L.MODE_DNA_RC, device=local)
+text = np.load(path + ".npy", mmap_mode="r+")       # writable mapping: the slice this rank uploads gets page-locked
 lib = L.load()
+
+
+def pin_slice(arr):
+    per = ((n + world - 1) // world + 255) // 256 * 256
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    a0 = (arr.ctypes.data + lo) // 4096 * 4096
+    a1 = (arr.ctypes.data + hi + 4095) // 4096 * 4096
+    return a0 if lib.nlz_host_register(a0, a1 - a0) == L.NLZ_OK else None
+
+
+pin_real = pin_slice(text)
+grp = nd.ProcessGroup(n, L.MODE_DNA_RC, device=local)
 rec = {"workload": f"configs[4]: c5_text_into(n={n}, seed=5): planted repeats (families <= 500 kbp, tandem arrays <= 5 Mbp), RC mode, "
                    f"{2 * n + 3} indexed suffixes, one text across {world} GPUs", "n_bases": n, "n_gpus": world, "runs": []}
 
@@ -70,7 +81,12 @@ if rank == 0:
     rec["rc_factors_real"] = int((got[:, 2] >> np.uint64(63)).sum())
     rec["max_factor_length_real"] = int(got[:, 1].max())
     print(f"[c5] real text: factors tile the text; {chk} verified in {time.perf_counter() - t0:.1f} s", flush=True)
-    lengths_real = got[:, 1].copy()
+    # the on-disk factor file of the reference (noLZSSv2: factors, one empty name, footer; factorizer.cpp:597-635)
+    real_bin = "/dev/shm/nlz_c5_real.bin"
+    t0 = time.perf_counter()
+    L.check(lib.nlz_write_factor_file(real_bin.encode(), got.ctypes.data, len(got), b"\0", 1, 1, 0, n))
+    rec["real_bin_bytes"] = os.path.getsize(real_bin)
+    rec["real_bin_write_s"] = time.perf_counter() - t0
     del got
 if shuffled:
     spath = path + ".shuf.npy"
@@ -86,26 +102,32 @@ if shuffled:
         del sm
         print(f"[c5] shuffled control generated in {time.perf_counter() - t0:.1f} s", flush=True)
     dist.barrier()
-    stext = np.load(spath, mmap_mode="r")
+    stext = np.load(spath, mmap_mode="r+")
+    pin_shuf = pin_slice(stext)
     got = one(stext, "shuffled")
     if rank == 0:
         chk = wl.verify_factors_sample(np.asarray(stext), got, 100_000)
         rec["check_shuffled"] = chk
-        from nolzss_b200.genomics import significance as sig
+        from nolzss_b200 import genomics
 
-        # the consumer of configs[4]: factor-length threshold from the real and the shuffled length distributions
-        try:
-            res = sig.infer_length_significance(lengths_real.astype(np.int64), got[:, 1].astype(np.int64), tau_expected_fp=10.0)
-            rec["threshold"] = {k: (int(v) if isinstance(v, (int, np.integer)) else v) for k, v in res.items() if k in ("L_star", "N_real", "N_shuf")}
-        except Exception as e:                           # the helper's name differs: report and go on
-            rec["threshold_error"] = repr(e)
-        print(f"[c5] shuffled: {chk}", flush=True)
+        shuf_bin = "/dev/shm/nlz_c5_shuf.bin"
+        L.check(lib.nlz_write_factor_file(shuf_bin.encode(), got.ctypes.data, len(got), b"\0", 1, 1, 0, n))
+        rec["shuf_bin_bytes"] = os.path.getsize(shuf_bin)
+        del got
+        # the consumer of configs[4]: factor-length threshold from the two factor files
+        t0 = time.perf_counter()
+        res = genomics.calculate_factor_length_threshold(real_bin, shuf_bin, tau_expected_fp=10.0)
+        rec["threshold"] = {k: (int(v) if isinstance(v, (int, np.integer)) else v) for k, v in res.items()
+                            if k in ("L_star", "N_real", "N_shuf", "tau_expected_fp")}
+        rec["threshold_s"] = time.perf_counter() - t0
+        print(f"[c5] shuffled: {chk}; threshold {rec['threshold']} in {rec['threshold_s']:.1f} s", flush=True)
+        os.unlink(shuf_bin)
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "r2_c5.json"), "w") as f:
         json.dump(rec, f, indent=1)
     print(json.dumps(rec), flush=True)
-    for p in (path + ".npy", path + ".npy.shuf.npy"):
+    for p in (path + ".npy", path + ".npy.shuf.npy", path + ".shuf.npy", "/dev/shm/nlz_c5_real.bin"):
         if os.path.exists(p):
             os.unlink(p)
 dist.barrier()
