@@ -1160,10 +1160,11 @@ const char* nlz_version(void) { return "1.2.0+b200.r1"; }
 void nlz_free(void* p) { free(p); }
 int nlz_host_register(void* p, uint64_t bytes) {
     if (!p || !bytes) { set_error("null range"); return ERR_INVALID; }
-    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+    // portable: pinned for every CUDA context of the process, whichever device was current at the time of the call
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
     if (e != cudaSuccess) {                       // a read-only mapping (np.load(..., mmap_mode="r")) needs the read-only flag
         cudaGetLastError();
-        e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterReadOnly);
+        e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();

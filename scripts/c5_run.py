@@ -46,8 +46,9 @@ def pin_slice(arr):
     return a0 if lib.nlz_host_register(a0, a1 - a0) == L.NLZ_OK else None
 
 
-pin_real = pin_slice(text)
 grp = nd.ProcessGroup(n, L.MODE_DNA_RC, device=local)
+pin_real = pin_slice(text)
+print(f"[c5] rank {rank}: text slice page-locked: {pin_real is not None}", flush=True)
 rec = {"workload": f"configs[4]: c5_text_into(n={n}, seed=5): planted repeats (families <= 500 kbp, tandem arrays <= 5 Mbp), RC mode, "
                    f"{2 * n + 3} indexed suffixes, one text across {world} GPUs", "n_bases": n, "n_gpus": world, "runs": []}
 
