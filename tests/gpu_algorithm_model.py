@@ -14,7 +14,19 @@ LR_RC_FLAG = 0x80000000
 
 
 # ------------------------------------------------------------------ stage 1: suffix array
-def choose_layout(data: bytes, n1: int, force_bits=None):
+def layout_symbols(sigma: int, b: int, R: int, D: int, n1: int) -> int:
+    """api.cu layout_symbols: the smallest window whose sigma^W key space is >= 64 n', widened to fill whole 8-bit passes."""
+    wmax = min(29, (64 - R - D) // b)
+    space, wmin = 1.0, 0
+    while wmin < wmax and space < 64.0 * n1:
+        space *= max(sigma, 2)
+        wmin += 1
+    wmin = max(wmin, 1)
+    passes = (R + wmin * b + D + 7) // 8
+    return max(min((passes * 8 - R - D) // b, wmax), wmin)
+
+
+def choose_layout(data: bytes, n1: int, force_bits=None, force_w=None):
     hist = [0] * 256
     for c in data:
         hist[c] += 1
@@ -34,8 +46,13 @@ def choose_layout(data: bytes, n1: int, force_bits=None):
     if force_bits == 64:
         use32 = False
     if use32:
-        return cls, dict(key_bits=32, b=b, W=w32, D=4)
-    return cls, dict(key_bits=64, b=b, W=min(29, 59 // b), D=5)
+        lay = dict(key_bits=32, b=b, W=w32, D=4, R=0)
+    else:
+        lay = dict(key_bits=64, b=b, W=layout_symbols(sigma, b, 0, 5, n1), D=5, R=0)
+    if force_w:
+        lay["W"] = min(force_w, lay["W"])
+    lay["dshift"] = lay["key_bits"] - lay["R"] - lay["W"] * b - lay["D"]     # KeyLayout::dshift(): [R][W*b symbols][D][zeros]
+    return cls, lay
 
 
 def build_keys(data: bytes, cls, lay):
@@ -53,8 +70,47 @@ def build_keys(data: bytes, cls, lay):
                 break
             key |= c << sh
             sh -= b
-        keys.append(key | dist)
+        keys.append(key | (dist << lay["dshift"]))
     return keys
+
+
+def key_pair_lcp(a: int, b_: int, lay) -> int:
+    """sa.cuh key_pair_lcp: leading symbols two keys share, cut at the first sentinel of either window."""
+    kb, b, W, D, R = lay["key_bits"], lay["b"], lay["W"], lay["D"], lay["R"]
+    dmask = (1 << D) - 1
+    x = a ^ b_
+    common = W
+    if x:
+        p = kb - x.bit_length()               # identical leading bits (clz)
+        if p < R:
+            return 0
+        common = min(common, (p - R) // b)
+    da, db = (a >> lay["dshift"]) & dmask, (b_ >> lay["dshift"]) & dmask
+    if da != dmask:
+        common = min(common, da)
+    if db != dmask:
+        common = min(common, db)
+    return common
+
+
+def seed_lcp(skeys, order, lay):
+    """The INITIAL regroup's LCP seeding (k_regroup_apply, LcpSeed): every member of a tie group is left to the Kasai kernel
+    (NEED by text position, None = LCP_PENDING by slot), every other slot gets the LCP its key pair gives."""
+    m = len(skeys)
+    dmask = ((1 << lay["D"]) - 1) << lay["dshift"]
+
+    def head(e):
+        return e == 0 or e >= m or (skeys[e] & dmask) != dmask or skeys[e] != skeys[e - 1]
+
+    LCP = [0] * (m + 1)
+    need = [0] * m
+    for e in range(m):
+        if not (head(e) and head(e + 1)):
+            LCP[e] = None
+            need[order[e]] = 1
+        else:
+            LCP[e] = 0 if e == 0 else key_pair_lcp(skeys[e - 1], skeys[e], lay)
+    return LCP, need
 
 
 def regroup(keys, vals, slots, dist_mask, SA, RANK):
@@ -85,15 +141,19 @@ def regroup(keys, vals, slots, dist_mask, SA, RANK):
     return nxt
 
 
-def suffix_array(data: bytes, force_bits=None):
+def suffix_array(data: bytes, force_bits=None, force_w=None, seed_out=None):
+    """seed_out (a dict): receives "seed" = seed_lcp(...) of the initial sort, for lcp_array(seed=...)."""
     L = len(data)
     n1 = L + 1
-    cls, lay = choose_layout(data, n1, force_bits)
+    cls, lay = choose_layout(data, n1, force_bits, force_w)
     keys = build_keys(data, cls, lay)
     order = sorted(range(n1), key=lambda p: keys[p])          # stable LSD radix sort
     SA = [0] * n1
     RANK = [0] * n1
-    act = regroup([keys[p] for p in order], order, None, (1 << lay["D"]) - 1, SA, RANK)
+    if seed_out is not None:
+        seed_out["seed"] = seed_lcp([keys[p] for p in order], order, lay)
+        seed_out["lay"] = lay
+    act = regroup([keys[p] for p in order], order, None, ((1 << lay["D"]) - 1) << lay["dshift"], SA, RANK)
     h = lay["W"]
     rounds = 0
     while act:
@@ -126,7 +186,7 @@ def suffix_array_hybrid(data: bytes, gcap: int = 8, out_cap: int = 16, force_bit
     order = sorted(range(n1), key=lambda p: keys[p])
     SA = [0] * n1
     RANK = [0] * n1
-    act = regroup([keys[p] for p in order], order, None, (1 << lay["D"]) - 1, SA, RANK)
+    act = regroup([keys[p] for p in order], order, None, ((1 << lay["D"]) - 1) << lay["dshift"], SA, RANK)
     h = lay["W"]
     stats = dict(rounds=0, hybrid_rounds=0, fallbacks=0, stream_groups=0, renamed=0, kept=0)
 
@@ -237,13 +297,18 @@ def suffix_array_hybrid(data: bytes, gcap: int = 8, out_cap: int = 16, force_bit
 
 
 # ------------------------------------------------------------------ stage 2: LCP (chunked Kasai)
-def lcp_array(data: bytes, SA, RANK, Q=16):
+def lcp_array(data: bytes, SA, RANK, Q=16, seed=None):
+    """k_lcp_kasai: Kasai in runs of Q text positions.  seed = (LCP, need) from seed_lcp: only marked positions are
+    computed (an unmarked one breaks the carry), the others keep their key-derived value."""
     L = len(data)
     n1 = L + 1
-    LCP = [0] * (n1 + 1)
+    LCP = [0] * (n1 + 1) if seed is None else list(seed[0])
     for c0 in range(0, n1, Q):
         l = 0
         for i in range(c0, min(c0 + Q, n1)):
+            if seed is not None and not seed[1][i]:
+                l = 0
+                continue
             r = RANK[i]
             if r == 0:
                 l = 0
@@ -705,8 +770,9 @@ def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, forc
             raise ValueError("start_pos must be less than the original sequence length")
         rc, nfac = True, N
     n1 = len(data) + 1
-    SA, RANK, _ = suffix_array(data, force_bits)
-    LCP = lcp_array(data, SA, RANK)
+    so = {}
+    SA, RANK, _ = suffix_array(data, force_bits, seed_out=so)
+    LCP = lcp_array(data, SA, RANK, seed=so["seed"])          # key-derived LCP + Kasai over the marked positions
     T = Trees(LCP, SA, rc, N)
     LR = walk(T, n1, nfac, RANK, k_lin, walk_q)
     return chain(LR, nfac, start_pos, rc, chunk)

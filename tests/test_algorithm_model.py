@@ -57,6 +57,47 @@ def test_gpu_symbol_order_recode_matches_model():
         assert list(sa) == SA and list(lcp) == gm.lcp_array(s, SA, RANK)
 
 
+def test_key_derived_lcp_and_marks():
+    """sa.cuh key_pair_lcp / LcpSeed: outside tie groups the LCP read off adjacent sort keys IS the LCP; every other slot
+    is a tie-group member whose TEXT POSITION is marked; Kasai over the marked positions alone completes the array.
+    Short windows (force_w) push most suffixes into tie groups, long ones almost none; texts with sentinels inside the
+    window (unique bytes) exercise the offset field."""
+    rnd = random.Random(21)
+    for it in range(300):
+        sig = rnd.randint(1, 4)
+        s = bytes(rnd.choice(b"ACGT"[:sig]) for _ in range(rnd.randint(1, 120)))
+        if it % 3 == 0:
+            s = s + b"\x01" + s[::-1] + b"\x02"
+        if it % 7 == 0:
+            s = s[: len(s) // 2] + b"N" + s[len(s) // 2:]       # a unique byte mid-text: sentinel class
+        sa, lcp = orc.gpu_order_sa_lcp(s)
+        so = {}
+        SA, RANK, _ = gm.suffix_array(s, rnd.choice([None, 32, 64]), rnd.choice([None, 1, 2, 3, 5]), seed_out=so)
+        assert list(sa) == SA
+        seeded, need = so["seed"]
+        for r in range(len(SA)):
+            if seeded[r] is None:
+                pass                                             # marks are by text position of the INITIAL occupant ...
+            else:
+                assert seeded[r] == lcp[r], (s, r)
+                assert not need[SA[r]]                           # ... and a slot outside tie groups is final: same suffix
+        # every marked position ends in a pending slot and vice versa (tie groups are closed under the doubling rounds)
+        assert sorted(SA[r] for r in range(len(SA)) if seeded[r] is None) == [i for i in range(len(SA)) if need[i]]
+        assert list(lcp) == gm.lcp_array(s, SA, RANK, Q=rnd.choice([1, 4, 32]), seed=so["seed"])
+
+
+def test_layout_symbols_fills_whole_radix_passes():
+    # DESIGN.md section 3: 250 Mbp RC text (n' = 5 * 10^8 + 3, sigma 4) -> 21 symbols + 5 offset bits = 47 bits, 6 passes
+    assert gm.layout_symbols(4, 2, 0, 5, 500_000_003) == 21
+    assert gm.layout_symbols(4, 2, 0, 5, 6_200_000_003) == 21                 # configs[4]: still 6 passes
+    for sigma, b in [(2, 1), (4, 2), (5, 3), (20, 5), (200, 8)]:
+        for n1 in [10, 10_000, 10**7, 10**10]:
+            W = gm.layout_symbols(sigma, b, 0, 5, n1)
+            assert 1 <= W <= min(29, 59 // b)
+            assert W == min(29, 59 // b) or max(sigma, 2) ** W >= 64 * n1     # key space covers the text
+            assert W == min(29, 59 // b) or (W + 1) * b + 5 > (W * b + 5 + 7) // 8 * 8   # one more symbol = one more pass
+
+
 def test_model_hybrid_rounds_and_representative_ranks():
     """Model of the hybrid doubling rounds (csrc/big_groups.cuh) and of ranks-as-representatives: tandem-heavy texts
     with tiny tile / outlier capacities so that the split, the pivot partition, the S/B routing, the renaming rule
