@@ -705,12 +705,23 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
     P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
     c->trees = T;
     if (!LR) return OK;                                  // trees only (edge staircases of a distributed run)
-    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
-       (rc ? k_node_tables<true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
-           : k_node_tables<false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
+    // NLZ_STAGE3_R1=1: the round-1 kernels (one thread per rank for the node table, neighbour hops for the RC candidate)
+    // ("rank": only the rank kernel of round 1, on the new table)
+    static const char* s3env = getenv("NLZ_STAGE3_R1");
+    static const bool stage3_r1 = s3env != nullptr;
+    static const bool nodes_r1 = s3env != nullptr && strcmp(s3env, "rank") != 0;
+    if (nodes_r1) {
+        KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
+           (rc ? k_node_tables<true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
+               : k_node_tables<false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
+    } else {
+        KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
+           (rc ? k_node_tables2<true><<<ceil_div_u32((u64)n1 + 1, NT_PER_CTA), 256, 0, st>>>(T, wp, w.NODE)
+               : k_node_tables2<false><<<ceil_div_u32((u64)n1 + 1, NT_PER_CTA), 256, 0, st>>>(T, wp, w.NODE)));
+    }
     RNear rn;
     memset(&rn, 0, sizeof(rn));
-    if (rc) {
+    if (rc && stage3_r1) {
         // nearest rc(T) rank on either side of every rank + LCP minimum on the way (two segmented scans)
         u32* PR = reinterpret_cast<u32*>(w.KEY[1]);
         u32* ML = PR + n1;
@@ -748,12 +759,23 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
         k_forward_ranks<2><<<tiles, 256, 0, st>>>(F0, wp, w.PMAX, list);
         nwork = nreal < wp.nfac ? nreal : wp.nfac;
         const u32 grid = ceil_div_u32(nwork ? nwork : 1, 256);
-        if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
-        else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+        if (stage3_r1) {
+            if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+            else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+        } else {
+            if (bylist) k_lpnf_rank2<true, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+            else k_lpnf_rank2<true, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+        }
     } else {
         nwork = nreal;
-        if (bylist) k_lpnf_rank<false, true><<<ceil_div_u32(nreal ? nreal : 1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
-        else k_lpnf_rank<false, false><<<ceil_div_u32(n1, 256), 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+        const u32 grid = bylist ? ceil_div_u32(nreal ? nreal : 1, 256) : ceil_div_u32(n1, 256);
+        if (stage3_r1) {
+            if (bylist) k_lpnf_rank<false, true><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+            else k_lpnf_rank<false, false><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+        } else {
+            if (bylist) k_lpnf_rank2<false, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+            else k_lpnf_rank2<false, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+        }
     }
     P.end(KC_WALK, (u64)n1 * (rc ? 12 : 4) + (u64)nreal * 17, st, rc ? 4 : 1);
     {

@@ -406,6 +406,98 @@ __device__ __forceinline__ u32 lcp_range_min(const Trees& T, i64 a, i64 b) {
     return m;
 }
 
+// ---- cooperative (8-lane) versions: RC candidate depth of one leaf from scratch ---------------------------------------
+// bit k set iff R-tree node (lev, gstart + k) > thr   (whole line; entries past the end of the level are masked)
+__device__ __forceinline__ u32 mask_r_greater_v(const Trees& T, int lev, i64 gstart, u32 thr) {
+    const Tile8 t = tile8();
+    const u32 q = t.thread_rank();
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(T.r[lev] + gstart) + q);
+    const u32 m4 = (x.x > thr ? 1u : 0u) | (x.y > thr ? 2u : 0u) | (x.z > thr ? 4u : 0u) | (x.w > thr ? 8u : 0u);
+    const u32 m = cg::reduce(t, m4 << (4 * q), cg::bit_or<u32>());
+    return m & valid_mask((i64)T.cntS[lev] - gstart);
+}
+// largest k <= q with R0[k] > thr, or -1
+__device__ __forceinline__ i64 find_prev_r_greater_v(const Trees& T, i64 q, u32 thr) {
+    if (q < 0) return -1;
+    int lev = 0;
+    i64 idx = q;
+    for (;;) {
+        const i64 gstart = idx & ~31LL;
+        const u32 m = mask_r_greater_v(T, lev, gstart, thr) & bits_upto((u32)(idx - gstart));
+        if (m) { idx = gstart + (31 - __clz(m)); break; }
+        if (gstart == 0) return -1;
+        idx = (gstart >> 5) - 1;
+        ++lev;
+    }
+    while (lev > 0) {
+        --lev;
+        const i64 gstart = idx << 5;
+        idx = gstart + (31 - __clz(mask_r_greater_v(T, lev, gstart, thr)));   // non-empty: the parent's maximum is one of them
+    }
+    return idx;
+}
+// smallest k >= q with R0[k] > thr, or -1
+__device__ __forceinline__ i64 find_next_r_greater_v(const Trees& T, i64 q, u32 thr) {
+    if (q >= (i64)T.cntS[0]) return -1;
+    int lev = 0;
+    i64 idx = q;
+    for (;;) {
+        const i64 gstart = idx & ~31LL;
+        const u32 m = mask_r_greater_v(T, lev, gstart, thr) & ~(bits_upto((u32)(idx - gstart)) >> 1);
+        if (m) { idx = gstart + (__ffs(m) - 1); break; }
+        idx = (gstart >> 5) + 1;
+        ++lev;
+        if (lev >= T.nlev || idx >= (i64)T.cntS[lev]) return -1;
+    }
+    while (lev > 0) {
+        --lev;
+        const i64 gstart = idx << 5;
+        idx = gstart + (__ffs(mask_r_greater_v(T, lev, gstart, thr)) - 1);
+    }
+    return idx;
+}
+// minimum of entries [lob, hib] of LCP-tree line (lev, gstart)
+__device__ __forceinline__ u32 lcp_line_min_v(const Trees& T, int lev, i64 gstart, u32 lob, u32 hib) {
+    const Tile8 t = tile8();
+    const u32 q = t.thread_rank();
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(T.lcp[lev] + gstart) + q);
+    const u32 v4[4] = {x.x, x.y, x.z, x.w};
+    u32 v = NONE_MIN;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const u32 k = 4 * q + j;
+        if (k >= lob && k <= hib) v = min(v, v4[j]);
+    }
+    return cg::reduce(t, v, cg::less<u32>());
+}
+// min LCP[a..b] (inclusive, a <= b)
+__device__ __forceinline__ u32 lcp_range_min_v(const Trees& T, i64 a, i64 b) {
+    u32 m = NONE_MIN;
+    int lev = 0;
+    while (a <= b) {
+        const i64 ga = a & ~31LL, gb = b & ~31LL;
+        if (ga == gb) return min(m, lcp_line_min_v(T, lev, ga, (u32)(a - ga), (u32)(b - ga)));
+        if (a != ga) { m = min(m, lcp_line_min_v(T, lev, ga, (u32)(a - ga), 31u)); a = ga + 32; }
+        if (((b + 1) & 31) != 0) { m = min(m, lcp_line_min_v(T, lev, gb, 0u, (u32)(b - gb))); b = gb - 1; }
+        if (a > b) return m;
+        a >>= 5;
+        b = ((b + 1) >> 5) - 1;
+        ++lev;
+    }
+    return m;
+}
+// Depth of the deepest ancestor of leaf r that holds an rc(T) suffix whose value exceeds thr (0: none but the root) = the
+// LCA of r with the nearest such rank on either side.  k_lpnf_rank finds it on its climb; this is for the positions whose
+// climb ran out of budget first (inside long tandem arrays the qualifying rank can be millions of ranks away).
+__device__ __forceinline__ u32 rc_depth_v(const Trees& T, u32 r, u32 thr) {
+    u32 dl = 0, dr = 0;
+    const i64 kl = find_prev_r_greater_v(T, (i64)r - 1, thr);
+    if (kl >= 0) dl = lcp_range_min_v(T, kl + 1, (i64)r);
+    const i64 kr = find_next_r_greater_v(T, (i64)r + 1, thr);
+    if (kr >= 0) dr = lcp_range_min_v(T, (i64)r + 1, kr);
+    return max(dl, dr);
+}
+
 // ---- nearest rc(T) rank on either side, with the LCP minimum on the way -----------------------
 // PR[k] = largest k' <= k with SA[k'] in rc(T) (NONE_MIN if none), ML[k] = min LCP[PR[k]+1 .. k]
 // NR[k] = smallest k' >= k with SA[k'] in rc(T) (NONE_MIN if none), MR[k] = min LCP[k+1 .. NR[k]]
@@ -692,6 +784,77 @@ k_node_tables(Trees T, WalkParams p, uint4* __restrict__ NODE) {
     NODE[k] = make_uint4(la >= lb ? a : b1, fmin, d, 0u);
 }
 
+// Round-2 layout of the same table, built without idle lanes: NODE[k] = {parent name, F-min, depth, R-max} (the R-max of the
+// node's interval lets the climb of k_lpnf_rank settle the RC candidate too).  Interval sizes follow a 1/s law -- a third
+// of the ranks name a node that reaches more than NT_SCAN entries to one side, and every warp holds several -- so one
+// thread per rank spent most of its issue slots in a few lanes' scalar tree searches (r2 profile: 10 of 32 lanes active).
+// Here a lane only scans NT_SCAN entries to either side, folding the aggregates as it goes; the ranks it cannot finish
+// are queued in shared memory and the CTA's 32 eight-lane tiles share the queue evenly, each entry costing a few 128-byte
+// lines (find_prev_less / find_next_less / agg_range, cooperative flavour).
+constexpr int NT_SCAN = 16;
+constexpr int NT_ITEMS = 2;
+constexpr int NT_PER_CTA = 256 * NT_ITEMS;
+template <bool RC>
+__global__ void __launch_bounds__(256)
+k_node_tables2(Trees T, WalkParams p, uint4* __restrict__ NODE) {
+    __shared__ u32 queue[NT_PER_CTA];
+    __shared__ u32 qn;
+    const u32* __restrict__ l0 = T.lcp[0];
+    const u32* __restrict__ f0 = T.f[0];
+    const u32* __restrict__ r0 = T.r[0];
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int it = 0; it < NT_ITEMS; ++it) {
+        const u64 k64 = (u64)blockIdx.x * NT_PER_CTA + (u64)(it * 256) + threadIdx.x;
+        if (k64 > (u64)p.n1) continue;
+        const u32 k = (u32)k64;
+        const u32 d = (k == 0 || k == p.n1) ? 0u : l0[k];
+        if (d == 0) { NODE[k] = make_uint4(k, NONE_MIN, 0u, 0u); continue; }
+        u32 fm = NONE_MIN, rm = 0;
+        // leaves k-1, k-2, ... down to the first whose LCP entry is < d (that leaf is the node's first)
+        u32 j = k - 1;
+        bool ok = false;
+#pragma unroll 1
+        for (int s = 0; s < NT_SCAN; ++s) {
+            fm = min(fm, f0[j]);
+            if (RC) rm = max(rm, r0[j]);
+            if (l0[j] < d) { ok = true; break; }      // j = 0 always stops here (LCP[0] = 0)
+            --j;
+        }
+        const u32 a = j;
+        u32 b1 = 0;
+        if (ok) {
+            // leaves k, k+1, ... up to the one before the first LCP entry < d (LCP[n1] = 0 stops the scan)
+            ok = false;
+            j = k;
+#pragma unroll 1
+            for (int s = 0; s < NT_SCAN; ++s) {
+                fm = min(fm, f0[j]);
+                if (RC) rm = max(rm, r0[j]);
+                ++j;
+                if (l0[j] < d) { ok = true; break; }
+            }
+            b1 = j;
+        }
+        if (ok) NODE[k] = make_uint4(l0[a] >= l0[b1] ? a : b1, fm, d, rm);
+        else queue[atomicAdd(&qn, 1u)] = k;
+    }
+    __syncthreads();
+    const u32 n = qn;
+    const Tile8 t8 = tile8();
+#pragma unroll 1
+    for (u32 e = threadIdx.x >> 3; e < n; e += 32) {
+        const u32 k = queue[e];
+        const u32 d = l0[k];
+        const u32 a = find_prev_less<true>(T, k - 1, d);
+        const u32 b1 = find_next_less<true>(T, k + 1, d);
+        u32 fm = NONE_MIN, rm = 0;
+        agg_range<RC, RC, true>(T, p, (i64)a, (i64)b1 - 1, fm, rm);
+        if (t8.thread_rank() == 0) NODE[k] = make_uint4(l0[a] >= l0[b1] ? a : b1, fm, d, rm);
+    }
+}
+
 // ---- ranks to evaluate ---------------------------------------------------------------------------
 // RC mode: half of the ranks hold rc(T) suffixes and have no factor to compute.  The ranks that do
 // (real rank, suffix start < nfac) are compacted, in rank order, so that every lane of k_lpnf_rank works.
@@ -791,6 +954,106 @@ k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, con
             // (distributed runs: neighbouring positions live on other GPUs).
             const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
             LR[o] = ((u64)lb0 << 32) | (u64)dR;
+            HARD[o] = FLAG_HARD;
+            hard = 1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        visited += __shfl_xor_sync(0xffffffffu, visited, o);
+        hard += __shfl_xor_sync(0xffffffffu, hard, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (visited) atomicAdd(counters, (unsigned long long)visited);
+        if (hard) atomicAdd(counters + 1, (unsigned long long)hard);
+    }
+}
+
+// ---- kernel 1, round 2: one climb settles both candidates ----------------------------------------------------------
+// With the R-max in the node table the RC candidate node vR (deepest ancestor holding an rc(T) suffix whose T-end lies
+// before i, factorizer_core.hpp:269-271) is the first ancestor with NODE.w > N - i, met on the same climb that looks for
+// vF; the RC source position (:290-299) is that node's R-max itself.  Nothing above vF can beat the forward candidate
+// (fwd_len >= depth(vF), forward wins ties), so the climb ends at vF.  The neighbour hops of k_lpnf_rank, its two
+// segmented scans (k_rnear_*) and the interval search for the RC source are gone: 4200 -> a few hundred issue slots per
+// warp.  A position whose climb runs out of budget is hard, as before; if no qualifying ancestor was met by then its RC
+// depth is left to k_lpnf_hard (DR_UNRESOLVED).
+constexpr u32 DR_UNRESOLVED = 0xFFFFFFFFu;
+template <bool RC, bool BYLIST>
+__global__ void __launch_bounds__(256, 8)
+k_lpnf_rank2(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __restrict__ list,
+             const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
+             unsigned long long* __restrict__ counters) {
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    u32 r = list ? 0xFFFFFFFFu : t + (BYLIST ? p.real_lo : 0u);
+    if (list && t < *nlist) r = list[t];                    // compacted forward ranks (RC mode)
+    u32 visited = 0, hard = 0;
+    const u32* LCP = T.lcp[0];
+    const u32* F0 = T.f[0];
+    u32 i = 0xFFFFFFFFu;
+    if (r >= p.real_lo && r < p.real_hi) i = F0[r];         // r = 0xFFFFFFFF: no work
+    if (i < p.nfac) {
+        const u32 o = BYLIST ? t : i;                       // where this position's results go
+        bool have_f = false, at_root = false;
+        u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
+        u32 childF = i;                  // F-min of the last node that failed (starts at the leaf)
+        u32 dR = 0, mR = 0;              // RC candidate node: depth and R-max (0: not met yet)
+        const u32 thr = p.N - i;         // an rc suffix qualifies when its T-end N - R0 is < i
+        {
+            const u32 dl = LCP[r], dh = LCP[r + 1];
+            u32 k = dl >= dh ? r : r + 1;            // names the parent of the leaf
+#pragma unroll 1
+            for (int step = 0;; ++step) {
+                const uint4 nd = __ldg(NODE + k);    // {parent, F-min, depth, R-max}
+                const u32 d = nd.z;
+                if (d == 0) { at_root = true; break; }
+                if (step == max_nodes) break;
+                ++visited;
+                if (RC && dR == 0 && nd.w > thr) { dR = d; mR = nd.w; }          // factorizer_core.hpp:269-271
+                const u32 m = nd.y;
+                if (m != NONE_MIN && (u64)m + d <= (u64)i) {                      // :75 / :264-266
+                    have_f = true; dF = d; jF = m; belowF = childF;
+                    break;
+                }
+                childF = m;
+                k = nd.x;
+            }
+        }
+        if (have_f || at_root) {
+            u32 len, ref;
+            bool is_rc = false;
+            u32 gen_len, gen_ref, fwd_len = 0;
+            if (have_f) {
+                const u32 part = (belowF != i) ? i - belowF : 0;
+                if (part > dF) { gen_len = part; gen_ref = belowF; }    // :104-107
+                else { gen_len = dF; gen_ref = jF; }                    // :89-94, :98-102
+                fwd_len = (belowF == jF) ? (i - jF) : dF;               // :322-326
+            } else {
+                gen_len = (childF != i) ? i - childF : 0;               // :96-107 with u = root, or literal
+                gen_ref = childF;
+            }
+            if (!RC) {
+                if (gen_len >= 1) { len = gen_len; ref = gen_ref; }
+                else { len = 1; ref = i; }
+            } else {
+                const bool have_r = dR >= 1;
+                bool use_fwd = false, use_lit = false;
+                if (have_f && fwd_len >= 1) use_fwd = !(have_r && dR > fwd_len);   // :338-344
+                else if (!(have_r && dR > 1)) use_lit = true;                      // :346-351
+                if (use_lit) { len = 1; ref = i; }
+                else if (use_fwd) { len = fwd_len; ref = jF; }
+                else {
+                    const u32 e = p.N - mR;                  // smallest RC end in T coordinates (R0 = s - N, e = 2N - s)
+                    len = dR;
+                    ref = e - dR + 1;                        // :362-364
+                    is_rc = true;
+                }
+            }
+            LR[o] = ((u64)ref << 32) | (u64)len;
+            if (is_rc) HARD[o] = FLAG_RC;           // the plane is zeroed beforehand: most positions need no (scattered) store
+        } else {
+            // parked for k_lpnf_hard: a depth known to satisfy the forward predicate (see k_lpnf_rank) and the RC depth
+            const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
+            LR[o] = ((u64)lb0 << 32) | (u64)((RC && dR == 0) ? DR_UNRESOLVED : dR);
             HARD[o] = FLAG_HARD;
             hard = 1;
         }
@@ -914,7 +1177,11 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, const u32* __re
                 }
             }
         }
-        const u32 dR = (u32)parked;
+        u32 dR = (u32)parked;
+        if (RC && dR == DR_UNRESOLVED) {                         // the climb of k_lpnf_rank2 met no qualifying ancestor
+            dR = rc_depth_v(T, r, p.N - i);
+            ++visited;
+        }
         bool is_rc;
         const u64 lr = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR, is_rc);
         t8.sync();                                               // every lane has read the parked value

@@ -177,7 +177,9 @@ def factorize_dist_model(data: bytes, mode: str, G: int, K: int = 3, chunk=1024,
         if ll:
             LCPx[0] = 0
         T = gm.Trees(LCPx, SAx, rc, N)
-        part = gm.walk(T, len(SAx), nfac, None, k_lin, 16, real=(len(sl), len(sl) + hi - lo))
+        # round-2 stage 3 (tabulated climb) and the search-based model of round 1 must agree on the virtual-rank arrays too
+        part = gm.walk_tables(T, len(SAx), nfac, None, k_lin, 16, real=(len(sl), len(sl) + hi - lo))
+        assert part == gm.walk(T, len(SAx), nfac, None, k_lin, 16, real=(len(sl), len(sl) + hi - lo))
         for i, v in enumerate(part):
             if v is not None:
                 assert LR[i] is None

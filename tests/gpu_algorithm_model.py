@@ -707,6 +707,157 @@ def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16, real=None):
     return LR
 
 
+# ---- round-2 stage 3: node tables carry the R-max too; ONE climb settles the forward and the RC candidate ---------------
+NT_SCAN = 16            # k_node_tables: entries a lane scans on either side before the rank goes to the cooperative queue
+DR_UNRESOLVED = 0xFFFFFFFF
+
+
+def node_tables(T: Trees, n1, nt_scan=NT_SCAN, stats=None):
+    """k_node_tables: NODE[k] = (rank naming the parent, min forward start, string depth, max rc value) of the LCP interval
+    rank k names.  Cheap phase = linear scans with the aggregates folded on the way; the rest goes through the summary trees."""
+    LCP, SA = T.lcp[0], T.f[0]
+    NODE = [None] * (n1 + 1)
+    for k in range(n1 + 1):
+        d = 0 if k in (0, n1) else LCP[k]
+        if d == 0:
+            NODE[k] = (k, NONE_MIN, 0, 0)
+            continue
+        fm, rm = NONE_MIN, 0
+        j, ok = k - 1, False
+        for _ in range(nt_scan):
+            fm = min(fm, T.fval(SA[j])); rm = max(rm, T.rval(SA[j])) if T.rc else 0
+            if LCP[j] < d:
+                ok = True
+                break
+            j -= 1
+        a = j
+        if ok:
+            ok = False
+            j = k
+            for _ in range(nt_scan):
+                fm = min(fm, T.fval(SA[j])); rm = max(rm, T.rval(SA[j])) if T.rc else 0
+                j += 1
+                if LCP[j] < d:
+                    ok = True
+                    break
+            b1 = j
+        if not ok:                                   # cooperative queue: summary-tree searches + range aggregate
+            a = T.find_prev_less(k - 1, d)
+            b1 = T.find_next_less(k + 1, d)
+            fm, rm = T.agg(a, b1 - 1, NONE_MIN, 0)
+            if stats is not None:
+                stats["queued"] = stats.get("queued", 0) + 1
+        NODE[k] = (a if LCP[a] >= LCP[b1] else b1, fm, d, rm if T.rc else 0)
+    return NODE
+
+
+def walk_tables(T: Trees, n1, nfac, RANK, max_nodes=4, Q=16, real=None, nt_scan=NT_SCAN):
+    """k_node_tables + k_lpnf_rank + k_lpnf_hard as of round 2: the leaf climbs its tabulated ancestors once; the first
+    (deepest) ancestor whose R-max qualifies IS the RC candidate node vR (factorizer_core.hpp:269-271), the first whose
+    F-min + depth <= i is vF (:264-266); nothing above vF can beat it (forward wins ties), so the climb ends there.  A
+    position that exhausts the climb budget is hard; if its RC candidate was not met on the way, k_lpnf_hard finds it from
+    the nearest qualifying rc rank on either side (summary-tree searches)."""
+    SA, LCP = T.f[0], T.lcp[0]
+    rc, twoN = T.rc, T.twoN
+    NODE = node_tables(T, n1, nt_scan)
+    LR = [None] * nfac
+    HARD = [None] * nfac
+    for r in (range(n1) if real is None else range(real[0], real[1])):
+        i = SA[r]
+        if i >= nfac:
+            continue
+        thr = twoN - i
+        k = r if LCP[r] >= LCP[r + 1] else r + 1
+        have_f = at_root = False
+        dF = jF = 0
+        belowF = childF = i
+        dR = mR = 0
+        steps = 0
+        while True:
+            par, m, d, rm = NODE[k]
+            if d == 0:
+                at_root = True
+                break
+            if steps == max_nodes:
+                break
+            steps += 1
+            if rc and dR == 0 and rm > thr:
+                dR, mR = d, rm
+            if m != NONE_MIN and m + d <= i:
+                have_f, dF, jF, belowF = True, d, m, childF
+                break
+            childF = m
+            k = par
+        rinfo = (dR >= 1, dR, mR)
+        gen, fwd_len = None, 0
+        if have_f:
+            part = (i - belowF) if belowF != i else 0
+            gen = (part, belowF) if part > dF else (dF, jF)
+            fwd_len = (i - jF) if belowF == jF else dF
+        elif at_root:
+            gen = (i - childF, childF) if childF != i else None
+        else:
+            lb0 = i - childF if (childF != NONE_MIN and childF < i) else 0
+            HARD[i] = (r, dR if (dR >= 1 or not rc) else DR_UNRESOLVED, lb0)
+            continue
+        LR[i] = _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo)
+
+    def pred_f(st, D):
+        return st[2] != NONE_MIN and st[2] + D <= i
+
+    for c0 in range(0, nfac, Q):
+        prevF = 0
+        for i in range(c0, min(c0 + Q, nfac)):
+            if HARD[i] is None:
+                prevF = 0
+                continue
+            r, dR, lb0 = HARD[i]
+            leaf = (r, r, i, 0)
+            Dtop = max(LCP[r], LCP[r + 1]) + 1
+            lb = max(prevF - 1 if prevF > 0 else 0, lb0)
+            U = L = leaf
+            if lb >= 1 and lb + 1 < Dtop:
+                st = _extend(T, leaf, lb + 1)
+                if pred_f(st, lb + 1):
+                    Ds, U, L = _search(T, leaf, lb + 1, Dtop, pred_f, st)
+                else:
+                    Ds, L = lb, st
+                    U = _extend(T, st, lb)
+            elif lb >= 1:
+                Ds, L = lb, leaf
+                U = _extend(T, leaf, lb)
+            else:
+                Ds, U, L = _search(T, leaf, 0, Dtop, pred_f)
+                if U is None:
+                    U = leaf
+            prevF = Ds
+            gen = (Ds, U[2]) if Ds >= 1 else None
+            have_f, fwd_len, jF = False, 0, 0
+            if rc and Ds >= 1:
+                if (U[0], U[1]) != (L[0], L[1]):
+                    have_f, jF = True, U[2]
+                    fwd_len = (i - jF) if L[2] == U[2] else Ds
+                else:
+                    du = max(LCP[U[0]], LCP[U[1] + 1])
+                    if du > 0:
+                        P = _extend(T, U, du)
+                        have_f, jF = True, P[2]
+                        fwd_len = (i - jF) if U[2] == P[2] else du
+            rinfo = (False, 0, 0)
+            if rc:
+                if dR == DR_UNRESOLVED:              # rc_depth_v: nearest qualifying rc rank on either side
+                    thr = twoN - i
+                    kl = T.find_prev_r_greater(r - 1, thr)
+                    kr = T.find_next_r_greater(r + 1, thr)
+                    dl = T.lcp_range_min(kl + 1, r) if kl >= 0 else 0
+                    dr = T.lcp_range_min(r + 1, kr) if kr >= 0 else 0
+                    dR = max(dl, dr)
+                if dR >= 1:
+                    rinfo = (True, dR, _extend(T, leaf, dR)[3])
+            LR[i] = _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo)
+    return LR
+
+
 # ------------------------------------------------------------------ stage 4: chain
 def chain(LR, nfac, start_pos, rc, chunk=1024):
     nchunks = (nfac + chunk - 1) // chunk
@@ -753,7 +904,7 @@ def chain(LR, nfac, start_pos, rc, chunk=1024):
 
 # ------------------------------------------------------------------ whole pipeline
 def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, force_bits=None, chunk=1024,
-                    k_lin=K_LIN, walk_q=16):
+                    k_lin=K_LIN, walk_q=16, tables=True, nt_scan=NT_SCAN):
     """mode: 'general' | 'rc_prepared'."""
     data = bytes(data)
     if mode == "general":
@@ -774,5 +925,5 @@ def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, forc
     SA, RANK, _ = suffix_array(data, force_bits, seed_out=so)
     LCP = lcp_array(data, SA, RANK, seed=so["seed"])          # key-derived LCP + Kasai over the marked positions
     T = Trees(LCP, SA, rc, N)
-    LR = walk(T, n1, nfac, RANK, k_lin, walk_q)
+    LR = (walk_tables(T, n1, nfac, RANK, k_lin, walk_q, nt_scan=nt_scan) if tables else walk(T, n1, nfac, RANK, k_lin, walk_q))
     return chain(LR, nfac, start_pos, rc, chunk)

@@ -98,6 +98,33 @@ def test_layout_symbols_fills_whole_radix_passes():
             assert W == min(29, 59 // b) or (W + 1) * b + 5 > (W * b + 5 + 7) // 8 * 8   # one more symbol = one more pass
 
 
+def test_tabulated_climb_settles_both_candidates():
+    """Round-2 stage 3 (walk_tables: node tables with F-min AND R-max, one climb, RC depth of budget-exhausted positions found
+    by the hard kernel) against the search-based model of round 1 (walk) at EVERY position, not only along the chain."""
+    rnd = random.Random(33)
+    for it in range(250):
+        sig = rnd.choice([1, 2, 2, 3, 4])
+        n = rnd.randint(1, 90)
+        s = bytes(rnd.choice(b"ACGT"[:sig]) for _ in range(n))
+        if it % 4 == 0:                                            # tandem array inside random text: long forward-only climbs
+            u = bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 4)))
+            s = s[: n // 2] + u * rnd.randint(5, 30) + s[n // 2:]
+        for mode in ("general", "rc"):
+            if mode == "rc":
+                S = wl.prepare_w_rc_single(s)
+                N = len(S) // 2 - 1
+                rc, nfac = True, N
+            else:
+                S, N, rc, nfac = s, 0, False, len(s)
+            n1 = len(S) + 1
+            SA, RANK, _ = gm.suffix_array(S)
+            LCP = gm.lcp_array(S, SA, RANK)
+            T = gm.Trees(LCP, SA, rc, N)
+            ref = gm.walk(T, n1, nfac, RANK, 4, 16)
+            for budget, scan in [(1, 1), (2, 3), (4, 16), (64, 16), (rnd.randint(1, 8), rnd.randint(1, 20))]:
+                assert gm.walk_tables(T, n1, nfac, RANK, budget, rnd.choice([1, 4, 16]), nt_scan=scan) == ref, (s, mode, budget, scan)
+
+
 def test_model_hybrid_rounds_and_representative_ranks():
     """Model of the hybrid doubling rounds (csrc/big_groups.cuh) and of ranks-as-representatives: tandem-heavy texts
     with tiny tile / outlier capacities so that the split, the pivot partition, the S/B routing, the renaming rule
