@@ -705,39 +705,9 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
     P.end(KC_TREE, (u64)n1 * 8 + (u64)n1 / 2, st, (u32)lev);
     c->trees = T;
     if (!LR) return OK;                                  // trees only (edge staircases of a distributed run)
-    // NLZ_STAGE3_R1=1: the round-1 kernels (one thread per rank for the node table, neighbour hops for the RC candidate)
-    // ("rank": only the rank kernel of round 1, on the new table)
-    static const char* s3env = getenv("NLZ_STAGE3_R1");
-    static const bool stage3_r1 = s3env != nullptr;
-    static const bool nodes_r1 = s3env != nullptr && strcmp(s3env, "rank") != 0;
-    if (nodes_r1) {
-        KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
-           (rc ? k_node_tables<true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
-               : k_node_tables<false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
-    } else {
-        KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
-           (rc ? k_node_tables2<true><<<ceil_div_u32((u64)n1 + 1, NT_PER_CTA), 256, 0, st>>>(T, wp, w.NODE)
-               : k_node_tables2<false><<<ceil_div_u32((u64)n1 + 1, NT_PER_CTA), 256, 0, st>>>(T, wp, w.NODE)));
-    }
-    RNear rn;
-    memset(&rn, 0, sizeof(rn));
-    if (rc && stage3_r1) {
-        // nearest rc(T) rank on either side of every rank + LCP minimum on the way (two segmented scans)
-        u32* PR = reinterpret_cast<u32*>(w.KEY[1]);
-        u32* ML = PR + n1;
-        u32* NR = w.VAL[0];
-        u32* MR = w.VAL[1];
-        const u32 tiles = ceil_div_u32(n1, RN_TILE);
-        P.begin(st);
-        k_rnear_reduce<0><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM);
-        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
-        k_rnear_apply<0><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM, PR, ML);
-        k_rnear_reduce<1><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM);
-        k_rnear_scan_tiles<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles);
-        k_rnear_apply<1><<<tiles, RN_THREADS, 0, st>>>(R0, LCP, wp, w.PMAX, w.PSUM, NR, MR);
-        P.end(KC_RNEAR, (u64)n1 * (4 * 8 + 4 * 4), st, 6);
-        rn.PR = PR; rn.ML = ML; rn.NR = NR; rn.MR = MR;
-    }
+    KL(P, KC_NODES, (u64)n1 * (4 + 8 + 16), st,
+       (rc ? k_node_tables<true, true><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)
+           : k_node_tables<false, false><<<ceil_div_u32((u64)n1 + 1, 256), 256, 0, st>>>(T, wp, w.NODE)));
     unsigned long long* visit_ctr = reinterpret_cast<unsigned long long*>(w.CTR + 16);   // [0] probes, [1] hard
     NLZ_CK(cudaMemsetAsync(visit_ctr, 0, 16, st));
     // flag plane: zero = ordinary forward / literal factor; k_lpnf_rank stores only the hard and the RC marks
@@ -758,26 +728,17 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
         k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.PMAX, tiles, w.CTR + 5);
         k_forward_ranks<2><<<tiles, 256, 0, st>>>(F0, wp, w.PMAX, list);
         nwork = nreal < wp.nfac ? nreal : wp.nfac;
-        const u32 grid = ceil_div_u32(nwork ? nwork : 1, 256);
-        if (stage3_r1) {
-            if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
-            else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
-        } else {
-            if (bylist) k_lpnf_rank2<true, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
-            else k_lpnf_rank2<true, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
-        }
+        const u32 grid = ceil_div_u32(nwork ? nwork : 1, 256 * RK_ILP);
+        if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, 0u, walk_nodes, LR, FLAGS, visit_ctr);
+        else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, 0u, walk_nodes, LR, FLAGS, visit_ctr);
     } else {
         nwork = nreal;
-        const u32 grid = bylist ? ceil_div_u32(nreal ? nreal : 1, 256) : ceil_div_u32(n1, 256);
-        if (stage3_r1) {
-            if (bylist) k_lpnf_rank<false, true><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
-            else k_lpnf_rank<false, false><<<grid, 256, 0, st>>>(T, wp, rn, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
-        } else {
-            if (bylist) k_lpnf_rank2<false, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
-            else k_lpnf_rank2<false, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
-        }
+        const u32 items = bylist ? nreal : n1;
+        const u32 grid = ceil_div_u32(items ? items : 1, 256 * RK_ILP);
+        if (bylist) k_lpnf_rank<false, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, items, walk_nodes, LR, FLAGS, visit_ctr);
+        else k_lpnf_rank<false, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, items, walk_nodes, LR, FLAGS, visit_ctr);
     }
-    P.end(KC_WALK, (u64)n1 * (rc ? 12 : 4) + (u64)nreal * 17, st, rc ? 4 : 1);
+    P.end(KC_WALK, (u64)n1 * 4 + (u64)nreal * 17, st, rc ? 4 : 1);
     {
         const u64 items = bylist ? (u64)nwork : (u64)wp.nfac;
         const u32 grid = ceil_div_u32((u64)ceil_div_u32(items ? items : 1, WALK_Q) * 8, 256);   // one 8-lane tile per run

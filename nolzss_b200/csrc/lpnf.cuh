@@ -176,6 +176,42 @@ __device__ __forceinline__ u32 mask_lcp_less_v(const Trees& T, int lev, i64 gsta
     return m & valid_mask((i64)T.cntL[lev] - gstart);
 }
 
+// Per-thread line probes (scalar flavour): a 128-byte line is read in 16-byte pieces, four entries per load and compare
+// group, with an exit after every piece -- the entry-by-entry loops this replaces spent ~6 instructions per entry and up
+// to 31 entries per line and level, and in k_node_tables a warp waits for its slowest lane.
+// highest index <= hi (0..31) of the line whose entry is < d, or -1
+__device__ __forceinline__ int line_prev_less(const u32* __restrict__ line, int hi, u32 d) {
+    const uint4* q = reinterpret_cast<const uint4*>(line);
+    u32 keep = (2u << (hi & 3)) - 1u;
+#pragma unroll 1
+    for (int c = hi >> 2; c >= 0; --c) {
+        const uint4 x = __ldg(q + c);
+        const u32 m4 = ((x.x < d ? 1u : 0u) | (x.y < d ? 2u : 0u) | (x.z < d ? 4u : 0u) | (x.w < d ? 8u : 0u)) & keep;
+        if (m4) return 4 * c + (31 - __clz(m4));
+        keep = 0xFu;
+    }
+    return -1;
+}
+// lowest index in [lo, last] (0..31) of the line whose entry is < d, or -1
+__device__ __forceinline__ int line_next_less(const u32* __restrict__ line, int lo, int last, u32 d) {
+    const uint4* q = reinterpret_cast<const uint4*>(line);
+    u32 keep = 0xFu & ~((1u << (lo & 3)) - 1u);
+    const int cl = last >> 2;
+#pragma unroll 1
+    for (int c = lo >> 2; c <= cl; ++c) {
+        const uint4 x = __ldg(q + c);
+        u32 m4 = ((x.x < d ? 1u : 0u) | (x.y < d ? 2u : 0u) | (x.z < d ? 4u : 0u) | (x.w < d ? 8u : 0u)) & keep;
+        if (c == cl) m4 &= (2u << (last & 3)) - 1u;
+        if (m4) return 4 * c + (__ffs(m4) - 1);
+        keep = 0xFu;
+    }
+    return -1;
+}
+__device__ __forceinline__ int line_last(const Trees& T, int lev, i64 gstart) {   // last valid entry of the line
+    const i64 rest = (i64)T.cntL[lev] - 1 - gstart;
+    return rest > 31 ? 31 : (int)rest;
+}
+
 // largest k <= pos with LCP[k] < d   (exists: LCP[0] = 0 < d since d >= 1)
 template <bool VEC>
 __device__ __forceinline__ u32 find_prev_less(const Trees& T, u32 pos, u32 d) {
@@ -198,29 +234,21 @@ __device__ __forceinline__ u32 find_prev_less(const Trees& T, u32 pos, u32 d) {
     }
     const u32* l0 = T.lcp[0];
 #pragma unroll 1
-    for (int s = 0; s < 12; ++s) {
+    for (int s = 0; s < 4; ++s) {        // the common case in rank order: the boundary is a neighbour
         if (l0[idx] < d) return (u32)idx;
         --idx;
     }
     for (;;) {
-        const u32* a = T.lcp[lev];
         const i64 gstart = idx & ~31LL;
-        i64 j = idx;
-        for (; j >= gstart; --j)
-            if (a[j] < d) break;
-        if (j >= gstart) { idx = j; break; }
+        const int j = line_prev_less(T.lcp[lev] + gstart, (int)(idx - gstart), d);
+        if (j >= 0) { idx = gstart + j; break; }
         idx = (gstart >> 5) - 1;
         ++lev;
     }
     while (lev > 0) {
         --lev;
-        const u32* a = T.lcp[lev];
         const i64 base = idx << 5;
-        i64 j = base + 31;
-        if (j > (i64)T.cntL[lev] - 1) j = (i64)T.cntL[lev] - 1;
-        for (; j > base; --j)
-            if (a[j] < d) break;
-        idx = j;
+        idx = base + line_prev_less(T.lcp[lev] + base, line_last(T, lev, base), d);   // exists: the parent's minimum
     }
     return (u32)idx;
 }
@@ -247,91 +275,23 @@ __device__ __forceinline__ u32 find_next_less(const Trees& T, u32 pos, u32 d) {
     }
     const u32* l0 = T.lcp[0];
 #pragma unroll 1
-    for (int s = 0; s < 12; ++s) {
+    for (int s = 0; s < 4; ++s) {
         if (l0[idx] < d) return (u32)idx;
         ++idx;
     }
     for (;;) {
-        const u32* a = T.lcp[lev];
-        i64 gend = idx | 31;
-        if (gend > (i64)T.cntL[lev] - 1) gend = (i64)T.cntL[lev] - 1;
-        i64 j = idx;
-        for (; j <= gend; ++j)
-            if (a[j] < d) break;
-        if (j <= gend) { idx = j; break; }
-        idx = (idx >> 5) + 1;
+        const i64 gstart = idx & ~31LL;
+        const int j = line_next_less(T.lcp[lev] + gstart, (int)(idx - gstart), line_last(T, lev, gstart), d);
+        if (j >= 0) { idx = gstart + j; break; }
+        idx = (gstart >> 5) + 1;
         ++lev;
     }
     while (lev > 0) {
         --lev;
-        const u32* a = T.lcp[lev];
         const i64 base = idx << 5;
-        i64 top = base + 31;
-        if (top > (i64)T.cntL[lev] - 1) top = (i64)T.cntL[lev] - 1;
-        i64 j = base;
-        for (; j < top; ++j)
-            if (a[j] < d) break;
-        idx = j;
+        idx = base + line_next_less(T.lcp[lev] + base, 0, line_last(T, lev, base), d);
     }
     return (u32)idx;
-}
-
-__device__ __forceinline__ u32 r_node(const Trees& T, const WalkParams& p, int lev, i64 j) {
-    return T.r[lev][j];
-}
-// largest k <= q with r_value(SA[k]) > thr, or -1 (scalar; fallback of the RC neighbour hop)
-__device__ __forceinline__ i64 find_prev_r_greater(const Trees& T, const WalkParams& p, i64 q, u32 thr) {
-    if (q < 0) return -1;
-    int lev = 0;
-    i64 idx = q;
-    for (;;) {
-        const i64 gstart = idx & ~31LL;
-        i64 j = idx;
-        for (; j >= gstart; --j)
-            if (r_node(T, p, lev, j) > thr) break;
-        if (j >= gstart) { idx = j; break; }
-        if (gstart == 0) return -1;
-        idx = (gstart >> 5) - 1;
-        ++lev;
-    }
-    while (lev > 0) {
-        --lev;
-        const i64 base = idx << 5;
-        i64 j = base + 31;
-        if (j > (i64)T.cntS[lev] - 1) j = (i64)T.cntS[lev] - 1;
-        for (; j > base; --j)
-            if (r_node(T, p, lev, j) > thr) break;
-        idx = j;
-    }
-    return idx;
-}
-// smallest k >= q with r_value(SA[k]) > thr, or -1
-__device__ __forceinline__ i64 find_next_r_greater(const Trees& T, const WalkParams& p, i64 q, u32 thr) {
-    if (q >= (i64)T.cntS[0]) return -1;
-    int lev = 0;
-    i64 idx = q;
-    for (;;) {
-        i64 gend = idx | 31;
-        if (gend > (i64)T.cntS[lev] - 1) gend = (i64)T.cntS[lev] - 1;
-        i64 j = idx;
-        for (; j <= gend; ++j)
-            if (r_node(T, p, lev, j) > thr) break;
-        if (j <= gend) { idx = j; break; }
-        idx = (idx >> 5) + 1;
-        ++lev;
-        if (lev >= T.nlev || idx >= (i64)T.cntS[lev]) return -1;
-    }
-    while (lev > 0) {
-        --lev;
-        const i64 base = idx << 5;
-        i64 top = base + 31;
-        if (top > (i64)T.cntS[lev] - 1) top = (i64)T.cntS[lev] - 1;
-        i64 j = base;
-        for (; j < top; ++j)
-            if (r_node(T, p, lev, j) > thr) break;
-        idx = j;
-    }
-    return idx;
 }
 
 // fold entries [lob, hib] of node line (lev, gstart) into the F-min / R-max aggregates
@@ -362,11 +322,30 @@ __device__ __forceinline__ void agg_line(const Trees& T, const WalkParams& p, in
         return;
     }
     {
-        const u32* fa = T.f[lev] + gstart;
-        const u32* ra = T.r[lev] + gstart;
-        for (u32 k = lob; k <= hib; ++k) {
-            fmin = min(fmin, fa[k]);
-            if (WANT_R) rmax = max(rmax, ra[k]);
+        // one thread: 16-byte pieces, whole pieces folded with three min / max each
+        const uint4* fa = reinterpret_cast<const uint4*>(T.f[lev] + gstart);
+        const uint4* ra = reinterpret_cast<const uint4*>(T.r[lev] + gstart);
+        const u32 c0 = lob >> 2, c1 = hib >> 2;
+#pragma unroll 1
+        for (u32 c = c0; c <= c1; ++c) {
+            const uint4 xf = __ldg(fa + c);
+            uint4 xr = make_uint4(0, 0, 0, 0);
+            if (WANT_R) xr = __ldg(ra + c);
+            const u32 lo = c == c0 ? (lob & 3u) : 0u, hi = c == c1 ? (hib & 3u) : 3u;
+            if (lo == 0 && hi == 3) {
+                fmin = min(fmin, min(min(xf.x, xf.y), min(xf.z, xf.w)));
+                if (WANT_R) rmax = max(rmax, max(max(xr.x, xr.y), max(xr.z, xr.w)));
+            } else {
+                const u32 fv[4] = {xf.x, xf.y, xf.z, xf.w};
+                const u32 rv[4] = {xr.x, xr.y, xr.z, xr.w};
+#pragma unroll
+                for (u32 e = 0; e < 4; ++e) {
+                    if (e >= lo && e <= hi) {
+                        fmin = min(fmin, fv[e]);
+                        if (WANT_R) rmax = max(rmax, rv[e]);
+                    }
+                }
+            }
         }
     }
 }
@@ -386,24 +365,6 @@ __device__ __forceinline__ void agg_range(const Trees& T, const WalkParams& p, i
         b = ((b + 1) >> 5) - 1;
         ++lev;
     }
-}
-
-// min LCP[a..b] (inclusive, a <= b), scalar
-__device__ __forceinline__ u32 lcp_range_min(const Trees& T, i64 a, i64 b) {
-    u32 m = NONE_MIN;
-    int lev = 0;
-    while (a <= b) {
-        const u32* la = T.lcp[lev];
-        const i64 ga = a & ~31LL, gb = b & ~31LL;
-        if (ga == gb) { for (i64 k = a; k <= b; ++k) m = min(m, la[k]); return m; }
-        if (a != ga) { for (i64 k = a; k < ga + 32; ++k) m = min(m, la[k]); a = ga + 32; }
-        if (((b + 1) & 31) != 0) { for (i64 k = gb; k <= b; ++k) m = min(m, la[k]); b = gb - 1; }
-        if (a > b) return m;
-        a >>= 5;
-        b = ((b + 1) >> 5) - 1;
-        ++lev;
-    }
-    return m;
 }
 
 // ---- cooperative (8-lane) versions: RC candidate depth of one leaf from scratch ---------------------------------------
@@ -498,197 +459,6 @@ __device__ __forceinline__ u32 rc_depth_v(const Trees& T, u32 r, u32 thr) {
     return max(dl, dr);
 }
 
-// ---- nearest rc(T) rank on either side, with the LCP minimum on the way -----------------------
-// PR[k] = largest k' <= k with SA[k'] in rc(T) (NONE_MIN if none), ML[k] = min LCP[PR[k]+1 .. k]
-// NR[k] = smallest k' >= k with SA[k'] in rc(T) (NONE_MIN if none), MR[k] = min LCP[k+1 .. NR[k]]
-// (ML/MR = NONE_MIN when the range is empty, i.e. k itself is an rc(T) rank.)  Three-phase
-// segmented scans; tiles of RN_TILE ranks.
-constexpr int RN_THREADS = 256;
-constexpr int RN_ITEMS = 8;
-constexpr int RN_TILE = RN_THREADS * RN_ITEMS;
-
-struct RnState { u32 idx; u32 mn; };   // last rc rank seen (NONE_MIN: none yet) and min LCP since
-__device__ __forceinline__ RnState rn_combine(RnState a, RnState b) {   // a then b
-    RnState o;
-    if (b.idx != NONE_MIN) { o.idx = b.idx; o.mn = b.mn; }
-    else { o.idx = a.idx; o.mn = min(a.mn, b.mn); }
-    return o;
-}
-
-// element e of the scan in direction DIR (0: left-to-right over k, 1: right-to-left)
-template <int DIR>
-__device__ __forceinline__ RnState rn_element(const u32* __restrict__ R0, const u32* __restrict__ LCP, u32 k,
-                                              const WalkParams& p) {
-    RnState e;
-    if (R0[k] != 0) { e.idx = k; e.mn = NONE_MIN; }
-    else { e.idx = NONE_MIN; e.mn = DIR == 0 ? LCP[k] : LCP[k + 1]; }
-    return e;
-}
-
-template <int DIR>
-__global__ void __launch_bounds__(RN_THREADS)
-k_rnear_reduce(const u32* __restrict__ R0, const u32* __restrict__ LCP, WalkParams p, u32* __restrict__ tile_idx,
-               u32* __restrict__ tile_mn) {
-    __shared__ RnState wagg[RN_THREADS / 32];
-    const u32 n1 = p.n1;
-    const u64 tile_start = (u64)blockIdx.x * RN_TILE;
-    RnState acc; acc.idx = NONE_MIN; acc.mn = NONE_MIN;
-#pragma unroll
-    for (int q = 0; q < RN_ITEMS; ++q) {
-        const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;     // scan position
-        if (o < n1) {
-            const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
-            acc = rn_combine(acc, rn_element<DIR>(R0, LCP, k, p));
-        }
-    }
-    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        RnState t;
-        t.idx = __shfl_up_sync(0xffffffffu, acc.idx, o);
-        t.mn = __shfl_up_sync(0xffffffffu, acc.mn, o);
-        if (lane >= (u32)o) acc = rn_combine(t, acc);
-    }
-    if (lane == 31) wagg[w] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        RnState a = wagg[0];
-        for (int i = 1; i < RN_THREADS / 32; ++i) a = rn_combine(a, wagg[i]);
-        tile_idx[blockIdx.x] = a.idx;
-        tile_mn[blockIdx.x] = a.mn;
-    }
-}
-
-// exclusive scan of the tile aggregates by one CTA (sequential per thread chunk + warp scans)
-__global__ void __launch_bounds__(1024)
-k_rnear_scan_tiles(u32* __restrict__ tile_idx, u32* __restrict__ tile_mn, u32 ntiles) {
-    __shared__ RnState wagg[32];
-    const u32 per = (ntiles + 1023) / 1024;
-    u32 b = threadIdx.x * per, e = b + per;
-    if (b > ntiles) b = ntiles;
-    if (e > ntiles) e = ntiles;
-    RnState acc; acc.idx = NONE_MIN; acc.mn = NONE_MIN;
-    for (u32 i = b; i < e; ++i) { RnState t; t.idx = tile_idx[i]; t.mn = tile_mn[i]; acc = rn_combine(acc, t); }
-    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    RnState inc = acc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        RnState t;
-        t.idx = __shfl_up_sync(0xffffffffu, inc.idx, o);
-        t.mn = __shfl_up_sync(0xffffffffu, inc.mn, o);
-        if (lane >= (u32)o) inc = rn_combine(t, inc);
-    }
-    if (lane == 31) wagg[w] = inc;
-    __syncthreads();
-    RnState carry; carry.idx = NONE_MIN; carry.mn = NONE_MIN;
-    for (u32 i = 0; i < w; ++i) carry = rn_combine(carry, wagg[i]);
-    RnState prevl;
-    prevl.idx = __shfl_up_sync(0xffffffffu, inc.idx, 1);
-    prevl.mn = __shfl_up_sync(0xffffffffu, inc.mn, 1);
-    if (lane > 0) carry = rn_combine(carry, prevl);
-    for (u32 i = b; i < e; ++i) {
-        RnState t; t.idx = tile_idx[i]; t.mn = tile_mn[i];
-        tile_idx[i] = carry.idx; tile_mn[i] = carry.mn;
-        carry = rn_combine(carry, t);
-    }
-}
-
-template <int DIR>
-__global__ void __launch_bounds__(RN_THREADS)
-k_rnear_apply(const u32* __restrict__ R0, const u32* __restrict__ LCP, WalkParams p, const u32* __restrict__ tile_idx,
-              const u32* __restrict__ tile_mn, u32* __restrict__ out_idx, u32* __restrict__ out_mn) {
-    __shared__ RnState wagg[RN_THREADS / 32];
-    const u32 n1 = p.n1;
-    const u64 tile_start = (u64)blockIdx.x * RN_TILE;
-    RnState el[RN_ITEMS];
-    RnState acc; acc.idx = NONE_MIN; acc.mn = NONE_MIN;
-#pragma unroll
-    for (int q = 0; q < RN_ITEMS; ++q) {
-        const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;
-        el[q].idx = NONE_MIN; el[q].mn = NONE_MIN;
-        if (o < n1) {
-            const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
-            el[q] = rn_element<DIR>(R0, LCP, k, p);
-            acc = rn_combine(acc, el[q]);
-        }
-    }
-    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    RnState inc = acc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        RnState t;
-        t.idx = __shfl_up_sync(0xffffffffu, inc.idx, o);
-        t.mn = __shfl_up_sync(0xffffffffu, inc.mn, o);
-        if (lane >= (u32)o) inc = rn_combine(t, inc);
-    }
-    if (lane == 31) wagg[w] = inc;
-    __syncthreads();
-    RnState carry; carry.idx = tile_idx[blockIdx.x]; carry.mn = tile_mn[blockIdx.x];
-    for (u32 i = 0; i < w; ++i) carry = rn_combine(carry, wagg[i]);
-    RnState prevl;
-    prevl.idx = __shfl_up_sync(0xffffffffu, inc.idx, 1);
-    prevl.mn = __shfl_up_sync(0xffffffffu, inc.mn, 1);
-    if (lane > 0) carry = rn_combine(carry, prevl);
-#pragma unroll
-    for (int q = 0; q < RN_ITEMS; ++q) {
-        const u64 o = tile_start + (u64)threadIdx.x * RN_ITEMS + q;
-        if (o < n1) {
-            const u32 k = DIR == 0 ? (u32)o : (u32)(n1 - 1 - o);
-            carry = rn_combine(carry, el[q]);       // inclusive state at k
-            out_idx[k] = carry.idx;
-            out_mn[k] = carry.mn;
-        }
-    }
-}
-
-struct RNear {
-    const u32* PR; const u32* ML;   // left
-    const u32* NR; const u32* MR;   // right
-};
-
-// depth of the LCA of leaf r with the nearest rc(T) suffix whose T-end is < i (value > thr), on one side
-// (DIR 0: left).  Hops over rc ranks only; falls back to the summary trees after RHOP_MAX hops.
-constexpr int RHOP_MAX = 24;
-template <int DIR>
-__device__ __forceinline__ u32 rc_side_depth(const Trees& T, const WalkParams& p, const RNear& rn, u32 r, u32 thr) {
-    const u32* R0 = T.r[0];
-    const u32* LCP = T.lcp[0];
-    u32 k = r;            // current rank (start: the F-class leaf itself)
-    u32 run = NONE_MIN;   // min LCP between k and r
-#pragma unroll 1
-    for (int hop = 0; hop < RHOP_MAX; ++hop) {
-        // step to the neighbouring rank, then (if it is not an rc rank) jump to the nearest rc rank beyond it
-        if (DIR == 0) {
-            if (k == 0) return 0;
-            run = min(run, LCP[k]);
-            u32 nb = k - 1;
-            const u32 tgt = rn.PR[nb];
-            if (tgt == NONE_MIN) return 0;
-            if (tgt != nb) run = min(run, rn.ML[nb]);
-            k = tgt;
-        } else {
-            if (k + 1 >= p.n1) return 0;
-            run = min(run, LCP[k + 1]);
-            u32 nb = k + 1;
-            const u32 tgt = rn.NR[nb];
-            if (tgt == NONE_MIN) return 0;
-            if (tgt != nb) run = min(run, rn.MR[nb]);
-            k = tgt;
-        }
-        if (run == 0) return 0;                       // left the last non-root ancestor
-        if (R0[k] > thr) return run;                  // rc rank whose T-end N - R0 lies before i
-    }
-    // rare: many non-qualifying rc suffixes in a row -> summary-tree search from k
-    if (DIR == 0) {
-        const i64 kl = find_prev_r_greater(T, p, (i64)k - 1, thr);
-        if (kl < 0) return 0;
-        return min(run, lcp_range_min(T, kl + 1, (i64)k));
-    }
-    const i64 kr = find_next_r_greater(T, p, (i64)k + 1, thr);
-    if (kr < 0) return 0;
-    return min(run, lcp_range_min(T, (i64)k + 1, kr));
-}
-
 // ---- the factor rule ------------------------------------------------------------------------
 // LR[i] = ref << 32 | len for every factorized position i; FLAGS[i] (one byte): bit 0 = "hard" (left to k_lpnf_hard),
 // bit 1 = the factor is a reverse-complement one.  (ref and len both need 32 bits at genome scale -- refs of a 3.1 Gbp
@@ -765,11 +535,18 @@ __device__ __forceinline__ u64 select_factor(const Trees& T, const WalkParams& p
 // ---- per-node table ----------------------------------------------------------------------------
 // Every rank k with LCP[k] > 0 names the LCP interval ("node") [a, b1-1] of string depth LCP[k] (a / b1 =
 // nearest strictly smaller LCP value to the left / right).  NODE[k] = {rank that names the parent node, minimum
-// forward start inside the node, string depth, -}: the suffix tree's internal nodes, tabulated once, so that
-// a leaf climbs to the root with ONE 16-byte load per ancestor.  The parent of [a, b1-1] is named by a if
-// LCP[a] >= LCP[b1], else by b1.  Ranks with LCP 0 (and the guard entry n1) name the root: depth 0.
-// Rank order, scalar probes: neighbouring lanes name nested or identical nodes and share the cache lines.
-template <bool RC>
+// forward start inside the node, string depth, maximum rc value inside the node (RC mode)}: the suffix tree's internal
+// nodes, tabulated once, so that a leaf climbs to the root with ONE 16-byte load per ancestor and meets both candidates
+// on the way.  The parent of [a, b1-1] is named by a if LCP[a] >= LCP[b1], else by b1.  Ranks with LCP 0 (and the guard
+// entry n1) name the root: depth 0.
+// Rank order, one thread per rank: neighbouring lanes name nested or identical nodes and share the cache lines.  Interval
+// sizes follow a 1/s law -- a third of the ranks name a node that reaches more than 16 entries to one side, every warp
+// holds several, and the warp waits for them: the searches and the range aggregate read the lines in 16-byte pieces
+// (line_prev_less / line_next_less / agg_line).  Tried and dropped (r2, 250 Mbp text, 33 ms for this kernel with scalar
+// entry-by-entry loops): short scans for every rank + a shared-memory queue of the rest served by 8-lane tiles (43 ms: the
+// four tiles of a warp diverge and serialise) or by whole warps (77 ms: one dependent chain per warp instead of 32), and
+// the same scans + a compacted list for a second kernel (33 ms: the list's entries cost ~3700 instructions each).
+template <bool RC, bool WANT_R>
 __global__ void __launch_bounds__(256)
 k_node_tables(Trees T, WalkParams p, uint4* __restrict__ NODE) {
     const u32 k = blockIdx.x * 256 + threadIdx.x;
@@ -779,80 +556,9 @@ k_node_tables(Trees T, WalkParams p, uint4* __restrict__ NODE) {
     const u32 a = find_prev_less<false>(T, k - 1, d);
     const u32 b1 = find_next_less<false>(T, k + 1, d);
     u32 fmin = NONE_MIN, rmax = 0;
-    agg_range<RC, false, false>(T, p, (i64)a, (i64)b1 - 1, fmin, rmax);
+    agg_range<RC, WANT_R, false>(T, p, (i64)a, (i64)b1 - 1, fmin, rmax);
     const u32 la = T.lcp[0][a], lb = T.lcp[0][b1];
-    NODE[k] = make_uint4(la >= lb ? a : b1, fmin, d, 0u);
-}
-
-// Round-2 layout of the same table, built without idle lanes: NODE[k] = {parent name, F-min, depth, R-max} (the R-max of the
-// node's interval lets the climb of k_lpnf_rank settle the RC candidate too).  Interval sizes follow a 1/s law -- a third
-// of the ranks name a node that reaches more than NT_SCAN entries to one side, and every warp holds several -- so one
-// thread per rank spent most of its issue slots in a few lanes' scalar tree searches (r2 profile: 10 of 32 lanes active).
-// Here a lane only scans NT_SCAN entries to either side, folding the aggregates as it goes; the ranks it cannot finish
-// are queued in shared memory and the CTA's 32 eight-lane tiles share the queue evenly, each entry costing a few 128-byte
-// lines (find_prev_less / find_next_less / agg_range, cooperative flavour).
-constexpr int NT_SCAN = 16;
-constexpr int NT_ITEMS = 2;
-constexpr int NT_PER_CTA = 256 * NT_ITEMS;
-template <bool RC>
-__global__ void __launch_bounds__(256)
-k_node_tables2(Trees T, WalkParams p, uint4* __restrict__ NODE) {
-    __shared__ u32 queue[NT_PER_CTA];
-    __shared__ u32 qn;
-    const u32* __restrict__ l0 = T.lcp[0];
-    const u32* __restrict__ f0 = T.f[0];
-    const u32* __restrict__ r0 = T.r[0];
-    if (threadIdx.x == 0) qn = 0;
-    __syncthreads();
-#pragma unroll 1
-    for (int it = 0; it < NT_ITEMS; ++it) {
-        const u64 k64 = (u64)blockIdx.x * NT_PER_CTA + (u64)(it * 256) + threadIdx.x;
-        if (k64 > (u64)p.n1) continue;
-        const u32 k = (u32)k64;
-        const u32 d = (k == 0 || k == p.n1) ? 0u : l0[k];
-        if (d == 0) { NODE[k] = make_uint4(k, NONE_MIN, 0u, 0u); continue; }
-        u32 fm = NONE_MIN, rm = 0;
-        // leaves k-1, k-2, ... down to the first whose LCP entry is < d (that leaf is the node's first)
-        u32 j = k - 1;
-        bool ok = false;
-#pragma unroll 1
-        for (int s = 0; s < NT_SCAN; ++s) {
-            fm = min(fm, f0[j]);
-            if (RC) rm = max(rm, r0[j]);
-            if (l0[j] < d) { ok = true; break; }      // j = 0 always stops here (LCP[0] = 0)
-            --j;
-        }
-        const u32 a = j;
-        u32 b1 = 0;
-        if (ok) {
-            // leaves k, k+1, ... up to the one before the first LCP entry < d (LCP[n1] = 0 stops the scan)
-            ok = false;
-            j = k;
-#pragma unroll 1
-            for (int s = 0; s < NT_SCAN; ++s) {
-                fm = min(fm, f0[j]);
-                if (RC) rm = max(rm, r0[j]);
-                ++j;
-                if (l0[j] < d) { ok = true; break; }
-            }
-            b1 = j;
-        }
-        if (ok) NODE[k] = make_uint4(l0[a] >= l0[b1] ? a : b1, fm, d, rm);
-        else queue[atomicAdd(&qn, 1u)] = k;
-    }
-    __syncthreads();
-    const u32 n = qn;
-    const Tile8 t8 = tile8();
-#pragma unroll 1
-    for (u32 e = threadIdx.x >> 3; e < n; e += 32) {
-        const u32 k = queue[e];
-        const u32 d = l0[k];
-        const u32 a = find_prev_less<true>(T, k - 1, d);
-        const u32 b1 = find_next_less<true>(T, k + 1, d);
-        u32 fm = NONE_MIN, rm = 0;
-        agg_range<RC, RC, true>(T, p, (i64)a, (i64)b1 - 1, fm, rm);
-        if (t8.thread_rank() == 0) NODE[k] = make_uint4(l0[a] >= l0[b1] ? a : b1, fm, d, rm);
-    }
+    NODE[k] = make_uint4(la >= lb ? a : b1, fmin, d, rmax);
 }
 
 // ---- ranks to evaluate ---------------------------------------------------------------------------
@@ -883,146 +589,110 @@ k_forward_ranks(const u32* __restrict__ F0, WalkParams p, u32* __restrict__ cta_
     if (MODE == 1 && threadIdx.x == 0) cta_off[blockIdx.x] = run;
 }
 
-// ---- kernel 1: rank order ---------------------------------------------------------------------
+// ---- kernel 1: rank order, one climb settles both candidates -------------------------------------------------------
+// One thread per suffix-array rank that holds a factorized position (RC mode: the compacted forward ranks).  The leaf
+// climbs its tabulated ancestors: the first (deepest) one whose R-max exceeds N - i is the RC candidate node vR (deepest
+// ancestor holding an rc(T) suffix whose T-end lies before i, factorizer_core.hpp:269-271) and that R-max is the RC source
+// (:290-299); the first one with F-min + depth <= i is vF (:264-266).  Nothing above vF can beat the forward candidate
+// (fwd_len >= depth(vF), forward wins ties), so the climb ends at vF.  (Round 1 found the RC candidate by hopping over the
+// neighbouring rc(T) ranks -- two segmented scans to prepare, up to 24 hops and a scalar tree search per lane, 4200 issue
+// slots per warp against a few hundred now.)  A position whose climb runs out of budget is hard; if no qualifying ancestor
+// was met by then its RC depth is left to k_lpnf_hard (DR_UNRESOLVED).
 // BYLIST (distributed runs): results are indexed by the thread's work index t (the position in the compacted list of
 // forward ranks, or r - real_lo without a list) instead of by the text position -- the text positions of a rank range
 // are scattered over the whole text, and the results travel to their position owners as (position, value) records.
+constexpr u32 DR_UNRESOLVED = 0xFFFFFFFFu;
+// The kernel waits on dependent loads (list -> leaf -> ancestor -> ancestor ...; r2 profile: 50 stall cycles per issue slot,
+// a quarter of the issue slots used at full occupancy), so every thread climbs RK_ILP leaves in lockstep: the ancestor
+// loads of its leaves are in flight together.
+constexpr int RK_ILP = 2;
+struct ClimbState {
+    u32 r, i, o, k;          // rank, text position, result index, name of the next ancestor
+    u32 dF, jF, belowF;      // deepest ok-forward node: depth, min start, F-min of its path child
+    u32 childF;              // F-min of the last node that failed (starts at the leaf)
+    u32 dR, mR;              // RC candidate node: depth and R-max (0: not met yet)
+    int step;
+    bool run, have_f, at_root;
+};
 template <bool RC, bool BYLIST>
-__global__ void __launch_bounds__(256, BYLIST ? 6 : 8)   // 32 registers: 8 CTAs per SM (the kernel is latency-bound; 40 registers cost 14 %); the by-item variant spills at 32
-k_lpnf_rank(Trees T, WalkParams p, RNear rn, const uint4* __restrict__ NODE, const u32* __restrict__ list,
-            const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
+__global__ void __launch_bounds__(256, 6)
+k_lpnf_rank(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __restrict__ list,
+            const u32* __restrict__ nlist, u32 nitems, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
             unsigned long long* __restrict__ counters) {
-    const u32 t = blockIdx.x * 256 + threadIdx.x;
-    u32 r = list ? 0xFFFFFFFFu : t + (BYLIST ? p.real_lo : 0u);
-    if (list && t < *nlist) r = list[t];                    // compacted forward ranks (RC mode)
-    u32 visited = 0, hard = 0;
     const u32* LCP = T.lcp[0];
     const u32* F0 = T.f[0];
-    u32 i = 0xFFFFFFFFu;
-    if (r >= p.real_lo && r < p.real_hi) i = F0[r];         // r = 0xFFFFFFFF: no work
-    if (i < p.nfac) {
-        const u32 o = BYLIST ? t : i;                       // where this position's results go
-        bool have_f = false, at_root = false;
-        u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
-        u32 childF = i;                  // F-min of the last node that failed (starts at the leaf)
-        {
-            const u32 dl = LCP[r], dh = LCP[r + 1];
-            u32 k = dl >= dh ? r : r + 1;            // names the parent of the leaf
+    u32 visited = 0, hard = 0;
+    if (list) nitems = *nlist;                               // compacted forward ranks (RC mode)
+    ClimbState s[RK_ILP];
+#pragma unroll
+    for (int j = 0; j < RK_ILP; ++j) {
+        const u64 t = ((u64)blockIdx.x * RK_ILP + j) * 256 + threadIdx.x;
+        s[j].run = t < (u64)nitems;
+        s[j].o = (u32)t;
+        s[j].r = 0;
+        if (s[j].run) s[j].r = list ? list[t] : (u32)t + (BYLIST ? p.real_lo : 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < RK_ILP; ++j) {
+        s[j].i = 0xFFFFFFFFu;
+        if (s[j].run && s[j].r >= p.real_lo && s[j].r < p.real_hi) s[j].i = F0[s[j].r];
+        s[j].run = s[j].i < p.nfac;
+    }
+#pragma unroll
+    for (int j = 0; j < RK_ILP; ++j) {
+        s[j].k = 0;
+        if (s[j].run) {
+            const u32 dl = LCP[s[j].r], dh = LCP[s[j].r + 1];
+            s[j].k = dl >= dh ? s[j].r : s[j].r + 1;         // names the parent of the leaf
+        }
+        if (!BYLIST) s[j].o = s[j].i;                        // where this position's results go
+        s[j].dF = 0; s[j].jF = 0; s[j].belowF = s[j].i; s[j].childF = s[j].i;
+        s[j].dR = 0; s[j].mR = 0; s[j].step = 0;
+        s[j].have_f = false; s[j].at_root = false;
+    }
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < RK_ILP; ++j) any |= s[j].run;
 #pragma unroll 1
-            for (int step = 0;; ++step) {
-                const uint4 nd = __ldg(NODE + k);    // {parent, min forward start, depth}
-                const u32 d = nd.z;
-                if (d == 0) { at_root = true; break; }
-                if (step == max_nodes) break;
-                ++visited;
-                const u32 m = nd.y;
-                if (m != NONE_MIN && (u64)m + d <= (u64)i) {          // factorizer_core.hpp:75 / :266
-                    have_f = true; dF = d; jF = m; belowF = childF;
-                    break;
-                }
-                childF = m;
-                k = nd.x;
+    while (any) {
+        uint4 nd[RK_ILP];
+#pragma unroll
+        for (int j = 0; j < RK_ILP; ++j)
+            if (s[j].run) nd[j] = __ldg(NODE + s[j].k);      // {parent, F-min, depth, R-max}
+        any = false;
+#pragma unroll
+        for (int j = 0; j < RK_ILP; ++j) {
+            if (!s[j].run) continue;
+            const u32 d = nd[j].z;
+            if (d == 0) { s[j].at_root = true; s[j].run = false; continue; }
+            if (s[j].step == max_nodes) { s[j].run = false; continue; }
+            ++s[j].step;
+            ++visited;
+            const u32 i = s[j].i;
+            if (RC && s[j].dR == 0 && nd[j].w > p.N - i) { s[j].dR = d; s[j].mR = nd[j].w; }   // factorizer_core.hpp:269-271 (T-end N - R0 < i)
+            const u32 m = nd[j].y;
+            if (m != NONE_MIN && (u64)m + d <= (u64)i) {                                       // :75 / :264-266
+                s[j].have_f = true; s[j].dF = d; s[j].jF = m; s[j].belowF = s[j].childF;
+                s[j].run = false;
+                continue;
             }
-        }
-        u32 dR = 0;
-        if (RC) {
-            const u32 thr = p.N - i;                        // an rc suffix qualifies when its T-end N - R0 is < i
-            dR = max(rc_side_depth<0>(T, p, rn, r, thr), rc_side_depth<1>(T, p, rn, r, thr));
-            visited += 2;
-        }
-        if (have_f || at_root) {
-            u32 gen_len, gen_ref, fwd_len = 0;
-            if (have_f) {
-                const u32 part = (belowF != i) ? i - belowF : 0;
-                if (part > dF) { gen_len = part; gen_ref = belowF; }    // :104-107
-                else { gen_len = dF; gen_ref = jF; }                    // :89-94, :98-102
-                fwd_len = (belowF == jF) ? (i - jF) : dF;               // :322-326
-            } else {
-                const u32 v_min = childF;                               // child of the root (or the leaf itself)
-                gen_len = (v_min != i) ? i - v_min : 0;                 // :96-107 with u = root, or literal
-                gen_ref = v_min;
-            }
-            bool is_rc;
-            LR[o] = select_factor<RC, false>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR, is_rc);
-            if (is_rc) HARD[o] = FLAG_RC;           // the plane is zeroed beforehand: most positions need no (scattered) store
-        } else {
-            // Park the RC candidate depth for k_lpnf_hard, and a depth that is KNOWN to satisfy the forward predicate:
-            // the last ancestor A that failed has minF(A) + depth(A) > i, and every D < depth(A) has interval(D)
-            // containing A, so minF(interval(D)) <= minF(A); at D0 = i - minF(A) the predicate minF + D <= i holds.
-            // Inside a tandem array (minF = first position of the phase, constant along the climb) D0 IS the answer,
-            // so the depth search of k_lpnf_hard starts two probes away from it even without a carried bound
-            // (distributed runs: neighbouring positions live on other GPUs).
-            const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
-            LR[o] = ((u64)lb0 << 32) | (u64)dR;
-            HARD[o] = FLAG_HARD;
-            hard = 1;
+            s[j].childF = m;
+            s[j].k = nd[j].x;
+            any = true;
         }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        visited += __shfl_xor_sync(0xffffffffu, visited, o);
-        hard += __shfl_xor_sync(0xffffffffu, hard, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (visited) atomicAdd(counters, (unsigned long long)visited);
-        if (hard) atomicAdd(counters + 1, (unsigned long long)hard);
-    }
-}
-
-// ---- kernel 1, round 2: one climb settles both candidates ----------------------------------------------------------
-// With the R-max in the node table the RC candidate node vR (deepest ancestor holding an rc(T) suffix whose T-end lies
-// before i, factorizer_core.hpp:269-271) is the first ancestor with NODE.w > N - i, met on the same climb that looks for
-// vF; the RC source position (:290-299) is that node's R-max itself.  Nothing above vF can beat the forward candidate
-// (fwd_len >= depth(vF), forward wins ties), so the climb ends at vF.  The neighbour hops of k_lpnf_rank, its two
-// segmented scans (k_rnear_*) and the interval search for the RC source are gone: 4200 -> a few hundred issue slots per
-// warp.  A position whose climb runs out of budget is hard, as before; if no qualifying ancestor was met by then its RC
-// depth is left to k_lpnf_hard (DR_UNRESOLVED).
-constexpr u32 DR_UNRESOLVED = 0xFFFFFFFFu;
-template <bool RC, bool BYLIST>
-__global__ void __launch_bounds__(256, 8)
-k_lpnf_rank2(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __restrict__ list,
-             const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
-             unsigned long long* __restrict__ counters) {
-    const u32 t = blockIdx.x * 256 + threadIdx.x;
-    u32 r = list ? 0xFFFFFFFFu : t + (BYLIST ? p.real_lo : 0u);
-    if (list && t < *nlist) r = list[t];                    // compacted forward ranks (RC mode)
-    u32 visited = 0, hard = 0;
-    const u32* LCP = T.lcp[0];
-    const u32* F0 = T.f[0];
-    u32 i = 0xFFFFFFFFu;
-    if (r >= p.real_lo && r < p.real_hi) i = F0[r];         // r = 0xFFFFFFFF: no work
-    if (i < p.nfac) {
-        const u32 o = BYLIST ? t : i;                       // where this position's results go
-        bool have_f = false, at_root = false;
-        u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
-        u32 childF = i;                  // F-min of the last node that failed (starts at the leaf)
-        u32 dR = 0, mR = 0;              // RC candidate node: depth and R-max (0: not met yet)
-        const u32 thr = p.N - i;         // an rc suffix qualifies when its T-end N - R0 is < i
-        {
-            const u32 dl = LCP[r], dh = LCP[r + 1];
-            u32 k = dl >= dh ? r : r + 1;            // names the parent of the leaf
-#pragma unroll 1
-            for (int step = 0;; ++step) {
-                const uint4 nd = __ldg(NODE + k);    // {parent, F-min, depth, R-max}
-                const u32 d = nd.z;
-                if (d == 0) { at_root = true; break; }
-                if (step == max_nodes) break;
-                ++visited;
-                if (RC && dR == 0 && nd.w > thr) { dR = d; mR = nd.w; }          // factorizer_core.hpp:269-271
-                const u32 m = nd.y;
-                if (m != NONE_MIN && (u64)m + d <= (u64)i) {                      // :75 / :264-266
-                    have_f = true; dF = d; jF = m; belowF = childF;
-                    break;
-                }
-                childF = m;
-                k = nd.x;
-            }
-        }
-        if (have_f || at_root) {
+    for (int j = 0; j < RK_ILP; ++j) {
+        const u32 i = s[j].i;
+        if (i >= p.nfac) continue;
+        const u32 o = s[j].o;
+        const u32 childF = s[j].childF, dR = s[j].dR;
+        if (s[j].have_f || s[j].at_root) {
             u32 len, ref;
             bool is_rc = false;
             u32 gen_len, gen_ref, fwd_len = 0;
-            if (have_f) {
+            if (s[j].have_f) {
+                const u32 dF = s[j].dF, jF = s[j].jF, belowF = s[j].belowF;
                 const u32 part = (belowF != i) ? i - belowF : 0;
                 if (part > dF) { gen_len = part; gen_ref = belowF; }    // :104-107
                 else { gen_len = dF; gen_ref = jF; }                    // :89-94, :98-102
@@ -1037,12 +707,12 @@ k_lpnf_rank2(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* _
             } else {
                 const bool have_r = dR >= 1;
                 bool use_fwd = false, use_lit = false;
-                if (have_f && fwd_len >= 1) use_fwd = !(have_r && dR > fwd_len);   // :338-344
-                else if (!(have_r && dR > 1)) use_lit = true;                      // :346-351
+                if (s[j].have_f && fwd_len >= 1) use_fwd = !(have_r && dR > fwd_len);   // :338-344
+                else if (!(have_r && dR > 1)) use_lit = true;                           // :346-351
                 if (use_lit) { len = 1; ref = i; }
-                else if (use_fwd) { len = fwd_len; ref = jF; }
+                else if (use_fwd) { len = fwd_len; ref = s[j].jF; }
                 else {
-                    const u32 e = p.N - mR;                  // smallest RC end in T coordinates (R0 = s - N, e = 2N - s)
+                    const u32 e = p.N - s[j].mR;             // smallest RC end in T coordinates (R0 = s - N, e = 2N - s)
                     len = dR;
                     ref = e - dR + 1;                        // :362-364
                     is_rc = true;
@@ -1051,11 +721,15 @@ k_lpnf_rank2(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* _
             LR[o] = ((u64)ref << 32) | (u64)len;
             if (is_rc) HARD[o] = FLAG_RC;           // the plane is zeroed beforehand: most positions need no (scattered) store
         } else {
-            // parked for k_lpnf_hard: a depth known to satisfy the forward predicate (see k_lpnf_rank) and the RC depth
+            // Parked for k_lpnf_hard: the RC depth, and a depth that is KNOWN to satisfy the forward predicate: the last
+            // ancestor A that failed has minF(A) + depth(A) > i, and every D < depth(A) has interval(D) containing A, so
+            // minF(interval(D)) <= minF(A); at D0 = i - minF(A) the predicate minF + D <= i holds.  Inside a tandem array
+            // (minF = first position of the phase, constant along the climb) D0 IS the answer, so the depth search starts
+            // two probes away from it even without a carried bound.
             const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
             LR[o] = ((u64)lb0 << 32) | (u64)((RC && dR == 0) ? DR_UNRESOLVED : dR);
             HARD[o] = FLAG_HARD;
-            hard = 1;
+            ++hard;
         }
     }
 #pragma unroll
@@ -1178,9 +852,19 @@ k_lpnf_hard(Trees T, WalkParams p, const u32* __restrict__ RANK, const u32* __re
             }
         }
         u32 dR = (u32)parked;
-        if (RC && dR == DR_UNRESOLVED) {                         // the climb of k_lpnf_rank2 met no qualifying ancestor
-            dR = rc_depth_v(T, r, p.N - i);
+        if (RC && dR == DR_UNRESOLVED) {
+            // The climb of k_lpnf_rank met no qualifying ancestor before its budget ran out.  An RC candidate only counts
+            // when it is deeper than the forward one, and every ancestor deeper than Ds lies inside L = interval(Ds + 1):
+            // without a qualifying rc suffix in L the candidate depth is at most Ds (at most depth(vF) when Ds lies inside an
+            // edge) <= fwd_len, forward or literal wins whatever the exact value -- the common case inside tandem arrays, where
+            // the nearest qualifying rank is millions of ranks away.  Otherwise the exact depth comes from the nearest
+            // qualifying rank on either side.
+            const u32 thr = p.N - i;
+            u32 fL = NONE_MIN, rL = 0;
+            agg_range<RC, true, true>(T, p, (i64)L.lo, (i64)L.hi, fL, rL);
             ++visited;
+            dR = 0;
+            if (rL > thr) { dR = rc_depth_v(T, r, thr); ++visited; }
         }
         bool is_rc;
         const u64 lr = select_factor<RC, true>(T, p, r, i, have_f, fwd_len, jF, gen_len, gen_ref, dR, is_rc);

@@ -708,50 +708,27 @@ def walk(T: Trees, n1, nfac, RANK, k_lin=K_LIN, Q=16, real=None):
 
 
 # ---- round-2 stage 3: node tables carry the R-max too; ONE climb settles the forward and the RC candidate ---------------
-NT_SCAN = 16            # k_node_tables: entries a lane scans on either side before the rank goes to the cooperative queue
 DR_UNRESOLVED = 0xFFFFFFFF
 
 
-def node_tables(T: Trees, n1, nt_scan=NT_SCAN, stats=None):
+def node_tables(T: Trees, n1):
     """k_node_tables: NODE[k] = (rank naming the parent, min forward start, string depth, max rc value) of the LCP interval
-    rank k names.  Cheap phase = linear scans with the aggregates folded on the way; the rest goes through the summary trees."""
-    LCP, SA = T.lcp[0], T.f[0]
+    rank k names (previous / next strictly smaller LCP value; aggregates over the interval from the summary trees)."""
+    LCP = T.lcp[0]
     NODE = [None] * (n1 + 1)
     for k in range(n1 + 1):
         d = 0 if k in (0, n1) else LCP[k]
         if d == 0:
             NODE[k] = (k, NONE_MIN, 0, 0)
             continue
-        fm, rm = NONE_MIN, 0
-        j, ok = k - 1, False
-        for _ in range(nt_scan):
-            fm = min(fm, T.fval(SA[j])); rm = max(rm, T.rval(SA[j])) if T.rc else 0
-            if LCP[j] < d:
-                ok = True
-                break
-            j -= 1
-        a = j
-        if ok:
-            ok = False
-            j = k
-            for _ in range(nt_scan):
-                fm = min(fm, T.fval(SA[j])); rm = max(rm, T.rval(SA[j])) if T.rc else 0
-                j += 1
-                if LCP[j] < d:
-                    ok = True
-                    break
-            b1 = j
-        if not ok:                                   # cooperative queue: summary-tree searches + range aggregate
-            a = T.find_prev_less(k - 1, d)
-            b1 = T.find_next_less(k + 1, d)
-            fm, rm = T.agg(a, b1 - 1, NONE_MIN, 0)
-            if stats is not None:
-                stats["queued"] = stats.get("queued", 0) + 1
+        a = T.find_prev_less(k - 1, d)
+        b1 = T.find_next_less(k + 1, d)
+        fm, rm = T.agg(a, b1 - 1, NONE_MIN, 0)
         NODE[k] = (a if LCP[a] >= LCP[b1] else b1, fm, d, rm if T.rc else 0)
     return NODE
 
 
-def walk_tables(T: Trees, n1, nfac, RANK, max_nodes=4, Q=16, real=None, nt_scan=NT_SCAN):
+def walk_tables(T: Trees, n1, nfac, RANK, max_nodes=4, Q=16, real=None):
     """k_node_tables + k_lpnf_rank + k_lpnf_hard as of round 2: the leaf climbs its tabulated ancestors once; the first
     (deepest) ancestor whose R-max qualifies IS the RC candidate node vR (factorizer_core.hpp:269-271), the first whose
     F-min + depth <= i is vF (:264-266); nothing above vF can beat it (forward wins ties), so the climb ends there.  A
@@ -759,7 +736,7 @@ def walk_tables(T: Trees, n1, nfac, RANK, max_nodes=4, Q=16, real=None, nt_scan=
     the nearest qualifying rc rank on either side (summary-tree searches)."""
     SA, LCP = T.f[0], T.lcp[0]
     rc, twoN = T.rc, T.twoN
-    NODE = node_tables(T, n1, nt_scan)
+    NODE = node_tables(T, n1)
     LR = [None] * nfac
     HARD = [None] * nfac
     for r in (range(n1) if real is None else range(real[0], real[1])):
@@ -845,13 +822,17 @@ def walk_tables(T: Trees, n1, nfac, RANK, max_nodes=4, Q=16, real=None, nt_scan=
                         fwd_len = (i - jF) if U[2] == P[2] else du
             rinfo = (False, 0, 0)
             if rc:
-                if dR == DR_UNRESOLVED:              # rc_depth_v: nearest qualifying rc rank on either side
+                if dR == DR_UNRESOLVED:
+                    # an RC candidate only counts when it is deeper than the forward one: without a qualifying rc suffix
+                    # inside L = interval(Ds + 1) its depth is <= fwd_len and the exact value does not matter
                     thr = twoN - i
-                    kl = T.find_prev_r_greater(r - 1, thr)
-                    kr = T.find_next_r_greater(r + 1, thr)
-                    dl = T.lcp_range_min(kl + 1, r) if kl >= 0 else 0
-                    dr = T.lcp_range_min(r + 1, kr) if kr >= 0 else 0
-                    dR = max(dl, dr)
+                    dR = 0
+                    if T.agg(L[0], L[1], NONE_MIN, 0)[1] > thr:
+                        kl = T.find_prev_r_greater(r - 1, thr)       # rc_depth_v: nearest qualifying rc rank on either side
+                        kr = T.find_next_r_greater(r + 1, thr)
+                        dl = T.lcp_range_min(kl + 1, r) if kl >= 0 else 0
+                        dr = T.lcp_range_min(r + 1, kr) if kr >= 0 else 0
+                        dR = max(dl, dr)
                 if dR >= 1:
                     rinfo = (True, dR, _extend(T, leaf, dR)[3])
             LR[i] = _finish(rc, twoN, i, have_f, fwd_len, jF, gen, rinfo)
@@ -904,7 +885,7 @@ def chain(LR, nfac, start_pos, rc, chunk=1024):
 
 # ------------------------------------------------------------------ whole pipeline
 def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, force_bits=None, chunk=1024,
-                    k_lin=K_LIN, walk_q=16, tables=True, nt_scan=NT_SCAN):
+                    k_lin=K_LIN, walk_q=16, tables=True):
     """mode: 'general' | 'rc_prepared'."""
     data = bytes(data)
     if mode == "general":
@@ -925,5 +906,5 @@ def factorize_model(data: bytes, mode: str = "general", start_pos: int = 0, forc
     SA, RANK, _ = suffix_array(data, force_bits, seed_out=so)
     LCP = lcp_array(data, SA, RANK, seed=so["seed"])          # key-derived LCP + Kasai over the marked positions
     T = Trees(LCP, SA, rc, N)
-    LR = (walk_tables(T, n1, nfac, RANK, k_lin, walk_q, nt_scan=nt_scan) if tables else walk(T, n1, nfac, RANK, k_lin, walk_q))
+    LR = (walk_tables(T, n1, nfac, RANK, k_lin, walk_q) if tables else walk(T, n1, nfac, RANK, k_lin, walk_q))
     return chain(LR, nfac, start_pos, rc, chunk)

@@ -121,8 +121,8 @@ def test_tabulated_climb_settles_both_candidates():
             LCP = gm.lcp_array(S, SA, RANK)
             T = gm.Trees(LCP, SA, rc, N)
             ref = gm.walk(T, n1, nfac, RANK, 4, 16)
-            for budget, scan in [(1, 1), (2, 3), (4, 16), (64, 16), (rnd.randint(1, 8), rnd.randint(1, 20))]:
-                assert gm.walk_tables(T, n1, nfac, RANK, budget, rnd.choice([1, 4, 16]), nt_scan=scan) == ref, (s, mode, budget, scan)
+            for budget in [1, 2, 4, 64, rnd.randint(1, 8)]:
+                assert gm.walk_tables(T, n1, nfac, RANK, budget, rnd.choice([1, 4, 16])) == ref, (s, mode, budget)
 
 
 def test_model_hybrid_rounds_and_representative_ranks():
