@@ -400,13 +400,14 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
     // the LCP array from adjacent key pairs and marks the suffixes whose LCP needs the text (lcp.cuh).
     LcpSeed seed;
     seed.LCP = w.LCP; seed.NEED = w.NEED; seed.lay = lay; seed.first_pending = false; seed.RANKOUT = nullptr;
+    seed.need_in_rankout = false;
     RankDst rdst0 = local_rank_dst(c);
     // RANK beyond the L2 cache: partitioned scatter of the inverse suffix array (see LcpSeed::RANKOUT); the node table
     // (dead until stage 3) lends the three n'-word buffers
     static const bool no_part = getenv("NLZ_NO_PARTITIONED_ISA") != nullptr;
     const bool part_isa = cnt > (48u << 20) && !no_part;
     u32* NR = reinterpret_cast<u32*>(w.NODE);
-    if (part_isa) { seed.RANKOUT = NR; rdst0.rank = nullptr; }
+    if (part_isa) { seed.RANKOUT = NR; rdst0.rank = nullptr; seed.need_in_rankout = n1 < 0x80000000u; }
     NLZ_CK(cudaMemsetAsync(w.NEED, 0, (size_t)n1 + 64, st));
     NLZ_CK(cudaMemsetAsync(w.LCP + n1, 0, 4, st));              // right guard used by the interval walks
     P.begin(st);
@@ -425,7 +426,11 @@ static int initial_sort_and_regroup(nlz_ctx* c, const Problem& pb, const ClassTa
         int pres = 0;
         NLZ_TRY(radix_sort_pairs<u32>(pk, pv, cnt, pp, w.HIST, st, &pres, P));
         u32 grid = ceil_div_u32(cnt, 256 * 8);
-        KL(P, KC_REGROUP, (u64)cnt * 12, st, (k_scatter_pairs<<<grid, 256, 0, st>>>(pk[pres], pv[pres], cnt, w.RANK)));
+        if (seed.need_in_rankout) {
+            KL(P, KC_REGROUP, (u64)cnt * 12, st, (k_scatter_pairs<true><<<grid, 256, 0, st>>>(pk[pres], pv[pres], cnt, w.RANK, w.NEED)));
+        } else {
+            KL(P, KC_REGROUP, (u64)cnt * 12, st, (k_scatter_pairs<false><<<grid, 256, 0, st>>>(pk[pres], pv[pres], cnt, w.RANK, nullptr)));
+        }
     }
     *cur_out = res ^ 1;
     NLZ_CK(cudaMemcpyAsync(c->h_pinned, w.CTR, 16, cudaMemcpyDeviceToHost, st));

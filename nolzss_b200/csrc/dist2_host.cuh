@@ -370,7 +370,7 @@ static int d2_stage_sa(D2& r, const D2Problem& pb, const KeyLayout& lay, const D
         k_regroup_reduce<u64, true><<<tiles, RG_THREADS, 0, st>>>(k[res], cnt, dist_mask, w.PMAX, w.PSUM);
         k_regroup_scan_partials<<<1, 1024, 0, st>>>(w.PMAX, w.PSUM, tiles, w.CTR);
         LcpSeed seed;                                        // LCP values that follow from adjacent key pairs; the rest is marked
-        seed.LCP = w.LCP; seed.NEED = nullptr; seed.lay = lay; seed.first_pending = r.base[r.me] > 0; seed.RANKOUT = nullptr;
+        seed.LCP = w.LCP; seed.NEED = nullptr; seed.lay = lay; seed.first_pending = r.base[r.me] > 0; seed.RANKOUT = nullptr; seed.need_in_rankout = false;
         k_regroup_apply<u64, true, GS><<<tiles, RG_THREADS, 0, st>>>(k[res], nullptr, nullptr, cnt, dist_mask, w.PMAX, w.PSUM,
                                                                      w.SA, rdst, w.KEY[res ^ 1], w.VAL[res ^ 1], w.SLOT[0], w.CTR + 3, seed);
         P.end(KC_REGROUP, (u64)cnt * (2 * 8 + 4 + 8), st, 3);

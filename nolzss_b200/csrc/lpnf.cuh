@@ -104,8 +104,7 @@ k_tree_level1(const u32* __restrict__ LCP, u32 cntL0, const u32* __restrict__ F0
     const u64 e = (u64)node * 32 + lane;
     if (node < cntL1) {
         u32 v = e < cntL0 ? LCP[e] : NONE_MIN;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        v = __reduce_min_sync(0xffffffffu, v);
         if (lane == 0) lcp1[node] = v;
     }
     if (node < cntS1) {
@@ -114,11 +113,8 @@ k_tree_level1(const u32* __restrict__ LCP, u32 cntL0, const u32* __restrict__ F0
             fv = F0[e];
             if (RC) rv = R0[e];
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            fv = min(fv, __shfl_xor_sync(0xffffffffu, fv, o));
-            if (RC) rv = max(rv, __shfl_xor_sync(0xffffffffu, rv, o));
-        }
+        fv = __reduce_min_sync(0xffffffffu, fv);
+        if (RC) rv = __reduce_max_sync(0xffffffffu, rv);
         if (lane == 0) { f1[node] = fv; if (RC) r1[node] = rv; }
     }
 }
@@ -133,18 +129,14 @@ k_tree_level_up(const u32* __restrict__ lcpA, u32 cntLA, const u32* __restrict__
     const u64 e = (u64)node * 32 + lane;
     if (node < cntLB) {
         u32 v = e < cntLA ? lcpA[e] : NONE_MIN;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        v = __reduce_min_sync(0xffffffffu, v);
         if (lane == 0) lcpB[node] = v;
     }
     if (node < cntSB) {
         u32 fv = e < cntSA ? fA[e] : NONE_MIN;
         u32 rv = (RC && e < cntSA) ? rA[e] : 0u;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            fv = min(fv, __shfl_xor_sync(0xffffffffu, fv, o));
-            if (RC) rv = max(rv, __shfl_xor_sync(0xffffffffu, rv, o));
-        }
+        fv = __reduce_min_sync(0xffffffffu, fv);
+        if (RC) rv = __reduce_max_sync(0xffffffffu, rv);
         if (lane == 0) { fB[node] = fv; if (RC) rB[node] = rv; }
     }
 }
@@ -603,9 +595,10 @@ k_forward_ranks(const u32* __restrict__ F0, WalkParams p, u32* __restrict__ cta_
 // are scattered over the whole text, and the results travel to their position owners as (position, value) records.
 constexpr u32 DR_UNRESOLVED = 0xFFFFFFFFu;
 // The kernel waits on dependent loads (list -> leaf -> ancestor -> ancestor ...; r2 profile: 50 stall cycles per issue slot,
-// a quarter of the issue slots used at full occupancy), so every thread climbs RK_ILP leaves in lockstep: the ancestor
-// loads of its leaves are in flight together.
-constexpr int RK_ILP = 2;
+// a quarter of the issue slots used at full occupancy).  RK_ILP leaves per thread climb in lockstep, their ancestor loads in
+// flight together -- measured with 2: 17.8 -> 17.3 ms on the 250 Mbp text, 0.32 -> 0.53 ms on the 5 Mbp one (fewer
+// resident leaves per SM at 40 registers): the bound is the random-access rate of the table, not the latency.  Left at 1.
+constexpr int RK_ILP = 1;
 struct ClimbState {
     u32 r, i, o, k;          // rank, text position, result index, name of the next ancestor
     u32 dF, jF, belowF;      // deepest ok-forward node: depth, min start, F-min of its path child
@@ -615,7 +608,7 @@ struct ClimbState {
     bool run, have_f, at_root;
 };
 template <bool RC, bool BYLIST>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, RK_ILP == 1 ? 8 : 6)
 k_lpnf_rank(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __restrict__ list,
             const u32* __restrict__ nlist, u32 nitems, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
             unsigned long long* __restrict__ counters) {

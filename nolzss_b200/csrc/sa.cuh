@@ -152,7 +152,7 @@ __device__ __forceinline__ KeyT kb_key(const u8* cls, const u8* tile, int o, u64
 // one by shifting a symbol out and one in (one key per ~25 instructions instead of one per 10 W), with the sentinel flags
 // of the window rolling along in a bit mask (symbols from the first sentinel on are zero in the key, its offset goes into
 // the offset field -- kb_key above is the definition).  The keys leave through shared memory so that the stores are
-// coalesced.  250 Mbp text: 7.9 -> ... ms.
+// coalesced.  250 Mbp text: 7.9 -> 1.9 ms.
 constexpr int KB_Q = KB_TP / 256;
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
@@ -328,10 +328,23 @@ struct LcpSeed {
     // (suffix, rank) pairs are partitioned by the top 8 bits of the suffix position (one radix pass), and a last
     // kernel scatters them window by window (8 MB of RANK at a time: L2-resident).  nullptr: direct scatter.
     u32* RANKOUT;
+    // With RANKOUT and n' < 2^31 the mark travels in bit 31 of the rank and k_scatter_pairs sets NEED inside the same
+    // L2-resident window (110 M scattered byte stores of the 250 Mbp text otherwise: ~64 B of DRAM traffic each).
+    bool need_in_rankout;
 };
+constexpr u32 RANKOUT_NEED_BIT = 0x80000000u;
+template <bool NEEDBIT>
 __global__ void __launch_bounds__(256)
-k_scatter_pairs(const u32* __restrict__ pos, const u32* __restrict__ val, u32 m, u32* __restrict__ dst) {
-    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < m; e += gridDim.x * 256) dst[pos[e]] = val[e];
+k_scatter_pairs(const u32* __restrict__ pos, const u32* __restrict__ val, u32 m, u32* __restrict__ dst, u8* __restrict__ need) {
+    for (u32 e = blockIdx.x * 256 + threadIdx.x; e < m; e += gridDim.x * 256) {
+        const u32 s = pos[e], v = val[e];
+        if (NEEDBIT) {
+            dst[s] = v & ~RANKOUT_NEED_BIT;
+            if (v & RANKOUT_NEED_BIT) need[s] = 1;
+        } else {
+            dst[s] = v;
+        }
+    }
 }
 constexpr u64 UPD_NEED_BIT = 1ull << 63;      // INITIAL records: the suffix is a member of a tie group (its LCP is pending)
 
@@ -343,7 +356,7 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
                 u32 m, KeyT dist_mask, const u32* __restrict__ pmax, const u32* __restrict__ psum,
                 u32* __restrict__ SA, RankDst RANK, u64* __restrict__ key_next,
                 u32* __restrict__ val_next, u32* __restrict__ slot_next, u32* __restrict__ maxg_out,
-                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{64, 1, 1, 1, 0}, false, nullptr}) {
+                LcpSeed seed = LcpSeed{nullptr, nullptr, KeyLayout{64, 1, 1, 1, 0}, false, nullptr, false}) {
     __shared__ u8 sh_head[RG_TILE + 8];
     __shared__ u32 wmax[RG_THREADS / 32], wsum[RG_THREADS / 32];
     const u64 tile_start = (u64)blockIdx.x * RG_TILE;
@@ -414,9 +427,9 @@ k_regroup_apply(const KeyT* __restrict__ keys, const u32* __restrict__ vals, con
                 // that lands in the head slot it recomputes what the key pair says).
                 lcp_pending = act[q] || (e == 0 && seed.first_pending);
                 seed.LCP[slot - RANK.base] = lcp_pending ? LCP_PENDING : (e == 0 ? 0u : key_pair_lcp<KeyT>(keys[e - 1], keys[e], seed.lay));
-                if (lcp_pending && seed.NEED) seed.NEED[s] = 1;
+                if (lcp_pending && seed.NEED && !seed.need_in_rankout) seed.NEED[s] = 1;
             }
-            if (INITIAL && seed.RANKOUT) seed.RANKOUT[e] = newrank;
+            if (INITIAL && seed.RANKOUT) seed.RANKOUT[e] = newrank | ((seed.need_in_rankout && lcp_pending) ? RANKOUT_NEED_BIT : 0u);
             if (changed) {
                 if (RANK.rank) RANK.rank[s] = newrank;
                 if (RANK.upd) {
