@@ -733,15 +733,15 @@ static int stage_lpnf(nlz_ctx* c, bool rc, cudaStream_t st, const u32* F0, const
         k_scan_u32_single_cta<<<1, 1024, 0, st>>>(w.PMAX, tiles, w.CTR + 5);
         k_forward_ranks<2><<<tiles, 256, 0, st>>>(F0, wp, w.PMAX, list);
         nwork = nreal < wp.nfac ? nreal : wp.nfac;
-        const u32 grid = ceil_div_u32(nwork ? nwork : 1, 256 * RK_ILP);
-        if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, 0u, walk_nodes, LR, FLAGS, visit_ctr);
-        else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, 0u, walk_nodes, LR, FLAGS, visit_ctr);
+        const u32 grid = ceil_div_u32(nwork ? nwork : 1, 256);
+        if (bylist) k_lpnf_rank<true, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
+        else k_lpnf_rank<true, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, list, w.CTR + 5, walk_nodes, LR, FLAGS, visit_ctr);
     } else {
         nwork = nreal;
         const u32 items = bylist ? nreal : n1;
-        const u32 grid = ceil_div_u32(items ? items : 1, 256 * RK_ILP);
-        if (bylist) k_lpnf_rank<false, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, items, walk_nodes, LR, FLAGS, visit_ctr);
-        else k_lpnf_rank<false, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, items, walk_nodes, LR, FLAGS, visit_ctr);
+        const u32 grid = ceil_div_u32(items ? items : 1, 256);
+        if (bylist) k_lpnf_rank<false, true><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
+        else k_lpnf_rank<false, false><<<grid, 256, 0, st>>>(T, wp, w.NODE, nullptr, nullptr, walk_nodes, LR, FLAGS, visit_ctr);
     }
     P.end(KC_WALK, (u64)n1 * 4 + (u64)nreal * 17, st, rc ? 4 : 1);
     {

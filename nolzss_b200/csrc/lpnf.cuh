@@ -594,98 +594,55 @@ k_forward_ranks(const u32* __restrict__ F0, WalkParams p, u32* __restrict__ cta_
 // forward ranks, or r - real_lo without a list) instead of by the text position -- the text positions of a rank range
 // are scattered over the whole text, and the results travel to their position owners as (position, value) records.
 constexpr u32 DR_UNRESOLVED = 0xFFFFFFFFu;
-// The kernel waits on dependent loads (list -> leaf -> ancestor -> ancestor ...; r2 profile: 50 stall cycles per issue slot,
-// a quarter of the issue slots used at full occupancy).  RK_ILP leaves per thread climb in lockstep, their ancestor loads in
-// flight together -- measured with 2: 17.8 -> 17.3 ms on the 250 Mbp text, 0.32 -> 0.53 ms on the 5 Mbp one (fewer
-// resident leaves per SM at 40 registers): the bound is the random-access rate of the table, not the latency.  Left at 1.
-constexpr int RK_ILP = 1;
-struct ClimbState {
-    u32 r, i, o, k;          // rank, text position, result index, name of the next ancestor
-    u32 dF, jF, belowF;      // deepest ok-forward node: depth, min start, F-min of its path child
-    u32 childF;              // F-min of the last node that failed (starts at the leaf)
-    u32 dR, mR;              // RC candidate node: depth and R-max (0: not met yet)
-    int step;
-    bool run, have_f, at_root;
-};
+// (The kernel waits on dependent loads -- list -> leaf -> ancestor -> ancestor ...; r2 profile: 50 stall cycles per issue
+// slot, a quarter of the issue slots used at full occupancy.  Two leaves per thread climbing in lockstep, their ancestor
+// loads in flight together, gave 17.8 -> 17.3 ms on the 250 Mbp text and 0.32 -> 0.53 ms on the 5 Mbp one: the bound is the
+// random-access rate of the table, and the longer loop body costs more than the overlap gains.  One leaf per thread.)
 template <bool RC, bool BYLIST>
-__global__ void __launch_bounds__(256, RK_ILP == 1 ? 8 : 6)
+__global__ void __launch_bounds__(256, 8)
 k_lpnf_rank(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __restrict__ list,
-            const u32* __restrict__ nlist, u32 nitems, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
-            unsigned long long* __restrict__ counters) {
+             const u32* __restrict__ nlist, int max_nodes, u64* __restrict__ LR, u8* __restrict__ HARD,
+             unsigned long long* __restrict__ counters) {
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    u32 r = list ? 0xFFFFFFFFu : t + (BYLIST ? p.real_lo : 0u);
+    if (list && t < *nlist) r = list[t];                    // compacted forward ranks (RC mode)
+    u32 visited = 0, hard = 0;
     const u32* LCP = T.lcp[0];
     const u32* F0 = T.f[0];
-    u32 visited = 0, hard = 0;
-    if (list) nitems = *nlist;                               // compacted forward ranks (RC mode)
-    ClimbState s[RK_ILP];
-#pragma unroll
-    for (int j = 0; j < RK_ILP; ++j) {
-        const u64 t = ((u64)blockIdx.x * RK_ILP + j) * 256 + threadIdx.x;
-        s[j].run = t < (u64)nitems;
-        s[j].o = (u32)t;
-        s[j].r = 0;
-        if (s[j].run) s[j].r = list ? list[t] : (u32)t + (BYLIST ? p.real_lo : 0u);
-    }
-#pragma unroll
-    for (int j = 0; j < RK_ILP; ++j) {
-        s[j].i = 0xFFFFFFFFu;
-        if (s[j].run && s[j].r >= p.real_lo && s[j].r < p.real_hi) s[j].i = F0[s[j].r];
-        s[j].run = s[j].i < p.nfac;
-    }
-#pragma unroll
-    for (int j = 0; j < RK_ILP; ++j) {
-        s[j].k = 0;
-        if (s[j].run) {
-            const u32 dl = LCP[s[j].r], dh = LCP[s[j].r + 1];
-            s[j].k = dl >= dh ? s[j].r : s[j].r + 1;         // names the parent of the leaf
-        }
-        if (!BYLIST) s[j].o = s[j].i;                        // where this position's results go
-        s[j].dF = 0; s[j].jF = 0; s[j].belowF = s[j].i; s[j].childF = s[j].i;
-        s[j].dR = 0; s[j].mR = 0; s[j].step = 0;
-        s[j].have_f = false; s[j].at_root = false;
-    }
-    bool any = false;
-#pragma unroll
-    for (int j = 0; j < RK_ILP; ++j) any |= s[j].run;
+    u32 i = 0xFFFFFFFFu;
+    if (r >= p.real_lo && r < p.real_hi) i = F0[r];         // r = 0xFFFFFFFF: no work
+    if (i < p.nfac) {
+        const u32 o = BYLIST ? t : i;                       // where this position's results go
+        bool have_f = false, at_root = false;
+        u32 dF = 0, jF = 0, belowF = i;  // deepest ok-forward node: depth, min start, F-min of its path child
+        u32 childF = i;                  // F-min of the last node that failed (starts at the leaf)
+        u32 dR = 0, mR = 0;              // RC candidate node: depth and R-max (0: not met yet)
+        const u32 thr = p.N - i;         // an rc suffix qualifies when its T-end N - R0 is < i
+        {
+            const u32 dl = LCP[r], dh = LCP[r + 1];
+            u32 k = dl >= dh ? r : r + 1;            // names the parent of the leaf
 #pragma unroll 1
-    while (any) {
-        uint4 nd[RK_ILP];
-#pragma unroll
-        for (int j = 0; j < RK_ILP; ++j)
-            if (s[j].run) nd[j] = __ldg(NODE + s[j].k);      // {parent, F-min, depth, R-max}
-        any = false;
-#pragma unroll
-        for (int j = 0; j < RK_ILP; ++j) {
-            if (!s[j].run) continue;
-            const u32 d = nd[j].z;
-            if (d == 0) { s[j].at_root = true; s[j].run = false; continue; }
-            if (s[j].step == max_nodes) { s[j].run = false; continue; }
-            ++s[j].step;
-            ++visited;
-            const u32 i = s[j].i;
-            if (RC && s[j].dR == 0 && nd[j].w > p.N - i) { s[j].dR = d; s[j].mR = nd[j].w; }   // factorizer_core.hpp:269-271 (T-end N - R0 < i)
-            const u32 m = nd[j].y;
-            if (m != NONE_MIN && (u64)m + d <= (u64)i) {                                       // :75 / :264-266
-                s[j].have_f = true; s[j].dF = d; s[j].jF = m; s[j].belowF = s[j].childF;
-                s[j].run = false;
-                continue;
+            for (int step = 0;; ++step) {
+                const uint4 nd = __ldg(NODE + k);    // {parent, F-min, depth, R-max}
+                const u32 d = nd.z;
+                if (d == 0) { at_root = true; break; }
+                if (step == max_nodes) break;
+                ++visited;
+                if (RC && dR == 0 && nd.w > thr) { dR = d; mR = nd.w; }          // factorizer_core.hpp:269-271
+                const u32 m = nd.y;
+                if (m != NONE_MIN && (u64)m + d <= (u64)i) {                      // :75 / :264-266
+                    have_f = true; dF = d; jF = m; belowF = childF;
+                    break;
+                }
+                childF = m;
+                k = nd.x;
             }
-            s[j].childF = m;
-            s[j].k = nd[j].x;
-            any = true;
         }
-    }
-#pragma unroll
-    for (int j = 0; j < RK_ILP; ++j) {
-        const u32 i = s[j].i;
-        if (i >= p.nfac) continue;
-        const u32 o = s[j].o;
-        const u32 childF = s[j].childF, dR = s[j].dR;
-        if (s[j].have_f || s[j].at_root) {
+        if (have_f || at_root) {
             u32 len, ref;
             bool is_rc = false;
             u32 gen_len, gen_ref, fwd_len = 0;
-            if (s[j].have_f) {
-                const u32 dF = s[j].dF, jF = s[j].jF, belowF = s[j].belowF;
+            if (have_f) {
                 const u32 part = (belowF != i) ? i - belowF : 0;
                 if (part > dF) { gen_len = part; gen_ref = belowF; }    // :104-107
                 else { gen_len = dF; gen_ref = jF; }                    // :89-94, :98-102
@@ -700,12 +657,12 @@ k_lpnf_rank(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __
             } else {
                 const bool have_r = dR >= 1;
                 bool use_fwd = false, use_lit = false;
-                if (s[j].have_f && fwd_len >= 1) use_fwd = !(have_r && dR > fwd_len);   // :338-344
-                else if (!(have_r && dR > 1)) use_lit = true;                           // :346-351
+                if (have_f && fwd_len >= 1) use_fwd = !(have_r && dR > fwd_len);   // :338-344
+                else if (!(have_r && dR > 1)) use_lit = true;                      // :346-351
                 if (use_lit) { len = 1; ref = i; }
-                else if (use_fwd) { len = fwd_len; ref = s[j].jF; }
+                else if (use_fwd) { len = fwd_len; ref = jF; }
                 else {
-                    const u32 e = p.N - s[j].mR;             // smallest RC end in T coordinates (R0 = s - N, e = 2N - s)
+                    const u32 e = p.N - mR;                  // smallest RC end in T coordinates (R0 = s - N, e = 2N - s)
                     len = dR;
                     ref = e - dR + 1;                        // :362-364
                     is_rc = true;
@@ -714,15 +671,11 @@ k_lpnf_rank(Trees T, WalkParams p, const uint4* __restrict__ NODE, const u32* __
             LR[o] = ((u64)ref << 32) | (u64)len;
             if (is_rc) HARD[o] = FLAG_RC;           // the plane is zeroed beforehand: most positions need no (scattered) store
         } else {
-            // Parked for k_lpnf_hard: the RC depth, and a depth that is KNOWN to satisfy the forward predicate: the last
-            // ancestor A that failed has minF(A) + depth(A) > i, and every D < depth(A) has interval(D) containing A, so
-            // minF(interval(D)) <= minF(A); at D0 = i - minF(A) the predicate minF + D <= i holds.  Inside a tandem array
-            // (minF = first position of the phase, constant along the climb) D0 IS the answer, so the depth search starts
-            // two probes away from it even without a carried bound.
+            // parked for k_lpnf_hard: a depth known to satisfy the forward predicate (see k_lpnf_rank) and the RC depth
             const u32 lb0 = (childF != NONE_MIN && childF < i) ? i - childF : 0u;
             LR[o] = ((u64)lb0 << 32) | (u64)((RC && dR == 0) ? DR_UNRESOLVED : dR);
             HARD[o] = FLAG_HARD;
-            ++hard;
+            hard = 1;
         }
     }
 #pragma unroll
