@@ -174,6 +174,7 @@ k_d2_keys(const u8* __restrict__ x, u64 L, u64 pos_lo, u64 pos_hi, ClassTable ta
     __shared__ __align__(16) u8 tile[KB_TP + KB_HALO];
     __shared__ u32 wcnt[8][MAX_PEERS];
     __shared__ u32 s_run[MAX_PEERS];
+    __shared__ u64 skey[KB_SKEY];
     // kb_stage with an explicit base
     cls[threadIdx.x] = tab.cls[threadIdx.x];
     const u64 base = pos_lo + (u64)blockIdx.x * KB_TP;          // pos_lo is a multiple of KB_TP: aligned word loads
@@ -188,6 +189,7 @@ k_d2_keys(const u8* __restrict__ x, u64 L, u64 pos_lo, u64 pos_hi, ClassTable ta
     if (MODE != 0 && threadIdx.x < MAX_PEERS) s_run[threadIdx.x] = MODE == 2 ? hist_or_counts[(size_t)threadIdx.x * nctas + blockIdx.x] : 0u;
     for (int i = threadIdx.x; i < 8 * MAX_PEERS; i += 256) (&wcnt[0][0])[i] = 0;
     __syncthreads();
+    kb_tile_keys<u64>(cls, tile, base, L, lay, skey);            // rolling windows (sa.cuh); lay.R = 0 here
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 mine[MAX_PEERS];
 #pragma unroll
@@ -199,7 +201,7 @@ k_d2_keys(const u8* __restrict__ x, u64 L, u64 pos_lo, u64 pos_hi, ClassTable ta
         u64 key = 0;
         int dest = -1;
         if (p < pos_hi) {
-            key = kb_key<u64>(cls, tile, o, p, L, lay, nullptr);
+            key = skey[o + (o >> 3)];
             const u32 pre = (u32)(key >> (lay.key_bits - pbits));
             if (MODE == 0) atomicAdd(&hist_or_counts[pre], 1u);
             else {

@@ -151,52 +151,57 @@ __device__ __forceinline__ KeyT kb_key(const u8* cls, const u8* tile, int o, u64
 // Every thread builds the keys of KB_Q CONSECUTIVE suffixes: the window of the first one symbol by symbol, every further
 // one by shifting a symbol out and one in (one key per ~25 instructions instead of one per 10 W), with the sentinel flags
 // of the window rolling along in a bit mask (symbols from the first sentinel on are zero in the key, its offset goes into
-// the offset field -- kb_key above is the definition).  The keys leave through shared memory so that the stores are
-// coalesced.  250 Mbp text: 7.9 -> 1.9 ms.
+// the offset field -- kb_key above is the definition).  The keys are left in shared memory (index o + (o >> 3): one pad
+// element per 8, so a thread's run of 8 starts in its own banks) for coalesced stores.  250 Mbp text: 7.9 -> 1.9 ms.
+// On entry `tile` holds the CTA's text window (kb_stage), on exit the symbol classes; `base` = text position of tile[0].
 constexpr int KB_Q = KB_TP / 256;
+constexpr int KB_SKEY = KB_TP + KB_TP / 8;
+template <typename KeyT>
+__device__ __forceinline__ void kb_tile_keys(const u8* cls, u8* tile, u64 base, u64 L, const KeyLayout& lay, KeyT* skey) {
+    // bytes -> classes, in place; positions at or past L count as sentinels
+    for (int j = threadIdx.x; j < KB_TP + KB_HALO; j += 256) tile[j] = (base + j < L) ? cls[tile[j]] : (u8)SENT_CLASS;
+    __syncthreads();
+    const int b = lay.b, W = lay.W;
+    const int o0 = threadIdx.x * KB_Q;
+    u64 K = 0;                                        // the W symbols of the window, sentinels as 0
+    u32 SM = 0;                                       // bit t: symbol t of the window is a sentinel
+    for (int t = 0; t < W; ++t) {
+        u32 c = tile[o0 + t];
+        if (c == SENT_CLASS) { SM |= 1u << t; c = 0; }
+        K = (K << b) | c;
+    }
+    const u64 wmask = (1ull << (W * b)) - 1;          // W * b <= 59
+    const int symsh = lay.key_bits - lay.R - W * b, dsh = lay.dshift();
+    const KeyT none = ((KeyT)1 << lay.D) - 1;
+#pragma unroll 1
+    for (int q = 0; q < KB_Q; ++q) {
+        u64 ks = K;
+        KeyT dist = none;
+        if (SM) {
+            const int t = __ffs(SM) - 1;
+            dist = (KeyT)t;
+            ks = K & ~((1ull << ((W - t) * b)) - 1);  // symbols t .. W-1 dropped
+        }
+        const int o = o0 + q;
+        skey[o + (o >> 3)] = ((KeyT)ks << symsh) | (dist << dsh);
+        u32 c = tile[o + W];                          // <= KB_TP - 1 + W < KB_TP + KB_HALO
+        SM >>= 1;
+        if (c == SENT_CLASS) { SM |= 1u << (W - 1); c = 0; }
+        K = ((K << b) & wmask) | c;
+    }
+    __syncthreads();
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 k_build_keys(const u8* __restrict__ x, u64 L, u32 n1, ClassTable tab, KeyLayout lay, const u32* __restrict__ REC,
              KeyT* __restrict__ keys, u32* __restrict__ vals) {
     __shared__ u8 cls[256];
     __shared__ __align__(16) u8 tile[KB_TP + KB_HALO];
-    __shared__ KeyT skey[KB_TP + KB_TP / 8];              // one pad element per 8: a thread's run of 8 starts in its own banks
+    __shared__ KeyT skey[KB_SKEY];
     kb_stage(x, L, tab, cls, tile);
     const u64 base = (u64)blockIdx.x * KB_TP;
-    // bytes -> classes, in place; positions at or past L count as sentinels
-    for (int j = threadIdx.x; j < KB_TP + KB_HALO; j += 256) tile[j] = (base + j < L) ? cls[tile[j]] : (u8)SENT_CLASS;
-    __syncthreads();
-    {
-        const int b = lay.b, W = lay.W;
-        const int o0 = threadIdx.x * KB_Q;
-        u64 K = 0;                                        // the W symbols of the window, sentinels as 0
-        u32 SM = 0;                                       // bit t: symbol t of the window is a sentinel
-        for (int t = 0; t < W; ++t) {
-            u32 c = tile[o0 + t];
-            if (c == SENT_CLASS) { SM |= 1u << t; c = 0; }
-            K = (K << b) | c;
-        }
-        const u64 wmask = (1ull << (W * b)) - 1;          // W * b <= 59
-        const int symsh = lay.key_bits - lay.R - W * b, dsh = lay.dshift();
-        const KeyT none = ((KeyT)1 << lay.D) - 1;
-#pragma unroll 1
-        for (int q = 0; q < KB_Q; ++q) {
-            u64 ks = K;
-            KeyT dist = none;
-            if (SM) {
-                const int t = __ffs(SM) - 1;
-                dist = (KeyT)t;
-                ks = K & ~((1ull << ((W - t) * b)) - 1);  // symbols t .. W-1 dropped
-            }
-            const int o = o0 + q;
-            skey[o + (o >> 3)] = ((KeyT)ks << symsh) | (dist << dsh);
-            u32 c = tile[o + W];                          // <= KB_TP - 1 + W < KB_TP + KB_HALO
-            SM >>= 1;
-            if (c == SENT_CLASS) { SM |= 1u << (W - 1); c = 0; }
-            K = ((K << b) & wmask) | c;
-        }
-    }
-    __syncthreads();
+    kb_tile_keys<KeyT>(cls, tile, base, L, lay, skey);
 #pragma unroll 1
     for (int r = 0; r < KB_Q; ++r) {
         const int o = r * 256 + threadIdx.x;
