@@ -74,6 +74,43 @@ def build_keys(data: bytes, cls, lay):
     return keys
 
 
+def build_keys_rolling(data: bytes, cls, lay, Q=8):
+    """sa.cuh kb_tile_keys: every thread builds the keys of Q consecutive suffixes -- the first window symbol by symbol,
+    the following ones by shifting a symbol out and one in; the sentinel flags of the window roll along in a bit mask
+    (bit t: symbol t of the window is a sentinel) and everything from the first sentinel on is dropped from the key."""
+    L = len(data)
+    n1 = L + 1
+    kb, b, W, D = lay["key_bits"], lay["b"], lay["W"], lay["D"]
+    none = (1 << D) - 1
+    symsh = kb - lay["R"] - W * b
+    wmask = (1 << (W * b)) - 1
+    tile = [(cls[data[j]] if j < L else SENT) for j in range(n1 + Q + W + 1)]       # positions at or past L: sentinels
+    keys = [None] * n1
+    for o0 in range(0, n1, Q):
+        K = SM = 0
+        for t in range(W):
+            c = tile[o0 + t]
+            if c == SENT:
+                SM |= 1 << t
+                c = 0
+            K = (K << b) | c
+        for q in range(Q):
+            ks, dist = K, none
+            if SM:
+                t = (SM & -SM).bit_length() - 1
+                dist = t
+                ks = K & ~((1 << ((W - t) * b)) - 1)
+            if o0 + q < n1:
+                keys[o0 + q] = (ks << symsh) | (dist << lay["dshift"])
+            c = tile[o0 + q + W]
+            SM >>= 1
+            if c == SENT:
+                SM |= 1 << (W - 1)
+                c = 0
+            K = ((K << b) & wmask) | c
+    return keys
+
+
 def key_pair_lcp(a: int, b_: int, lay) -> int:
     """sa.cuh key_pair_lcp: leading symbols two keys share, cut at the first sentinel of either window."""
     kb, b, W, D, R = lay["key_bits"], lay["b"], lay["W"], lay["D"], lay["R"]

@@ -86,6 +86,21 @@ def test_key_derived_lcp_and_marks():
         assert list(lcp) == gm.lcp_array(s, SA, RANK, Q=rnd.choice([1, 4, 32]), seed=so["seed"])
 
 
+def test_rolling_window_keys_equal_the_definition():
+    """kb_tile_keys (rolling windows, sentinel flags in a bit mask) against kb_key (symbol by symbol), incl. sentinels inside
+    the window, windows running past the end of the text, and 32-bit keys."""
+    rnd = random.Random(2)
+    for it in range(300):
+        sig = rnd.randint(1, 6)
+        s = bytes(rnd.choice(b"ACGTXY"[:sig]) for _ in range(rnd.randint(1, 200)))
+        if it % 2:
+            s = s + b"\x01" + s[::-1] + b"\x02"
+        if it % 5 == 0:
+            s = s[: len(s) // 3] + b"N" + s[len(s) // 3:]
+        cls, lay = gm.choose_layout(s, len(s) + 1, rnd.choice([None, 32, 64]), rnd.choice([None, 1, 2, 5]))
+        assert gm.build_keys_rolling(s, cls, lay, rnd.choice([1, 3, 8])) == gm.build_keys(s, cls, lay)
+
+
 def test_layout_symbols_fills_whole_radix_passes():
     # DESIGN.md section 3: 250 Mbp RC text (n' = 5 * 10^8 + 3, sigma 4) -> 21 symbols + 5 offset bits = 47 bits, 6 passes
     assert gm.layout_symbols(4, 2, 0, 5, 500_000_003) == 21
