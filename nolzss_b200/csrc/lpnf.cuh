@@ -16,25 +16,20 @@
 //
 // Interval boundaries (previous/next smaller LCP value) and the range aggregates (min / max of SA
 // over an interval) are answered from 32-ary summary trees (one 128-byte line per tree node).
-//   k_rnear_*    two segmented scans over the suffix array give, for every rank, the nearest rank
-//                to the left / right that holds an rc(T) suffix and the minimum LCP on the way
-//                (PR/ML, NR/MR).  With them the RC candidate -- the LCA of leaf r with the nearest
-//                QUALIFYING rc(T) suffix on either side, PSV/NSV-style -- is found by hopping over
-//                rc(T) ranks only, skipping the long forward-only runs that tandem repeats create.
-//   k_node_tables for every rank k, the LCP interval it names (previous / next smaller LCP value)
-//                and the minimum forward start inside it: the suffix tree's internal nodes,
-//                tabulated once so that a climb step is five word loads and no search.
+//   k_node_tables for every rank k, the LCP interval it names (previous / next smaller LCP value),
+//                the minimum forward start AND the maximum rc value inside it: the suffix tree's
+//                internal nodes, tabulated once so that a climb step is one 16-byte load.
 //   k_lpnf_rank  one thread per suffix-array RANK (a warp shares the cache lines around its ranks):
-//                climbs the ancestors of its leaf for the forward candidate (1-2 nodes on random
-//                DNA, up to the copy count inside tandem arrays), then applies the selection rule.
-//                The RC source position (a range max over the chosen node) is only evaluated when
-//                the RC candidate wins.  Positions that exhaust the climb budget (low-complexity
-//                text) are flagged.
+//                ONE climb over the ancestors of its leaf meets vR (first ancestor whose R-max
+//                qualifies; that R-max is the RC source) and vF (1-2 nodes on random DNA, up to the
+//                copy count inside tandem arrays), then applies the selection rule.  Positions that
+//                exhaust the climb budget (low-complexity text) are flagged.
 //   k_lpnf_hard  text order over the flagged positions: the forward predicate is monotone in the
 //                string depth D, so the answer is a binary search over D that grows interval(D)
 //                incrementally from the deepest failing node; a Kasai-style carry (the match at i
 //                is at least the match at i-1 minus one) makes consecutive positions O(1) probes.
 //                Tree lines are read with eight independent 16-byte loads (one latency per level).
+//                Also settles the RC candidate of flagged positions whose climb met no vR.
 #pragma once
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
