@@ -388,9 +388,46 @@ class Trees:
     def rval(self, s):
         return s if (self.N < s <= self.twoN) else 0
 
+    # lpnf.cuh line_prev_less / line_next_less: a 32-entry line is probed in pieces of four entries (one 16-byte load and
+    # one compare group each), with an exit after every piece
+    @staticmethod
+    def line_prev_less(line, hi, d):
+        """highest index <= hi of `line` (a list of up to 32 entries) whose entry is < d, or -1"""
+        keep = (2 << (hi & 3)) - 1
+        for c in range(hi >> 2, -1, -1):
+            m4 = 0
+            for e in range(4):
+                j = 4 * c + e
+                if j < len(line) and line[j] < d:
+                    m4 |= 1 << e
+            m4 &= keep
+            if m4:
+                return 4 * c + m4.bit_length() - 1
+            keep = 0xF
+        return -1
+
+    @staticmethod
+    def line_next_less(line, lo, last, d):
+        """lowest index in [lo, last] of `line` whose entry is < d, or -1"""
+        keep = 0xF & ~((1 << (lo & 3)) - 1)
+        cl = last >> 2
+        for c in range(lo >> 2, cl + 1):
+            m4 = 0
+            for e in range(4):
+                j = 4 * c + e
+                if j < len(line) and line[j] < d:
+                    m4 |= 1 << e
+            m4 &= keep
+            if c == cl:
+                m4 &= (2 << (last & 3)) - 1
+            if m4:
+                return 4 * c + (m4 & -m4).bit_length() - 1
+            keep = 0xF
+        return -1
+
     def find_prev_less(self, p, d):
         k = p
-        for _ in range(12):
+        for _ in range(4):
             if self.lcp[0][k] < d:
                 return k
             k -= 1
@@ -398,11 +435,9 @@ class Trees:
         while True:
             a = self.lcp[lev]
             gstart = idx & ~31
-            j = idx
-            while j >= gstart and not a[j] < d:
-                j -= 1
-            if j >= gstart:
-                idx = j
+            j = self.line_prev_less(a[gstart:gstart + 32], idx - gstart, d)
+            if j >= 0:
+                idx = gstart + j
                 break
             idx = (gstart >> 5) - 1
             lev += 1
@@ -410,39 +445,34 @@ class Trees:
             lev -= 1
             a = self.lcp[lev]
             base = idx << 5
-            j = min(base + 31, len(a) - 1)
-            while j > base and not a[j] < d:
-                j -= 1
-            idx = j
+            j = self.line_prev_less(a[base:base + 32], min(31, len(a) - 1 - base), d)
+            assert j >= 0                                  # the parent's minimum is one of them
+            idx = base + j
         return idx
 
     def find_next_less(self, p, d):
         k = p
-        for _ in range(12):
+        for _ in range(4):
             if self.lcp[0][k] < d:
                 return k
             k += 1
         lev, idx = 0, k
         while True:
             a = self.lcp[lev]
-            gend = min(idx | 31, len(a) - 1)
-            j = idx
-            while j <= gend and not a[j] < d:
-                j += 1
-            if j <= gend:
-                idx = j
+            gstart = idx & ~31
+            j = self.line_next_less(a[gstart:gstart + 32], idx - gstart, min(31, len(a) - 1 - gstart), d)
+            if j >= 0:
+                idx = gstart + j
                 break
-            idx = (idx >> 5) + 1
+            idx = (gstart >> 5) + 1
             lev += 1
         while lev > 0:
             lev -= 1
             a = self.lcp[lev]
             base = idx << 5
-            top = min(base + 31, len(a) - 1)
-            j = base
-            while j < top and not a[j] < d:
-                j += 1
-            idx = j
+            j = self.line_next_less(a[base:base + 32], 0, min(31, len(a) - 1 - base), d)
+            assert j >= 0
+            idx = base + j
         return idx
 
     def find_prev_r_greater(self, p, thr):

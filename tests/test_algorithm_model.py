@@ -101,6 +101,22 @@ def test_rolling_window_keys_equal_the_definition():
         assert gm.build_keys_rolling(s, cls, lay, rnd.choice([1, 3, 8])) == gm.build_keys(s, cls, lay)
 
 
+def test_piecewise_line_probes():
+    """lpnf.cuh line_prev_less / line_next_less (16-byte pieces with masks for the first and last piece) against a scan."""
+    rnd = random.Random(8)
+    for _ in range(3000):
+        n = rnd.randint(1, 32)
+        line = [rnd.randint(0, 6) for _ in range(n)]
+        d = rnd.randint(0, 7)
+        hi = rnd.randint(0, n - 1)
+        exp = max([j for j in range(hi + 1) if line[j] < d], default=-1)
+        assert gm.Trees.line_prev_less(line, hi, d) == exp
+        lo = rnd.randint(0, n - 1)
+        last = rnd.randint(lo, n - 1)
+        exp = min([j for j in range(lo, last + 1) if line[j] < d], default=-1)
+        assert gm.Trees.line_next_less(line, lo, last, d) == exp
+
+
 def test_layout_symbols_fills_whole_radix_passes():
     # DESIGN.md section 3: 250 Mbp RC text (n' = 5 * 10^8 + 3, sigma 4) -> 21 symbols + 5 offset bits = 47 bits, 6 passes
     assert gm.layout_symbols(4, 2, 0, 5, 500_000_003) == 21
