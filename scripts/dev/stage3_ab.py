@@ -1,4 +1,5 @@
-"""Development aid (GPU): sha256 of the factor arrays of a set of texts -- run once per NLZ_STAGE3_R1 setting and diff."""
+"""Development aid (GPU): sha256 of the factor arrays of a set of texts (general / RC, tandem-heavy, degenerate) with the
+stage-3 time of each -- run once per build or per debug switch and diff the hashes (profiles/r2_stage3_rework.md)."""
 import hashlib
 import os
 import sys
